@@ -1,0 +1,515 @@
+"""Host-side mirror of the reference's method surface, bound to libddp.so through ctypes.
+
+The reference is Julia (``iLQG``, ``iLQGkl``, ``back_pass``, ``back_pass_gps``, ``forward_pass``,
+``boxQP``, ``GaussianPolicy`` -- src/DifferentialDynamicProgramming.jl:6); Julia is not available in
+the build container, so this Python layer carries the same names, argument order/meaning and
+error behaviour and is what the parity tests drive.  ``julia/DifferentialDynamicProgramming.jl``
+is the equivalent ``ccall`` shim.  Nothing here computes: every call lands in a CUDA kernel, and
+without libddp.so / a GPU the calls raise.
+
+Array conventions (identical to ``oracle/``): time-first *math layout*, optional leading batch axis.
+    cx (N,n) | (B,N,n)          fx (n,n) | (N,n,n) | (B, 1|N, n,n)       K (N,m,n) | (B,N,m,n)
+A matrix tensor with 2 dims is shared and time-invariant, with 3 dims time-varying and shared
+across the batch, with 4 dims ``(B|1, N|1, r, c)``.  The device layout is the reference's
+column-major ``(r,c,T,B)`` (== C order ``[B][T][c][r]``); packing transposes the last two axes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from . import _lib as L
+
+# ---------------------------------------------------------------------------------------------
+# engine / device memory
+# ---------------------------------------------------------------------------------------------
+
+
+class DevArray:
+    """A device buffer owned by an Engine (ddp_malloc / ddp_free)."""
+
+    def __init__(self, eng: "Engine", shape, dtype=np.float64):
+        self.eng = eng
+        self.shape = tuple(int(s) for s in shape)
+        self.dtype = np.dtype(dtype)
+        self.nbytes = int(np.prod(self.shape, dtype=np.int64)) * self.dtype.itemsize
+        p = C.c_void_p()
+        eng._ck(eng.lib.ddp_malloc(eng.h, C.byref(p), max(self.nbytes, 8)))
+        self.ptr = p.value
+
+    def numpy(self) -> np.ndarray:
+        out = np.empty(self.shape, dtype=self.dtype)
+        if self.nbytes:
+            self.eng._ck(self.eng.lib.ddp_download(self.eng.h, out.ctypes.data, self.ptr, self.nbytes))
+        return out
+
+    def set(self, a: np.ndarray):
+        a = np.ascontiguousarray(a, dtype=self.dtype)
+        assert a.nbytes == self.nbytes, (a.shape, self.shape)
+        if self.nbytes:
+            self.eng._ck(self.eng.lib.ddp_upload(self.eng.h, self.ptr, a.ctypes.data, self.nbytes))
+        return self
+
+    def zero(self):
+        self.eng._ck(self.eng.lib.ddp_memset(self.eng.h, self.ptr, 0, self.nbytes))
+        return self
+
+    def free(self):
+        if self.ptr is not None and self.eng.h is not None:
+            self.eng.lib.ddp_free(self.eng.h, self.ptr)
+        self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Engine:
+    """One libddp handle: fixed problem size (n, m, T, B) on one GPU, one stream."""
+
+    def __init__(self, n: int, m: int, T: int, B: int = 1, device: int = 0, force_generic: bool = False):
+        self.lib = L.load()
+        self.h = None
+        h = C.c_void_p()
+        rc = self.lib.ddp_create(C.byref(h), device, n, m, T, B, 1 if force_generic else 0)
+        if rc != 0:
+            raise L.DDPError(rc, self.lib.ddp_last_error(None).decode())
+        self.h = h
+        self.n, self.m, self.T, self.B, self.device = n, m, T, B, device
+
+    def _ck(self, rc: int):
+        if rc != 0:
+            raise L.DDPError(rc, self.lib.ddp_last_error(self.h).decode())
+
+    def close(self):
+        if self.h is not None:
+            self.lib.ddp_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream: int):
+        self._ck(self.lib.ddp_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    def synchronize(self):
+        self._ck(self.lib.ddp_synchronize(self.h))
+
+    @property
+    def kernel_variant(self) -> str:
+        return self.lib.ddp_kernel_variant(self.h).decode()
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.ddp_launch_count(self.h))
+
+    def empty(self, shape, dtype=np.float64) -> DevArray:
+        return DevArray(self, shape, dtype)
+
+    def upload(self, a: np.ndarray, dtype=np.float64) -> DevArray:
+        a = np.ascontiguousarray(a, dtype=dtype)
+        return DevArray(self, a.shape, dtype).set(a)
+
+
+def _tensor(ptr: Optional[int], sb: int = 0, st: int = 0) -> L.Tensor:
+    return L.Tensor(ptr, sb, st)
+
+
+def _pack_vec(eng: Engine, a, B: int, N: int, d: int, name: str):
+    """(N,d) | (B,N,d) -> device (d,T,B) + strides."""
+    a = np.asarray(a, dtype=np.float64)
+    if a.ndim == 2:
+        a = a[None]
+    if a.shape[1:] != (N, d) or a.shape[0] not in (1, B):
+        raise ValueError(f"size({name}) should be ({d}, {N}) per trajectory, got {a.shape}")
+    dev = eng.upload(a)
+    return dev, _tensor(dev.ptr, N * d if a.shape[0] == B else 0, d)
+
+
+def _pack_mat(eng: Engine, a, B: int, N: int, r: int, c: int, name: str):
+    """(r,c) | (N,r,c) | (B|1,N|1,r,c) math layout -> device column-major + strides."""
+    a = np.asarray(a, dtype=np.float64)
+    if a.ndim == 2:
+        a = a[None, None]
+    elif a.ndim == 3:
+        a = a[None]
+    if a.ndim != 4 or a.shape[2:] != (r, c) or a.shape[0] not in (1, B) or a.shape[1] not in (1, N):
+        raise ValueError(f"size({name}) should be ({r}, {c}[, {N}]), got {a.shape}")
+    dev = eng.upload(np.swapaxes(a, -1, -2))
+    Nx = a.shape[1]
+    st = r * c if (Nx == N and N > 1) else 0
+    sb = Nx * r * c if (a.shape[0] == B and B > 1) else 0
+    return dev, _tensor(dev.ptr, sb, st)
+
+
+def _lims_dev(eng: Engine, lims, m: int):
+    if lims is None or np.asarray(lims).size == 0:
+        return None
+    lims = np.asarray(lims, dtype=np.float64).reshape(m, 2)
+    return eng.upload(np.ascontiguousarray(lims.T))      # [lower(m); upper(m)]
+
+
+# ---------------------------------------------------------------------------------------------
+# GaussianPolicy  (iLQG.jl:39-53)
+# ---------------------------------------------------------------------------------------------
+
+
+@dataclass
+class GaussianPolicy:
+    T: int = 0
+    n: int = 0
+    m: int = 0
+    K: Optional[np.ndarray] = None
+    k: Optional[np.ndarray] = None
+    Sigma: Optional[np.ndarray] = None
+    Sigmai: Optional[np.ndarray] = None
+
+    @staticmethod
+    def empty() -> "GaussianPolicy":
+        return GaussianPolicy()
+
+    @staticmethod
+    def identity(T: int, n: int, m: int) -> "GaussianPolicy":
+        eye = np.tile(np.eye(m), (T, 1, 1))
+        return GaussianPolicy(T, n, m, np.zeros((T, m, n)), np.zeros((T, m)), eye.copy(), eye.copy())
+
+    def isempty(self) -> bool:
+        return self.T == 0 and self.n == 0 and self.m == 0
+
+    def __len__(self) -> int:
+        return self.T
+
+
+# ---------------------------------------------------------------------------------------------
+# back_pass / back_pass_gps
+# ---------------------------------------------------------------------------------------------
+
+
+def _back_common(cx, cu, cxx, cxu, cuu, fx, fu, lims, u, force_generic, engine):
+    cx = np.asarray(cx, dtype=np.float64)
+    cu = np.asarray(cu, dtype=np.float64)
+    batched = cx.ndim == 3
+    B = cx.shape[0] if batched else 1
+    N, n = cx.shape[-2:]
+    m = cu.shape[-1]
+    if cu.shape[-2] != N:
+        raise ValueError("size(cu) should be (m, N)")
+    eng = engine or Engine(n, m, N, B, force_generic=force_generic)
+    keep = []
+    a = L.BackPassArgs()
+    for name, arr, d in (("cx", cx, n), ("cu", cu, m)):
+        dev, t = _pack_vec(eng, arr, B, N, d, name)
+        keep.append(dev)
+        setattr(a, name, t)
+    for name, arr, r, c in (("cxx", cxx, n, n), ("cxu", cxu, n, m), ("cuu", cuu, m, m), ("fx", fx, n, n), ("fu", fu, n, m)):
+        dev, t = _pack_mat(eng, arr, B, N, r, c, name)
+        keep.append(dev)
+        setattr(a, name, t)
+    ld = _lims_dev(eng, lims, m)
+    if ld is not None:
+        keep.append(ld)
+        a.lims = ld.ptr
+        dev, t = _pack_vec(eng, u, B, N, m, "u")
+        keep.append(dev)
+        a.u = t
+    return eng, a, keep, batched, B, N, n, m
+
+
+def _back_outputs(eng, a, B, N, n, m, want_Vxx, want_Quu):
+    out = dict(diverge=eng.empty((B,), np.int32), K=eng.empty((B, N, n, m)), k=eng.empty((B, N, m)),
+               Vx=eng.empty((B, N, n)), dV=eng.empty((B, 2)), Vxx1=eng.empty((B, n, n)))
+    if want_Vxx:
+        out["Vxx"] = eng.empty((B, N, n, n))
+    if want_Quu:
+        out["Quu"] = eng.empty((B, N, m, m))
+    for key, dev in out.items():
+        setattr(a, key, dev.ptr)
+    return out
+
+
+def back_pass(cx, cu, cxx, cxu, cuu, fx, fu, lam, regType, lims, x, u, *, want_Vxx=True, force_generic=False,
+              engine: Engine = None):
+    """``back_pass(cx,cu,cxx,cxu,cuu,fx,fu,λ,regType,lims,x,u)`` -- backward_pass.jl:162-252.
+
+    Returns ``(diverge, GaussianPolicy, Vx, Vxx, dV)``; with a leading batch axis on the inputs the
+    outputs carry it too (``diverge`` becomes an int array, the policy holds batched arrays).
+    """
+    eng, a, keep, batched, B, N, n, m = _back_common(cx, cu, cxx, cxu, cuu, fx, fu, lims, u, force_generic, engine)
+    lam_dev = eng.upload(np.broadcast_to(np.asarray(lam, dtype=np.float64), (B,)))
+    a.lam = lam_dev.ptr
+    a.reg_type = int(regType)
+    out = _back_outputs(eng, a, B, N, n, m, want_Vxx, True)
+    eng._ck(eng.lib.ddp_back_pass_f64(eng.h, C.byref(a)))
+    eng.synchronize()
+    res = _collect_back(out, batched, B, N, n, m, None)
+    del keep
+    return res
+
+
+def _collect_back(out, batched, B, N, n, m, Quui):
+    diverge = out["diverge"].numpy()
+    K = np.swapaxes(out["K"].numpy(), -1, -2)                # (B,N,n,m) col-major -> (B,N,m,n)
+    k = out["k"].numpy()
+    Vx = out["Vx"].numpy()
+    Vxx = np.swapaxes(out["Vxx"].numpy(), -1, -2) if "Vxx" in out else np.swapaxes(out["Vxx1"].numpy(), -1, -2)
+    Quu = np.swapaxes(out["Quu"].numpy(), -1, -2) if "Quu" in out else None
+    dV = out["dV"].numpy()
+    Sig = np.swapaxes(Quui.numpy(), -1, -2) if Quui is not None else None
+    if not batched:
+        pol = GaussianPolicy(N, n, m, K[0], k[0], None if Sig is None else Sig[0], None if Quu is None else Quu[0])
+        return int(diverge[0]), pol, Vx[0], Vxx[0], dV[0]
+    return diverge, GaussianPolicy(N, n, m, K, k, Sig, Quu), Vx, Vxx, dV
+
+
+def back_pass_gps(cx, cu, cxx, cxu, cuu, fx, fu, lims, x, u, kl_cost_terms, *, force_generic=False, engine: Engine = None):
+    """``back_pass_gps(cx,cu,cxx,cxu,cuu,fx,fu,lims,x,u,kl_cost_terms)`` -- backward_pass.jl:259-350.
+
+    ``kl_cost_terms = (traj_prev, ηbracket)``: the KL terms of ``∇kl`` (klutils.jl:8-23) are formed
+    on the device from the previous policy, so the policy itself is passed instead of the five
+    pre-multiplied tensors.  ``ηbracket`` is ``(3,)`` or ``(B,3)``.
+    """
+    traj_prev, etabracket = kl_cost_terms
+    eng, a, keep, batched, B, N, n, m = _back_common(cx, cu, cxx, cxu, cuu, fx, fu, lims, u, force_generic, engine)
+    eta = np.asarray(etabracket, dtype=np.float64)
+    eta = np.broadcast_to(eta.reshape(-1, 3)[:, 1], (B,)) if eta.size >= 3 else np.broadcast_to(eta, (B,))
+    eta_dev = eng.upload(eta)
+    g = L.GpsArgs()
+    Kp, g.K_prev = _pack_mat(eng, traj_prev.K if batched else traj_prev.K[None], B, N, m, n, "K_prev")
+    Sp, g.Sigi_prev = _pack_mat(eng, traj_prev.Sigmai if batched else traj_prev.Sigmai[None], B, N, m, m, "Sigi_prev")
+    kp, g.k_prev = _pack_vec(eng, traj_prev.k, B, N, m, "k_prev")
+    g.eta = eta_dev.ptr
+    out = _back_outputs(eng, a, B, N, n, m, True, True)
+    Quui = eng.empty((B, N, m, m))
+    g.Quui = Quui.ptr
+    eng._ck(eng.lib.ddp_back_pass_gps_f64(eng.h, C.byref(a), C.byref(g)))
+    eng.synchronize()
+    res = _collect_back(out, batched, B, N, n, m, Quui)
+    del keep, Kp, Sp, kp
+    return res
+
+
+# ---------------------------------------------------------------------------------------------
+# boxQP
+# ---------------------------------------------------------------------------------------------
+
+
+class PosDefException(Exception):
+    pass
+
+
+def boxQP(H, g, lower, upper, x0, *, maxIter=100, minGrad=1e-8, minRelImprove=1e-8, stepDec=0.6, minStep=1e-22,
+          Armijo=0.1, engine: Engine = None):
+    """``boxQP(H,g,lower,upper,x0)`` -- boxQP.jl:29-188.  Returns ``(x, result, Hfree, free, nfactor)``.
+
+    Unbatched calls raise :class:`PosDefException` where the reference's ``cholesky`` throws;
+    batched calls (H of shape (B,m,m)) report ``result == -1`` for those problems instead.
+    """
+    H = np.asarray(H, dtype=np.float64)
+    batched = H.ndim == 3
+    Hb = H if batched else H[None]
+    B, m, _ = Hb.shape
+    eng = engine or Engine(max(m, 1), m, 1, B)
+    vec = lambda v: eng.upload(np.broadcast_to(np.asarray(v, dtype=np.float64).reshape(-1, m), (B, m)))
+    dH = eng.upload(np.swapaxes(Hb, -1, -2))
+    dg, dl, du, dx0 = vec(g), vec(lower), vec(upper), vec(x0)
+    x, res, Hf = eng.empty((B, m)), eng.empty((B,), np.int32), eng.empty((B, m, m))
+    fm, nf = eng.empty((B,), np.uint32), eng.empty((B,), np.int32)
+    o = L.BoxQPOpts(maxIter, minGrad, minRelImprove, stepDec, minStep, Armijo)
+    eng._ck(eng.lib.ddp_boxqp_f64(eng.h, B, dH.ptr, dg.ptr, dl.ptr, du.ptr, dx0.ptr, C.byref(o), x.ptr, res.ptr, Hf.ptr,
+                                  fm.ptr, nf.ptr))
+    eng.synchronize()
+    xs, rs, Hfs, fms, nfs = x.numpy(), res.numpy(), np.swapaxes(Hf.numpy(), -1, -2), fm.numpy(), nf.numpy()
+    free = ((fms[:, None] >> np.arange(m)[None, :]) & 1).astype(bool)
+    if batched:
+        return xs, rs, Hfs, free, nfs
+    if rs[0] < 0:
+        raise PosDefException("matrix is not positive definite; Cholesky factorization failed")
+    nfree = int(np.count_nonzero(np.diag(Hfs[0])))
+    return xs[0], int(rs[0]), Hfs[0][:nfree, :nfree], free[0], int(nfs[0])
+
+
+# ---------------------------------------------------------------------------------------------
+# models: the reference's user callbacks (f, costfun, df) as device descriptors
+# ---------------------------------------------------------------------------------------------
+
+
+class _DeviceCallback:
+    """Stands where the reference takes a Julia closure.  It cannot be called on the host."""
+
+    def __init__(self, model, role):
+        self.model, self.role = model, role
+
+    def __call__(self, *a, **k):
+        raise RuntimeError(f"{type(self.model).__name__}.{self.role} is a device model descriptor; it is "
+                           "evaluated inside the CUDA kernels (there is no CPU fallback)")
+
+
+class LinearModel:
+    """x+ = A x + B u, cost ½Σx'Qx + ½Σu'Ru  (demo_linear.jl:35-50).  A: (n,n)|(N,n,n)|(B,1|N,n,n)."""
+
+    kind = 1
+    terminal_cost = 0
+
+    def __init__(self, A, B, Q, R):
+        self.A, self.B, self.Q, self.R = (np.asarray(v, dtype=np.float64) for v in (A, B, Q, R))
+        self.goal = None
+        self.f, self.costfun, self.df = (_DeviceCallback(self, r) for r in ("f", "costfun", "df"))
+
+
+class PendcartModel:
+    """Pendulum on a cart, Euler step (system_pendcart.jl:51-54,83-106)."""
+
+    kind = 2
+    terminal_cost = 1
+
+    def __init__(self, g=9.82, l=0.35, h=0.01, d=0.99, Q=None, R=1.0, goal=None):
+        self.p = (g, l, h, d)
+        self.Q = np.diag([10.0, 1.0, 2.0, 1.0]) if Q is None else np.asarray(Q, dtype=np.float64)
+        self.R = np.atleast_2d(np.asarray(R, dtype=np.float64))
+        self.goal = np.array([math.pi, 0.0, 0.0, 0.0]) if goal is None else np.asarray(goal, dtype=np.float64)
+        self.f, self.costfun, self.df = (_DeviceCallback(self, r) for r in ("f", "costfun", "df"))
+
+
+def _model_of(f, costfun=None):
+    model = getattr(f, "model", None)
+    if not isinstance(f, _DeviceCallback) or (costfun is not None and getattr(costfun, "model", None) is not model):
+        raise TypeError("f/costfun must be the callbacks of a device model descriptor (LinearModel, PendcartModel): "
+                        "arbitrary host closures cannot run on the GPU and there is no CPU fallback")
+    return model
+
+
+def _pack_model(eng: Engine, model, B, N, n, m):
+    keep = []
+    M = L.Model()
+    M.kind = model.kind
+    M.terminal_cost = model.terminal_cost
+    if model.kind == 1:
+        dev, M.A = _pack_mat(eng, model.A, B, N, n, n, "A"); keep.append(dev)
+        dev, M.Bm = _pack_mat(eng, model.B, B, N, n, m, "B"); keep.append(dev)
+    else:
+        for i, v in enumerate(model.p):
+            M.p[i] = v
+    dev, M.Q = _pack_mat(eng, model.Q, B, 1, n, n, "Q"); keep.append(dev)
+    dev, M.R = _pack_mat(eng, model.R, B, 1, m, m, "R"); keep.append(dev)
+    if model.goal is not None:
+        gd = eng.upload(model.goal); keep.append(gd)
+        M.goal = gd.ptr
+    return M, keep
+
+
+# ---------------------------------------------------------------------------------------------
+# forward_pass
+# ---------------------------------------------------------------------------------------------
+
+
+def forward_pass(traj_new: GaussianPolicy, x0, u, x, alpha, f, costfun, lims, diff=None, *, u_scale=1.0,
+                 per_step_cost=False, want_derivs=False, force_generic=False, engine: Engine = None):
+    """``forward_pass(traj_new,x0,u,x,α,f,costfun,lims,diff)`` -- forward_pass.jl:9-33.
+
+    ``f``/``costfun`` are the callbacks of a device model descriptor; ``diff`` must be the default
+    ``-``.  Returns ``(xnew, unew, cnew)`` (+ ``(cx, cu)`` with ``want_derivs``); ``cnew`` is the
+    total cost (per-step vector with ``per_step_cost``).
+    """
+    if diff is not None:
+        raise NotImplementedError("only the default diff_fun (-) is supported on the device")
+    model = _model_of(f, costfun)
+    u = np.asarray(u, dtype=np.float64)
+    batched = u.ndim == 3
+    B = u.shape[0] if batched else 1
+    N, m = u.shape[-2:]
+    x0 = np.asarray(x0, dtype=np.float64)
+    n = x0.shape[-1]
+    eng = engine or Engine(n, m, N, B, force_generic=force_generic)
+    M, keep = _pack_model(eng, model, B, N, n, m)
+    a = L.ForwardPassArgs()
+    x0b = np.broadcast_to(x0.reshape(-1, n), (B, n)) if x0.ndim <= 1 or x0.shape[0] != B else x0
+    dx0 = eng.upload(x0b); keep.append(dx0)
+    a.x0 = _tensor(dx0.ptr, n, 0)
+    du, a.u = _pack_vec(eng, u, B, N, m, "u"); keep.append(du)
+    if traj_new is not None and not traj_new.isempty():
+        K = np.asarray(traj_new.K, dtype=np.float64)
+        dK = eng.upload(np.swapaxes(K.reshape(B, N, m, n), -1, -2)); keep.append(dK)
+        dk = eng.upload(np.asarray(traj_new.k, dtype=np.float64).reshape(B, N, m)); keep.append(dk)
+        a.K, a.k = dK.ptr, dk.ptr
+        dx, a.x = _pack_vec(eng, x, B, N, n, "x"); keep.append(dx)
+    alpha = np.asarray(alpha, dtype=np.float64)
+    if alpha.ndim == 0:
+        a.alpha_scalar = float(alpha)
+    else:
+        dal = eng.upload(np.broadcast_to(alpha, (B,))); keep.append(dal)
+        a.alpha = dal.ptr
+    a.u_scale = float(u_scale)
+    ld = _lims_dev(eng, lims, m)
+    if ld is not None:
+        keep.append(ld)
+        a.lims = ld.ptr
+    xnew, unew, cost = eng.empty((B, N, n)), eng.empty((B, N, m)), eng.empty((B,))
+    a.xnew, a.unew, a.cost = xnew.ptr, unew.ptr, cost.ptr
+    Tc = N + model.terminal_cost
+    cost_t = eng.empty((B, Tc)) if per_step_cost else None
+    if cost_t is not None:
+        a.cost_t = cost_t.ptr
+    cxo = cuo = None
+    if want_derivs:
+        cxo, cuo = eng.empty((B, N, n)), eng.empty((B, N, m))
+        a.cx, a.cu = cxo.ptr, cuo.ptr
+    eng._ck(eng.lib.ddp_forward_pass_f64(eng.h, C.byref(M), C.byref(a)))
+    eng.synchronize()
+    xn, un = xnew.numpy(), unew.numpy()
+    cn = cost_t.numpy() if per_step_cost else cost.numpy()
+    if not batched:
+        xn, un, cn = xn[0], un[0], (cn[0] if per_step_cost else float(cn[0]))
+    if want_derivs:
+        cxn, cun = cxo.numpy(), cuo.numpy()
+        return xn, un, cn, ((cxn, cun) if batched else (cxn[0], cun[0]))
+    return xn, un, cn
+
+
+# ---------------------------------------------------------------------------------------------
+# KL divergence (forward_covariance + kl_div_wiki)
+# ---------------------------------------------------------------------------------------------
+
+
+def kl_div_wiki(xnew, xold, fx, R1, traj_new: GaussianPolicy, traj_prev: GaussianPolicy, *, engine: Engine = None):
+    """Per-step KL divergence between the new and previous policy (klutils.jl:70-100) with the state
+    covariance of ``forward_covariance`` (forward_pass.jl:37-56) propagated on the device.
+
+    The reference takes ``Σ_new`` from ``forward_covariance(model, x, u, traj_new)``, whose ``fx`` and
+    ``R1`` come from the un-vendored LinearTimeVaryingModelsBase; here they are arguments.
+    Returns ``(kl_t, kl_mean)``.
+    """
+    xnew = np.asarray(xnew, dtype=np.float64)
+    batched = xnew.ndim == 3
+    B = xnew.shape[0] if batched else 1
+    N, n = xnew.shape[-2:]
+    m = traj_new.m
+    eng = engine or Engine(n, m, N, B)
+    keep = []
+    a = L.KlArgs()
+    dev, a.fx = _pack_mat(eng, fx, B, N, n, n, "fx"); keep.append(dev)
+    dev, a.R1 = _pack_mat(eng, R1, B, 1, n, n, "R1"); keep.append(dev)
+    up = lambda v, shp: eng.upload(np.asarray(v, dtype=np.float64).reshape(shp))
+    dxn, dxo = up(xnew, (B, N, n)), up(xold, (B, N, n))
+    dKn = eng.upload(np.swapaxes(np.asarray(traj_new.K).reshape(B, N, m, n), -1, -2))
+    dkn = up(traj_new.k, (B, N, m))
+    dSn = eng.upload(np.swapaxes(np.asarray(traj_new.Sigma).reshape(B, N, m, m), -1, -2))
+    a.xnew, a.xold, a.K_new, a.k_new, a.Sig_new = dxn.ptr, dxo.ptr, dKn.ptr, dkn.ptr, dSn.ptr
+    dev, a.K_prev = _pack_mat(eng, np.asarray(traj_prev.K).reshape(B, N, m, n), B, N, m, n, "K_prev"); keep.append(dev)
+    dev, a.Sig_prev = _pack_mat(eng, np.asarray(traj_prev.Sigma).reshape(B, N, m, m), B, N, m, m, "Sig_prev"); keep.append(dev)
+    dev, a.Sigi_prev = _pack_mat(eng, np.asarray(traj_prev.Sigmai).reshape(B, N, m, m), B, N, m, m, "Sigi_prev"); keep.append(dev)
+    dev, a.k_prev = _pack_vec(eng, np.asarray(traj_prev.k).reshape(B, N, m), B, N, m, "k_prev"); keep.append(dev)
+    klt, klm = eng.empty((B, N)), eng.empty((B,))
+    a.kl_t, a.kl_mean = klt.ptr, klm.ptr
+    eng._ck(eng.lib.ddp_kl_div_f64(eng.h, C.byref(a)))
+    eng.synchronize()
+    t, mn = klt.numpy(), klm.numpy()
+    return (t, mn) if batched else (t[0], float(mn[0]))

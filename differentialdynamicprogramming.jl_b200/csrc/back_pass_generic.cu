@@ -1,0 +1,420 @@
+// Generic backward sweep: any n <= 64, m <= 16, all branches (Cholesky / boxQP / KL-augmented).
+// One CTA (128 threads) walks one trajectory backwards in time with every per-step block resident
+// in shared memory.  This is the coverage kernel: the specialised kernels in back_pass_tile.cu
+// (n=32,m=8 class, DMMA tiles) and back_pass_small.cu (n<=8, thread-per-trajectory) take the
+// benchmarked shapes; everything else lands here.
+//
+// Replaces back_pass / back_pass_gps of src/backward_pass.jl:162-252, :259-350 (+ macros :3-79).
+#include "boxqp.cuh"
+
+namespace {
+
+constexpr int NT = 128;
+
+struct Smem {
+    double *V, *Fx, *Fu, *W, *Z, *Qxx, *Qux, *Quxr, *K, *QK, *Kp, *S;
+    double *Quu, *QuuF, *R, *Si, *Inv;
+    double *Vx, *Qx, *Qu, *k, *kw, *Quuk, *lo, *up, *kp, *Sik, *VxN;
+    int* flags;   // [0] status (0 ok / 1 diverged), [1] free mask, [2] nfree
+};
+
+__host__ __device__ inline size_t smem_doubles(int n, int m, bool gps) {
+    int ldn = n | 1, ldm = m | 1;
+    size_t d = 0;
+    d += (size_t)ldn * n * 4;           // V, Fx, W, Qxx
+    d += (size_t)ldn * m * 2;           // Fu, Z
+    d += (size_t)ldm * n * 4;           // Qux, Quxr, K, QK
+    if (gps) d += (size_t)ldm * n * 2;  // Kp, S
+    d += (size_t)m * m * 5;             // Quu, QuuF, R, Si, Inv
+    d += (size_t)n * 3 + (size_t)m * 8 + 8;
+    return d;
+}
+
+__device__ inline void carve(double* base, int n, int m, bool gps, Smem& s) {
+    int ldn = n | 1, ldm = m | 1;
+    double* p = base;
+    s.V = p; p += ldn * n;
+    s.Fx = p; p += ldn * n;
+    s.W = p; p += ldn * n;
+    s.Qxx = p; p += ldn * n;
+    s.Fu = p; p += ldn * m;
+    s.Z = p; p += ldn * m;
+    s.Qux = p; p += ldm * n;
+    s.Quxr = p; p += ldm * n;
+    s.K = p; p += ldm * n;
+    s.QK = p; p += ldm * n;
+    if (gps) { s.Kp = p; p += ldm * n; s.S = p; p += ldm * n; } else { s.Kp = s.S = nullptr; }
+    s.Quu = p; p += m * m;
+    s.QuuF = p; p += m * m;
+    s.R = p; p += m * m;
+    s.Si = p; p += m * m;
+    s.Inv = p; p += m * m;
+    s.Vx = p; p += n;
+    s.Qx = p; p += n;
+    s.VxN = p; p += n;
+    s.Qu = p; p += m;
+    s.k = p; p += m;
+    s.kw = p; p += m;
+    s.Quuk = p; p += m;
+    s.lo = p; p += m;
+    s.up = p; p += m;
+    s.kp = p; p += m;
+    s.Sik = p; p += m;
+    s.flags = reinterpret_cast<int*>(p);
+}
+
+// general inverse by Gauss-Jordan with partial pivoting (stands for Julia's `inv`, LU based,
+// backward_pass.jl:283,346).  A (m x m, ld m) is destroyed; Ainv receives the inverse.
+__device__ void inv_gj(int m, double* A, double* Ainv) {
+    for (int i = 0; i < m; i++)
+        for (int j = 0; j < m; j++) Ainv[i + m * j] = (i == j) ? 1.0 : 0.0;
+    for (int c = 0; c < m; c++) {
+        int piv = c;
+        double best = fabs(A[c + m * c]);
+        for (int r = c + 1; r < m; r++)
+            if (fabs(A[r + m * c]) > best) { best = fabs(A[r + m * c]); piv = r; }
+        if (piv != c)
+            for (int j = 0; j < m; j++) {
+                double t = A[c + m * j]; A[c + m * j] = A[piv + m * j]; A[piv + m * j] = t;
+                t = Ainv[c + m * j]; Ainv[c + m * j] = Ainv[piv + m * j]; Ainv[piv + m * j] = t;
+            }
+        double d = 1.0 / A[c + m * c];
+        for (int j = 0; j < m; j++) { A[c + m * j] *= d; Ainv[c + m * j] *= d; }
+        for (int r = 0; r < m; r++) {
+            if (r == c) continue;
+            double f = A[r + m * c];
+            if (f != 0.0)
+                for (int j = 0; j < m; j++) { A[r + m * j] -= f * A[c + m * j]; Ainv[r + m * j] -= f * Ainv[c + m * j]; }
+        }
+    }
+}
+
+template <bool GPS>
+__global__ void __launch_bounds__(NT) bp_generic_kernel(BackParams P) {
+    extern __shared__ double smem_raw[];
+    const int n = P.n, m = P.m, N = P.T;
+    const int ldn = n | 1, ldm = m | 1;
+    const int tid = threadIdx.x;
+    Smem s;
+    carve(smem_raw, n, m, GPS, s);
+    const bool use_qp = (P.lims != nullptr) && !(P.lims[0] > P.lims[m]);   // backward_pass.jl:31
+    const long long nn = (long long)n * n, mn = (long long)m * n, mm = (long long)m * m;
+
+    for (long long b = blockIdx.x; b < P.B; b += gridDim.x) {
+        if (P.active && !P.active[b]) continue;
+        __syncthreads();
+        const double lam = GPS ? 0.0 : P.lambda[b];
+        const double eta = GPS ? P.eta[b] : 1.0;
+        double* Kb = P.K + b * (long long)N * mn;
+        double* kb = P.k + b * (long long)N * m;
+        double* Vxb = P.Vx + b * (long long)N * n;
+        double* Vxxb = P.Vxx ? P.Vxx + b * (long long)N * nn : nullptr;
+        double* Quub = P.Quu ? P.Quu + b * (long long)N * mm : nullptr;
+        double* Quuib = (GPS && P.Quui) ? P.Quui + b * (long long)N * mm : nullptr;
+        // ---- terminal step (backward_pass.jl:21-23 / :280-283)
+        {
+            const double* cxN = tp(P.cx, b, N - 1);
+            const double* cxxN = tp(P.cxx, b, N - 1);
+            const double* cuuN = tp(P.cuu, b, N - 1);
+            for (int i = tid; i < n; i += NT) { s.Vx[i] = cxN[i]; Vxb[(long long)(N - 1) * n + i] = cxN[i]; }
+            for (int e = tid; e < n * n; e += NT) {
+                int i = e % n, j = e / n;
+                double v = cxxN[e];
+                s.V[i + ldn * j] = v;
+                if (Vxxb) Vxxb[(long long)(N - 1) * nn + e] = v;
+            }
+            for (int e = tid; e < m * n; e += NT) Kb[(long long)(N - 1) * mn + e] = 0.0;
+            for (int a = tid; a < m; a += NT) { kb[(long long)(N - 1) * m + a] = 0.0; s.kw[a] = 0.0; }
+            if (GPS) {
+                const double* SiN = tp(P.Sip, b, N - 1);
+                for (int e = tid; e < m * m; e += NT) {
+                    double v = cuuN[e] / eta + SiN[e];
+                    s.Quu[e] = v;
+                    s.QuuF[e] = v;
+                    if (Quub) Quub[(long long)(N - 1) * mm + e] = v;
+                }
+                __syncthreads();
+                if (tid == 0) inv_gj(m, s.QuuF, s.Inv);
+                __syncthreads();
+                if (Quuib)
+                    for (int e = tid; e < m * m; e += NT) Quuib[(long long)(N - 1) * mm + e] = s.Inv[e];
+            } else if (Quub) {
+                for (int e = tid; e < m * m; e += NT) Quub[(long long)(N - 1) * mm + e] = cuuN[e];
+            }
+            if (tid == 0) s.flags[0] = 0;
+        }
+        double dV0 = 0.0, dV1 = 0.0;   // thread 0 only
+        int diverge = 0;
+        const bool lti = (P.fx.st == 0 && P.fu.st == 0);
+        for (int i = N - 2; i >= 0; i--) {
+            // ---- stage the step's dynamics
+            if (!lti || i == N - 2) {
+                const double* fxi = tp(P.fx, b, i);
+                const double* fui = tp(P.fu, b, i);
+                for (int e = tid; e < n * n; e += NT) s.Fx[(e % n) + ldn * (e / n)] = fxi[e];
+                for (int e = tid; e < n * m; e += NT) s.Fu[(e % n) + ldn * (e / n)] = fui[e];
+            }
+            if (GPS) {
+                const double* Kpi = tp(P.Kp, b, i);
+                const double* Sii = tp(P.Sip, b, i);
+                for (int e = tid; e < m * n; e += NT) s.Kp[(e % m) + ldm * (e / m)] = Kpi[e];
+                for (int e = tid; e < m * m; e += NT) s.Si[e] = Sii[e];
+                for (int a = tid; a < m; a += NT) s.kp[a] = P.kp.p ? tp(P.kp, b, i)[a] : 0.0;
+            }
+            __syncthreads();
+            // ---- W = Vxx fx, Z = Vxx fu
+            for (int e = tid; e < n * (n + m); e += NT) {
+                int r = e % n, c = e / n;
+                const double* col = (c < n) ? (s.Fx + ldn * c) : (s.Fu + ldn * (c - n));
+                double acc = 0.0;
+                for (int q = 0; q < n; q++) acc = fma(s.V[r + ldn * q], col[q], acc);
+                if (c < n) s.W[r + ldn * c] = acc; else s.Z[r + ldn * (c - n)] = acc;
+            }
+            if (GPS) {   // S = Σi K_prev ; Sik = Σi k_prev
+                for (int e = tid; e < m * n; e += NT) {
+                    int a = e % m, j = e / m;
+                    double acc = 0.0;
+                    for (int q = 0; q < m; q++) acc = fma(s.Si[a + m * q], s.Kp[q + ldm * j], acc);
+                    s.S[a + ldm * j] = acc;
+                }
+                for (int a = tid; a < m; a += NT) {
+                    double acc = 0.0;
+                    for (int q = 0; q < m; q++) acc = fma(s.Si[a + m * q], s.kp[q], acc);
+                    s.Sik[a] = acc;
+                }
+            }
+            __syncthreads();
+            // ---- Q expansion (backward_pass.jl:240-247)
+            {
+                const double* cxi = tp(P.cx, b, i);
+                const double* cui = tp(P.cu, b, i);
+                const double* cxxi = tp(P.cxx, b, i);
+                const double* cxui = tp(P.cxu, b, i);
+                const double* cuui = tp(P.cuu, b, i);
+                for (int e = tid; e < n * n; e += NT) {          // Qxx = cxx + fx' W
+                    int r = e % n, c = e / n;
+                    double acc = 0.0;
+                    for (int q = 0; q < n; q++) acc = fma(s.Fx[q + ldn * r], s.W[q + ldn * c], acc);
+                    double v = cxxi[e] + acc;
+                    if (GPS) {
+                        double kl = 0.0;                          // cxxkl = K' Σi K
+                        for (int q = 0; q < m; q++) kl = fma(s.Kp[q + ldm * r], s.S[q + ldm * c], kl);
+                        v = v / eta + kl;
+                    }
+                    s.Qxx[r + ldn * c] = v;
+                }
+                for (int e = tid; e < m * n; e += NT) {          // Qux = cxu' + fu' W
+                    int a = e % m, j = e / m;
+                    double acc = 0.0;
+                    for (int q = 0; q < n; q++) acc = fma(s.Fu[q + ldn * a], s.W[q + ldn * j], acc);
+                    double v = cxui[j + n * a] + acc;
+                    double vr = v;
+                    if (GPS) {
+                        v = v / eta - s.S[a + ldm * j];           // cxukl = -Σi K
+                        vr = v;
+                    } else if (P.reg_type == 2) {                 // fu'(Vxx + λI)fx = Qux + λ fu'fx
+                        double ff = 0.0;
+                        for (int q = 0; q < n; q++) ff = fma(s.Fu[q + ldn * a], s.Fx[q + ldn * j], ff);
+                        vr = v + lam * ff;
+                    }
+                    s.Qux[a + ldm * j] = v;
+                    s.Quxr[a + ldm * j] = vr;
+                }
+                for (int e = tid; e < m * m; e += NT) {          // Quu = cuu + fu' Z
+                    int a = e % m, c = e / m;
+                    double acc = 0.0;
+                    for (int q = 0; q < n; q++) acc = fma(s.Fu[q + ldn * a], s.Z[q + ldn * c], acc);
+                    double v = cuui[e] + acc;
+                    double vf = v;
+                    if (GPS) {
+                        v = v / eta + s.Si[e];                    // cuukl = Σi
+                        vf = v;
+                    } else if (P.reg_type == 2) {
+                        double ff = 0.0;
+                        for (int q = 0; q < n; q++) ff = fma(s.Fu[q + ldn * a], s.Fu[q + ldn * c], ff);
+                        vf = v + lam * ff;
+                    } else if (P.reg_type == 1 && a == c) {
+                        vf = v + lam;
+                    }
+                    s.Quu[e] = v;
+                    s.QuuF[e] = vf;
+                }
+                for (int r = tid; r < n; r += NT) {              // Qx = cx + fx' Vx
+                    double acc = 0.0;
+                    for (int q = 0; q < n; q++) acc = fma(s.Fx[q + ldn * r], s.Vx[q], acc);
+                    double v = cxi[r] + acc;
+                    if (GPS) {
+                        double kl = 0.0;                          // cxkl = K' Σi k
+                        for (int q = 0; q < m; q++) kl = fma(s.Kp[q + ldm * r], s.Sik[q], kl);
+                        v = v / eta + kl;
+                    }
+                    s.Qx[r] = v;
+                }
+                for (int a = tid; a < m; a += NT) {              // Qu = cu + fu' Vx
+                    double acc = 0.0;
+                    for (int q = 0; q < n; q++) acc = fma(s.Fu[q + ldn * a], s.Vx[q], acc);
+                    double v = cui[a] + acc;
+                    if (GPS) v = v / eta - s.Sik[a];              // cukl = -Σi k
+                    s.Qu[a] = v;
+                    if (use_qp) {                                  // :45-46
+                        double ui = tp(P.u, b, i)[a];
+                        s.lo[a] = P.lims[a] - ui;
+                        s.up[a] = P.lims[m + a] - ui;
+                    }
+                }
+            }
+            __syncthreads();
+            if (GPS) {                                            // Quu = ½(Quu + Quu')  :301
+                for (int e = tid; e < m * m; e += NT) {
+                    int a = e % m, c = e / m;
+                    if (a < c) {                                  // each unordered pair owned by one thread
+                        double w = 0.5 * (s.Quu[a + m * c] + s.Quu[c + m * a]);
+                        s.Quu[a + m * c] = w; s.Quu[c + m * a] = w;
+                        s.QuuF[a + m * c] = w; s.QuuF[c + m * a] = w;
+                    }
+                }
+                __syncthreads();
+            }
+            // ---- factorisation / QP (one thread, fixed sequential order shared with the oracle)
+            if (tid == 0) {
+                int st = 0;
+                if (!use_qp) {
+                    int idx[DDP_MAX_M];
+                    for (int a = 0; a < m; a++) idx[a] = a;
+                    if (!chol_upper_sub<DDP_MAX_M>(s.QuuF, m, idx, m, s.R, m)) {
+                        st = 1;
+                    } else {
+                        for (int a = 0; a < m; a++) s.k[a] = s.Qu[a];
+                        chol_solve<DDP_MAX_M>(s.R, m, m, s.k);
+                        for (int a = 0; a < m; a++) s.k[a] = -s.k[a];
+                        s.flags[1] = (m >= 32) ? -1 : (int)((1u << m) - 1u);
+                        s.flags[2] = m;
+                    }
+                } else {
+                    unsigned fm = 0;
+                    int nfac = 0;
+                    int res = boxqp_seq<DDP_MAX_M>(m, s.QuuF, m, s.Qu, s.lo, s.up, s.kw, P.qp, s.k, s.R, m, &fm, &nfac);
+                    if (res < 1) st = 1;                           // :50-56
+                    s.flags[1] = (int)fm;
+                    s.flags[2] = __popc(fm);
+                }
+                s.flags[0] = st;
+            }
+            __syncthreads();
+            if (s.flags[0] != 0) { diverge = i + 1; break; }
+            // ---- gains K (:42 / :57-61): one column per thread
+            {
+                const unsigned fm = (unsigned)s.flags[1];
+                const int nf = s.flags[2];
+                for (int j = tid; j < n; j += NT) {
+                    double v[DDP_MAX_M];
+                    int p = 0;
+                    for (int a = 0; a < m; a++)
+                        if ((fm >> a) & 1u) v[p++] = s.Quxr[a + ldm * j];
+                    if (nf > 0) chol_solve<DDP_MAX_M>(s.R, m, nf, v);
+                    p = 0;
+                    for (int a = 0; a < m; a++) s.K[a + ldm * j] = ((fm >> a) & 1u) ? -v[p++] : 0.0;
+                }
+            }
+            __syncthreads();
+            // ---- QK = Quu K, Quuk = Quu k
+            for (int e = tid; e < m * n; e += NT) {
+                int a = e % m, j = e / m;
+                double acc = 0.0;
+                for (int q = 0; q < m; q++) acc = fma(s.Quu[a + m * q], s.K[q + ldm * j], acc);
+                s.QK[a + ldm * j] = acc;
+            }
+            for (int a = tid; a < m; a += NT) {
+                double acc = 0.0;
+                for (int q = 0; q < m; q++) acc = fma(s.Quu[a + m * q], s.k[q], acc);
+                s.Quuk[a] = acc;
+            }
+            __syncthreads();
+            // ---- value backup (:64-72)
+            if (tid == 0) {
+                double a0 = 0.0, a1 = 0.0;
+                for (int a = 0; a < m; a++) { a0 = fma(s.k[a], s.Qu[a], a0); a1 = fma(s.k[a], s.Quuk[a], a1); }
+                dV0 += a0;
+                dV1 += 0.5 * a1;
+            }
+            for (int r = tid; r < n; r += NT) {
+                double t1 = 0.0, t2 = 0.0, t3 = 0.0;
+                for (int q = 0; q < m; q++) {
+                    t1 = fma(s.K[q + ldm * r], s.Quuk[q], t1);
+                    t2 = fma(s.K[q + ldm * r], s.Qu[q], t2);
+                    t3 = fma(s.Qux[q + ldm * r], s.k[q], t3);
+                }
+                s.VxN[r] = ((s.Qx[r] + t1) + t2) + t3;
+            }
+            for (int e = tid; e < n * n; e += NT) {
+                int r = e % n, c = e / n;
+                double t1 = 0.0, t2 = 0.0, t3 = 0.0;
+                for (int q = 0; q < m; q++) {
+                    t1 = fma(s.K[q + ldm * r], s.QK[q + ldm * c], t1);
+                    t2 = fma(s.K[q + ldm * r], s.Qux[q + ldm * c], t2);
+                    t3 = fma(s.Qux[q + ldm * r], s.K[q + ldm * c], t3);
+                }
+                s.W[r + ldn * c] = ((s.Qxx[r + ldn * c] + t1) + t2) + t3;
+            }
+            if (GPS && tid == 32) {                               // Σ = inv(Quu)  :346
+                for (int e = 0; e < m * m; e++) s.QuuF[e] = s.Quu[e];
+                inv_gj(m, s.QuuF, s.Inv);
+            }
+            __syncthreads();
+            // ---- symmetrise, commit, store
+            for (int e = tid; e < n * n; e += NT) {
+                int r = e % n, c = e / n;
+                double v = 0.5 * (s.W[r + ldn * c] + s.W[c + ldn * r]);
+                s.V[r + ldn * c] = v;
+                if (Vxxb) Vxxb[(long long)i * nn + e] = v;
+            }
+            for (int r = tid; r < n; r += NT) { s.Vx[r] = s.VxN[r]; Vxb[(long long)i * n + r] = s.VxN[r]; }
+            for (int e = tid; e < m * n; e += NT) Kb[(long long)i * mn + e] = s.K[(e % m) + ldm * (e / m)];
+            for (int a = tid; a < m; a += NT) { kb[(long long)i * m + a] = s.k[a]; s.kw[a] = s.k[a]; }
+            if (Quub)
+                for (int e = tid; e < m * m; e += NT) Quub[(long long)i * mm + e] = s.Quu[e];
+            if (Quuib)
+                for (int e = tid; e < m * m; e += NT) Quuib[(long long)i * mm + e] = s.Inv[e];
+            __syncthreads();
+        }
+        // ---- epilogue
+        if (diverge > 0) {
+            // the reference returns with everything below the failed step still zero (quirk Q10)
+            const int upto = diverge - 1;   // 0-based failed step; steps 0..upto stay zero
+            for (long long e = tid; e < (long long)(upto + 1) * mn; e += NT) Kb[e] = 0.0;
+            for (long long e = tid; e < (long long)(upto + 1) * m; e += NT) kb[e] = 0.0;
+            for (long long e = tid; e < (long long)(upto + 1) * n; e += NT) Vxb[e] = 0.0;
+            if (Vxxb)
+                for (long long e = tid; e < (long long)(upto + 1) * nn; e += NT) Vxxb[e] = 0.0;
+        }
+        if (P.Vxx1)
+            for (int e = tid; e < n * n; e += NT)
+                P.Vxx1[b * nn + e] = (diverge > 0) ? 0.0 : s.V[(e % n) + ldn * (e / n)];
+        if (tid == 0) {
+            P.diverge[b] = diverge;
+            P.dV[2 * b] = dV0;
+            P.dV[2 * b + 1] = dV1;
+        }
+    }
+}
+
+}  // namespace
+
+int launch_back_pass_generic(ddp_handle_s* h, const BackParams& P, bool gps) {
+    size_t bytes = smem_doubles(P.n, P.m, gps) * sizeof(double);
+    if ((long long)bytes > h->max_smem_optin) return (int)cudaErrorInvalidValue;
+    cudaError_t e;
+    if (gps) e = cudaFuncSetAttribute(bp_generic_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    else e = cudaFuncSetAttribute(bp_generic_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return (int)e;
+    int per_sm = (int)((size_t)h->max_smem_optin / (bytes + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 16) per_sm = 16;
+    long long grid = (long long)h->sm_count * per_sm;
+    if (grid > P.B) grid = P.B;
+    if (grid < 1) grid = 1;
+    if (gps) bp_generic_kernel<true><<<(unsigned)grid, NT, bytes, h->stream>>>(P);
+    else bp_generic_kernel<false><<<(unsigned)grid, NT, bytes, h->stream>>>(P);
+    h->launches++;
+    return (int)cudaGetLastError();
+}

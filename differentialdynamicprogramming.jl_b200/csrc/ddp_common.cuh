@@ -1,0 +1,93 @@
+// Shared declarations for the libddp.so kernels (sm_100a).  Not part of the public ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include "../../include/ddp.h"
+
+struct TensorD {                 // device-side mirror of ddp_tensor
+    const double* p;
+    long long sb, st;
+};
+__host__ __device__ inline TensorD mk(const ddp_tensor& t) { return TensorD{t.ptr, (long long)t.stride_b, (long long)t.stride_t}; }
+__device__ __forceinline__ const double* tp(const TensorD& t, long long b, int i) { return t.p + b * t.sb + (long long)i * t.st; }
+
+struct QPOpts {
+    int max_iter;
+    double min_grad, min_rel_improve, step_dec, min_step, armijo;
+};
+
+struct BackParams {
+    int n, m, T;
+    long long B;
+    TensorD cx, cu, cxx, cxu, cuu, fx, fu, u;
+    const double* lambda;
+    int reg_type;
+    const double* lims;          // (m,2) or nullptr (Cholesky branch)
+    const unsigned char* active;
+    // gps
+    TensorD Kp, kp, Sip;
+    const double* eta;
+    double* Quui;
+    // outputs
+    int* diverge;
+    double *K, *k, *Vx, *Vxx, *Vxx1, *Quu, *dV;
+    QPOpts qp;
+};
+
+struct ModelD {
+    int kind;
+    TensorD A, Bm, Q, R;
+    const double* goal;
+    double p[8];
+    int terminal_cost;
+};
+
+struct FwdParams {
+    int n, m, T;
+    long long B;
+    ModelD model;
+    const double *K, *k;
+    TensorD x0, x, u;
+    const double* alpha;
+    double alpha_scalar, u_scale;
+    const double* lims;
+    const unsigned char* active;
+    double *xnew, *unew, *cost, *cost_t, *cx, *cu;
+};
+
+struct KlParams {
+    int n, m, T;
+    long long B;
+    TensorD fx, R1, Kp, kp, Sp, Sip;
+    const double *xnew, *xold, *Kn, *kn, *Sn;
+    double *kl_t, *kl_mean;
+};
+
+struct ddp_handle_s {
+    int device, n, m, T;
+    long long B;
+    uint32_t flags;
+    cudaStream_t stream;
+    bool own_stream;
+    int sm_count;
+    int max_smem_optin;
+    long long launches;
+    std::string err;
+    // scratch for the solve driver / host-iteration pipeline is allocated lazily by those entry points
+};
+
+// launchers implemented in the .cu files; each returns a cudaError_t-compatible int (0 = ok) and
+// sets *launched to the number of kernels it enqueued.
+int launch_back_pass_generic(ddp_handle_s* h, const BackParams& P, bool gps);
+int launch_back_pass_tile(ddp_handle_s* h, const BackParams& P, bool gps, bool* handled);
+int launch_back_pass_small(ddp_handle_s* h, const BackParams& P, bool gps, bool* handled);
+int launch_forward_generic(ddp_handle_s* h, const FwdParams& P);
+int launch_forward_fast(ddp_handle_s* h, const FwdParams& P, bool* handled);
+int launch_boxqp(ddp_handle_s* h, long long B, int m, const double* H, const double* g, const double* lower,
+                 const double* upper, const double* x0, QPOpts o, double* x, int* result, double* Hfree,
+                 unsigned* free_mask, int* nfactor);
+int launch_kl_div(ddp_handle_s* h, const KlParams& P);
+int launch_batch_stats(ddp_handle_s* h, long long B, const double* cost_old, const double* cost_new, const double* dV,
+                       const double* alpha, double alpha_scalar, const int* diverge, const unsigned char* active,
+                       double* stats8);

@@ -1,0 +1,274 @@
+// Standalone batched boxQP, KL divergence (+ covariance propagation) and batch statistics.
+//   boxqp_kernel      <- boxQP                  src/boxQP.jl:29-188
+//   kl_div_kernel     <- forward_covariance + kl_div_wiki   src/forward_pass.jl:37-56, src/klutils.jl:70-100
+//   batch_stats_kernel<- the per-iteration scalars of iLQG.jl:269-281 reduced over the batch
+#include "boxqp.cuh"
+
+namespace {
+
+template <int MM>
+__global__ void __launch_bounds__(128) boxqp_kernel(long long B, int m, const double* __restrict__ H,
+                                                    const double* __restrict__ g, const double* __restrict__ lower,
+                                                    const double* __restrict__ upper, const double* __restrict__ x0,
+                                                    QPOpts o, double* __restrict__ x, int* __restrict__ result,
+                                                    double* __restrict__ Hfree, unsigned* __restrict__ free_mask,
+                                                    int* __restrict__ nfactor) {
+    long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double Hl[MM * MM], gl[MM], lo[MM], up[MM], xs[MM], xo[MM], Rf[MM * MM];
+#pragma unroll
+    for (int j = 0; j < MM; j++)
+#pragma unroll
+        for (int i = 0; i < MM; i++) {
+            Hl[i + MM * j] = (i < m && j < m) ? H[b * m * m + i + m * j] : 0.0;
+            Rf[i + MM * j] = 0.0;
+        }
+#pragma unroll
+    for (int i = 0; i < MM; i++) {
+        bool in = i < m;
+        gl[i] = in ? g[b * m + i] : 0.0;
+        lo[i] = in ? lower[b * m + i] : 0.0;
+        up[i] = in ? upper[b * m + i] : 0.0;
+        xs[i] = in ? x0[b * m + i] : 0.0;
+        xo[i] = 0.0;
+    }
+    unsigned fm = 0;
+    int nfac = 0;
+    int nf = 0;
+    int res = boxqp_seq<MM>(m, Hl, MM, gl, lo, up, xs, o, xo, Rf, MM, &fm, &nfac, &nf);
+    for (int i = 0; i < m; i++) x[b * m + i] = xo[i];
+    result[b] = res;
+    if (free_mask) free_mask[b] = fm;
+    if (nfactor) nfactor[b] = nfac;
+    if (Hfree) {
+        // the factor belongs to the clamped set of the last factorisation (nf x nf)
+        for (int j = 0; j < m; j++)
+            for (int i = 0; i < m; i++) Hfree[b * m * m + i + m * j] = (i <= j && j < nf) ? Rf[i + MM * j] : 0.0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// KL divergence.  One CTA per trajectory; Σ_t (n x n) is propagated in shared memory.
+//   kl_t = max(0, ½(tr(Σip Σn) + Δk'ΣipΔk − m + logdetΣp − logdetΣn)
+//                 + ½(μ'ΔK'ΣipΔKμ + tr(ΔK'ΣipΔK Σt)) + Δk'ΣipΔKμ)
+constexpr int KT = 128;
+
+__device__ double logdet_chol(int m, const double* A, double* R) {   // A sym PD (m x m, ld m)
+    double ld = 0.0;
+    for (int j = 0; j < m; j++) {
+        for (int i = 0; i < j; i++) {
+            double s = A[i + m * j];
+            for (int p = 0; p < i; p++) s -= R[p + m * i] * R[p + m * j];
+            R[i + m * j] = s / R[i + m * i];
+        }
+        double d = A[j + m * j];
+        for (int p = 0; p < j; p++) d -= R[p + m * j] * R[p + m * j];
+        if (!(d > 0.0)) return nan("");
+        R[j + m * j] = sqrt(d);
+        ld += log(d);
+    }
+    return ld;   // = 2 Σ log R_jj
+}
+
+__global__ void __launch_bounds__(KT) kl_div_kernel(KlParams P) {
+    extern __shared__ double sm[];
+    const int n = P.n, m = P.m, N = P.T, ldn = n | 1, ldm = m | 1;
+    const int tid = threadIdx.x;
+    double* Sg = sm;                    // Σ_t           n x n
+    double* Tm = Sg + ldn * n;          // fx Σ          n x n
+    double* Fx = Tm + ldn * n;          // fx            n x n
+    double* dK = Fx + ldn * n;          // ΔK            m x n
+    double* Mm = dK + ldm * n;          // Σip ΔK        m x n
+    double* Pm = Mm + ldm * n;          // M Σt          m x n
+    double* Sip = Pm + ldm * n;         // m x m
+    double* Sp = Sip + m * m;
+    double* Sn = Sp + m * m;
+    double* Rw = Sn + m * m;            // 2 x (m x m) cholesky work
+    double* mu = Rw + 2 * m * m;        // n
+    double* dk = mu + n;                // m
+    double* Mmu = dk + m;               // m
+    double* dKmu = Mmu + m;             // m
+    double* Sdk = dKmu + m;             // m
+    double* red = Sdk + m;              // KT
+    double* scal = red + KT;            // 4
+    const long long nn = (long long)n * n, mn = (long long)m * n, mm = (long long)m * m;
+    for (long long b = blockIdx.x; b < P.B; b += gridDim.x) {
+        __syncthreads();
+        const double* R1 = P.R1.p + b * P.R1.sb;
+        for (int e = tid; e < n * n; e += KT) Sg[(e % n) + ldn * (e / n)] = R1[e];       // Σ_1 = R1
+        const bool lti = (P.fx.st == 0);
+        double klsum = 0.0;
+        for (int t = 0; t < N; t++) {
+            if (!lti || t == 0) {
+                const double* fxt = tp(P.fx, b, t);
+                for (int e = tid; e < n * n; e += KT) Fx[(e % n) + ldn * (e / n)] = fxt[e];
+            }
+            const double* Kn = P.Kn + (b * N + t) * mn;
+            const double* Kp = tp(P.Kp, b, t);
+            for (int e = tid; e < m * n; e += KT) dK[(e % m) + ldm * (e / m)] = Kp[e] - Kn[e];
+            for (int e = tid; e < m * m; e += KT) {
+                Sip[e] = tp(P.Sip, b, t)[e];
+                Sp[e] = tp(P.Sp, b, t)[e];
+                Sn[e] = P.Sn[(b * N + t) * mm + e];
+            }
+            for (int i = tid; i < n; i += KT) mu[i] = P.xnew[(b * N + t) * n + i] - P.xold[(b * N + t) * n + i];
+            for (int a = tid; a < m; a += KT) dk[a] = (P.kp.p ? tp(P.kp, b, t)[a] : 0.0) - P.kn[(b * N + t) * m + a];
+            __syncthreads();
+            for (int e = tid; e < m * n; e += KT) {       // M = Σip ΔK
+                int a = e % m, j = e / m;
+                double acc = 0.0;
+                for (int q = 0; q < m; q++) acc = fma(Sip[a + m * q], dK[q + ldm * j], acc);
+                Mm[a + ldm * j] = acc;
+            }
+            for (int a = tid; a < m; a += KT) {
+                double acc = 0.0, acc2 = 0.0;
+                for (int j = 0; j < n; j++) acc = fma(dK[a + ldm * j], mu[j], acc);
+                for (int q = 0; q < m; q++) acc2 = fma(Sip[a + m * q], dk[q], acc2);
+                dKmu[a] = acc;
+                Sdk[a] = acc2;
+            }
+            if (tid == 64) scal[0] = logdet_chol(m, Sp, Rw);
+            if (tid == 96) scal[1] = logdet_chol(m, Sn, Rw + m * m);
+            __syncthreads();
+            double part = 0.0;
+            for (int e = tid; e < m * n; e += KT) {       // P = M Σt ; tr(ΔK' M Σt) = Σ P∘ΔK
+                int a = e % m, j = e / m;
+                double acc = 0.0;
+                for (int q = 0; q < n; q++) acc = fma(Mm[a + ldm * q], Sg[q + ldn * j], acc);
+                part = fma(acc, dK[a + ldm * j], part);
+            }
+            part *= 0.5;
+            for (int a = tid; a < m; a += KT) {
+                double acc = 0.0;
+                for (int j = 0; j < n; j++) acc = fma(Mm[a + ldm * j], mu[j], acc);   // (M μ)_a
+                part += 0.5 * dKmu[a] * acc;              // ½ μ'ΔK'ΣipΔKμ
+                part += dk[a] * acc;                      // Δk'ΣipΔKμ
+                part += 0.5 * dk[a] * Sdk[a];             // ½ Δk'ΣipΔk
+            }
+            for (int e = tid; e < m * m; e += KT) {       // ½ tr(Σip Σn)
+                int a = e % m, c = e / m;
+                part += 0.5 * Sip[a + m * c] * Sn[c + m * a];
+            }
+            red[tid] = part;
+            __syncthreads();
+            for (int o = KT / 2; o > 0; o >>= 1) {
+                if (tid < o) red[tid] += red[tid + o];
+                __syncthreads();
+            }
+            if (tid == 0) {
+                double v = red[0] + 0.5 * (-(double)m + scal[0] - scal[1]);
+                v = fmax(0.0, v);
+                if (v != v) v = INFINITY;                 // the reference returns Inf when logdet throws
+                if (P.kl_t) P.kl_t[b * N + t] = v;
+                klsum += v;
+            }
+            // ---- Σ_{t+1} = fx Σ_t fx' + R1  (forward_pass.jl:50)
+            if (t < N - 1) {
+                for (int e = tid; e < n * n; e += KT) {
+                    int r = e % n, c = e / n;
+                    double acc = 0.0;
+                    for (int q = 0; q < n; q++) acc = fma(Fx[r + ldn * q], Sg[q + ldn * c], acc);
+                    Tm[r + ldn * c] = acc;
+                }
+                __syncthreads();
+                for (int e = tid; e < n * n; e += KT) {
+                    int r = e % n, c = e / n;
+                    double acc = 0.0;
+                    for (int q = 0; q < n; q++) acc = fma(Tm[r + ldn * q], Fx[c + ldn * q], acc);
+                    Sg[r + ldn * c] = acc + R1[e];
+                }
+            }
+            __syncthreads();
+        }
+        if (tid == 0) P.kl_mean[b] = klsum / (double)N;
+    }
+}
+
+__host__ __device__ inline size_t kl_smem_doubles(int n, int m) {
+    int ldn = n | 1, ldm = m | 1;
+    return (size_t)ldn * n * 3 + (size_t)ldm * n * 3 + (size_t)m * m * 5 + n + 4 * (size_t)m + KT + 8;
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) batch_stats_kernel(long long B, const double* __restrict__ cost_old,
+                                                          const double* __restrict__ cost_new,
+                                                          const double* __restrict__ dV, const double* __restrict__ alpha,
+                                                          double alpha_scalar, const int* __restrict__ diverge,
+                                                          const unsigned char* __restrict__ active, double* stats) {
+    double v[6] = {0, 0, 0, 0, 0, 0};
+    for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
+        if (active && !active[b]) continue;
+        double a = alpha ? alpha[b] : alpha_scalar;
+        double cn = cost_new ? cost_new[b] : 0.0, co = cost_old ? cost_old[b] : 0.0;
+        double dc = co - cn;
+        double ex = dV ? -a * (dV[2 * b] + a * dV[2 * b + 1]) : 0.0;      // iLQG.jl:270
+        double ratio = ex > 0 ? dc / ex : (dc > 0 ? 1.0 : (dc < 0 ? -1.0 : 0.0));
+        v[0] += cn;
+        v[1] += dc;
+        v[2] += ex;
+        v[3] += (ratio > 0) ? 1.0 : 0.0;
+        v[4] += (diverge && diverge[b] > 0) ? 1.0 : 0.0;
+        v[5] += 1.0;
+    }
+    __shared__ double red[6][8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < 6; q++) {
+        double s = v[q];
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) red[q][w] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        double s = 0;
+        for (int i = 0; i < 8; i++) s += red[threadIdx.x][i];
+        atomicAdd(&stats[threadIdx.x], s);
+    }
+}
+
+}  // namespace
+
+int launch_boxqp(ddp_handle_s* h, long long B, int m, const double* H, const double* g, const double* lower,
+                 const double* upper, const double* x0, QPOpts o, double* x, int* result, double* Hfree,
+                 unsigned* free_mask, int* nfactor) {
+    unsigned grid = (unsigned)((B + 127) / 128);
+    if (grid == 0) return 0;
+#define LAUNCH_QP(MM) boxqp_kernel<MM><<<grid, 128, 0, h->stream>>>(B, m, H, g, lower, upper, x0, o, x, result, Hfree, free_mask, nfactor)
+    if (m <= 1) LAUNCH_QP(1);
+    else if (m <= 2) LAUNCH_QP(2);
+    else if (m <= 4) LAUNCH_QP(4);
+    else if (m <= 8) LAUNCH_QP(8);
+    else LAUNCH_QP(16);
+#undef LAUNCH_QP
+    h->launches++;
+    return (int)cudaGetLastError();
+}
+
+int launch_kl_div(ddp_handle_s* h, const KlParams& P) {
+    size_t bytes = kl_smem_doubles(P.n, P.m) * sizeof(double);
+    if ((long long)bytes > h->max_smem_optin) return (int)cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(kl_div_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return (int)e;
+    int per_sm = (int)((size_t)h->max_smem_optin / (bytes + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 8) per_sm = 8;
+    long long grid = (long long)h->sm_count * per_sm;
+    if (grid > P.B) grid = P.B;
+    if (grid < 1) grid = 1;
+    kl_div_kernel<<<(unsigned)grid, KT, bytes, h->stream>>>(P);
+    h->launches++;
+    return (int)cudaGetLastError();
+}
+
+int launch_batch_stats(ddp_handle_s* h, long long B, const double* cost_old, const double* cost_new, const double* dV,
+                       const double* alpha, double alpha_scalar, const int* diverge, const unsigned char* active,
+                       double* stats8) {
+    cudaError_t e = cudaMemsetAsync(stats8, 0, 8 * sizeof(double), h->stream);
+    if (e != cudaSuccess) return (int)e;
+    long long grid = (B + 255) / 256;
+    if (grid > h->sm_count * 8) grid = h->sm_count * 8;
+    if (grid < 1) grid = 1;
+    batch_stats_kernel<<<(unsigned)grid, 256, 0, h->stream>>>(B, cost_old, cost_new, dV, alpha, alpha_scalar, diverge, active, stats8);
+    h->launches++;
+    return (int)cudaGetLastError();
+}

@@ -1,0 +1,279 @@
+/* ddp.h -- C ABI of libddp.so: the B200-native batched iLQG/DDP hot path.
+ *
+ * The reference (baggepinnen/DifferentialDynamicProgramming.jl v0.5.0) is pure Julia and has no
+ * FFI of its own; the boundary it offers is its method surface.  Each entry point below replaces
+ * one reference method, batched over B independent trajectories, and is what a Julia `ccall`
+ * (see INTEGRATION.md / julia/) or the Python ctypes mirror binds:
+ *
+ *   ddp_back_pass_f64      <- back_pass(cx,cu,cxx,cxu,cuu,fx,fu,λ,regType,lims,x,u)
+ *                             src/backward_pass.jl:162-252 (+ macros :3-79)
+ *   ddp_back_pass_gps_f64  <- back_pass_gps(cx,cu,cxx,cxu,cuu,fx,fu,lims,x,u,kl_cost_terms)
+ *                             src/backward_pass.jl:259-350 (+ ∇kl, src/klutils.jl:8-23)
+ *   ddp_boxqp_f64          <- boxQP(H,g,lower,upper,x0)                 src/boxQP.jl:29-188
+ *   ddp_forward_pass_f64   <- forward_pass(traj,x0,u,x,α,f,costfun,lims,diff)
+ *                             src/forward_pass.jl:9-33 (f/costfun = built-in model descriptors)
+ *   ddp_kl_div_f64         <- forward_covariance + kl_div_wiki
+ *                             src/forward_pass.jl:37-56, src/klutils.jl:70-100
+ *   ddp_ilqg_solve_f64     <- iLQG(f,costfun,df,x0,u0;kw...)           src/iLQG.jl:143-341
+ *   ddp_ilqg_iter_host_f64 <- one back_pass + forward_pass (α given) on HOST buffers, chunked
+ *                             and overlapped with the PCIe copies (the end-to-end path)
+ *
+ * Conventions
+ *   - All arithmetic is FP64.  No exceptions cross the ABI: every function returns DDP_OK (0) or
+ *     a negative error code; ddp_last_error() gives the text.  Numerical outcomes (Cholesky
+ *     failure, QP result codes) are per-trajectory output arrays, never errors.
+ *   - Memory layout is the reference's column-major Julia arrays with the batch appended as the
+ *     trailing dimension, i.e. C order [B][T][col][row]:  fx (n,n,T,B), fu (n,m,T,B),
+ *     cx (n,T,B), cu (m,T,B), K (m,n,T,B), k (m,T,B), Vx (n,T,B), Vxx (n,n,T,B), Quu (m,m,T,B).
+ *   - Input tensors are described by {device pointer, batch stride, time stride} in elements;
+ *     a stride of 0 broadcasts.  This replaces the reference's dispatch on array rank
+ *     (time-invariant 2-D vs time-varying 3-D arguments, backward_pass.jl:162/179/217).
+ *   - `diverge` is the reference's 1-based timestep index of the failed step, 0 on success.
+ *   - A handle owns one CUDA stream (or borrows one via ddp_set_stream) and is not thread-safe.
+ *     Calls are asynchronous on that stream unless stated; ddp_synchronize() waits.
+ *   - There is NO CPU fallback: without a CUDA device ddp_create fails.
+ */
+#ifndef DDP_H_
+#define DDP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define DDP_API __attribute__((visibility("default")))
+#else
+#define DDP_API
+#endif
+
+#define DDP_VERSION 100          /* 0.1.0 */
+#define DDP_MAX_N 64
+#define DDP_MAX_M 16
+
+enum {
+    DDP_OK = 0,
+    DDP_ERR_INVALID = -1,        /* bad argument / shape */
+    DDP_ERR_CUDA = -2,           /* CUDA runtime error */
+    DDP_ERR_UNSUPPORTED = -3,    /* size or option outside the built kernels */
+    DDP_ERR_NOMEM = -4
+};
+
+typedef struct ddp_handle_s* ddp_handle_t;
+
+/* Strided view of a device array of doubles.  ptr == NULL means "absent". */
+typedef struct ddp_tensor {
+    const double* ptr;
+    int64_t stride_b;            /* elements between consecutive trajectories (0 = shared)      */
+    int64_t stride_t;            /* elements between consecutive timesteps    (0 = time-invariant) */
+} ddp_tensor;
+
+/* boxQP options, defaults of src/boxQP.jl:29-36 */
+typedef struct ddp_boxqp_opts {
+    int32_t max_iter;            /* 100   */
+    double min_grad;             /* 1e-8  */
+    double min_rel_improve;      /* 1e-8  */
+    double step_dec;             /* 0.6   */
+    double min_step;             /* 1e-22 */
+    double armijo;               /* 0.1   */
+} ddp_boxqp_opts;
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+DDP_API int ddp_version(void);
+DDP_API int ddp_device_count(void);
+/* n <= 64 states, m <= 16 controls, T timesteps (= N of the reference), B trajectories. */
+DDP_API int ddp_create(ddp_handle_t* h, int device, int n, int m, int T, int64_t B, uint32_t flags);
+DDP_API int ddp_destroy(ddp_handle_t h);
+DDP_API const char* ddp_last_error(ddp_handle_t h);           /* h may be NULL: last create error */
+DDP_API int ddp_set_stream(ddp_handle_t h, void* cuda_stream); /* borrow a cudaStream_t (NULL = own) */
+DDP_API int ddp_synchronize(ddp_handle_t h);
+/* which kernel family the dimensions of this handle dispatch to: "tile32x8", "small4x1", "generic" */
+DDP_API const char* ddp_kernel_variant(ddp_handle_t h);
+/* number of kernels launched through this handle since creation (bench.py's gpu_launches) */
+DDP_API int64_t ddp_launch_count(ddp_handle_t h);
+
+/* ---- device memory (so a Julia/C host needs no CUDA binding of its own) ------------------ */
+DDP_API int ddp_malloc(ddp_handle_t h, void** dptr, size_t bytes);
+DDP_API int ddp_free(ddp_handle_t h, void* dptr);
+DDP_API int ddp_memset(ddp_handle_t h, void* dptr, int value, size_t bytes);
+DDP_API int ddp_upload(ddp_handle_t h, void* dst_dev, const void* src_host, size_t bytes);    /* sync */
+DDP_API int ddp_download(ddp_handle_t h, void* dst_host, const void* src_dev, size_t bytes);  /* sync */
+DDP_API int ddp_host_alloc(void** hptr, size_t bytes);        /* pinned host memory */
+DDP_API int ddp_host_free(void* hptr);
+
+/* ---- backward pass ---------------------------------------------------------------------- */
+typedef struct ddp_back_pass_args {
+    /* inputs (device) */
+    ddp_tensor cx;               /* (n,T,B)                                   */
+    ddp_tensor cu;               /* (m,T,B)                                   */
+    ddp_tensor cxx;              /* (n,n[,T][,B])                             */
+    ddp_tensor cxu;              /* (n,m[,T][,B])  (used transposed, as the reference does) */
+    ddp_tensor cuu;              /* (m,m[,T][,B])                             */
+    ddp_tensor fx;               /* (n,n[,T][,B])  fx[i,j] = df_i/dx_j        */
+    ddp_tensor fu;               /* (n,m[,T][,B])                             */
+    const double* lambda;        /* [B] Levenberg parameter per trajectory (ignored by gps)      */
+    int32_t reg_type;            /* 1: Quu + λI, 2: Vxx + λI  (iLQG.jl regType)                   */
+    const double* lims;          /* (m,2) column-major [lower(m); upper(m)], NULL or lower[0] >  */
+                                 /* upper[0]  => Cholesky branch (backward_pass.jl:31)           */
+    ddp_tensor u;                /* (m,T,B), read only when lims is active                       */
+    const uint8_t* active;       /* [B] or NULL; trajectories with active[b]==0 are skipped      */
+    /* outputs (device) */
+    int32_t* diverge;            /* [B] 1-based failed timestep, 0 = ok                          */
+    double* K;                   /* (m,n,T,B)                                                    */
+    double* k;                   /* (m,T,B)                                                      */
+    double* Vx;                  /* (n,T,B)                                                      */
+    double* Vxx;                 /* (n,n,T,B) or NULL: full value-Hessian history is optional    */
+    double* Vxx1;                /* (n,n,B) or NULL: Vxx at the first timestep only              */
+    double* Quu;                 /* (m,m,T,B) or NULL: unregularised Quu (the policy's Σi)       */
+    double* dV;                  /* (2,B) expected cost reduction terms                          */
+    ddp_boxqp_opts qp;           /* used when lims is active; max_iter == 0 => defaults          */
+} ddp_back_pass_args;
+
+DDP_API int ddp_back_pass_f64(ddp_handle_t h, const ddp_back_pass_args* a);
+
+/* KL-augmented sweep.  The KL cost terms of ∇kl (klutils.jl:8-23) are formed on the fly from the
+ * previous policy; cxx/cxu/cuu/fx/fu may be time-invariant (stride_t = 0) as a convenience. */
+typedef struct ddp_gps_args {
+    ddp_tensor K_prev;           /* (m,n,T,B)                         */
+    ddp_tensor k_prev;           /* (m,T,B) or absent (= zeros, as iLQGkl.jl:52 sets) */
+    ddp_tensor Sigi_prev;        /* (m,m,T,B)  traj_prev.Σi           */
+    const double* eta;           /* [B] dual variable η per trajectory */
+    double* Quui;                /* (m,m,T,B) out: Σ = inv(Quu), required */
+} ddp_gps_args;
+
+/* a->Quu is required here (it is the new policy's Σi); a->lambda / a->reg_type are ignored. */
+DDP_API int ddp_back_pass_gps_f64(ddp_handle_t h, const ddp_back_pass_args* a, const ddp_gps_args* g);
+
+/* ---- box-constrained QP ------------------------------------------------------------------ */
+/* H (m,m,B), g/lower/upper/x0 (m,B) -> x (m,B), result[B] (0..6 as boxQP.jl:172-179, or -1 where
+ * the reference's cholesky would throw), Hfree (m,m,B; leading nfree x nfree block, upper),
+ * free[B] bitmask (bit i = dimension i free), nfactor[B].  Any output may be NULL except x,result.
+ * m here is the handle's m.  Bit-reproducible against oracle/ (fixed summation order, no FMA). */
+DDP_API int ddp_boxqp_f64(ddp_handle_t h, int64_t B, const double* H, const double* g, const double* lower,
+                  const double* upper, const double* x0, const ddp_boxqp_opts* opts, double* x,
+                  int32_t* result, double* Hfree, uint32_t* free_mask, int32_t* nfactor);
+
+/* ---- models: the reference's user callbacks f / costfun / df as device descriptors ------- */
+enum { DDP_MODEL_LINEAR = 1, DDP_MODEL_PENDCART = 2 };
+
+typedef struct ddp_model {
+    int32_t kind;
+    /* DDP_MODEL_LINEAR (demo_linear.jl:35-50): x+ = A x + B u, cost = ½Σ x'Qx + ½Σ u'Ru        */
+    ddp_tensor A;                /* (n,n[,T][,B]) */
+    ddp_tensor Bm;               /* (n,m[,T][,B]) */
+    /* both kinds */
+    ddp_tensor Q;                /* (n,n[,B]) state cost  */
+    ddp_tensor R;                /* (m,m[,B]) control cost */
+    const double* goal;          /* [n] or NULL (zeros); cost is on x - goal                      */
+    /* DDP_MODEL_PENDCART (system_pendcart.jl:51-54,83-106): Euler step; p = {g, l, h, d}         */
+    double p[8];
+    int32_t terminal_cost;       /* 1: add ½ d'Qd at the last state again (cost has T+1 entries,  */
+                                 /*    system_pendcart.jl:104)                                    */
+} ddp_model;
+
+/* ---- forward pass ------------------------------------------------------------------------ */
+typedef struct ddp_forward_pass_args {
+    const double* K;             /* (m,n,T,B) or NULL: empty policy (iLQG.jl:185 initial rollout) */
+    const double* k;             /* (m,T,B)  or NULL                                              */
+    ddp_tensor x0;               /* (n[,B]) initial state                                         */
+    ddp_tensor x;                /* (n,T,B) previous trajectory (absent for an empty policy)      */
+    ddp_tensor u;                /* (m,T,B) previous controls                                     */
+    const double* alpha;         /* [B] per-trajectory step size, or NULL to use alpha_scalar     */
+    double alpha_scalar;
+    double u_scale;              /* multiplies u before use (the initial rollout's αi*u); 0 => 1  */
+    const double* lims;          /* (m,2) or NULL; clamp is applied whenever non-NULL (Q6)        */
+    const uint8_t* active;       /* [B] or NULL                                                   */
+    /* outputs */
+    double* xnew;                /* (n,T,B) */
+    double* unew;                /* (m,T,B) */
+    double* cost;                /* [B] total cost Σ_t                                            */
+    double* cost_t;              /* (T+terminal,B) per-step cost or NULL                          */
+    /* optional fused derivative outputs for the next backward pass (linear/pendcart cost):
+     * cx = Q (x - goal), cu = R u  (demo_linear.jl:38-39, system_pendcart.jl:108-112)            */
+    double* cx;                  /* (n,T,B) or NULL */
+    double* cu;                  /* (m,T,B) or NULL */
+} ddp_forward_pass_args;
+
+DDP_API int ddp_forward_pass_f64(ddp_handle_t h, const ddp_model* model, const ddp_forward_pass_args* a);
+
+/* ---- batch statistics: the vector a multi-GPU run all-reduces once per iteration --------- */
+/* stats[0]=Σcost_new, [1]=Σ(cost_old-cost_new), [2]=Σ expected reduction (α=alpha), [3]=#accepted
+ * (ratio > 0), [4]=#diverged back passes, [5]=#active.  All doubles so one SUM all-reduce does. */
+DDP_API int ddp_batch_stats_f64(ddp_handle_t h, const double* cost_old, const double* cost_new, const double* dV,
+                        const double* alpha, double alpha_scalar, const int32_t* diverge,
+                        const uint8_t* active, double* stats8 /* device, 8 doubles */);
+
+/* ---- KL divergence between the new and previous policy ----------------------------------- */
+typedef struct ddp_kl_args {
+    ddp_tensor fx;               /* (n,n[,T][,B]) model Jacobian used by forward_covariance       */
+    ddp_tensor R1;               /* (n,n[,B]) process-noise covariance (Σ0 = R1)                  */
+    const double* xnew;          /* (n,T,B) */
+    const double* xold;          /* (n,T,B) */
+    const double* K_new;         /* (m,n,T,B) */
+    const double* k_new;         /* (m,T,B)   */
+    const double* Sig_new;       /* (m,m,T,B) Σ  of the new policy (Quui)                          */
+    ddp_tensor K_prev;           /* (m,n,T,B) */
+    ddp_tensor k_prev;           /* (m,T,B) or absent (zeros) */
+    ddp_tensor Sig_prev;         /* (m,m,T,B) */
+    ddp_tensor Sigi_prev;        /* (m,m,T,B) */
+    double* kl_t;                /* (T,B) per-step divergence (clipped at 0) or NULL               */
+    double* kl_mean;             /* [B] mean over time                                             */
+} ddp_kl_args;
+
+DDP_API int ddp_kl_div_f64(ddp_handle_t h, const ddp_kl_args* a);
+
+/* ---- whole iLQG solve, device resident --------------------------------------------------- */
+typedef struct ddp_ilqg_opts {          /* defaults: iLQG.jl:143-163 */
+    int32_t n_alpha;                    /* <= 16 */
+    double alpha[16];                   /* 10.^range(0,-3,11) */
+    double tol_fun, tol_grad;           /* 1e-7, 1e-4 */
+    int32_t max_iter;                   /* 500 */
+    double lambda, dlambda, lambda_factor, lambda_max, lambda_min;   /* 1,1,1.6,1e10,1e-6 */
+    int32_t reg_type;                   /* 1 */
+    double reduce_ratio_min;            /* 0 */
+    const double* lims;                 /* DEVICE (m,2) or NULL */
+} ddp_ilqg_opts;
+
+/* per-trajectory solver state, one struct per trajectory (device array of B) */
+typedef struct ddp_ilqg_state {
+    double lambda, dlambda, cost, g_norm, last_dcost, last_alpha;
+    int32_t iter;                       /* the reference's `iter` counter (1-based, at exit)       */
+    int32_t accepted_iter;
+    int32_t status;                     /* -1 running, 0 tol_grad, 1 tol_fun, 2 λ>λmax, 3 max_iter,
+                                           4 initial rollout diverged (reference returns nothing) */
+    int32_t pad;
+} ddp_ilqg_state;
+
+/* x0 (n,B), u0 (m,T,B) device -> x (n,T,B), u (m,T,B), K, k, Vx, Vxx1 (may be NULL), cost_t NULL-able,
+ * state[B].  Synchronous.  Returns the number of outer iterations executed in *n_outer if non-NULL. */
+DDP_API int ddp_ilqg_solve_f64(ddp_handle_t h, const ddp_model* model, const ddp_ilqg_opts* opts, const double* x0,
+                       const double* u0, double* x, double* u, double* K, double* k, double* Vx,
+                       double* Vxx1, ddp_ilqg_state* state, int32_t* n_outer);
+
+/* ---- end-to-end iteration on HOST buffers ------------------------------------------------ */
+/* One backward sweep + one forward rollout for a linear model with per-trajectory LTI dynamics
+ * (the headline workload), taking pinned HOST arrays: the batch is cut into chunks whose H2D
+ * copies, kernels and D2H copies are pipelined on separate streams.  The policy (K,k) stays on the
+ * device (the shim's GaussianPolicy holds it and downloads lazily).  Synchronous.
+ * Host inputs:  fx (n,n,B), fu (n,m,B), cx (n,T,B), cu (m,T,B), x (n,T,B), u (m,T,B), lambda[B].
+ * Host outputs: xnew (n,T,B), unew (m,T,B), cost[B], dV (2,B), diverge[B].
+ * Q (n,n), R (m,m), cxu (n,m) are small shared host matrices.                                     */
+typedef struct ddp_iter_host_args {
+    const double *fx, *fu, *cx, *cu, *x, *u, *lambda;
+    const double *Q, *R, *cxu;
+    int32_t reg_type;
+    double alpha;
+    double *xnew, *unew, *cost, *dV;
+    int32_t* diverge;
+    int64_t chunk;               /* trajectories per chunk, 0 = library default */
+    int64_t h2d_bytes, d2h_bytes; /* out: bytes moved */
+} ddp_iter_host_args;
+
+DDP_API int ddp_ilqg_iter_host_f64(ddp_handle_t h, ddp_iter_host_args* a);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DDP_H_ */

@@ -1,0 +1,74 @@
+"""GPU parity: ddp_back_pass_f64 (through the C ABI) vs the CPU oracle on the same seeded inputs.
+Tolerance (BASELINE.json north_star): K, k, Vx, Vxx within 1e-8 relative (max-norm per tensor),
+`diverge` and boxQP-derived integer outcomes exact."""
+import numpy as np
+import pytest
+
+from helpers import make_batch_lq, relerr
+from oracle import ddp_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-8
+
+
+def _check(ddp, B, n, m, N, regType, lims=None, lam=1.0, ltv=False, tv_cost=False, force_generic=False, seed=0):
+    A, Bm, Q, R, x, u = make_batch_lq(seed, B, n, m, N)
+    cx = x @ Q.T
+    cu = u @ R.T
+    cxu = 0.01 * np.random.default_rng(seed + 1).standard_normal((n, m))
+    if ltv:
+        rng = np.random.default_rng(seed + 2)
+        fx = A[:, None] + 1e-3 * rng.standard_normal((B, N, n, n))
+        fu = Bm[:, None] + 1e-3 * rng.standard_normal((B, N, n, m))
+    else:
+        fx, fu = A[:, None], Bm[:, None]
+    if tv_cost:
+        cxx = np.tile(Q, (N, 1, 1)) * (1 + 0.1 * np.arange(N))[:, None, None]
+        cuu = np.tile(R, (N, 1, 1)) * (1 + 0.05 * np.arange(N))[:, None, None]
+        cxu_ = np.tile(cxu, (N, 1, 1))
+    else:
+        cxx, cuu, cxu_ = Q, R, cxu
+    lam_b = lam * (1 + 0.1 * np.arange(B))
+    dv, pol, Vx, Vxx, dV = ddp.back_pass(cx, cu, cxx, cxu_, cuu, fx, fu, lam_b, regType, lims, x, u, force_generic=force_generic)
+    for b in range(B):
+        fxb = fx[b] if ltv else fx[b, 0]
+        fub = fu[b] if ltv else fu[b, 0]
+        d0, p0, Vx0, Vxx0, dV0 = O.back_pass(cx[b], cu[b], cxx, cxu_, cuu, fxb, fub, lam_b[b], regType, lims, x[b], u[b])
+        assert dv[b] == d0
+        assert relerr(pol.K[b], p0.K) < TOL
+        assert relerr(pol.k[b], p0.k) < TOL
+        assert relerr(Vx[b], Vx0) < TOL
+        assert relerr(Vxx[b], Vxx0) < TOL
+        assert relerr(dV[b], dV0) < TOL
+        assert relerr(pol.Sigmai[b][d0:], p0.Sigmai[d0:]) < TOL    # Quu, written slices only
+
+
+@pytest.mark.parametrize("n,m,N", [(10, 2, 40), (4, 1, 30), (7, 3, 25), (32, 8, 20), (64, 16, 6)])
+@pytest.mark.parametrize("regType", [1, 2])
+def test_generic_cholesky_lti(ddp, n, m, N, regType):
+    _check(ddp, 3, n, m, N, regType, force_generic=True)
+
+
+def test_generic_ltv_tvcost(ddp):
+    _check(ddp, 3, 10, 2, 30, 1, ltv=True, tv_cost=True, force_generic=True)
+    _check(ddp, 2, 6, 2, 30, 2, ltv=True, tv_cost=False, force_generic=True)
+
+
+@pytest.mark.parametrize("n,m", [(4, 1), (10, 2), (12, 4)])
+def test_generic_boxqp_branch(ddp, n, m):
+    lims = np.tile(np.array([[-0.05, 0.05]]), (m, 1))
+    _check(ddp, 4, n, m, 30, 1, lims=lims, lam=1e-3, force_generic=True, seed=3)
+    _check(ddp, 4, n, m, 30, 2, lims=lims, lam=1e-3, force_generic=True, seed=4)
+
+
+def test_generic_diverge_non_pd(ddp):
+    """forced non-PD cuu => Cholesky fails at the first processed step: diverge == N-1 (1-based)."""
+    B, n, m, N = 2, 6, 2, 12
+    A, Bm, Q, R, x, u = make_batch_lq(5, B, n, m, N)
+    cx, cu = x @ Q.T, u @ R.T
+    Rneg = -np.eye(m)
+    dv, pol, Vx, Vxx, dV = ddp.back_pass(cx, cu, Q, np.zeros((n, m)), Rneg, A[:, None], Bm[:, None], 0.0, 1, None, x, u, force_generic=True)
+    d0, p0, Vx0, Vxx0, dV0 = O.back_pass(cx[0], cu[0], Q, np.zeros((n, m)), Rneg, A[0], Bm[0], 0.0, 1, None, x[0], u[0])
+    assert d0 == N - 1 and np.all(dv == N - 1)
+    assert np.all(pol.K == 0) and np.all(pol.k == 0)
+    assert np.array_equal(Vx[0], Vx0) and np.array_equal(Vxx[0], Vxx0)
