@@ -111,12 +111,7 @@ const char* ddp_last_error(ddp_handle_t h) { return h ? h->err.c_str() : g_creat
 int ddp_set_stream(ddp_handle_t h, void* s) {
     if (!h) return DDP_ERR_INVALID;
     if (h->own_stream) { cudaStreamDestroy(h->stream); h->own_stream = false; }
-    if (s == nullptr) {
-        CU(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-        h->own_stream = true;
-    } else {
-        h->stream = (cudaStream_t)s;
-    }
+    h->stream = (cudaStream_t)s;      // NULL is the legacy default stream (what torch's default stream is)
     return DDP_OK;
 }
 

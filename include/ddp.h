@@ -87,7 +87,7 @@ DDP_API int ddp_device_count(void);
 DDP_API int ddp_create(ddp_handle_t* h, int device, int n, int m, int T, int64_t B, uint32_t flags);
 DDP_API int ddp_destroy(ddp_handle_t h);
 DDP_API const char* ddp_last_error(ddp_handle_t h);           /* h may be NULL: last create error */
-DDP_API int ddp_set_stream(ddp_handle_t h, void* cuda_stream); /* borrow a cudaStream_t (NULL = own) */
+DDP_API int ddp_set_stream(ddp_handle_t h, void* cuda_stream); /* borrow a cudaStream_t (NULL = default stream) */
 DDP_API int ddp_synchronize(ddp_handle_t h);
 /* which kernel family the dimensions of this handle dispatch to: "tile32x8", "small4x1", "generic" */
 DDP_API const char* ddp_kernel_variant(ddp_handle_t h);

@@ -72,3 +72,44 @@ def test_generic_diverge_non_pd(ddp):
     assert d0 == N - 1 and np.all(dv == N - 1)
     assert np.all(pol.K == 0) and np.all(pol.k == 0)
     assert np.array_equal(Vx[0], Vx0) and np.array_equal(Vxx[0], Vxx0)
+
+
+# ---- specialised n=32, m=8 DMMA kernel (ddp_kernel_variant == "tile32x8") -----------------------
+
+@pytest.mark.parametrize("regType", [1, 2])
+@pytest.mark.parametrize("ltv", [False, True])
+def test_tile32x8_vs_oracle(ddp, regType, ltv):
+    _check(ddp, 5, 32, 8, 24, regType, ltv=ltv, force_generic=False, seed=20)
+
+
+def test_tile32x8_tvcost_and_many(ddp):
+    _check(ddp, 3, 32, 8, 16, 1, ltv=True, tv_cost=True, force_generic=False, seed=21)
+    _check(ddp, 37, 32, 8, 9, 1, force_generic=False, seed=22)        # ragged vs the 4-warp CTA
+
+
+def test_tile32x8_diverge(ddp):
+    B, n, m, N = 3, 32, 8, 10
+    A, Bm, Q, R, x, u = make_batch_lq(5, B, n, m, N)
+    cx, cu = x @ Q.T, u @ R.T
+    # cuu = -0.5 I: lambda = 1 keeps QuuF positive definite, lambda = 0.1 does not (trajectory 1 only)
+    Rneg = -0.5 * np.eye(m)
+    lam = np.array([1.0, 0.1, 1.0])
+    dv, pol, Vx, Vxx, dV = ddp.back_pass(cx, cu, Q, np.zeros((n, m)), Rneg, A[:, None], Bm[:, None], lam, 1, None, x, u)
+    for b in range(B):
+        d0, p0, Vx0, Vxx0, dV0 = O.back_pass(cx[b], cu[b], Q, np.zeros((n, m)), Rneg, A[b], Bm[b], lam[b], 1, None, x[b], u[b])
+        assert dv[b] == d0
+        assert relerr(pol.K[b], p0.K) < TOL and relerr(Vx[b], Vx0) < TOL and relerr(Vxx[b], Vxx0) < TOL
+    assert dv[1] == N - 1 and dv[0] == 0 and dv[2] == 0
+    assert np.all(pol.K[1] == 0) and np.all(Vxx[1][: N - 1] == 0)
+
+
+def test_tile32x8_matches_generic_kernel(ddp):
+    A, Bm, Q, R, x, u = make_batch_lq(30, 6, 32, 8, 40)
+    cx, cu = x @ Q.T, u @ R.T
+    args = (cx, cu, Q, np.zeros((32, 8)), R, A[:, None], Bm[:, None], 0.5, 1, None, x, u)
+    r1 = ddp.back_pass(*args)
+    r2 = ddp.back_pass(*args, force_generic=True)
+    assert np.array_equal(r1[0], r2[0])
+    for a, b in ((r1[1].K, r2[1].K), (r1[1].k, r2[1].k), (r1[2], r2[2]), (r1[3], r2[3]), (r1[4], r2[4])):
+        assert relerr(a, b) < 1e-10
+    assert np.array_equal(r1[3], np.swapaxes(r1[3], -1, -2))          # Vxx exactly symmetric

@@ -1,0 +1,148 @@
+"""GPU parity for ddp_boxqp_f64 (bit-exact), ddp_forward_pass_f64, ddp_back_pass_gps_f64 and
+ddp_kl_div_f64 against the CPU oracle."""
+import numpy as np
+import pytest
+
+from helpers import make_batch_lq, make_lq, relerr, rollout
+from oracle import ddp_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-8
+
+
+@pytest.mark.parametrize("m", [1, 2, 3, 5, 8, 16])
+def test_boxqp_bit_exact(ddp, m):
+    """x, result, free set, nfactor and the subspace factor are bit-identical to the oracle
+    (fixed summation order, no FMA) on exactly symmetric H, as demoQP builds (boxQP.jl:193)."""
+    rng = np.random.default_rng(100 + m)
+    B = 64
+    Hs, gs, los, ups, x0s = [], [], [], [], []
+    for b in range(B):
+        G = rng.standard_normal((m, m))
+        H = G @ G.T + 0.05 * np.eye(m)
+        H = (H + H.T) / 2
+        Hs.append(H); gs.append(3 * rng.standard_normal(m))
+        w = 0.1 + rng.random(m)
+        los.append(-w); ups.append(w * rng.random(m) + 0.05); x0s.append(rng.standard_normal(m))
+    Hs, gs, los, ups, x0s = map(np.array, (Hs, gs, los, ups, x0s))
+    x, res, Hf, free, nf = ddp.boxQP(Hs, gs, los, ups, x0s)
+    codes = set()
+    for b in range(B):
+        x0_, r0, Hf0, free0, nf0 = O.boxQP(Hs[b], gs[b], los[b], ups[b], x0s[b])
+        assert res[b] == r0 and nf[b] == nf0
+        assert np.array_equal(free[b], free0)
+        assert np.array_equal(x[b], x0_), (b, x[b] - x0_)
+        k = Hf0.shape[0] if r0 != 6 or nf0 > 0 else 0
+        assert np.array_equal(Hf[b][:k, :k], Hf0[:k, :k])
+        codes.add(int(r0))
+    assert codes <= {4, 5, 6} and len(codes) >= 1
+
+
+def test_boxqp_not_pd_and_unbatched(ddp):
+    H = np.array([[1.0, 2.0], [2.0, 1.0]])      # indefinite
+    with pytest.raises(ddp.PosDefException):
+        ddp.boxQP(H, np.ones(2), -np.ones(2), np.ones(2), np.zeros(2))
+    with pytest.raises(O.PosDefException):
+        O.boxQP(H, np.ones(2), -np.ones(2), np.ones(2), np.zeros(2))
+    H = np.array([[2.0, 0.5], [0.5, 1.0]])
+    x, r, Hf, free, nf = ddp.boxQP(H, np.array([1.0, -4.0]), -np.ones(2), np.ones(2), np.zeros(2))
+    x0, r0, Hf0, free0, nf0 = O.boxQP(H, np.array([1.0, -4.0]), -np.ones(2), np.ones(2), np.zeros(2))
+    assert r == r0 and nf == nf0 and np.array_equal(x, x0) and np.array_equal(free, free0) and np.array_equal(Hf, Hf0)
+
+
+@pytest.mark.parametrize("n,m,N", [(10, 2, 50), (32, 8, 30), (5, 3, 20)])
+@pytest.mark.parametrize("lims", [None, 0.3])
+def test_forward_linear(ddp, n, m, N, lims):
+    B = 3
+    A, Bm, Q, R, x, u = make_batch_lq(7, B, n, m, N)
+    cx, cu = x @ Q.T, u @ R.T
+    lim = None if lims is None else np.tile(np.array([[-lims, lims]]), (m, 1))
+    alphas = np.array([1.0, 0.5, 0.125])
+    model = ddp.LinearModel(A[:, None], Bm[:, None], Q, R)
+    pols = []
+    for b in range(B):
+        d0, p0, _, _, _ = O.back_pass(cx[b], cu[b], Q, np.zeros((n, m)), R, A[b], Bm[b], 1.0, 1, None, x[b], u[b])
+        pols.append(p0)
+    pol = ddp.GaussianPolicy(N, n, m, np.array([p.K for p in pols]), np.array([p.k for p in pols]))
+    xn, un, cn, (cxn, cun) = ddp.forward_pass(pol, x[:, 0], u, x, alphas, model.f, model.costfun, lim, want_derivs=True,
+                                              force_generic=True)
+    xn2, un2, ct = ddp.forward_pass(pol, x[:, 0], u, x, alphas, model.f, model.costfun, lim, per_step_cost=True, force_generic=True)
+    for b in range(B):
+        om = O.LinearModel(A[b], Bm[b], Q, R, per_step_cost=True)
+        x0_, u0_, c0_ = O.forward_pass(pols[b], x[b, 0], u[b], x[b], alphas[b], om.f, om.costfun, lim)
+        assert relerr(xn[b], x0_) < TOL and relerr(un[b], u0_) < TOL
+        assert abs(cn[b] - np.sum(c0_)) < TOL * abs(np.sum(c0_))
+        assert relerr(ct[b], c0_) < TOL
+        assert relerr(cxn[b], x0_ @ Q.T) < TOL and relerr(cun[b], u0_ @ R.T) < TOL
+        if lim is not None:
+            assert np.all(un[b] <= lims) and np.all(un[b] >= -lims)
+            assert np.array_equal(un[b] == lims, u0_ == lims) and np.array_equal(un[b] == -lims, u0_ == -lims)
+
+
+def test_forward_empty_policy_and_pendcart(ddp):
+    """initial rollout (iLQG.jl:185): empty policy, αi*u; pendcart Euler dynamics + T+1 cost entries."""
+    N = 80
+    rng = np.random.default_rng(3)
+    B = 4
+    u = 2.0 * rng.standard_normal((B, N, 1))
+    x0 = np.stack([np.array([np.pi - 0.6 + 0.2 * rng.uniform(-1, 1), 0, 0, 0]) for _ in range(B)])
+    pm = ddp.PendcartModel()
+    lims = np.array([[-5.0, 5.0]])
+    xn, un, ct = ddp.forward_pass(ddp.GaussianPolicy.empty(), x0, u, None, 1.0, pm.f, pm.costfun, lims, u_scale=0.5,
+                                  per_step_cost=True, force_generic=True)
+    om = O.PendcartModel()
+    for b in range(B):
+        x0_, u0_, c0_ = O.forward_pass(O.GaussianPolicy.empty(), x0[b], 0.5 * u[b], None, 1, om.f, om.costfun, lims)
+        assert relerr(xn[b], x0_) < TOL and relerr(un[b], u0_) < TOL
+        assert ct.shape[1] == N + 1 and relerr(ct[b], c0_) < TOL
+
+
+def test_forward_rejects_host_callbacks(ddp):
+    with pytest.raises(TypeError):
+        ddp.forward_pass(ddp.GaussianPolicy.empty(), np.zeros(4), np.zeros((5, 1)), None, 1.0, lambda x, u, i: x,
+                         lambda x, u: 0.0, None)
+
+
+def _prev_policy(n, m, N, seed):
+    A, Bm, Q, R, x, u = make_batch_lq(seed, 1, n, m, N)
+    A, Bm, x, u = A[0], Bm[0], x[0], u[0]
+    cx, cu = x @ Q.T, u @ R.T
+    d, p, _, _, _ = O.back_pass(cx, cu, Q, np.zeros((n, m)), R, A, Bm, 1.0, 1, None, x, u)
+    Sigi = p.Sigmai.copy()
+    prev = O.GaussianPolicy(N, n, m, p.K.copy(), 0.02 * np.random.default_rng(seed).standard_normal((N, m)),
+                            np.array([np.linalg.inv(s) for s in Sigi]), Sigi)
+    return A, Bm, Q, R, x, u, cx, cu, prev
+
+
+@pytest.mark.parametrize("n,m,N,lims", [(10, 2, 30, None), (6, 2, 25, 0.2), (32, 8, 12, None), (4, 1, 30, 0.1)])
+def test_back_pass_gps(ddp, n, m, N, lims):
+    A, Bm, Q, R, x, u, cx, cu, prev = _prev_policy(n, m, N, 11)
+    lim = None if lims is None else np.tile(np.array([[-lims, lims]]), (m, 1))
+    eta = np.array([1e-8, 0.7, 1e16])
+    rep = lambda a: np.tile(a, (N, 1, 1))
+    terms = (O.grad_kl(prev), eta)
+    d0, p0, Vx0, Vxx0, dV0 = O.back_pass_gps(cx, cu, rep(Q), rep(np.zeros((n, m))), rep(R), rep(A), rep(Bm), lim, x, u, terms)
+    gp = ddp.GaussianPolicy(N, n, m, prev.K, prev.k, prev.Sigma, prev.Sigmai)
+    d1, p1, Vx1, Vxx1, dV1 = ddp.back_pass_gps(cx, cu, rep(Q), rep(np.zeros((n, m))), rep(R), rep(A), rep(Bm), lim, x, u,
+                                               (gp, eta), force_generic=True)
+    assert d0 == d1 == 0
+    for a, b in ((p1.K, p0.K), (p1.k, p0.k), (Vx1, Vx0), (Vxx1, Vxx0), (dV1, dV0), (p1.Sigmai, p0.Sigmai), (p1.Sigma, p0.Sigma)):
+        assert relerr(a, b) < TOL
+
+
+def test_kl_div(ddp):
+    n, m, N = 8, 2, 30
+    A, Bm, Q, R, x, u, cx, cu, prev = _prev_policy(n, m, N, 21)
+    rep = lambda a: np.tile(a, (N, 1, 1))
+    d0, pnew, _, _, _ = O.back_pass_gps(cx, cu, rep(Q), rep(np.zeros((n, m))), rep(R), rep(A), rep(Bm), None, x, u,
+                                        (O.grad_kl(prev), np.array([1e-8, 2.0, 1e16])))
+    om = O.LinearModel(A, Bm, Q, R)
+    xnew, unew, _ = O.forward_pass(pnew, x[0], u, x, 1, om.f, om.costfun, None)
+    R1 = 1e-4 * np.eye(n)
+    sig = O.forward_covariance(A, R1, pnew)
+    kl0 = O.kl_div_wiki(xnew, x, sig, pnew, prev)
+    gpn = ddp.GaussianPolicy(N, n, m, pnew.K, pnew.k, pnew.Sigma, pnew.Sigmai)
+    gpp = ddp.GaussianPolicy(N, n, m, prev.K, prev.k, prev.Sigma, prev.Sigmai)
+    klt, klm = ddp.kl_div_wiki(xnew, x, A, R1, gpn, gpp)
+    assert np.all(kl0 > 0)
+    assert relerr(klt, kl0) < TOL and abs(klm - kl0.mean()) < TOL * kl0.mean()
