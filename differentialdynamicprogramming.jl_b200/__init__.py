@@ -5,5 +5,5 @@ The directory name carries the reference's ``.jl``; import it as ``ddp_b200`` (t
 at the repository root) -- ``import ddp_b200 as ddp``.
 """
 from ._lib import DDPError, DDPLibraryMissing, LIB_PATH, load  # noqa: F401
-from .api import (DevArray, Engine, GaussianPolicy, LinearModel, PendcartModel, PosDefException,  # noqa: F401
-                  back_pass, back_pass_gps, boxQP, forward_pass, kl_div_wiki)
+from .api import (DEFAULT_ALPHA, STATUS, DevArray, Engine, GaussianPolicy, HostIteration, LinearModel,  # noqa: F401
+                  PendcartModel, PosDefException, back_pass, back_pass_gps, boxQP, forward_pass, iLQG, kl_div_wiki)

@@ -513,3 +513,131 @@ def kl_div_wiki(xnew, xold, fx, R1, traj_new: GaussianPolicy, traj_prev: Gaussia
     eng.synchronize()
     t, mn = klt.numpy(), klm.numpy()
     return (t, mn) if batched else (t[0], float(mn[0]))
+
+
+# ---------------------------------------------------------------------------------------------
+# iLQG  (iLQG.jl:143-341), whole outer loop device resident
+# ---------------------------------------------------------------------------------------------
+
+DEFAULT_ALPHA = 10.0 ** np.linspace(0, -3, 11)        # iLQG.jl:145
+STATUS = {-1: "running", 0: "SUCCESS: gradient norm < tol_grad", 1: "SUCCESS: cost change < tol_fun",
+          2: "EXIT: lambda > lambda_max", 3: "EXIT: Maximum iterations reached",
+          4: "EXIT: Initial control sequence caused divergence"}
+
+
+def iLQG(f, costfun, df, x0, u0, *, lims=None, alpha=None, tol_fun=1e-7, tol_grad=1e-4, max_iter=500, lam=1.0, dlam=1.0,
+         lamfactor=1.6, lammax=1e10, lammin=1e-6, regType=1, reduce_ratio_min=0.0, diff_fun=None, force_generic=False,
+         engine: Engine = None):
+    """``iLQG(f,costfun,df,x0,u0;kw...)`` -- iLQG.jl:143-341, for one trajectory or a batch.
+
+    ``f, costfun, df`` must be the callbacks of one device model descriptor.  ``x0`` is ``(n,)`` /
+    ``(B,n)``, ``u0`` is ``(N,m)`` / ``(B,N,m)``.  Returns ``(x, u, traj_new, Vx, Vxx, cost, trace)`` like the
+    reference; ``Vxx`` is the value Hessian at the first timestep only (the history is optional on
+    the device), ``cost`` the total cost, ``trace`` a dict with the per-trajectory final
+    ``status, iter, accepted_iter, lam, dlam, g_norm`` and ``n_outer``.  Unbatched calls return ``None``
+    when the initial controls diverge (iLQG.jl:209) and raise ``RuntimeError`` when no iteration
+    completed (iLQG.jl:335), as the reference does.
+    """
+    if diff_fun is not None:
+        raise NotImplementedError("only the default diff_fun (-) is supported on the device")
+    model = _model_of(f, costfun)
+    if getattr(df, "model", None) is not model:
+        raise TypeError("df must belong to the same device model descriptor as f and costfun")
+    u0 = np.asarray(u0, dtype=np.float64)
+    batched = u0.ndim == 3
+    B = u0.shape[0] if batched else 1
+    N, m = u0.shape[-2:]
+    x0 = np.asarray(x0, dtype=np.float64)
+    if x0.ndim == 2 and not batched and x0.shape[0] == N:
+        raise NotImplementedError("pre-rolled initial trajectories are not supported by the device driver")
+    n = x0.shape[-1]
+    alpha = DEFAULT_ALPHA if alpha is None else np.asarray(alpha, dtype=np.float64)
+    eng = engine or Engine(n, m, N, B, force_generic=force_generic)
+    M, keep = _pack_model(eng, model, B, N, n, m)
+    o = L.IlqgOpts()
+    o.n_alpha = len(alpha)
+    for i, v in enumerate(alpha):
+        o.alpha[i] = float(v)
+    o.tol_fun, o.tol_grad, o.max_iter = tol_fun, tol_grad, max_iter
+    o.lam, o.dlam, o.lam_factor, o.lam_max, o.lam_min = lam, dlam, lamfactor, lammax, lammin
+    o.reg_type, o.reduce_ratio_min = int(regType), float(reduce_ratio_min)
+    ld = _lims_dev(eng, lims, m)
+    if ld is not None:
+        keep.append(ld)
+        o.lims = ld.ptr
+    dx0 = eng.upload(np.broadcast_to(x0.reshape(-1, n), (B, n)))
+    du0 = eng.upload(u0.reshape(B, N, m))
+    x, u = eng.empty((B, N, n)), eng.empty((B, N, m))
+    K, k, Vx, Vxx1 = eng.empty((B, N, n, m)).zero(), eng.empty((B, N, m)).zero(), eng.empty((B, N, n)).zero(), eng.empty((B, n, n)).zero()
+    st = eng.empty((B, C.sizeof(L.IlqgState)), np.uint8)
+    n_outer = C.c_int32(0)
+    eng._ck(eng.lib.ddp_ilqg_solve_f64(eng.h, C.byref(M), C.byref(o), dx0.ptr, du0.ptr, x.ptr, u.ptr, K.ptr, k.ptr, Vx.ptr,
+                                       Vxx1.ptr, st.ptr, C.byref(n_outer)))
+    states = np.frombuffer(st.numpy().tobytes(), dtype=np.dtype(
+        [("lam", "f8"), ("dlam", "f8"), ("cost", "f8"), ("g_norm", "f8"), ("last_dcost", "f8"), ("last_alpha", "f8"),
+         ("iter", "i4"), ("accepted_iter", "i4"), ("status", "i4"), ("pad", "i4")]))
+    trace = {key: states[key].copy() for key in ("status", "iter", "accepted_iter", "lam", "dlam", "g_norm", "last_dcost", "last_alpha")}
+    trace["n_outer"] = int(n_outer.value)
+    xs, us = x.numpy(), u.numpy()
+    Ks, ks = np.swapaxes(K.numpy(), -1, -2), k.numpy()
+    Vxs, Vxxs = Vx.numpy(), np.swapaxes(Vxx1.numpy(), -1, -2)
+    cost = states["cost"].copy()
+    if batched:
+        return xs, us, GaussianPolicy(N, n, m, Ks, ks), Vxs, Vxxs, cost, trace
+    if trace["status"][0] == 4:
+        return None
+    if trace["iter"][0] == 1:
+        raise RuntimeError("Failure: no iterations completed, something is wrong.")
+    trace = {key: (v[0] if isinstance(v, np.ndarray) else v) for key, v in trace.items()}
+    return xs[0], us[0], GaussianPolicy(N, n, m, Ks[0], ks[0]), Vxs[0], Vxxs[0], float(cost[0]), trace
+
+
+# ---------------------------------------------------------------------------------------------
+# one end-to-end iteration on host buffers (the bench's e2e path)
+# ---------------------------------------------------------------------------------------------
+
+
+class HostIteration:
+    """Pinned host buffers + ``ddp_ilqg_iter_host_f64``: one backward sweep and one forward rollout
+    for a batch of per-trajectory LTI linear problems, host to host (device layout arrays)."""
+
+    FIELDS_IN = ("fx", "fu", "cx", "cu", "x", "u", "lam")
+    FIELDS_OUT = ("xnew", "unew", "cost", "dV")
+
+    def __init__(self, eng: Engine, Q, R, cxu=None, reg_type=1, alpha=1.0, chunk=0):
+        self.eng = eng
+        n, m, T, B = eng.n, eng.m, eng.T, eng.B
+        shapes = dict(fx=(B, n, n), fu=(B, m, n), cx=(B, T, n), cu=(B, T, m), x=(B, T, n), u=(B, T, m), lam=(B,),
+                      xnew=(B, T, n), unew=(B, T, m), cost=(B,), dV=(B, 2))
+        self._ptrs = []
+        self.bufs = {}
+        for name, shp in shapes.items():
+            self.bufs[name] = self._pinned(shp, np.float64)
+        self.bufs["diverge"] = self._pinned((B,), np.int32)
+        self.Q = np.ascontiguousarray(np.asarray(Q, dtype=np.float64).T)
+        self.R = np.ascontiguousarray(np.asarray(R, dtype=np.float64).T)
+        self.cxu = np.zeros((m, n)) if cxu is None else np.ascontiguousarray(np.asarray(cxu, dtype=np.float64).T)
+        self.args = L.IterHostArgs()
+        for name in self.FIELDS_IN + self.FIELDS_OUT + ("diverge",):
+            setattr(self.args, name, self.bufs[name].ctypes.data)
+        self.args.Q, self.args.R, self.args.cxu = self.Q.ctypes.data, self.R.ctypes.data, self.cxu.ctypes.data
+        self.args.reg_type, self.args.alpha, self.args.chunk = reg_type, alpha, chunk
+
+    def _pinned(self, shape, dtype):
+        nbytes = int(np.prod(shape, dtype=np.int64)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        rc = self.eng.lib.ddp_host_alloc(C.byref(p), max(nbytes, 8))
+        if rc != 0:
+            raise MemoryError("ddp_host_alloc failed")
+        self._ptrs.append(p.value)
+        buf = (C.c_char * max(nbytes, 8)).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape, dtype=np.int64))).reshape(shape)
+
+    def run(self):
+        self.eng._ck(self.eng.lib.ddp_ilqg_iter_host_f64(self.eng.h, C.byref(self.args)))
+        return int(self.args.h2d_bytes), int(self.args.d2h_bytes)
+
+    def close(self):
+        for p in self._ptrs:
+            self.eng.lib.ddp_host_free(p)
+        self._ptrs = []

@@ -101,6 +101,7 @@ int ddp_create(ddp_handle_t* out, int device, int n, int m, int T, int64_t B, ui
 int ddp_destroy(ddp_handle_t h) {
     if (!h) return DDP_OK;
     cudaSetDevice(h->device);
+    if (h->cache && h->cache_free) h->cache_free(h->cache);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
     return DDP_OK;

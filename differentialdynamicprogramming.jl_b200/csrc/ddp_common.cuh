@@ -74,6 +74,8 @@ struct ddp_handle_s {
     int max_smem_optin;
     long long launches;
     std::string err;
+    void* cache = nullptr;               // lazily created pipeline state (solve.cu)
+    void (*cache_free)(void*) = nullptr;
     // scratch for the solve driver / host-iteration pipeline is allocated lazily by those entry points
 };
 

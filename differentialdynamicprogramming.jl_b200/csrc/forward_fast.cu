@@ -1,3 +1,301 @@
-// placeholder: specialised forward kernels (filled in next)
+// Specialised forward line-search rollouts.
+//
+//  fwd_lin32x8_kernel : n = 32, m = 8, linear model with time-invariant per-trajectory A, B
+//                       (the headline workload).  One warp per trajectory; lane i owns state i and
+//                       keeps row i of A, B and Q in registers for all T steps.  The step's K (2 KB),
+//                       x, u, k are read with fully coalesced 16-byte loads, prefetched two steps
+//                       ahead so ~5 KB per warp are always in flight (the kernel is HBM-bound: it
+//                       streams K once).  cx = Q(x-goal), cu = R u of the NEW trajectory can be
+//                       written in the same pass (the reference's df for this model,
+//                       demo_linear.jl:38-39), which saves the next iteration a whole pass.
+//  fwd_pend_kernel    : n = 4, m = 1 pendulum-on-cart (Euler step), ONE THREAD per trajectory.
+//
+// Replaces forward_pass of src/forward_pass.jl:9-33 (+ f/costfun of demo_linear.jl:35-50 and
+// system_pendcart.jl:83-106).  Anything else dispatches to forward_generic.cu.
 #include "ddp_common.cuh"
-int launch_forward_fast(ddp_handle_s*, const FwdParams&, bool* handled) { *handled = false; return 0; }
+
+namespace {
+
+__device__ __forceinline__ double2 ldg2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+__device__ __forceinline__ void stg2(double* p, double a, double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
+
+constexpr int FW_WPB = 4;
+constexpr int FW_WARP_DOUBLES = 32 + 32 + 32 + 8;   // sx, sdx, sd, su
+
+struct Pre {
+    double2 K[4];
+    double2 u, k;
+    double xo;
+};
+
+template <bool POLICY>
+__device__ __forceinline__ void prefetch(Pre& p, const FwdParams& P, long long b, int t, int lane, int q) {
+    const int N = P.T;
+    if (POLICY) {
+        const double* Kt = P.K + (b * N + t) * 256;
+#pragma unroll
+        for (int i = 0; i < 4; i++) p.K[i] = ldg2(Kt + 2 * (lane + 32 * i));
+        p.k = ldg2(P.k + (b * N + t) * 8 + 2 * q);
+        p.xo = tp(P.x, b, t)[lane];
+    }
+    p.u = ldg2(tp(P.u, b, t) + 2 * q);
+}
+
+template <bool POLICY>
+__global__ void __launch_bounds__(FW_WPB * 32, 2) fwd_lin32x8_kernel(FwdParams P) {
+    __shared__ double smem[FW_WPB * FW_WARP_DOUBLES];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    double* sx = smem + w * FW_WARP_DOUBLES;
+    double* sdx = sx + 32;
+    double* sd = sdx + 32;
+    double* su = sd + 32;
+    const int N = P.T;
+    const bool has_goal = (P.model.goal != nullptr);
+    const bool has_lims = (P.lims != nullptr);
+    const long long warps_total = (long long)gridDim.x * FW_WPB;
+
+    for (long long b = (long long)blockIdx.x * FW_WPB + w; b < P.B; b += warps_total) {
+        if (P.active && !P.active[b]) continue;
+        const double alpha = P.alpha ? P.alpha[b] : P.alpha_scalar;
+        // ---- per-trajectory constants in registers: row `lane` of A, B, Q; row (lane & 7) of R
+        double Ar[32], Br[8], Qr[32], Rr[8];
+        {
+            const double* A = P.model.A.p + b * P.model.A.sb;        // column-major: A[i + 32 j]
+            const double* Bm = P.model.Bm.p + b * P.model.Bm.sb;
+            const double* Q = P.model.Q.p + b * P.model.Q.sb;
+            const double* R = P.model.R.p + b * P.model.R.sb;
+#pragma unroll
+            for (int j = 0; j < 32; j++) { Ar[j] = A[lane + 32 * j]; Qr[j] = Q[lane + 32 * j]; }
+#pragma unroll
+            for (int c = 0; c < 8; c++) { Br[c] = Bm[lane + 32 * c]; Rr[c] = R[(lane & 7) + 8 * c]; }
+        }
+        const double goal = has_goal ? P.model.goal[lane] : 0.0;
+        double lo0 = 0, lo1 = 0, hi0 = 0, hi1 = 0;
+        if (has_lims) { lo0 = P.lims[2 * q]; lo1 = P.lims[2 * q + 1]; hi0 = P.lims[8 + 2 * q]; hi1 = P.lims[8 + 2 * q + 1]; }
+        double x = (P.x0.p + b * P.x0.sb)[lane];
+        double cpart = 0.0;
+        double* xnb = P.xnew + b * (long long)N * 32;
+        double* unb = P.unew + b * (long long)N * 8;
+
+        auto step = [&](int t, const Pre& p) {
+            // 1. publish x (and dx, d) to the warp
+            const double d = x - goal;
+            sx[lane] = x;
+            if (POLICY) sdx[lane] = x - p.xo;
+            if (has_goal) sd[lane] = d;
+            xnb[(long long)t * 32 + lane] = x;
+            __syncwarp();
+            // 2. controls: u + alpha k + K dx   (lane holds K[2q..2q+1][g + 8i], i = 0..3)
+            double un0 = p.u.x * P.u_scale, un1 = p.u.y * P.u_scale;
+            if (POLICY) {
+                double p0 = 0.0, p1 = 0.0;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const double dxj = sdx[g + 8 * i];
+                    p0 = fma(p.K[i].x, dxj, p0);
+                    p1 = fma(p.K[i].y, dxj, p1);
+                }
+#pragma unroll
+                for (int o = 4; o < 32; o <<= 1) {
+                    p0 += __shfl_xor_sync(0xffffffffu, p0, o);
+                    p1 += __shfl_xor_sync(0xffffffffu, p1, o);
+                }
+                un0 = (un0 + p.k.x * alpha) + p0;        // forward_pass.jl:18,20: two separate roundings
+                un1 = (un1 + p.k.y * alpha) + p1;
+            }
+            if (has_lims) { un0 = fmin(fmax(un0, lo0), hi0); un1 = fmin(fmax(un1, lo1), hi1); }
+            if (un0 != un0) un0 = 0.0;
+            if (un1 != un1) un1 = 0.0;
+            if (g == 0) {
+                stg2(&su[2 * q], un0, un1);
+                stg2(unb + (long long)t * 8 + 2 * q, un0, un1);
+            }
+            __syncwarp();
+            // 3. x+ = A x + B u ; Qd ; Ru
+            double ax0 = 0.0, ax1 = 0.0, qd0 = 0.0, qd1 = 0.0;
+            if (!has_goal) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    const double2 xv = *reinterpret_cast<const double2*>(&sx[j]);
+                    ax0 = fma(Ar[j], xv.x, ax0);
+                    ax1 = fma(Ar[j + 1], xv.y, ax1);
+                    qd0 = fma(Qr[j], xv.x, qd0);
+                    qd1 = fma(Qr[j + 1], xv.y, qd1);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    const double2 xv = *reinterpret_cast<const double2*>(&sx[j]);
+                    const double2 dv = *reinterpret_cast<const double2*>(&sd[j]);
+                    ax0 = fma(Ar[j], xv.x, ax0);
+                    ax1 = fma(Ar[j + 1], xv.y, ax1);
+                    qd0 = fma(Qr[j], dv.x, qd0);
+                    qd1 = fma(Qr[j + 1], dv.y, qd1);
+                }
+            }
+            double bu = 0.0, ru = 0.0;
+#pragma unroll
+            for (int c = 0; c < 8; c += 2) {
+                const double2 uv = *reinterpret_cast<const double2*>(&su[c]);
+                bu = fma(Br[c], uv.x, bu);
+                bu = fma(Br[c + 1], uv.y, bu);
+                ru = fma(Rr[c], uv.x, ru);
+                ru = fma(Rr[c + 1], uv.y, ru);
+            }
+            const double qd = qd0 + qd1;
+            double cstep = 0.5 * d * qd;
+            if (lane < 8) cstep = fma(0.5 * su[lane], ru, cstep);
+            if (P.cx) P.cx[(b * N + t) * 32 + lane] = qd;
+            if (P.cu && lane < 8) P.cu[(b * N + t) * 8 + lane] = ru;
+            if (P.cost_t) {
+                double ct = cstep;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) ct += __shfl_xor_sync(0xffffffffu, ct, o);
+                if (lane == 0) P.cost_t[b * (N + P.model.terminal_cost) + t] = ct;
+            }
+            cpart += cstep;
+            if (t < N - 1) x = (ax0 + ax1) + bu;
+            __syncwarp();
+        };
+
+        Pre p0, p1;
+        prefetch<POLICY>(p0, P, b, 0, lane, q);
+        if (N > 1) prefetch<POLICY>(p1, P, b, 1, lane, q);
+        for (int t = 0; t < N; t += 2) {
+            Pre p2, p3;
+            if (t + 2 < N) prefetch<POLICY>(p2, P, b, t + 2, lane, q);
+            step(t, p0);
+            if (t + 3 < N) prefetch<POLICY>(p3, P, b, t + 3, lane, q);
+            if (t + 1 < N) step(t + 1, p1);
+            p0 = p2;
+            p1 = p3;
+        }
+        if (P.model.terminal_cost) {
+            // ½ d'Qd at the last state once more (system_pendcart.jl:104); sx/sd still hold step N-1
+            double qd = 0.0;
+            const double* sv = has_goal ? sd : sx;
+#pragma unroll
+            for (int j = 0; j < 32; j++) qd = fma(Qr[j], sv[j], qd);
+            double cterm = 0.5 * (x - goal) * qd;
+            if (P.cost_t) {
+                double ct = cterm;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) ct += __shfl_xor_sync(0xffffffffu, ct, o);
+                if (lane == 0) P.cost_t[b * (N + 1) + N] = ct;
+            }
+            cpart += cterm;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cpart += __shfl_xor_sync(0xffffffffu, cpart, o);
+        if (lane == 0) P.cost[b] = cpart;
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pendulum on a cart: one thread per trajectory, everything in registers
+template <bool POLICY>
+__global__ void __launch_bounds__(128) fwd_pend_kernel(FwdParams P) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= P.B) return;
+    if (P.active && !P.active[b]) return;
+    const int N = P.T;
+    const double alpha = P.alpha ? P.alpha[b] : P.alpha_scalar;
+    const double gg = P.model.p[0], l = P.model.p[1], h = P.model.p[2], dd = P.model.p[3];
+    const double* Qm = P.model.Q.p + b * P.model.Q.sb;
+    const double Rv = (P.model.R.p + b * P.model.R.sb)[0];
+    double Q[16], goal[4], x[4];
+#pragma unroll
+    for (int i = 0; i < 16; i++) Q[i] = Qm[i];
+#pragma unroll
+    for (int i = 0; i < 4; i++) { goal[i] = P.model.goal ? P.model.goal[i] : 0.0; x[i] = (P.x0.p + b * P.x0.sb)[i]; }
+    const bool has_lims = P.lims != nullptr;
+    const double lo = has_lims ? P.lims[0] : 0.0, hi = has_lims ? P.lims[1] : 0.0;
+    double* xnb = P.xnew + b * (long long)N * 4;
+    double* unb = P.unew + b * (long long)N;
+    double ctot = 0.0, clast = 0.0;
+    for (int t = 0; t < N; t++) {
+        double un = tp(P.u, b, t)[0] * P.u_scale;
+        if (POLICY) {
+            const double2 K01 = ldg2(P.K + (b * N + t) * 4), K23 = ldg2(P.K + (b * N + t) * 4 + 2);
+            const double* xo = tp(P.x, b, t);
+            const double2 xo01 = ldg2(xo), xo23 = ldg2(xo + 2);
+            un = un + P.k[b * N + t] * alpha;
+            double acc = K01.x * (x[0] - xo01.x);
+            acc = fma(K01.y, x[1] - xo01.y, acc);
+            acc = fma(K23.x, x[2] - xo23.x, acc);
+            acc = fma(K23.y, x[3] - xo23.y, acc);
+            un = un + acc;
+        }
+        if (has_lims) un = fmin(fmax(un, lo), hi);
+        if (un != un) un = 0.0;
+        stg2(xnb + (long long)t * 4, x[0], x[1]);
+        stg2(xnb + (long long)t * 4 + 2, x[2], x[3]);
+        unb[t] = un;
+        double d[4], qd[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) d[i] = x[i] - goal[i];
+        double cs = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            qd[i] = 0.0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) qd[i] = fma(Q[i + 4 * j], d[j], qd[i]);
+            cs = fma(0.5 * d[i], qd[i], cs);
+        }
+        clast = cs;
+        const double ru = Rv * un;
+        const double cstep = fma(0.5 * un, ru, cs);
+        if (P.cx) { stg2(P.cx + (b * N + t) * 4, qd[0], qd[1]); stg2(P.cx + (b * N + t) * 4 + 2, qd[2], qd[3]); }
+        if (P.cu) P.cu[b * N + t] = ru;
+        if (P.cost_t) P.cost_t[b * (N + P.model.terminal_cost) + t] = cstep;
+        ctot += cstep;
+        if (t < N - 1) {
+            double sn, cs2;
+            sincos(x[0], &sn, &cs2);
+            const double x0n = x[0] + h * x[1];
+            const double x1n = x[1] + h * (-gg / l * sn + un / l * cs2 - dd * x[1]);
+            const double x2n = x[2] + h * x[3];
+            const double x3n = x[3] + h * un;
+            x[0] = x0n; x[1] = x1n; x[2] = x2n; x[3] = x3n;
+        }
+    }
+    if (P.model.terminal_cost) {
+        if (P.cost_t) P.cost_t[b * (N + 1) + N] = clast;
+        ctot += clast;
+    }
+    P.cost[b] = ctot;
+}
+
+bool al16(const void* p) { return ((uintptr_t)p % 16) == 0; }
+
+}  // namespace
+
+int launch_forward_fast(ddp_handle_s* h, const FwdParams& P, bool* handled) {
+    *handled = false;
+    const bool policy = (P.K != nullptr);
+    if (P.model.kind == DDP_MODEL_LINEAR && P.n == 32 && P.m == 8 && P.model.A.st == 0 && P.model.Bm.st == 0) {
+        if (!al16(P.u.p) || (P.u.sb % 2) || (P.u.st % 2)) return 0;
+        if (policy && (!al16(P.K) || !al16(P.k))) return 0;
+        long long grid = (long long)h->sm_count * 2;
+        long long need = (P.B + FW_WPB - 1) / FW_WPB;
+        if (grid > need) grid = need;
+        if (policy) fwd_lin32x8_kernel<true><<<(unsigned)grid, FW_WPB * 32, 0, h->stream>>>(P);
+        else fwd_lin32x8_kernel<false><<<(unsigned)grid, FW_WPB * 32, 0, h->stream>>>(P);
+        h->launches++;
+        *handled = true;
+        return (int)cudaGetLastError();
+    }
+    if (P.model.kind == DDP_MODEL_PENDCART && P.n == 4 && P.m == 1) {
+        if (!al16(P.xnew) || (policy && (!al16(P.K) || !al16(P.x.p) || (P.x.sb % 2) || (P.x.st % 2)))) return 0;
+        if (P.cx && !al16(P.cx)) return 0;
+        unsigned grid = (unsigned)((P.B + 127) / 128);
+        if (policy) fwd_pend_kernel<true><<<grid, 128, 0, h->stream>>>(P);
+        else fwd_pend_kernel<false><<<grid, 128, 0, h->stream>>>(P);
+        h->launches++;
+        *handled = true;
+        return (int)cudaGetLastError();
+    }
+    return 0;
+}

@@ -146,3 +146,59 @@ def test_kl_div(ddp):
     klt, klm = ddp.kl_div_wiki(xnew, x, A, R1, gpn, gpp)
     assert np.all(kl0 > 0)
     assert relerr(klt, kl0) < TOL and abs(klm - kl0.mean()) < TOL * kl0.mean()
+
+
+# ---- specialised forward kernels (dispatch by shape; compare with the oracle and the generic kernel)
+
+@pytest.mark.parametrize("lims,goal", [(None, False), (0.3, False), (None, True)])
+def test_forward_fast_lin32x8(ddp, lims, goal):
+    B, n, m, N = 7, 32, 8, 41
+    A, Bm, Q, R, x, u = make_batch_lq(17, B, n, m, N)
+    rng = np.random.default_rng(5)
+    Qf = Q + 0.001 * (lambda M: M @ M.T)(rng.standard_normal((n, n)))      # dense Q
+    Rf = R + 0.0005 * (lambda M: M @ M.T)(rng.standard_normal((m, m)))
+    cx, cu = x @ Qf.T, u @ Rf.T
+    lim = None if lims is None else np.tile(np.array([[-lims, lims]]), (m, 1))
+    alphas = np.linspace(1.0, 0.1, B)
+    model = ddp.LinearModel(A[:, None], Bm[:, None], Qf, Rf)
+    if goal:
+        model.goal = 0.1 * rng.standard_normal(n)
+    pols = [O.back_pass(cx[b], cu[b], Qf, np.zeros((n, m)), Rf, A[b], Bm[b], 1.0, 1, None, x[b], u[b])[1] for b in range(B)]
+    pol = ddp.GaussianPolicy(N, n, m, np.array([p.K for p in pols]), np.array([p.k for p in pols]))
+    xn, un, ct, (cxn, cun) = ddp.forward_pass(pol, x[:, 0], u, x, alphas, model.f, model.costfun, lim, per_step_cost=True, want_derivs=True)
+    xg, ug, cg = ddp.forward_pass(pol, x[:, 0], u, x, alphas, model.f, model.costfun, lim, force_generic=True)
+    gl = model.goal if goal else np.zeros(n)
+    for b in range(B):
+        om = O.LinearModel(A[b], Bm[b], Qf, Rf, per_step_cost=True)
+        costf = (lambda xx, uu: 0.5 * np.sum((xx - gl) * ((xx - gl) @ Qf.T), axis=1) + 0.5 * np.sum(uu * (uu @ Rf.T), axis=1))
+        x0_, u0_, c0_ = O.forward_pass(pols[b], x[b, 0], u[b], x[b], alphas[b], om.f, costf, lim)
+        assert relerr(xn[b], x0_) < TOL and relerr(un[b], u0_) < TOL and relerr(ct[b], c0_) < TOL
+        assert relerr(cxn[b], (x0_ - gl) @ Qf.T) < TOL and relerr(cun[b], u0_ @ Rf.T) < TOL
+        assert relerr(xg[b], x0_) < TOL and abs(cg[b] - c0_.sum()) < TOL * abs(c0_.sum())
+
+
+def test_forward_fast_pendcart(ddp):
+    N, B = 120, 37
+    rng = np.random.default_rng(8)
+    x0 = np.stack([np.array([np.pi - 0.6 + 0.2 * rng.uniform(-1, 1), 0, 0, 0]) for _ in range(B)])
+    u = rng.standard_normal((B, N, 1))
+    pm, om = ddp.PendcartModel(), O.PendcartModel()
+    lims = np.array([[-5.0, 5.0]])
+    # a rollout to linearise around, then one oracle back pass per trajectory for a policy
+    xr, ur, _ = ddp.forward_pass(ddp.GaussianPolicy.empty(), x0, u, None, 1.0, pm.f, pm.costfun, lims)
+    pols = []
+    for b in range(B):
+        xo, uo, _ = O.forward_pass(O.GaussianPolicy.empty(), x0[b], u[b], None, 1, om.f, om.costfun, lims)
+        assert relerr(xr[b], xo) < TOL
+        fx, fu, _, _, _, cx, cu, cxx, cxu, cuu = om.df(xo, uo)
+        d, p, _, _, _ = O.back_pass(cx, cu, cxx, cxu, cuu, fx, fu, 1.0, 2, lims, xo, uo)
+        assert d == 0
+        pols.append((p, xo, uo))
+    pol = ddp.GaussianPolicy(N, 4, 1, np.array([p[0].K for p in pols]), np.array([p[0].k for p in pols]))
+    xs, us = np.array([p[1] for p in pols]), np.array([p[2] for p in pols])
+    xn, un, ct = ddp.forward_pass(pol, x0, us, xs, 0.7, pm.f, pm.costfun, lims, per_step_cost=True)
+    xg, ug, cg = ddp.forward_pass(pol, x0, us, xs, 0.7, pm.f, pm.costfun, lims, per_step_cost=True, force_generic=True)
+    for b in range(B):
+        x0_, u0_, c0_ = O.forward_pass(pols[b][0], x0[b], us[b], xs[b], 0.7, om.f, om.costfun, lims)
+        assert relerr(xn[b], x0_) < TOL and relerr(un[b], u0_) < TOL and relerr(ct[b], c0_) < TOL
+        assert relerr(xg[b], x0_) < TOL and relerr(cg[b], c0_) < TOL

@@ -1,0 +1,100 @@
+"""GPU parity for the device-resident iLQG driver (ddp_ilqg_solve_f64) and the host-buffer
+iteration (ddp_ilqg_iter_host_f64) against the CPU oracle's iLQG state machine.
+Integer outcomes (status, iter, accepted_iter) exact; x, u, cost within the stated tolerance."""
+import numpy as np
+import pytest
+
+from helpers import make_batch_lq, make_lq, relerr
+from oracle import ddp_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n,m,N,generic", [(10, 2, 120, True), (32, 8, 60, False), (32, 8, 40, True)])
+def test_ilqg_lq_batch(ddp, n, m, N, generic):
+    B = 5
+    rng = np.random.default_rng(42)
+    As, Bs, x0s, u0s = [], [], [], []
+    for b in range(B):
+        A, Bm, Q, R = make_lq(rng, n, m)
+        As.append(A); Bs.append(Bm); x0s.append(np.ones(n) * (1 + 0.1 * b)); u0s.append(0.1 * rng.standard_normal((N, m)))
+    As, Bs, x0s, u0s = map(np.array, (As, Bs, x0s, u0s))
+    model = ddp.LinearModel(As[:, None], Bs[:, None], Q, R)
+    x, u, pol, Vx, Vxx, cost, tr = ddp.iLQG(model.f, model.costfun, model.df, x0s, u0s, force_generic=generic)
+    for b in range(B):
+        om = O.LinearModel(As[b], Bs[b], Q, R)
+        x0_, u0_, p0, Vx0, Vxx0, c0, t0 = O.iLQG(om.f, om.costfun, om.df, x0s[b], u0s[b])
+        assert tr["status"][b] == t0["status"] and tr["iter"][b] == t0["iters"]
+        assert relerr(x[b], x0_) < 1e-7 and relerr(u[b], u0_) < 1e-7
+        assert abs(cost[b] - np.sum(c0)) < 1e-8 * abs(np.sum(c0))
+        assert abs(tr["lam"][b] - t0["lam_final"]) <= 1e-12 * t0["lam_final"]
+        assert relerr(pol.K[b], p0.K) < 1e-7 and relerr(pol.k[b], p0.k) < 1e-6 and relerr(Vx[b], Vx0) < 1e-6
+        assert relerr(Vxx[b], Vxx0[0]) < 1e-7
+
+
+def test_ilqg_thresholds_of_test_readme(ddp):
+    """test/test_readme.jl:82-84 on fresh instances of its problem distribution (n=10, m=2, T=1000)."""
+    rng = np.random.default_rng(0)
+    B, n, m, N = 10, 10, 2, 1000
+    As, Bs, u0s = [], [], []
+    for b in range(B):
+        A, Bm, Q, R = make_lq(rng, n, m)
+        As.append(A); Bs.append(Bm); u0s.append(0.1 * rng.standard_normal((N, m)))
+    model = ddp.LinearModel(np.array(As)[:, None], np.array(Bs)[:, None], Q, R)
+    x, u, pol, Vx, Vxx, cost, tr = ddp.iLQG(model.f, model.costfun, model.df, np.ones((B, n)), np.array(u0s))
+    assert np.all(tr["status"] == 0)
+    assert cost.max() < 25 and cost.mean() < 10 and cost.min() < 5
+
+
+def test_ilqg_pendcart_lims(ddp):
+    """demo_pendcart's settings (system_pendcart.jl:197-206) on a short horizon, a few iterations."""
+    N, B = 120, 3
+    x0 = np.array([[np.pi - 0.6, 0, 0, 0], [np.pi - 0.5, 0, 0, 0], [np.pi - 0.7, 0.1, 0, 0]])
+    u0 = np.zeros((B, N, 1))
+    lims = np.array([[-5.0, 5.0]])
+    kw = dict(lims=lims, regType=2, alpha=10.0 ** np.linspace(0.2, -3, 6), lammax=1e15, tol_fun=1e-8, tol_grad=1e-8, max_iter=6)
+    pm = ddp.PendcartModel()
+    x, u, pol, Vx, Vxx, cost, tr = ddp.iLQG(pm.f, pm.costfun, pm.df, x0, u0, **kw)
+    for b in range(B):
+        om = O.PendcartModel()
+        x0_, u0_, p0, Vx0, Vxx0, c0, t0 = O.iLQG(om.f, om.costfun, om.df, x0[b], u0[b], **kw)
+        assert tr["status"][b] == t0["status"] and tr["iter"][b] == t0["iters"]
+        assert relerr(x[b], x0_) < 1e-6 and relerr(u[b], u0_) < 1e-6
+        assert abs(cost[b] - np.sum(c0)) < 1e-7 * abs(np.sum(c0))
+
+
+def test_ilqg_unbatched_and_errors(ddp):
+    rng = np.random.default_rng(1)
+    A, Bm, Q, R = make_lq(rng, 6, 2)
+    model = ddp.LinearModel(A, Bm, Q, R)
+    u0 = 0.1 * rng.standard_normal((50, 2))
+    x, u, pol, Vx, Vxx, cost, tr = ddp.iLQG(model.f, model.costfun, model.df, np.ones(6), u0)
+    om = O.LinearModel(A, Bm, Q, R)
+    x0_, u0_, p0, Vx0, Vxx0, c0, t0 = O.iLQG(om.f, om.costfun, om.df, np.ones(6), u0)
+    assert tr["status"] == t0["status"] and tr["iter"] == t0["iters"] and relerr(x, x0_) < 1e-7
+    # an unstable system with huge controls diverges for every alpha -> reference returns nothing
+    Au = 40.0 * np.eye(6)
+    mu = ddp.LinearModel(Au, Bm, Q, R)
+    assert ddp.iLQG(mu.f, mu.costfun, mu.df, 1e6 * np.ones(6), 1e6 * np.ones((50, 2))) is None
+    with pytest.raises(TypeError):
+        ddp.iLQG(lambda x, u, i: x, lambda x, u: 0.0, lambda x, u: None, np.ones(6), u0)
+
+
+def test_iter_host_matches_separate_calls(ddp):
+    B, n, m, N = 50, 32, 8, 32
+    A, Bm, Q, R, x, u = make_batch_lq(9, B, n, m, N)
+    cx, cu = x @ Q.T, u @ R.T
+    eng = ddp.Engine(n, m, N, B)
+    it = ddp.HostIteration(eng, Q, R, reg_type=1, alpha=0.5, chunk=16)          # 4 ragged chunks
+    it.bufs["fx"][:] = np.swapaxes(A, -1, -2); it.bufs["fu"][:] = np.swapaxes(Bm, -1, -2)
+    it.bufs["cx"][:] = cx; it.bufs["cu"][:] = cu; it.bufs["x"][:] = x; it.bufs["u"][:] = u
+    it.bufs["lam"][:] = 1.0 + 0.01 * np.arange(B)
+    h2d, d2h = it.run()
+    assert h2d >= B * 8 * (n * n + n * m + 2 * N * n + 2 * N * m + 1) and d2h >= B * 8 * (N * n + N * m + 3)
+    dv, pol, Vx, Vxx, dV = ddp.back_pass(cx, cu, Q, np.zeros((n, m)), R, A[:, None], Bm[:, None], it.bufs["lam"].copy(), 1, None, x, u)
+    model = ddp.LinearModel(A[:, None], Bm[:, None], Q, R)
+    xn, un, cn = ddp.forward_pass(pol, x[:, 0], u, x, 0.5, model.f, model.costfun, None)
+    assert np.array_equal(it.bufs["diverge"], dv)
+    assert np.array_equal(it.bufs["xnew"], xn) and np.array_equal(it.bufs["unew"], un)
+    assert np.array_equal(it.bufs["cost"], cn) and np.array_equal(it.bufs["dV"], dV)
+    it.close()
