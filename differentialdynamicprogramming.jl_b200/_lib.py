@@ -36,7 +36,7 @@ class GpsArgs(C.Structure):         # ddp_gps_args
 
 class Model(C.Structure):           # ddp_model
     _fields_ = [("kind", C.c_int32), ("A", Tensor), ("Bm", Tensor), ("Q", Tensor), ("R", Tensor),
-                ("goal", C.c_void_p), ("p", C.c_double * 8), ("terminal_cost", C.c_int32)]
+                ("goal", C.c_void_p), ("p", C.c_double * 8), ("terminal_cost", C.c_int32), ("flags", C.c_int32)]
 
 
 class ForwardPassArgs(C.Structure):  # ddp_forward_pass_args
@@ -72,7 +72,7 @@ class IterHostArgs(C.Structure):    # ddp_iter_host_args
     _fields_ = [("fx", C.c_void_p), ("fu", C.c_void_p), ("cx", C.c_void_p), ("cu", C.c_void_p),
                 ("x", C.c_void_p), ("u", C.c_void_p), ("lam", C.c_void_p),
                 ("Q", C.c_void_p), ("R", C.c_void_p), ("cxu", C.c_void_p),
-                ("reg_type", C.c_int32), ("alpha", C.c_double),
+                ("reg_type", C.c_int32), ("q_diagonal", C.c_int32), ("alpha", C.c_double),
                 ("xnew", C.c_void_p), ("unew", C.c_void_p), ("cost", C.c_void_p), ("dV", C.c_void_p),
                 ("diverge", C.c_void_p), ("chunk", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
 

@@ -392,6 +392,8 @@ def _pack_model(eng: Engine, model, B, N, n, m):
     M = L.Model()
     M.kind = model.kind
     M.terminal_cost = model.terminal_cost
+    Qh = np.asarray(model.Q, dtype=np.float64)
+    M.flags = 1 if (Qh.ndim == 2 and np.count_nonzero(Qh - np.diag(np.diagonal(Qh))) == 0) else 0   # isdiag(Q)
     if model.kind == 1:
         dev, M.A = _pack_mat(eng, model.A, B, N, n, n, "A"); keep.append(dev)
         dev, M.Bm = _pack_mat(eng, model.B, B, N, n, m, "B"); keep.append(dev)
@@ -622,6 +624,7 @@ class HostIteration:
             setattr(self.args, name, self.bufs[name].ctypes.data)
         self.args.Q, self.args.R, self.args.cxu = self.Q.ctypes.data, self.R.ctypes.data, self.cxu.ctypes.data
         self.args.reg_type, self.args.alpha, self.args.chunk = reg_type, alpha, chunk
+        self.args.q_diagonal = 1 if np.count_nonzero(self.Q - np.diag(np.diagonal(self.Q))) == 0 else 0
 
     def _pinned(self, shape, dtype):
         nbytes = int(np.prod(shape, dtype=np.int64)) * np.dtype(dtype).itemsize

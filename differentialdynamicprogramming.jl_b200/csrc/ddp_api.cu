@@ -229,6 +229,7 @@ static bool fill_model(ddp_handle_s* h, const ddp_model* m, ModelD& M, std::stri
     M.A = mk(m->A); M.Bm = mk(m->Bm); M.Q = mk(m->Q); M.R = mk(m->R); M.goal = m->goal;
     for (int i = 0; i < 8; i++) M.p[i] = m->p[i];
     M.terminal_cost = m->terminal_cost ? 1 : 0;
+    M.flags = m->flags;
     if (m->kind == DDP_MODEL_LINEAR) {
         if (!m->A.ptr || !m->Bm.ptr) { why = "linear model needs A and B"; return false; }
     } else if (m->kind == DDP_MODEL_PENDCART) {

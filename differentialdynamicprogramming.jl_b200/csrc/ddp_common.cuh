@@ -41,6 +41,7 @@ struct ModelD {
     const double* goal;
     double p[8];
     int terminal_cost;
+    int flags;                   // DDP_MODEL_Q_DIAGONAL
 };
 
 struct FwdParams {

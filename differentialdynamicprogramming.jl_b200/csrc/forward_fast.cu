@@ -20,10 +20,10 @@ __device__ __forceinline__ double2 ldg2(const double* p) { return *reinterpret_c
 __device__ __forceinline__ void stg2(double* p, double a, double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
 
 constexpr int FW_WPB = 4;
-constexpr int FW_WARP_DOUBLES = 32 + 32 + 32 + 8;   // sx, sdx, sd, su
+constexpr int FW_WARP_DOUBLES = 32 + 32 + 32 + 8;   // sx, sdx, sd, su  (per warp)
 
 struct Pre {
-    double2 K[4];
+    double2 K0, K1, K2, K3;
     double2 u, k;
     double xo;
 };
@@ -32,18 +32,23 @@ template <bool POLICY>
 __device__ __forceinline__ void prefetch(Pre& p, const FwdParams& P, long long b, int t, int lane, int q) {
     const int N = P.T;
     if (POLICY) {
-        const double* Kt = P.K + (b * N + t) * 256;
-#pragma unroll
-        for (int i = 0; i < 4; i++) p.K[i] = ldg2(Kt + 2 * (lane + 32 * i));
+        const double* Kt = P.K + (b * N + t) * 256 + 2 * lane;
+        p.K0 = ldg2(Kt);
+        p.K1 = ldg2(Kt + 64);
+        p.K2 = ldg2(Kt + 128);
+        p.K3 = ldg2(Kt + 192);
         p.k = ldg2(P.k + (b * N + t) * 8 + 2 * q);
         p.xo = tp(P.x, b, t)[lane];
     }
     p.u = ldg2(tp(P.u, b, t) + 2 * q);
 }
 
-template <bool POLICY>
+// QMODE 0: Q diagonal (only the diagonal is read), 1: dense Q shared by the batch, staged once per CTA
+// in shared memory (column-major, conflict-free for "lane = row").
+template <bool POLICY, int QMODE>
 __global__ void __launch_bounds__(FW_WPB * 32, 2) fwd_lin32x8_kernel(FwdParams P) {
     __shared__ double smem[FW_WPB * FW_WARP_DOUBLES];
+    __shared__ double sQ[QMODE == 1 ? 1024 : 1];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int g = lane >> 2, q = lane & 3;
     double* sx = smem + w * FW_WARP_DOUBLES;
@@ -54,21 +59,26 @@ __global__ void __launch_bounds__(FW_WPB * 32, 2) fwd_lin32x8_kernel(FwdParams P
     const bool has_goal = (P.model.goal != nullptr);
     const bool has_lims = (P.lims != nullptr);
     const long long warps_total = (long long)gridDim.x * FW_WPB;
+    if (QMODE == 1) {
+        for (int e = threadIdx.x; e < 1024; e += FW_WPB * 32) sQ[e] = P.model.Q.p[e];
+        __syncthreads();
+    }
 
     for (long long b = (long long)blockIdx.x * FW_WPB + w; b < P.B; b += warps_total) {
         if (P.active && !P.active[b]) continue;
         const double alpha = P.alpha ? P.alpha[b] : P.alpha_scalar;
-        // ---- per-trajectory constants in registers: row `lane` of A, B, Q; row (lane & 7) of R
-        double Ar[32], Br[8], Qr[32], Rr[8];
+        // ---- per-trajectory constants in registers: row `lane` of A and B; row (lane & 7) of R
+        double Ar[32], Br[8], Rr[8];
+        double qdiag = 0.0;
         {
             const double* A = P.model.A.p + b * P.model.A.sb;        // column-major: A[i + 32 j]
             const double* Bm = P.model.Bm.p + b * P.model.Bm.sb;
-            const double* Q = P.model.Q.p + b * P.model.Q.sb;
             const double* R = P.model.R.p + b * P.model.R.sb;
 #pragma unroll
-            for (int j = 0; j < 32; j++) { Ar[j] = A[lane + 32 * j]; Qr[j] = Q[lane + 32 * j]; }
+            for (int j = 0; j < 32; j++) Ar[j] = A[lane + 32 * j];
 #pragma unroll
             for (int c = 0; c < 8; c++) { Br[c] = Bm[lane + 32 * c]; Rr[c] = R[(lane & 7) + 8 * c]; }
+            if (QMODE == 0) qdiag = (P.model.Q.p + b * P.model.Q.sb)[lane * 33];
         }
         const double goal = has_goal ? P.model.goal[lane] : 0.0;
         double lo0 = 0, lo1 = 0, hi0 = 0, hi1 = 0;
@@ -78,31 +88,32 @@ __global__ void __launch_bounds__(FW_WPB * 32, 2) fwd_lin32x8_kernel(FwdParams P
         double* xnb = P.xnew + b * (long long)N * 32;
         double* unb = P.unew + b * (long long)N * 8;
 
-        auto step = [&](int t, const Pre& p) {
+        // `p` holds the operands of step t; they are copied out and `p` is refilled for step t+2 at once,
+        // so two steps' worth of loads (~5 KB per warp) are always in flight and stay in registers.
+        auto step = [&](int t, Pre& p) {
+            const double2 K0 = p.K0, K1 = p.K1, K2 = p.K2, K3 = p.K3, uu = p.u, kk = p.k;
+            const double xo = p.xo;
+            if (t + 2 < N) prefetch<POLICY>(p, P, b, t + 2, lane, q);
             // 1. publish x (and dx, d) to the warp
             const double d = x - goal;
             sx[lane] = x;
-            if (POLICY) sdx[lane] = x - p.xo;
-            if (has_goal) sd[lane] = d;
+            if (POLICY) sdx[lane] = x - xo;
+            if (has_goal && QMODE == 1) sd[lane] = d;
             xnb[(long long)t * 32 + lane] = x;
             __syncwarp();
             // 2. controls: u + alpha k + K dx   (lane holds K[2q..2q+1][g + 8i], i = 0..3)
-            double un0 = p.u.x * P.u_scale, un1 = p.u.y * P.u_scale;
+            double un0 = uu.x * P.u_scale, un1 = uu.y * P.u_scale;
             if (POLICY) {
-                double p0 = 0.0, p1 = 0.0;
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const double dxj = sdx[g + 8 * i];
-                    p0 = fma(p.K[i].x, dxj, p0);
-                    p1 = fma(p.K[i].y, dxj, p1);
-                }
+                const double d0 = sdx[g], d1 = sdx[g + 8], d2 = sdx[g + 16], d3 = sdx[g + 24];
+                double p0 = fma(K3.x, d3, fma(K2.x, d2, fma(K1.x, d1, K0.x * d0)));
+                double p1 = fma(K3.y, d3, fma(K2.y, d2, fma(K1.y, d1, K0.y * d0)));
 #pragma unroll
                 for (int o = 4; o < 32; o <<= 1) {
                     p0 += __shfl_xor_sync(0xffffffffu, p0, o);
                     p1 += __shfl_xor_sync(0xffffffffu, p1, o);
                 }
-                un0 = (un0 + p.k.x * alpha) + p0;        // forward_pass.jl:18,20: two separate roundings
-                un1 = (un1 + p.k.y * alpha) + p1;
+                un0 = (un0 + kk.x * alpha) + p0;          // forward_pass.jl:18,20: two separate roundings
+                un1 = (un1 + kk.y * alpha) + p1;
             }
             if (has_lims) { un0 = fmin(fmax(un0, lo0), hi0); un1 = fmin(fmax(un1, lo1), hi1); }
             if (un0 != un0) un0 = 0.0;
@@ -113,25 +124,29 @@ __global__ void __launch_bounds__(FW_WPB * 32, 2) fwd_lin32x8_kernel(FwdParams P
             }
             __syncwarp();
             // 3. x+ = A x + B u ; Qd ; Ru
-            double ax0 = 0.0, ax1 = 0.0, qd0 = 0.0, qd1 = 0.0;
-            if (!has_goal) {
+            double ax0 = 0.0, ax1 = 0.0, ax2 = 0.0, ax3 = 0.0, qd0 = 0.0, qd1 = 0.0;
 #pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    const double2 xv = *reinterpret_cast<const double2*>(&sx[j]);
-                    ax0 = fma(Ar[j], xv.x, ax0);
-                    ax1 = fma(Ar[j + 1], xv.y, ax1);
-                    qd0 = fma(Qr[j], xv.x, qd0);
-                    qd1 = fma(Qr[j + 1], xv.y, qd1);
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    const double2 xv = *reinterpret_cast<const double2*>(&sx[j]);
-                    const double2 dv = *reinterpret_cast<const double2*>(&sd[j]);
-                    ax0 = fma(Ar[j], xv.x, ax0);
-                    ax1 = fma(Ar[j + 1], xv.y, ax1);
-                    qd0 = fma(Qr[j], dv.x, qd0);
-                    qd1 = fma(Qr[j + 1], dv.y, qd1);
+            for (int j = 0; j < 32; j += 4) {
+                const double2 xa = *reinterpret_cast<const double2*>(&sx[j]);
+                const double2 xb = *reinterpret_cast<const double2*>(&sx[j + 2]);
+                ax0 = fma(Ar[j], xa.x, ax0);
+                ax1 = fma(Ar[j + 1], xa.y, ax1);
+                ax2 = fma(Ar[j + 2], xb.x, ax2);
+                ax3 = fma(Ar[j + 3], xb.y, ax3);
+                if (QMODE == 1) {
+                    if (!has_goal) {
+                        qd0 = fma(sQ[lane + 32 * j], xa.x, qd0);
+                        qd1 = fma(sQ[lane + 32 * (j + 1)], xa.y, qd1);
+                        qd0 = fma(sQ[lane + 32 * (j + 2)], xb.x, qd0);
+                        qd1 = fma(sQ[lane + 32 * (j + 3)], xb.y, qd1);
+                    } else {
+                        const double2 da = *reinterpret_cast<const double2*>(&sd[j]);
+                        const double2 db = *reinterpret_cast<const double2*>(&sd[j + 2]);
+                        qd0 = fma(sQ[lane + 32 * j], da.x, qd0);
+                        qd1 = fma(sQ[lane + 32 * (j + 1)], da.y, qd1);
+                        qd0 = fma(sQ[lane + 32 * (j + 2)], db.x, qd0);
+                        qd1 = fma(sQ[lane + 32 * (j + 3)], db.y, qd1);
+                    }
                 }
             }
             double bu = 0.0, ru = 0.0;
@@ -143,7 +158,7 @@ __global__ void __launch_bounds__(FW_WPB * 32, 2) fwd_lin32x8_kernel(FwdParams P
                 ru = fma(Rr[c], uv.x, ru);
                 ru = fma(Rr[c + 1], uv.y, ru);
             }
-            const double qd = qd0 + qd1;
+            const double qd = (QMODE == 0) ? qdiag * d : (qd0 + qd1);
             double cstep = 0.5 * d * qd;
             if (lane < 8) cstep = fma(0.5 * su[lane], ru, cstep);
             if (P.cx) P.cx[(b * N + t) * 32 + lane] = qd;
@@ -155,28 +170,26 @@ __global__ void __launch_bounds__(FW_WPB * 32, 2) fwd_lin32x8_kernel(FwdParams P
                 if (lane == 0) P.cost_t[b * (N + P.model.terminal_cost) + t] = ct;
             }
             cpart += cstep;
-            if (t < N - 1) x = (ax0 + ax1) + bu;
+            if (t < N - 1) x = ((ax0 + ax1) + (ax2 + ax3)) + bu;
             __syncwarp();
         };
 
-        Pre p0, p1;
-        prefetch<POLICY>(p0, P, b, 0, lane, q);
-        if (N > 1) prefetch<POLICY>(p1, P, b, 1, lane, q);
+        Pre pa, pb;
+        prefetch<POLICY>(pa, P, b, 0, lane, q);
+        if (N > 1) prefetch<POLICY>(pb, P, b, 1, lane, q);
         for (int t = 0; t < N; t += 2) {
-            Pre p2, p3;
-            if (t + 2 < N) prefetch<POLICY>(p2, P, b, t + 2, lane, q);
-            step(t, p0);
-            if (t + 3 < N) prefetch<POLICY>(p3, P, b, t + 3, lane, q);
-            if (t + 1 < N) step(t + 1, p1);
-            p0 = p2;
-            p1 = p3;
+            step(t, pa);
+            if (t + 1 < N) step(t + 1, pb);
         }
         if (P.model.terminal_cost) {
-            // ½ d'Qd at the last state once more (system_pendcart.jl:104); sx/sd still hold step N-1
+            // ½ d'Qd at the last state once more (system_pendcart.jl:104)
             double qd = 0.0;
-            const double* sv = has_goal ? sd : sx;
+            if (QMODE == 0) qd = qdiag * (x - goal);
+            else {
+                const double* sv = has_goal ? sd : sx;
 #pragma unroll
-            for (int j = 0; j < 32; j++) qd = fma(Qr[j], sv[j], qd);
+                for (int j = 0; j < 32; j++) qd = fma(sQ[lane + 32 * j], sv[j], qd);
+            }
             double cterm = 0.5 * (x - goal) * qd;
             if (P.cost_t) {
                 double ct = cterm;
@@ -278,11 +291,18 @@ int launch_forward_fast(ddp_handle_s* h, const FwdParams& P, bool* handled) {
     if (P.model.kind == DDP_MODEL_LINEAR && P.n == 32 && P.m == 8 && P.model.A.st == 0 && P.model.Bm.st == 0) {
         if (!al16(P.u.p) || (P.u.sb % 2) || (P.u.st % 2)) return 0;
         if (policy && (!al16(P.K) || !al16(P.k))) return 0;
+        const bool qdiag = (P.model.flags & 1) != 0;
+        if (!qdiag && P.model.Q.sb != 0) return 0;        // per-trajectory dense Q: generic kernel
         long long grid = (long long)h->sm_count * 2;
         long long need = (P.B + FW_WPB - 1) / FW_WPB;
         if (grid > need) grid = need;
-        if (policy) fwd_lin32x8_kernel<true><<<(unsigned)grid, FW_WPB * 32, 0, h->stream>>>(P);
-        else fwd_lin32x8_kernel<false><<<(unsigned)grid, FW_WPB * 32, 0, h->stream>>>(P);
+        if (policy) {
+            if (qdiag) fwd_lin32x8_kernel<true, 0><<<(unsigned)grid, FW_WPB * 32, 0, h->stream>>>(P);
+            else fwd_lin32x8_kernel<true, 1><<<(unsigned)grid, FW_WPB * 32, 0, h->stream>>>(P);
+        } else {
+            if (qdiag) fwd_lin32x8_kernel<false, 0><<<(unsigned)grid, FW_WPB * 32, 0, h->stream>>>(P);
+            else fwd_lin32x8_kernel<false, 1><<<(unsigned)grid, FW_WPB * 32, 0, h->stream>>>(P);
+        }
         h->launches++;
         *handled = true;
         return (int)cudaGetLastError();

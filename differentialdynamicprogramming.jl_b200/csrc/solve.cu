@@ -388,6 +388,7 @@ int ddp_ilqg_solve_f64(ddp_handle_t h, const ddp_model* model, const ddp_ilqg_op
     M.kind = model->kind; M.A = mk(model->A); M.Bm = mk(model->Bm); M.Q = mk(model->Q); M.R = mk(model->R); M.goal = model->goal;
     for (int i = 0; i < 8; i++) M.p[i] = model->p[i];
     M.terminal_cost = model->terminal_cost ? 1 : 0;
+    M.flags = model->flags;
 
     init_state_kernel<<<gB, 256, 0, st>>>(B, s, opts->lambda, opts->dlambda, o.alpha[0]);
     h->launches++;
@@ -588,7 +589,7 @@ int ddp_ilqg_iter_host_f64(ddp_handle_t h, ddp_iter_host_args* a) {
     CUS(cudaMemcpyAsync(dR, a->R, (size_t)m * m * 8, cudaMemcpyHostToDevice, s_in));
     CUS(cudaMemcpyAsync(dcxu, a->cxu, nm * 8, cudaMemcpyHostToDevice, s_in));
     h2d += (long long)(nn + (size_t)m * m + nm) * 8;
-    M.kind = DDP_MODEL_LINEAR; M.goal = nullptr; M.terminal_cost = 0;
+    M.kind = DDP_MODEL_LINEAR; M.goal = nullptr; M.terminal_cost = 0; M.flags = a->q_diagonal ? DDP_MODEL_Q_DIAGONAL : 0;
     M.Q = TensorD{dQ, 0, 0}; M.R = TensorD{dR, 0, 0};
 
     {

@@ -157,6 +157,7 @@ DDP_API int ddp_boxqp_f64(ddp_handle_t h, int64_t B, const double* H, const doub
 
 /* ---- models: the reference's user callbacks f / costfun / df as device descriptors ------- */
 enum { DDP_MODEL_LINEAR = 1, DDP_MODEL_PENDCART = 2 };
+enum { DDP_MODEL_Q_DIAGONAL = 1 };   /* ddp_model.flags: Q is diagonal (e.g. Q = h*I of demo_linear.jl:18): only its diagonal is read */
 
 typedef struct ddp_model {
     int32_t kind;
@@ -171,6 +172,7 @@ typedef struct ddp_model {
     double p[8];
     int32_t terminal_cost;       /* 1: add ½ d'Qd at the last state again (cost has T+1 entries,  */
                                  /*    system_pendcart.jl:104)                                    */
+    int32_t flags;               /* DDP_MODEL_Q_DIAGONAL or 0 (a hint the host can check before upload) */
 } ddp_model;
 
 /* ---- forward pass ------------------------------------------------------------------------ */
@@ -264,6 +266,7 @@ typedef struct ddp_iter_host_args {
     const double *fx, *fu, *cx, *cu, *x, *u, *lambda;
     const double *Q, *R, *cxu;
     int32_t reg_type;
+    int32_t q_diagonal;          /* 1: Q is diagonal (hint, as DDP_MODEL_Q_DIAGONAL) */
     double alpha;
     double *xnew, *unew, *cost, *dV;
     int32_t* diverge;

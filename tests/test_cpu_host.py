@@ -1,0 +1,148 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol of include/ddp.h,
+fails loudly without a GPU, the C++/OpenMP baseline agrees with the NumPy oracle, and the N > 1
+sharding logic works under gloo with world_size 2."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from helpers import make_batch_lq, relerr
+from oracle import cpu_ref as CR
+from oracle import ddp_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(ddp):
+    hdr = open(os.path.join(ROOT, "include", "ddp.h")).read()
+    declared = set(re.findall(r"DDP_API\s+[\w\s\*]+?\b(ddp_\w+)\s*\(", hdr))
+    assert len(declared) >= 20
+    lib = ctypes.CDLL(ddp.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    bound = {s[0] for s in ddp._lib.SYMBOLS}
+    assert declared == bound                       # the ctypes mirror binds exactly the header's surface
+    assert ddp.load().ddp_version() == 100
+
+
+def test_struct_sizes_match_the_header(ddp):
+    """sizeof of every ABI struct, compiled from include/ddp.h with gcc, equals the ctypes mirror."""
+    src = r'''
+#include <stdio.h>
+#include "ddp.h"
+int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(ddp_tensor), sizeof(ddp_boxqp_opts),
+  sizeof(ddp_back_pass_args), sizeof(ddp_gps_args), sizeof(ddp_model), sizeof(ddp_forward_pass_args), sizeof(ddp_kl_args),
+  sizeof(ddp_ilqg_opts), sizeof(ddp_ilqg_state), sizeof(ddp_iter_host_args)); return 0; }
+'''
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        c = os.path.join(td, "s.c"); exe = os.path.join(td, "s")
+        open(c, "w").write(src)
+        subprocess.check_call(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
+        sizes = list(map(int, subprocess.check_output([exe]).split()))
+    L = ddp._lib
+    mirror = [L.Tensor, L.BoxQPOpts, L.BackPassArgs, L.GpsArgs, L.Model, L.ForwardPassArgs, L.KlArgs, L.IlqgOpts, L.IlqgState, L.IterHostArgs]
+    assert sizes == [ctypes.sizeof(t) for t in mirror]
+
+
+def test_no_cpu_fallback(ddp):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(ddp.DDPError, match="no CPU fallback"):
+        ddp.Engine(4, 1, 10, 1)
+    with pytest.raises(ddp.DDPError):
+        ddp.back_pass(np.zeros((5, 3)), np.zeros((5, 1)), np.eye(3), np.zeros((3, 1)), np.eye(1), np.eye(3), np.ones((3, 1)), 1.0, 1,
+                      None, np.zeros((5, 3)), np.zeros((5, 1)))
+    pm = ddp.PendcartModel()
+    with pytest.raises(RuntimeError, match="device model descriptor"):
+        pm.f(np.zeros(4), np.zeros(1), 1)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "differentialdynamicprogramming.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                # comments may mention the oracle; code must never import, link or load it
+                for banned in ("import oracle", "from oracle", "cpu_ref", "ddp_oracle import", "oracle."):
+                    assert banned not in txt, (f, banned)
+
+
+@pytest.mark.parametrize("n,m,N,reg,lims", [(10, 2, 40, 1, None), (32, 8, 16, 2, None), (4, 1, 30, 2, 0.05), (8, 3, 30, 1, 0.05)])
+def test_cpp_baseline_matches_oracle(n, m, N, reg, lims):
+    B = 3
+    A, Bm, Q, R, x, u = make_batch_lq(1, B, n, m, N)
+    cx, cu = x @ Q.T, u @ R.T
+    lim = None if lims is None else np.tile(np.array([[-lims, lims]]), (m, 1))
+    lam = 1e-3 if lims else 1.0
+    cxu = 0.01 * np.random.default_rng(2).standard_normal((n, m))
+    dv, K, k, Vx, Vxx, Vxx1, Quu, dV = CR.back_pass(cx, cu, Q.T, cxu.T, R.T, np.swapaxes(A, -1, -2), np.swapaxes(Bm, -1, -2), lam, reg, lim, u)
+    xn, un, cn = CR.forward_pass_linear(K, k, x[:, 0].copy(), x, u, 0.5, lim, np.swapaxes(A, -1, -2), np.swapaxes(Bm, -1, -2), Q.T, R.T)
+    for b in range(B):
+        d0, p0, Vx0, Vxx0, dV0 = O.back_pass(cx[b], cu[b], Q, cxu, R, A[b], Bm[b], lam, reg, lim, x[b], u[b])
+        assert d0 == dv[b]                       # (the regType-2 case with random cxu diverges: compared too)
+        assert max(relerr(np.swapaxes(K[b], -1, -2), p0.K), relerr(k[b], p0.k), relerr(Vx[b], Vx0),
+                   relerr(np.swapaxes(Vxx[b], -1, -2), Vxx0), relerr(dV[b], dV0)) < 1e-9
+        om = O.LinearModel(A[b], Bm[b], Q, R)
+        x0_, u0_, c0_ = O.forward_pass(p0, x[b, 0], u[b], x[b], 0.5, om.f, om.costfun, lim)
+        assert relerr(xn[b], x0_) < 1e-9 and relerr(un[b], u0_) < 1e-9 and abs(cn[b] - c0_) < 1e-9 * abs(c0_)
+
+
+def test_cpp_boxqp_bit_identical_to_oracle():
+    rng = np.random.default_rng(7)
+    m, B = 6, 40
+    Hs = []
+    for _ in range(B):
+        G = rng.standard_normal((m, m)); H = G @ G.T + 0.05 * np.eye(m); Hs.append((H + H.T) / 2)
+    Hs = np.array(Hs); g = 3 * rng.standard_normal((B, m)); lo = -rng.random((B, m)); up = rng.random((B, m)); x0 = rng.standard_normal((B, m))
+    x, res, Hf, free, nf = CR.boxqp(Hs, g, lo, up, x0)
+    for b in range(B):
+        x0_, r0, Hf0, free0, nf0 = O.boxQP(Hs[b], g[b], lo[b], up[b], x0[b])
+        assert r0 == res[b] and nf0 == nf[b] and np.array_equal(free0, free[b]) and np.array_equal(x0_, x[b])
+
+
+_WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+import numpy as np, torch, torch.distributed as dist
+from helpers import make_batch_lq
+from oracle import cpu_ref as CR
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+B, n, m, N = 8, 6, 2, 20
+A, Bm, Q, R, x, u = make_batch_lq(3, B, n, m, N)           # every rank builds the same global batch ...
+lo, hi = rank * B // world, (rank + 1) * B // world         # ... and owns a contiguous shard (SURVEY 8e)
+sl = slice(lo, hi)
+cx, cu = x @ Q.T, u @ R.T
+dv, K, k, Vx, _, _, _, dV = CR.back_pass(cx[sl], cu[sl], Q.T, np.zeros((m, n)), R.T, np.swapaxes(A[sl], -1, -2), np.swapaxes(Bm[sl], -1, -2), 1.0, 1, None, u[sl], want_Vxx=False)
+xn, un, cn = CR.forward_pass_linear(K, k, x[sl, 0].copy(), x[sl], u[sl], 1.0, None, np.swapaxes(A[sl], -1, -2), np.swapaxes(Bm[sl], -1, -2), Q.T, R.T)
+cost_old = 0.5 * np.sum(x[sl] * (x[sl] @ Q.T), axis=(1, 2)) + 0.5 * np.sum(u[sl] * (u[sl] @ R.T), axis=(1, 2))
+ex = -(dV[:, 0] + dV[:, 1])
+stats = torch.tensor([cn.sum(), (cost_old - cn).sum(), ex.sum(), float(((cost_old - cn) / ex > 0).sum()), float((dv > 0).sum()), float(hi - lo), 0, 0], dtype=torch.float64)
+dist.all_reduce(stats)                                      # the one collective of the path: a 64-byte SUM
+if rank == 0:
+    dv, K, k, Vx, _, _, _, dV = CR.back_pass(cx, cu, Q.T, np.zeros((m, n)), R.T, np.swapaxes(A, -1, -2), np.swapaxes(Bm, -1, -2), 1.0, 1, None, u, want_Vxx=False)
+    xn, un, cn = CR.forward_pass_linear(K, k, x[:, 0].copy(), x, u, 1.0, None, np.swapaxes(A, -1, -2), np.swapaxes(Bm, -1, -2), Q.T, R.T)
+    assert abs(stats[0].item() - cn.sum()) < 1e-12 * abs(cn.sum()), (stats[0].item(), cn.sum())
+    assert stats[5].item() == B and stats[3].item() == B and stats[4].item() == 0
+    print("SHARD_OK")
+dist.destroy_process_group()
+'''
+
+
+def test_batch_sharding_world_size_2_gloo(tmp_path):
+    """trajectories shard by contiguous ranges with no data-path collective; the only exchange is the
+    statistics vector.  Runs the sharded host logic under gloo, world_size 2."""
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, OMP_NUM_THREADS="2")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29613", str(script), ROOT], capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "SHARD_OK" in out.stdout
