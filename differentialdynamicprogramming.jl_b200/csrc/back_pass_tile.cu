@@ -35,7 +35,8 @@ constexpr int SQUU = SM1 + 256;              // Quu  (col-major 8 x 8)
 constexpr int SQUUF = SQUU + 64;             // regularised Quu
 constexpr int SVX = SQUUF + 64;              // Vx (32)
 constexpr int SQU = SVX + 32;                // Qu (8)
-constexpr int WARP_DOUBLES = SQU + 8 + 24;   // = 3328 -> 26,624 B
+constexpr int SFV = SQU + 8;                 // F'Vx (32)
+constexpr int WARP_DOUBLES = SFV + 32 + 8;   // = 3280 doubles -> 26,240 B per warp
 constexpr int SF2 = WARP_DOUBLES;            // second F buffer (time-varying dynamics only)
 constexpr int WARP_DOUBLES_LTV = WARP_DOUBLES + 1280;
 
@@ -65,6 +66,23 @@ __device__ __forceinline__ void load_F(double* sF, const double* fx, const doubl
     }
 }
 
+// 8 x 32 buffers (Qux, K, M1): column j at 8j, its four 16-byte row pairs XOR-swizzled by (j >> 1) so that both
+// "lane = column" accesses and the DMMA fragment loads are bank-conflict free
+__device__ __forceinline__ int cidx(int r, int j) { return 8 * j + ((((r >> 1) ^ (j >> 1)) & 3) << 1) + (r & 1); }
+
+// 1/sqrt(d) for d > 0, normal range: hardware seed + two Newton steps (the Cholesky pivots are O(1e-3..1e3);
+// non-positive pivots are caught before the value is used)
+__device__ __forceinline__ double rsqrt_nr(double d) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    const double h = 0.5 * d;
+    double e = fma(-h * y, y, 0.5);      // 0.5 - h y^2
+    y = fma(y, e, y);
+    e = fma(-h * y, y, 0.5);
+    y = fma(y, e, y);
+    return y;
+}
+
 constexpr int gidx(int at, int bt) { return at * 5 - (at * (at - 1)) / 2 + (bt - at); }   // upper-tile index, 15 tiles
 
 template <bool LTV>
@@ -81,6 +99,7 @@ __global__ void __launch_bounds__(WPB * 32, 2) bp_tile32x8_kernel(BackParams P) 
     double* sQuuF = sm + SQUUF;
     double* sVx = sm + SVX;
     double* sQu = sm + SQU;
+    double* sFV = sm + SFV;
     const int N = P.T;
     const long long warps_total = (long long)gridDim.x * WPB;
 
@@ -151,7 +170,7 @@ __global__ void __launch_bounds__(WPB * 32, 2) bp_tile32x8_kernel(BackParams P) 
             }
             // prefetch this step's cost gradients
             const double cxv = tp(P.cx, b, i)[lane];
-            const double cuv = (lane < 8) ? tp(P.cu, b, i)[lane] : 0.0;
+            const double cuv = tp(P.cu, b, i)[g];             // lanes (g, q == 0) publish Qu[g]
             const double* cxxi = tp(P.cxx, b, i);
             const double* cxui = tp(P.cxu, b, i);
             const double* cuui = tp(P.cuu, b, i);
@@ -163,62 +182,8 @@ __global__ void __launch_bounds__(WPB * 32, 2) bp_tile32x8_kernel(BackParams P) 
                     st2(Vxxb + (long long)(i + 1) * 1024 + col * 32 + r, t.x, t.y);
                 }
             }
-            // ---- step 1: W' = F' V
-            double W[5][4][2];
-#pragma unroll
-            for (int at = 0; at < 5; at++)
-#pragma unroll
-                for (int jt = 0; jt < 4; jt++) W[at][jt][0] = W[at][jt][1] = 0.0;
-#pragma unroll
-            for (int p = 0; p < 4; p++) {
-                const int row = 8 * p + 2 * q;
-                double2 fa[5], fb[4];
-#pragma unroll
-                for (int at = 0; at < 5; at++) fa[at] = ld2(&sF[swz(row, 8 * at + g)]);
-#pragma unroll
-                for (int jt = 0; jt < 4; jt++) fb[jt] = ld2(&sV[swz(row, 8 * jt + g)]);
-#pragma unroll
-                for (int at = 0; at < 5; at++)
-#pragma unroll
-                    for (int jt = 0; jt < 4; jt++) {
-                        dmma(W[at][jt][0], W[at][jt][1], fa[at].x, fb[jt].x);
-                        dmma(W[at][jt][0], W[at][jt][1], fa[at].y, fb[jt].y);
-                    }
-            }
-            // ---- Qx = cx + fx'Vx, Qu = cu + fu'Vx   (lane a owns output a; lanes 0..7 also own 32+a)
-            double qx, quv;
-            {
-                double a0 = 0.0, a1 = 0.0, c0 = 0.0, c1 = 0.0;
-                const int a2 = 32 + (lane & 7);
-#pragma unroll
-                for (int r = 0; r < 32; r += 2) {
-                    double2 vx = ld2(&sVx[r]);
-                    a0 = fma(sF[swz(r, lane)], vx.x, a0);
-                    a1 = fma(sF[swz(r + 1, lane)], vx.y, a1);
-                    c0 = fma(sF[swz(r, a2)], vx.x, c0);
-                    c1 = fma(sF[swz(r + 1, a2)], vx.y, c1);
-                }
-                qx = cxv + (a0 + a1);
-                quv = cuv + (c0 + c1);
-            }
-            // ---- step 2: G = W' F  (upper tiles)
+            // ---- G starts from the cost terms: their global loads are in flight during the tensor phase
             double G[15][2];
-#pragma unroll
-            for (int t = 0; t < 15; t++) G[t][0] = G[t][1] = 0.0;
-#pragma unroll
-            for (int p = 0; p < 4; p++) {
-                double2 ff[5];
-#pragma unroll
-                for (int bt = 0; bt < 5; bt++) ff[bt] = ld2(&sF[swz(8 * p + 2 * q, 8 * bt + g)]);
-#pragma unroll
-                for (int at = 0; at < 5; at++)
-#pragma unroll
-                    for (int bt = at; bt < 5; bt++) {
-                        dmma(G[gidx(at, bt)][0], G[gidx(at, bt)][1], W[at][p][0], ff[bt].x);
-                        dmma(G[gidx(at, bt)][0], G[gidx(at, bt)][1], W[at][p][1], ff[bt].y);
-                    }
-            }
-            // ---- cost terms
 #pragma unroll
             for (int at = 0; at < 4; at++) {
                 const int a = 8 * at + g;
@@ -227,34 +192,86 @@ __global__ void __launch_bounds__(WPB * 32, 2) bp_tile32x8_kernel(BackParams P) 
                     const int b0 = 8 * bt + 2 * q;
                     double2 lo = ld2(cxxi + a * 32 + b0);                    // cxx[b0..b0+1][a]
                     double u0 = cxxi[b0 * 32 + a], u1 = cxxi[(b0 + 1) * 32 + a];   // cxx[a][b0], cxx[a][b0+1]
-                    G[gidx(at, bt)][0] += 0.5 * (lo.x + u0);
-                    G[gidx(at, bt)][1] += 0.5 * (lo.y + u1);
+                    G[gidx(at, bt)][0] = 0.5 * (lo.x + u0);
+                    G[gidx(at, bt)][1] = 0.5 * (lo.y + u1);
                 }
-                G[gidx(at, 4)][0] += cxui[a + 32 * (2 * q)];                 // Qux[b'][a] = cxu[a][b'] + ...
-                G[gidx(at, 4)][1] += cxui[a + 32 * (2 * q + 1)];
+                G[gidx(at, 4)][0] = cxui[a + 32 * (2 * q)];                  // Qux[b'][a] = cxu[a][b'] + ...
+                G[gidx(at, 4)][1] = cxui[a + 32 * (2 * q + 1)];
             }
-            G[gidx(4, 4)][0] += cuui[g + 8 * (2 * q)];
-            G[gidx(4, 4)][1] += cuui[g + 8 * (2 * q + 1)];
+            G[gidx(4, 4)][0] = cuui[g + 8 * (2 * q)];
+            G[gidx(4, 4)][1] = cuui[g + 8 * (2 * q + 1)];
+            // ---- step 1: W' = F' V.  The A fragments also give F'Vx: each lane sums its 8 rows, two shuffles finish it
+            double W[5][4][2], fv[5];
+#pragma unroll
+            for (int at = 0; at < 5; at++) {
+                fv[at] = 0.0;
+#pragma unroll
+                for (int jt = 0; jt < 4; jt++) W[at][jt][0] = W[at][jt][1] = 0.0;
+            }
+#pragma unroll
+            for (int p = 0; p < 4; p++) {
+                const int row = 8 * p + 2 * q;
+                double2 fa[5], fb[4];
+#pragma unroll
+                for (int at = 0; at < 5; at++) fa[at] = ld2(&sF[swz(row, 8 * at + g)]);
+#pragma unroll
+                for (int jt = 0; jt < 4; jt++) fb[jt] = ld2(&sV[swz(row, 8 * jt + g)]);
+                const double2 vx = ld2(&sVx[row]);
+                // consecutive DMMAs go to different accumulator tiles (a tile is revisited 20 issues later)
+#pragma unroll
+                for (int at = 0; at < 5; at++)
+#pragma unroll
+                    for (int jt = 0; jt < 4; jt++) dmma(W[at][jt][0], W[at][jt][1], fa[at].x, fb[jt].x);
+#pragma unroll
+                for (int at = 0; at < 5; at++) fv[at] = fma(fa[at].y, vx.y, fma(fa[at].x, vx.x, fv[at]));
+#pragma unroll
+                for (int at = 0; at < 5; at++)
+#pragma unroll
+                    for (int jt = 0; jt < 4; jt++) dmma(W[at][jt][0], W[at][jt][1], fa[at].y, fb[jt].y);
+            }
+#pragma unroll
+            for (int at = 0; at < 5; at++) {
+                fv[at] += __shfl_xor_sync(0xffffffffu, fv[at], 1);
+                fv[at] += __shfl_xor_sync(0xffffffffu, fv[at], 2);
+            }
+            if (q == 0) {                                   // (F'Vx)[8at+g]; Qu[g] = cu[g] + (fu'Vx)[g]
+#pragma unroll
+                for (int at = 0; at < 4; at++) sFV[8 * at + g] = fv[at];
+                sQu[g] = cuv + fv[4];
+            }
+            // ---- step 2: G = W' F  (upper tiles)
+#pragma unroll
+            for (int p = 0; p < 4; p++) {
+                double2 ff[5];
+#pragma unroll
+                for (int bt = 0; bt < 5; bt++) ff[bt] = ld2(&sF[swz(8 * p + 2 * q, 8 * bt + g)]);
+#pragma unroll
+                for (int at = 0; at < 5; at++)
+#pragma unroll
+                    for (int bt = at; bt < 5; bt++) dmma(G[gidx(at, bt)][0], G[gidx(at, bt)][1], W[at][p][0], ff[bt].x);
+#pragma unroll
+                for (int at = 0; at < 5; at++)
+#pragma unroll
+                    for (int bt = at; bt < 5; bt++) dmma(G[gidx(at, bt)][0], G[gidx(at, bt)][1], W[at][p][1], ff[bt].y);
+            }
             // ---- spill Qux / Qux_reg / Quu / QuuF / Qu to shared memory
 #pragma unroll
             for (int at = 0; at < 4; at++) {
                 const int a = 8 * at + g;
                 double x0 = G[gidx(at, 4)][0], x1 = G[gidx(at, 4)][1];
-                st2(&sQux[a * 8 + 2 * q], x0, x1);
-                if (reg2) st2(&sM1[a * 8 + 2 * q], fma(lam, FF[at][0], x0), fma(lam, FF[at][1], x1));
+                st2(&sQux[cidx(2 * q, a)], x0, x1);
+                if (reg2) st2(&sM1[cidx(2 * q, a)], fma(lam, FF[at][0], x0), fma(lam, FF[at][1], x1));
             }
             {
                 double u0 = G[gidx(4, 4)][0], u1 = G[gidx(4, 4)][1];
-                sQuu[g + 8 * (2 * q)] = u0;
-                sQuu[g + 8 * (2 * q + 1)] = u1;
+                st2(&sQuu[8 * g + 2 * q], u0, u1);          // Quu and QuuF are kept ROW-major: [a][b] at 8a + b
                 double f0, f1;
                 if (reg2) { f0 = fma(lam, FF[4][0], u0); f1 = fma(lam, FF[4][1], u1); }
                 else { f0 = u0 + ((g == 2 * q) ? lam : 0.0); f1 = u1 + ((g == 2 * q + 1) ? lam : 0.0); }
-                sQuuF[g + 8 * (2 * q)] = f0;
-                sQuuF[g + 8 * (2 * q + 1)] = f1;
+                st2(&sQuuF[8 * g + 2 * q], f0, f1);
             }
-            if (lane < 8) sQu[lane] = quv;
             __syncwarp();
+            const double qx = cxv + sFV[lane];               // Qx = cx + fx'Vx, owned by lane = state index
             // ---- Cholesky of QuuF (upper triangle), redundantly on every lane
             double R[8][8], rinv[8];
             bool ok = true;
@@ -262,16 +279,16 @@ __global__ void __launch_bounds__(WPB * 32, 2) bp_tile32x8_kernel(BackParams P) 
             for (int j = 0; j < 8; j++) {
 #pragma unroll
                 for (int r = 0; r < j; r++) {
-                    double s = sQuuF[r + 8 * j];
+                    double s = sQuuF[8 * r + j];
 #pragma unroll
                     for (int p = 0; p < r; p++) s = fma(-R[p][r], R[p][j], s);
                     R[r][j] = s * rinv[r];
                 }
-                double d = sQuuF[j + 8 * j];
+                double d = sQuuF[9 * j];
 #pragma unroll
                 for (int p = 0; p < j; p++) d = fma(-R[p][j], R[p][j], d);
                 if (!(d > 0.0)) ok = false;
-                rinv[j] = rsqrt(d);
+                rinv[j] = rsqrt_nr(d);
             }
             if (!ok) { diverge = i + 1; break; }
             auto solve8 = [&](double (&v)[8]) {
@@ -293,12 +310,12 @@ __global__ void __launch_bounds__(WPB * 32, 2) bp_tile32x8_kernel(BackParams P) 
             // ---- gains: lane j owns column j of K; k is warp-uniform
             double Kc[8], Qc[8], kv[8], Quv[8];
             {
-                const double* src = (reg2 ? sM1 : sQux) + lane * 8;
+                const double* src = reg2 ? sM1 : sQux;
 #pragma unroll
-                for (int r = 0; r < 8; r += 2) { double2 t = ld2(src + r); Kc[r] = t.x; Kc[r + 1] = t.y; }
+                for (int r = 0; r < 8; r += 2) { double2 t = ld2(src + cidx(r, lane)); Kc[r] = t.x; Kc[r + 1] = t.y; }
                 if (reg2) {
 #pragma unroll
-                    for (int r = 0; r < 8; r += 2) { double2 t = ld2(sQux + lane * 8 + r); Qc[r] = t.x; Qc[r + 1] = t.y; }
+                    for (int r = 0; r < 8; r += 2) { double2 t = ld2(sQux + cidx(r, lane)); Qc[r] = t.x; Qc[r + 1] = t.y; }
                 } else {
 #pragma unroll
                     for (int r = 0; r < 8; r++) Qc[r] = Kc[r];
@@ -313,23 +330,30 @@ __global__ void __launch_bounds__(WPB * 32, 2) bp_tile32x8_kernel(BackParams P) 
             // ---- M1 = Quu K + Qux (column j), Quuk = Quu k (uniform)
             double M1c[8], Quuk[8];
 #pragma unroll
-            for (int r = 0; r < 8; r++) { M1c[r] = Qc[r]; Quuk[r] = 0.0; }
+            for (int r = 0; r < 8; r++) M1c[r] = Qc[r];
+            double quuk_own = 0.0;                 // lane a (mod 8) forms (Quu k)[a]; the 8 values are then shuffled
 #pragma unroll
-            for (int c = 0; c < 8; c++) {
+            for (int r = 0; r < 8; r++) {
 #pragma unroll
-                for (int r = 0; r < 8; r += 2) {
-                    double2 t = ld2(&sQuu[r + 8 * c]);
+                for (int c = 0; c < 8; c += 2) {
+                    double2 t = ld2(&sQuu[8 * r + c]);              // Quu[r][c], Quu[r][c+1]
                     M1c[r] = fma(t.x, Kc[c], M1c[r]);
-                    M1c[r + 1] = fma(t.y, Kc[c], M1c[r + 1]);
-                    Quuk[r] = fma(t.x, kv[c], Quuk[r]);
-                    Quuk[r + 1] = fma(t.y, kv[c], Quuk[r + 1]);
+                    M1c[r] = fma(t.y, Kc[c + 1], M1c[r]);
                 }
             }
+#pragma unroll
+            for (int c = 0; c < 8; c += 2) {
+                double2 t = ld2(&sQuu[8 * (lane & 7) + c]);
+                quuk_own = fma(t.x, kv[c], quuk_own);
+                quuk_own = fma(t.y, kv[c + 1], quuk_own);
+            }
+#pragma unroll
+            for (int r = 0; r < 8; r++) Quuk[r] = __shfl_sync(0xffffffffu, quuk_own, r);
             __syncwarp();     // everyone has read its Qux_reg column (sM1 aliases it)
 #pragma unroll
             for (int r = 0; r < 8; r += 2) {
-                st2(&sK[lane * 8 + r], Kc[r], Kc[r + 1]);
-                st2(&sM1[lane * 8 + r], M1c[r], M1c[r + 1]);
+                st2(&sK[cidx(r, lane)], Kc[r], Kc[r + 1]);
+                st2(&sM1[cidx(r, lane)], M1c[r], M1c[r + 1]);
             }
             // ---- Vx(i), dV  (backward_pass.jl:64-69)
             double vxn;
@@ -352,35 +376,40 @@ __global__ void __launch_bounds__(WPB * 32, 2) bp_tile32x8_kernel(BackParams P) 
             {
                 double* Kg = Kb + (long long)i * 256;
 #pragma unroll
-                for (int c = lane; c < 128; c += 32) { double2 t = ld2(&sK[2 * c]); st2(Kg + 2 * c, t.x, t.y); }
+                for (int c = lane; c < 128; c += 32) { double2 t = ld2(&sK[cidx(2 * (c & 3), c >> 2)]); st2(Kg + 2 * c, t.x, t.y); }
                 double ksel = kv[0];
 #pragma unroll
                 for (int r = 1; r < 8; r++) ksel = (lane == r) ? kv[r] : ksel;
                 if (lane < 8) kb[(long long)i * 8 + lane] = ksel;
                 Vxb[(long long)i * 32 + lane] = vxn;
-                if (Quub) { double2 t = ld2(&sQuu[2 * lane]); st2(Quub + (long long)i * 64 + 2 * lane, t.x, t.y); }
+                if (Quub) {                                   // column-major out: rows 2l%8, 2l%8+1 of column l/4
+                    const int r0 = (2 * lane) & 7, c0 = lane >> 2;
+                    st2(Quub + (long long)i * 64 + 2 * lane, sQuu[8 * r0 + c0], sQuu[8 * (r0 + 1) + c0]);
+                }
             }
             // ---- step 4: Vxx = Qxx + K' M1 + Qux' K  (upper 10 tiles), mirrored into sV
             {
                 double2 kf[4], mf[4], qf[4];
 #pragma unroll
                 for (int t = 0; t < 4; t++) {
-                    const int o = (8 * t + g) * 8 + 2 * q;
+                    const int o = cidx(2 * q, 8 * t + g);
                     kf[t] = ld2(&sK[o]);
                     mf[t] = ld2(&sM1[o]);
                     qf[t] = ld2(&sQux[o]);
                 }
 #pragma unroll
-                for (int at = 0; at < 4; at++)
+                for (int pass = 0; pass < 4; pass++)        // 10 independent tiles between revisits
 #pragma unroll
-                    for (int bt = at; bt < 4; bt++) {
-                        double& c0 = G[gidx(at, bt)][0];
-                        double& c1 = G[gidx(at, bt)][1];
-                        dmma(c0, c1, kf[at].x, mf[bt].x);
-                        dmma(c0, c1, kf[at].y, mf[bt].y);
-                        dmma(c0, c1, qf[at].x, kf[bt].x);
-                        dmma(c0, c1, qf[at].y, kf[bt].y);
-                    }
+                    for (int at = 0; at < 4; at++)
+#pragma unroll
+                        for (int bt = at; bt < 4; bt++) {
+                            double& c0 = G[gidx(at, bt)][0];
+                            double& c1 = G[gidx(at, bt)][1];
+                            if (pass == 0) dmma(c0, c1, kf[at].x, mf[bt].x);
+                            if (pass == 1) dmma(c0, c1, kf[at].y, mf[bt].y);
+                            if (pass == 2) dmma(c0, c1, qf[at].x, kf[bt].x);
+                            if (pass == 3) dmma(c0, c1, qf[at].y, kf[bt].y);
+                        }
             }
             // all lanes are past their step-1 reads of sV (the two __syncwarp above order them)
 #pragma unroll

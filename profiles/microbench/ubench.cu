@@ -44,6 +44,28 @@ __global__ void dmma_kernel(double* out, int iters) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// DMMA and DFMA interleaved (ratio 1 DMMA : NF DFMA): do the two share one FP64 datapath?
+template <int NF>
+__global__ void mixed_kernel(double* out, int iters) {
+    double a = threadIdx.x * 1e-3, b = 1.0 + threadIdx.x * 1e-4;
+    double c[8][2], f[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { c[i][0] = i; c[i][1] = -i; f[i] = i * 0.5; }
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+#pragma unroll
+            for (int j = 0; j < NF; j++) f[(i + j) & 7] = fma(f[(i + j) & 7], 1.0000001, 1e-9);
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += c[i][0] + c[i][1] + f[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 // LDS pattern benchmark: every lane loads from smem at an address derived from `mode`.
 // We count SM cycles per warp-level LDS instruction with `nw` warps resident.
 template <int VEC>  // 1 = LDS.64, 2 = LDS.128
@@ -124,6 +146,23 @@ int main() {
         CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&ms, e0, e1));
         double flops = 2.0 * 256 * 8 * (double)iters * (double)blocks * (threads / 32);
         printf("DMMA m8n8k4 threads/blk %4d: %.2f TFLOP/s (%.3f ms)\n", threads, flops / ms * 1e-9, ms);
+    }
+    // 2b. DMMA + DFMA mixed: time relative to DMMA alone tells whether the pipes are shared
+    {
+        int threads = 256, blocks = sms * 8, iters = 20000;
+        auto run = [&](auto kern, const char* name, int nf) {
+            kern<<<blocks, threads>>>(out, 1000);
+            CK(cudaEventRecord(e0));
+            kern<<<blocks, threads>>>(out, iters);
+            CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&ms, e0, e1));
+            double dm = 2.0 * 256 * 8 * (double)iters * (double)blocks * (threads / 32);
+            double df = 2.0 * nf * 8 * (double)iters * (double)blocks * threads;
+            printf("%s: %.3f ms  DMMA %.2f TF + DFMA %.2f TF = %.2f TF\n", name, ms, dm / ms * 1e-9, df / ms * 1e-9, (dm + df) / ms * 1e-9);
+        };
+        run(mixed_kernel<0>, "mixed 1 DMMA : 0 DFMA", 0);
+        run(mixed_kernel<2>, "mixed 1 DMMA : 2 DFMA", 2);
+        run(mixed_kernel<4>, "mixed 1 DMMA : 4 DFMA", 4);
+        run(mixed_kernel<8>, "mixed 1 DMMA : 8 DFMA", 8);
     }
     // 3. LDS patterns: 1 block on 1 SM, nw warps
     long long* dcyc; CK(cudaMalloc(&dcyc, 8));
