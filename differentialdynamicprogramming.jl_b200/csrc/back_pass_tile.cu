@@ -2,25 +2,31 @@
 //
 // Replaces back_pass (Cholesky branch) of src/backward_pass.jl:162-252 + :31-42, :64-76.
 //
-// The per-step dense algebra is mapped onto FP64 tensor tiles (mma.sync.m8n8k4.f64, "DMMA";
-// measured 37.1 TFLOP/s on B200 vs 34.1 for the DFMA pipe, profiles/microbench) -- tcgen05 has
-// no f64 kind, so this is the only matrix unit that keeps the 1e-8 FP64 parity contract:
+// The per-step dense algebra runs on FP64 tensor tiles (mma.sync.m8n8k4.f64, "DMMA"; measured
+// 37.1 TFLOP/s on B200, and it shares the FP64 datapath with DFMA -- profiles/microbench).
+// tcgen05 has no f64 kind, so this is the only matrix unit that keeps the 1e-8 FP64 contract.
+// Everything between the two big products stays in registers, in DMMA fragment layouts:
 //
-//   F  = [fx fu]            32 x 40    (shared memory, column-major, XOR-swizzled)
-//   W' = F' V               40 x 32    160 DMMA   (V = Vxx(i+1), symmetric, shared memory)
-//   G  = W' F = F' V F      40 x 40    120 DMMA   (upper 15 of 25 tiles: G is symmetric)
-//        G = [Qxx Qxu; . Quu] - cost terms; the W' accumulators are re-used directly as the
-//        A operand of the second product by permuting the contraction index (no smem round trip)
-//   Quu (8x8): every lane factors it redundantly in registers (reciprocal square roots), lane j
-//        solves for column j of K; k and Quu*k are computed warp-uniformly
-//   Vxx = Qxx + K'(Quu K + Qux) + Qux' K   40 DMMA onto the resident Qxx tiles, mirrored => exactly symmetric
+//   F  = [fx fu]            32 x 40    shared memory (column-major, XOR-swizzled), loaded once (LTI)
+//   W' = F' V               40 x 32    160 DMMA   V = Vxx(i+1), symmetric, shared memory
+//   G  = W' F = F' V F      40 x 40    120 DMMA   upper 15 of 25 tiles; accumulators start from the
+//                                                 cost terms; W' accumulators are re-used as the A
+//                                                 operand by permuting the contraction index
+//        G = [Qxx Qxu; . Quu].  In the accumulator layout a lane (g,q) holds Qux[2q..2q+1][8t+g]
+//        and Quu[g][2q..2q+1] -- exactly the A/B fragments the next products need.
+//   Minv = QuuF^-1          8 x 8      Gauss-Jordan in the accumulator layout, pivots broadcast by
+//                                      shuffles; a pivot <= 0 is the reference's Cholesky failure
+//   K'   = -Qux_reg' Minv   32 x 8     8 DMMA     (comes out as the fragment Vxx needs, and as
+//                                                 coalesced 16-byte global stores)
+//   M1'  = Qux' + K' Quu    32 x 8     8 DMMA
+//   Vxx  = Qxx + K'M1 + Qux'K          40 DMMA onto the resident Qxx tiles, mirrored => exactly symmetric
+//   k, Quu k, Vx, dV: a few FMAs per lane plus shuffles.
 //
-// 328 DMMA per step ~ 168 kflop, against the reference's 213 kflop formulation.
-// Shared memory: 26.6 KB per warp => 8 warps (trajectories) per SM, 2 per SM sub-partition, so
-// one warp's serial Cholesky/solve phase overlaps the other's tensor phase.
+// 336 DMMA per step ~ 172 kflop, against the reference's 213 kflop formulation.
+// Shared memory: 18.7 KB per warp (V, F, Vx); registers (255) limit residency to 8 warps per SM.
 //
 // Restrictions (anything else dispatches to the generic kernel): Cholesky branch only (lims ==
-// NULL), 16-byte aligned fx/fu with even strides, symmetric cxx (it is a Hessian).
+// NULL), 16-byte aligned fx/fu/cxx with even strides, symmetric cxx (it is a Hessian).
 #include "ddp_common.cuh"
 
 namespace {
@@ -28,18 +34,13 @@ namespace {
 constexpr int WPB = 4;                       // warps per CTA
 constexpr int SV = 0;                        // Vxx            32 x 32 swizzled
 constexpr int SF = SV + 1024;                // [fx fu]        32 x 40 swizzled
-constexpr int SQUX = SF + 1280;              // Qux  (8 x 32, column j at 8j)
-constexpr int SK = SQUX + 256;               // K
-constexpr int SM1 = SK + 256;                // Quu K + Qux   (aliases Qux_reg before the solve)
-constexpr int SQUU = SM1 + 256;              // Quu  (col-major 8 x 8)
-constexpr int SQUUF = SQUU + 64;             // regularised Quu
-constexpr int SVX = SQUUF + 64;              // Vx (32)
-constexpr int SQU = SVX + 32;                // Qu (8)
-constexpr int SFV = SQU + 8;                 // F'Vx (32)
-constexpr int WARP_DOUBLES = SFV + 32 + 8;   // = 3280 doubles -> 26,240 B per warp
+constexpr int SVX = SF + 1280;               // Vx (32)
+constexpr int WARP_DOUBLES = SVX + 32;       // 2336 doubles = 18,688 B per warp
 constexpr int SF2 = WARP_DOUBLES;            // second F buffer (time-varying dynamics only)
 constexpr int WARP_DOUBLES_LTV = WARP_DOUBLES + 1280;
 
+// column-major 32-row matrices: element (i, c) lives at (i ^ s(c)) + 32 c with s(c) = ((c&1)<<3) | (((c>>1)&3)<<1).
+// 16-byte row pairs stay together, DMMA fragment loads (LDS.128) are bank-conflict free.
 __device__ __forceinline__ int swz(int i, int c) { return (i ^ (((c & 1) << 3) | (((c >> 1) & 3) << 1))) + 32 * c; }
 
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
@@ -47,6 +48,8 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 }
 __device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
 __device__ __forceinline__ void st2(double* p, double a, double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
+__device__ __forceinline__ double shf(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ double shx(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 
 __device__ __forceinline__ void cp_async16(double* dst_smem, const double* src) {
     unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
@@ -66,19 +69,13 @@ __device__ __forceinline__ void load_F(double* sF, const double* fx, const doubl
     }
 }
 
-// 8 x 32 buffers (Qux, K, M1): column j at 8j, its four 16-byte row pairs XOR-swizzled by (j >> 1) so that both
-// "lane = column" accesses and the DMMA fragment loads are bank-conflict free
-__device__ __forceinline__ int cidx(int r, int j) { return 8 * j + ((((r >> 1) ^ (j >> 1)) & 3) << 1) + (r & 1); }
-
-// 1/sqrt(d) for d > 0, normal range: hardware seed + two Newton steps (the Cholesky pivots are O(1e-3..1e3);
-// non-positive pivots are caught before the value is used)
-__device__ __forceinline__ double rsqrt_nr(double d) {
+// 1/d for d > 0 in the normal range: hardware seed + two Newton steps
+__device__ __forceinline__ double rcp_nr(double d) {
     double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
-    const double h = 0.5 * d;
-    double e = fma(-h * y, y, 0.5);      // 0.5 - h y^2
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    double e = fma(-d, y, 1.0);
     y = fma(y, e, y);
-    e = fma(-h * y, y, 0.5);
+    e = fma(-d, y, 1.0);
     y = fma(y, e, y);
     return y;
 }
@@ -92,16 +89,19 @@ __global__ void __launch_bounds__(WPB * 32, 2) bp_tile32x8_kernel(BackParams P) 
     const int g = lane >> 2, q = lane & 3;
     double* sm = smem_raw + (size_t)w * (LTV ? WARP_DOUBLES_LTV : WARP_DOUBLES);
     double* sV = sm + SV;
-    double* sQux = sm + SQUX;
-    double* sK = sm + SK;
-    double* sM1 = sm + SM1;
-    double* sQuu = sm + SQUU;
-    double* sQuuF = sm + SQUUF;
     double* sVx = sm + SVX;
-    double* sQu = sm + SQU;
-    double* sFV = sm + SFV;
     const int N = P.T;
     const long long warps_total = (long long)gridDim.x * WPB;
+    // lane constants of the swizzled addressing: swz(8p + 2q, 8t + g) = (p even ? LAe : LAo) + 8p + 256t,
+    // swz(8at + g, 8bt + 2q + h) = LM + 8(at ^ h) + 32h + 256bt
+    const int gg = (g >> 1) & 3, par = g & 1;
+    const int LA = 2 * (q ^ gg) + 32 * g;
+    const int LAe = LA + 8 * par, LAo = LA - 8 * par;
+    const int LM = (g ^ (2 * q)) + 64 * q;
+#define FRAG(p, t) (((p) & 1 ? LAo : LAe) + 8 * (p) + 256 * (t))
+#define MIRR(at, bt, h) (LM + 8 * ((at) ^ (h)) + 32 * (h) + 256 * (bt))
+    const bool up0 = (2 * q >= g), st0 = (2 * q > g), up1 = (2 * q + 1 >= g), st1 = (2 * q + 1 > g);
+    const int c0src = 8 * q, c1src = 8 * q + 4;        // a lane of the group that owns entry 2q / 2q+1
 
     for (long long b = (long long)blockIdx.x * WPB + w; b < P.B; b += warps_total) {
         if (P.active && !P.active[b]) continue;
@@ -112,10 +112,12 @@ __global__ void __launch_bounds__(WPB * 32, 2) bp_tile32x8_kernel(BackParams P) 
         double* Vxb = P.Vx + b * (long long)N * 32;
         double* Vxxb = P.Vxx ? P.Vxx + b * (long long)N * 1024 : nullptr;
         double* Quub = P.Quu ? P.Quu + b * (long long)N * 64 : nullptr;
+        const double* cxb = P.cx.p + b * P.cx.sb;
+        const double* cub = P.cu.p + b * P.cu.sb;
         __syncwarp();
         // ---- terminal step
         {
-            const double* cxN = tp(P.cx, b, N - 1);
+            const double* cxN = cxb + (long long)(N - 1) * P.cx.st;
             const double* cxxN = tp(P.cxx, b, N - 1);
             const double* cuuN = tp(P.cuu, b, N - 1);
             double v = cxN[lane];
@@ -147,10 +149,10 @@ __global__ void __launch_bounds__(WPB * 32, 2) bp_tile32x8_kernel(BackParams P) 
             for (int t = 0; t < 5; t++) FF[t][0] = FF[t][1] = 0.0;
 #pragma unroll
             for (int p = 0; p < 4; p++) {
-                double2 fb = ld2(&sF[swz(8 * p + 2 * q, 32 + g)]);
+                double2 fb = ld2(&sF[FRAG(p, 4)]);
 #pragma unroll
                 for (int t = 0; t < 5; t++) {
-                    double2 fa = ld2(&sF[swz(8 * p + 2 * q, 8 * t + g)]);
+                    double2 fa = ld2(&sF[FRAG(p, t)]);
                     dmma(FF[t][0], FF[t][1], fa.x, fb.x);
                     dmma(FF[t][0], FF[t][1], fa.y, fb.y);
                 }
@@ -168,9 +170,12 @@ __global__ void __launch_bounds__(WPB * 32, 2) bp_tile32x8_kernel(BackParams P) 
                 if (i > 0) load_F<true>(sm + (buf ? SF : SF2), tp(P.fx, b, i - 1), tp(P.fu, b, i - 1), lane);
                 if (reg2) compute_FF(sF);
             }
-            // prefetch this step's cost gradients
-            const double cxv = tp(P.cx, b, i)[lane];
-            const double cuv = tp(P.cu, b, i)[g];             // lanes (g, q == 0) publish Qu[g]
+            // this step's cost gradients: lanes of group g own Qx[8t+g] (t = 0..3) and Qu[g]
+            const double* cxi = cxb + (long long)i * P.cx.st;
+            double cxv[4];
+#pragma unroll
+            for (int t = 0; t < 4; t++) cxv[t] = cxi[8 * t + g];
+            const double cuv = (cub + (long long)i * P.cu.st)[g];
             const double* cxxi = tp(P.cxx, b, i);
             const double* cxui = tp(P.cxu, b, i);
             const double* cuui = tp(P.cuu, b, i);
@@ -210,13 +215,12 @@ __global__ void __launch_bounds__(WPB * 32, 2) bp_tile32x8_kernel(BackParams P) 
             }
 #pragma unroll
             for (int p = 0; p < 4; p++) {
-                const int row = 8 * p + 2 * q;
                 double2 fa[5], fb[4];
 #pragma unroll
-                for (int at = 0; at < 5; at++) fa[at] = ld2(&sF[swz(row, 8 * at + g)]);
+                for (int at = 0; at < 5; at++) fa[at] = ld2(&sF[FRAG(p, at)]);
 #pragma unroll
-                for (int jt = 0; jt < 4; jt++) fb[jt] = ld2(&sV[swz(row, 8 * jt + g)]);
-                const double2 vx = ld2(&sVx[row]);
+                for (int jt = 0; jt < 4; jt++) fb[jt] = ld2(&sV[FRAG(p, jt)]);
+                const double2 vx = ld2(&sVx[8 * p + 2 * q]);
                 // consecutive DMMAs go to different accumulator tiles (a tile is revisited 20 issues later)
 #pragma unroll
                 for (int at = 0; at < 5; at++)
@@ -231,20 +235,15 @@ __global__ void __launch_bounds__(WPB * 32, 2) bp_tile32x8_kernel(BackParams P) 
             }
 #pragma unroll
             for (int at = 0; at < 5; at++) {
-                fv[at] += __shfl_xor_sync(0xffffffffu, fv[at], 1);
-                fv[at] += __shfl_xor_sync(0xffffffffu, fv[at], 2);
-            }
-            if (q == 0) {                                   // (F'Vx)[8at+g]; Qu[g] = cu[g] + (fu'Vx)[g]
-#pragma unroll
-                for (int at = 0; at < 4; at++) sFV[8 * at + g] = fv[at];
-                sQu[g] = cuv + fv[4];
+                fv[at] += shx(fv[at], 1);
+                fv[at] += shx(fv[at], 2);
             }
             // ---- step 2: G = W' F  (upper tiles)
 #pragma unroll
             for (int p = 0; p < 4; p++) {
                 double2 ff[5];
 #pragma unroll
-                for (int bt = 0; bt < 5; bt++) ff[bt] = ld2(&sF[swz(8 * p + 2 * q, 8 * bt + g)]);
+                for (int bt = 0; bt < 5; bt++) ff[bt] = ld2(&sF[FRAG(p, bt)]);
 #pragma unroll
                 for (int at = 0; at < 5; at++)
 #pragma unroll
@@ -254,182 +253,136 @@ __global__ void __launch_bounds__(WPB * 32, 2) bp_tile32x8_kernel(BackParams P) 
 #pragma unroll
                     for (int bt = at; bt < 5; bt++) dmma(G[gidx(at, bt)][0], G[gidx(at, bt)][1], W[at][p][1], ff[bt].y);
             }
-            // ---- spill Qux / Qux_reg / Quu / QuuF / Qu to shared memory
+            // ---- fragments straight from the accumulators:
+            //      qf[t]  = Qux[2q..2q+1][8t+g]   (unregularised), qr[t] = Qux_reg, (U0,U1) = Quu[g][2q..2q+1]
+            double2 qf[4], qr[4];
 #pragma unroll
-            for (int at = 0; at < 4; at++) {
-                const int a = 8 * at + g;
-                double x0 = G[gidx(at, 4)][0], x1 = G[gidx(at, 4)][1];
-                st2(&sQux[cidx(2 * q, a)], x0, x1);
-                if (reg2) st2(&sM1[cidx(2 * q, a)], fma(lam, FF[at][0], x0), fma(lam, FF[at][1], x1));
+            for (int t = 0; t < 4; t++) {
+                qf[t] = make_double2(G[gidx(t, 4)][0], G[gidx(t, 4)][1]);
+                qr[t] = reg2 ? make_double2(fma(lam, FF[t][0], qf[t].x), fma(lam, FF[t][1], qf[t].y)) : qf[t];
             }
-            {
-                double u0 = G[gidx(4, 4)][0], u1 = G[gidx(4, 4)][1];
-                st2(&sQuu[8 * g + 2 * q], u0, u1);          // Quu and QuuF are kept ROW-major: [a][b] at 8a + b
-                double f0, f1;
-                if (reg2) { f0 = fma(lam, FF[4][0], u0); f1 = fma(lam, FF[4][1], u1); }
-                else { f0 = u0 + ((g == 2 * q) ? lam : 0.0); f1 = u1 + ((g == 2 * q + 1) ? lam : 0.0); }
-                st2(&sQuuF[8 * g + 2 * q], f0, f1);
-            }
-            __syncwarp();
-            const double qx = cxv + sFV[lane];               // Qx = cx + fx'Vx, owned by lane = state index
-            // ---- Cholesky of QuuF (upper triangle), redundantly on every lane
-            double R[8][8], rinv[8];
+            const double U0 = G[gidx(4, 4)][0], U1 = G[gidx(4, 4)][1];
+            double I0, I1;                                   // QuuF, inverted in place below
+            if (reg2) { I0 = fma(lam, FF[4][0], U0); I1 = fma(lam, FF[4][1], U1); }
+            else { I0 = U0 + ((g == 2 * q) ? lam : 0.0); I1 = U1 + ((g == 2 * q + 1) ? lam : 0.0); }
+            // ---- Gauss-Jordan inverse of QuuF in the accumulator layout; pivot p <= 0  <=>  Cholesky fails
             bool ok = true;
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-#pragma unroll
-                for (int r = 0; r < j; r++) {
-                    double s = sQuuF[8 * r + j];
-#pragma unroll
-                    for (int p = 0; p < r; p++) s = fma(-R[p][r], R[p][j], s);
-                    R[r][j] = s * rinv[r];
-                }
-                double d = sQuuF[9 * j];
-#pragma unroll
-                for (int p = 0; p < j; p++) d = fma(-R[p][j], R[p][j], d);
+            for (int p = 0; p < 8; p++) {
+                const double own = (p & 1) ? I1 : I0;
+                const double d = shf(own, 4 * p + (p >> 1));             // A[p][p]
+                const double colp = shf(own, (lane & ~3) | (p >> 1));     // A[g][p]
+                const double rp0 = shf(I0, 4 * p + q), rp1 = shf(I1, 4 * p + q);   // A[p][2q], A[p][2q+1]
                 if (!(d > 0.0)) ok = false;
-                rinv[j] = rsqrt_nr(d);
+                const double r = rcp_nr(d);
+                const double n0 = ((2 * q == p) ? 1.0 : rp0) * r, n1 = ((2 * q + 1 == p) ? 1.0 : rp1) * r;
+                if (g == p) { I0 = n0; I1 = n1; }
+                else {
+                    I0 = fma(-colp, n0, (2 * q == p) ? 0.0 : I0);
+                    I1 = fma(-colp, n1, (2 * q + 1 == p) ? 0.0 : I1);
+                }
             }
             if (!ok) { diverge = i + 1; break; }
-            auto solve8 = [&](double (&v)[8]) {
+            // ---- K' = -Qux_reg' Minv : kf[t] = K[2q..2q+1][8t+g]
+            double2 kf[4];
 #pragma unroll
-                for (int r = 0; r < 8; r++) {
-                    double s = v[r];
+            for (int t = 0; t < 4; t++) kf[t] = make_double2(0.0, 0.0);
 #pragma unroll
-                    for (int p = 0; p < r; p++) s = fma(-R[p][r], v[p], s);
-                    v[r] = s * rinv[r];
-                }
+            for (int t = 0; t < 4; t++) dmma(kf[t].x, kf[t].y, qr[t].x, I0);
 #pragma unroll
-                for (int r = 7; r >= 0; r--) {
-                    double s = v[r];
+            for (int t = 0; t < 4; t++) dmma(kf[t].x, kf[t].y, qr[t].y, I1);
 #pragma unroll
-                    for (int p = r + 1; p < 8; p++) s = fma(-R[r][p], v[p], s);
-                    v[r] = s * rinv[r];
-                }
-            };
-            // ---- gains: lane j owns column j of K; k is warp-uniform
-            double Kc[8], Qc[8], kv[8], Quv[8];
+            for (int t = 0; t < 4; t++) { kf[t].x = -kf[t].x; kf[t].y = -kf[t].y; }
+            // ---- k = -Minv Qu, Quu k   (group g owns entry g; entries 2q, 2q+1 are fetched by shuffle)
+            const double Qu_own = cuv + fv[4];
+            const double Qu0 = shf(Qu_own, c0src), Qu1 = shf(Qu_own, c1src);
+            double ks = fma(I1, Qu1, I0 * Qu0);
+            ks += shx(ks, 1);
+            ks += shx(ks, 2);
+            const double k_own = -ks;
+            const double k0 = shf(k_own, c0src), k1 = shf(k_own, c1src);
+            double qs = fma(U1, k1, U0 * k0);
+            qs += shx(qs, 1);
+            qs += shx(qs, 2);
+            const double Quuk_own = qs;
+            const double z0 = shf(Quuk_own, c0src) + Qu0, z1 = shf(Quuk_own, c1src) + Qu1;   // (Quu k + Qu)[2q..2q+1]
+            // ---- M1' = Qux' + K' Quu : mf[t] = M1[2q..2q+1][8t+g]
+            double2 mf[4];
+#pragma unroll
+            for (int t = 0; t < 4; t++) mf[t] = qf[t];
+#pragma unroll
+            for (int t = 0; t < 4; t++) dmma(mf[t].x, mf[t].y, kf[t].x, U0);
+#pragma unroll
+            for (int t = 0; t < 4; t++) dmma(mf[t].x, mf[t].y, kf[t].y, U1);
+            // ---- Vx(i) = Qx + K'(Quu k + Qu) + Qux'k ; dV   (backward_pass.jl:64-69)
+            double vxn[4];
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                double sacc = fma(kf[t].y, z1, kf[t].x * z0);
+                sacc = fma(qf[t].x, k0, sacc);
+                sacc = fma(qf[t].y, k1, sacc);
+                sacc += shx(sacc, 1);
+                sacc += shx(sacc, 2);
+                vxn[t] = (cxv[t] + fv[t]) + sacc;
+            }
             {
-                const double* src = reg2 ? sM1 : sQux;
+                double d0 = k_own * Qu_own, d1 = k_own * Quuk_own;        // one term per group; sum over g
 #pragma unroll
-                for (int r = 0; r < 8; r += 2) { double2 t = ld2(src + cidx(r, lane)); Kc[r] = t.x; Kc[r + 1] = t.y; }
-                if (reg2) {
-#pragma unroll
-                    for (int r = 0; r < 8; r += 2) { double2 t = ld2(sQux + cidx(r, lane)); Qc[r] = t.x; Qc[r + 1] = t.y; }
-                } else {
-#pragma unroll
-                    for (int r = 0; r < 8; r++) Qc[r] = Kc[r];
-                }
-#pragma unroll
-                for (int r = 0; r < 8; r += 2) { double2 t = ld2(sQu + r); Quv[r] = t.x; Quv[r + 1] = t.y; kv[r] = t.x; kv[r + 1] = t.y; }
-            }
-            solve8(Kc);
-            solve8(kv);
-#pragma unroll
-            for (int r = 0; r < 8; r++) { Kc[r] = -Kc[r]; kv[r] = -kv[r]; }
-            // ---- M1 = Quu K + Qux (column j), Quuk = Quu k (uniform)
-            double M1c[8], Quuk[8];
-#pragma unroll
-            for (int r = 0; r < 8; r++) M1c[r] = Qc[r];
-            double quuk_own = 0.0;                 // lane a (mod 8) forms (Quu k)[a]; the 8 values are then shuffled
-#pragma unroll
-            for (int r = 0; r < 8; r++) {
-#pragma unroll
-                for (int c = 0; c < 8; c += 2) {
-                    double2 t = ld2(&sQuu[8 * r + c]);              // Quu[r][c], Quu[r][c+1]
-                    M1c[r] = fma(t.x, Kc[c], M1c[r]);
-                    M1c[r] = fma(t.y, Kc[c + 1], M1c[r]);
-                }
-            }
-#pragma unroll
-            for (int c = 0; c < 8; c += 2) {
-                double2 t = ld2(&sQuu[8 * (lane & 7) + c]);
-                quuk_own = fma(t.x, kv[c], quuk_own);
-                quuk_own = fma(t.y, kv[c + 1], quuk_own);
-            }
-#pragma unroll
-            for (int r = 0; r < 8; r++) Quuk[r] = __shfl_sync(0xffffffffu, quuk_own, r);
-            __syncwarp();     // everyone has read its Qux_reg column (sM1 aliases it)
-#pragma unroll
-            for (int r = 0; r < 8; r += 2) {
-                st2(&sK[cidx(r, lane)], Kc[r], Kc[r + 1]);
-                st2(&sM1[cidx(r, lane)], M1c[r], M1c[r + 1]);
-            }
-            // ---- Vx(i), dV  (backward_pass.jl:64-69)
-            double vxn;
-            {
-                double t1 = 0.0, t2 = 0.0, t3 = 0.0, d0 = 0.0, d1 = 0.0;
-#pragma unroll
-                for (int r = 0; r < 8; r++) {
-                    t1 = fma(Kc[r], Quuk[r], t1);
-                    t2 = fma(Kc[r], Quv[r], t2);
-                    t3 = fma(Qc[r], kv[r], t3);
-                    d0 = fma(kv[r], Quv[r], d0);
-                    d1 = fma(kv[r], Quuk[r], d1);
-                }
-                vxn = ((qx + t1) + t2) + t3;
+                for (int o = 4; o < 32; o <<= 1) { d0 += shx(d0, o); d1 += shx(d1, o); }
                 dV0 += d0;
                 dV1 += 0.5 * d1;
             }
-            __syncwarp();
-            // ---- outputs of this step that are complete now
+            // ---- outputs of this step
             {
-                double* Kg = Kb + (long long)i * 256;
+                double* Kg = Kb + (long long)i * 256 + 8 * g + 2 * q;       // K[2q..2q+1][8t+g]: 512 contiguous bytes per tile
 #pragma unroll
-                for (int c = lane; c < 128; c += 32) { double2 t = ld2(&sK[cidx(2 * (c & 3), c >> 2)]); st2(Kg + 2 * c, t.x, t.y); }
-                double ksel = kv[0];
+                for (int t = 0; t < 4; t++) st2(Kg + 64 * t, kf[t].x, kf[t].y);
+                if (q == 0) {
+                    kb[(long long)i * 8 + g] = k_own;
 #pragma unroll
-                for (int r = 1; r < 8; r++) ksel = (lane == r) ? kv[r] : ksel;
-                if (lane < 8) kb[(long long)i * 8 + lane] = ksel;
-                Vxb[(long long)i * 32 + lane] = vxn;
-                if (Quub) {                                   // column-major out: rows 2l%8, 2l%8+1 of column l/4
-                    const int r0 = (2 * lane) & 7, c0 = lane >> 2;
-                    st2(Quub + (long long)i * 64 + 2 * lane, sQuu[8 * r0 + c0], sQuu[8 * (r0 + 1) + c0]);
+                    for (int t = 0; t < 4; t++) Vxb[(long long)i * 32 + 8 * t + g] = vxn[t];
+                }
+                if (Quub) {
+                    Quub[(long long)i * 64 + g + 8 * (2 * q)] = U0;
+                    Quub[(long long)i * 64 + g + 8 * (2 * q + 1)] = U1;
                 }
             }
-            // ---- step 4: Vxx = Qxx + K' M1 + Qux' K  (upper 10 tiles), mirrored into sV
-            {
-                double2 kf[4], mf[4], qf[4];
+            // ---- step 4: Vxx = Qxx + K' M1 + Qux' K  (upper 10 tiles), all operands in registers
 #pragma unroll
-                for (int t = 0; t < 4; t++) {
-                    const int o = cidx(2 * q, 8 * t + g);
-                    kf[t] = ld2(&sK[o]);
-                    mf[t] = ld2(&sM1[o]);
-                    qf[t] = ld2(&sQux[o]);
-                }
+            for (int pass = 0; pass < 4; pass++)             // 10 independent tiles between revisits
 #pragma unroll
-                for (int pass = 0; pass < 4; pass++)        // 10 independent tiles between revisits
+                for (int at = 0; at < 4; at++)
 #pragma unroll
-                    for (int at = 0; at < 4; at++)
-#pragma unroll
-                        for (int bt = at; bt < 4; bt++) {
-                            double& c0 = G[gidx(at, bt)][0];
-                            double& c1 = G[gidx(at, bt)][1];
-                            if (pass == 0) dmma(c0, c1, kf[at].x, mf[bt].x);
-                            if (pass == 1) dmma(c0, c1, kf[at].y, mf[bt].y);
-                            if (pass == 2) dmma(c0, c1, qf[at].x, kf[bt].x);
-                            if (pass == 3) dmma(c0, c1, qf[at].y, kf[bt].y);
-                        }
-            }
-            // all lanes are past their step-1 reads of sV (the two __syncwarp above order them)
+                    for (int bt = at; bt < 4; bt++) {
+                        double& c0 = G[gidx(at, bt)][0];
+                        double& c1 = G[gidx(at, bt)][1];
+                        if (pass == 0) dmma(c0, c1, kf[at].x, mf[bt].x);
+                        if (pass == 1) dmma(c0, c1, kf[at].y, mf[bt].y);
+                        if (pass == 2) dmma(c0, c1, qf[at].x, kf[bt].x);
+                        if (pass == 3) dmma(c0, c1, qf[at].y, kf[bt].y);
+                    }
+            __syncwarp();          // every lane is past its reads of sV / sVx for this step
 #pragma unroll
             for (int at = 0; at < 4; at++) {
-                const int a = 8 * at + g;
 #pragma unroll
                 for (int bt = at; bt < 4; bt++) {
-                    const int b0 = 8 * bt + 2 * q;
                     const double v0 = G[gidx(at, bt)][0], v1 = G[gidx(at, bt)][1];
                     if (bt > at) {
-                        st2(&sV[swz(b0, a)], v0, v1);
-                        sV[swz(a, b0)] = v0;
-                        sV[swz(a, b0 + 1)] = v1;
-                    } else {                       // diagonal tile: keep the upper part, mirror it
-                        if (b0 >= a) { sV[swz(b0, a)] = v0; if (b0 > a) sV[swz(a, b0)] = v0; }
-                        if (b0 + 1 >= a) { sV[swz(b0 + 1, a)] = v1; if (b0 + 1 > a) sV[swz(a, b0 + 1)] = v1; }
+                        st2(&sV[FRAG(bt, at)], v0, v1);                  // V[8bt+2q..+1][8at+g]
+                        sV[MIRR(at, bt, 0)] = v0;                        // V[8at+g][8bt+2q]
+                        sV[MIRR(at, bt, 1)] = v1;
+                    } else {                                             // diagonal tile: keep the upper part, mirror it
+                        if (up0) sV[FRAG(at, at)] = v0;
+                        if (st0) sV[MIRR(at, at, 0)] = v0;
+                        if (up1) sV[FRAG(at, at) + 1] = v1;
+                        if (st1) sV[MIRR(at, at, 1)] = v1;
                     }
                 }
             }
-            sVx[lane] = vxn;
+            if (q == 0) {
+#pragma unroll
+                for (int t = 0; t < 4; t++) sVx[8 * t + g] = vxn[t];
+            }
             if (LTV) buf ^= 1;
             __syncwarp();
         }
@@ -443,7 +396,7 @@ __global__ void __launch_bounds__(WPB * 32, 2) bp_tile32x8_kernel(BackParams P) 
             for (long long e = lane; e < (long long)upto * 32; e += 32) Vxb[e] = 0.0;
             if (Vxxb) {
                 for (long long e = lane; e < (long long)upto * 512; e += 32) st2(Vxxb + 2 * e, 0.0, 0.0);
-                if (diverge < N - 1)               // Vxx(diverge) (0-based) was computed but not dumped yet
+                if (diverge < N - 1)               // Vxx(diverge) (0-based) is the last one computed
                     for (int c = lane; c < 512; c += 32) {
                         int col = c >> 4, r = (c & 15) << 1;
                         double2 t = ld2(&sV[swz(r, col)]);
@@ -470,6 +423,8 @@ __global__ void __launch_bounds__(WPB * 32, 2) bp_tile32x8_kernel(BackParams P) 
             P.dV[2 * b + 1] = dV1;
         }
     }
+#undef FRAG
+#undef MIRR
 }
 
 bool aligned16(const TensorD& t) { return ((uintptr_t)t.p % 16 == 0) && (t.sb % 2 == 0) && (t.st % 2 == 0); }
@@ -480,15 +435,14 @@ int launch_back_pass_tile(ddp_handle_s* h, const BackParams& P, bool gps, bool* 
     *handled = false;
     if (gps || P.n != 32 || P.m != 8 || P.lims != nullptr || P.T < 2) return 0;
     if (!aligned16(P.fx) || !aligned16(P.fu) || !aligned16(P.cxx)) return 0;
-    if (P.Vxx && ((uintptr_t)P.Vxx % 16)) return 0;
+    if (((uintptr_t)P.K % 16) || (P.Vxx && ((uintptr_t)P.Vxx % 16)) || (P.Vxx1 && ((uintptr_t)P.Vxx1 % 16))) return 0;
     const bool ltv = (P.fx.st != 0 || P.fu.st != 0);
     const size_t bytes = (size_t)(ltv ? WARP_DOUBLES_LTV : WARP_DOUBLES) * sizeof(double) * WPB;
     cudaError_t e;
     if (ltv) e = cudaFuncSetAttribute(bp_tile32x8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     else e = cudaFuncSetAttribute(bp_tile32x8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return (int)e;
-    int per_sm = ltv ? 1 : 2;
-    long long grid = (long long)h->sm_count * per_sm;
+    long long grid = (long long)h->sm_count * 2;
     long long need = (P.B + WPB - 1) / WPB;
     if (grid > need) grid = need;
     if (ltv) bp_tile32x8_kernel<true><<<(unsigned)grid, WPB * 32, bytes, h->stream>>>(P);
