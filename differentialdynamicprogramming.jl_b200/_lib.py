@@ -102,6 +102,7 @@ SYMBOLS = [
     ("ddp_batch_stats_f64", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                       C.c_void_p, C.c_void_p, C.c_void_p]),
     ("ddp_kl_div_f64", C.c_int, [C.c_void_p, C.POINTER(KlArgs)]),
+    ("ddp_model_derivs_f64", C.c_int, [C.c_void_p, C.POINTER(Model)] + [C.c_void_p] * 6),
     ("ddp_ilqg_solve_f64", C.c_int, [C.c_void_p, C.POINTER(Model), C.POINTER(IlqgOpts)] + [C.c_void_p] * 9 +
      [C.POINTER(C.c_int32)]),
     ("ddp_ilqg_iter_host_f64", C.c_int, [C.c_void_p, C.POINTER(IterHostArgs)]),

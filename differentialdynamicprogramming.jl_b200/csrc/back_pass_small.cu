@@ -1,3 +1,299 @@
-// placeholder: specialised small-n thread-per-trajectory kernel (filled in next)
-#include "ddp_common.cuh"
-int launch_back_pass_small(ddp_handle_s*, const BackParams&, bool, bool* handled) { *handled = false; return 0; }
+// Specialised backward sweep for small systems (n <= 4, m <= 2; config 3 is n = 4, m = 1 with
+// control limits): ONE THREAD PER TRAJECTORY, every block of the step in registers, the next step's
+// inputs prefetched into registers while the current one is processed.
+//
+// Replaces back_pass of src/backward_pass.jl:162-252 with both branches of @end_backward_pass
+// (:31-42 Cholesky, :43-62 boxQP).  The factorisation, the triangular solves and the QP are the
+// same sequential, FMA-free device functions as the generic kernel and the oracle (boxqp.cuh), so
+// the integer outcomes (diverge, clamped set, QP result) follow the oracle's branch decisions.
+//
+// This shape is HBM/latency bound (0.4 Mflop vs 245 KB per trajectory-iteration): a thread reads its
+// own 128-byte fx line per step, i.e. every sector fetched is fully used.
+#include "boxqp.cuh"
+
+namespace {
+
+template <int N, int M>
+struct StepIn {
+    double fx[N * N], fu[N * M], cx[N], cu[M], u[M];
+};
+
+template <int N, int M>
+__device__ __forceinline__ void load_step(StepIn<N, M>& s, const BackParams& P, long long b, int i, bool use_qp) {
+    const double* fx = tp(P.fx, b, i);
+    const double* fu = tp(P.fu, b, i);
+    const double* cx = tp(P.cx, b, i);
+    const double* cu = tp(P.cu, b, i);
+    if ((N * N) % 2 == 0 && ((uintptr_t)fx % 16) == 0) {
+#pragma unroll
+        for (int e = 0; e < N * N; e += 2) { double2 t = *reinterpret_cast<const double2*>(fx + e); s.fx[e] = t.x; s.fx[e + 1] = t.y; }
+    } else {
+#pragma unroll
+        for (int e = 0; e < N * N; e++) s.fx[e] = fx[e];
+    }
+#pragma unroll
+    for (int e = 0; e < N * M; e++) s.fu[e] = fu[e];
+#pragma unroll
+    for (int e = 0; e < N; e++) s.cx[e] = cx[e];
+#pragma unroll
+    for (int e = 0; e < M; e++) { s.cu[e] = cu[e]; s.u[e] = use_qp ? tp(P.u, b, i)[e] : 0.0; }
+}
+
+template <int N, int M>
+__global__ void __launch_bounds__(128) bp_small_kernel(BackParams P) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= P.B) return;
+    if (P.active && !P.active[b]) return;
+    const int T = P.T;
+    const bool use_qp = (P.lims != nullptr) && !(P.lims[0] > P.lims[M]);     // backward_pass.jl:31
+    const double lam = P.lambda[b];
+    const bool reg2 = (P.reg_type == 2);
+    double* Kb = P.K + b * (long long)T * N * M;
+    double* kb = P.k + b * (long long)T * M;
+    double* Vxb = P.Vx + b * (long long)T * N;
+    double* Vxxb = P.Vxx ? P.Vxx + b * (long long)T * N * N : nullptr;
+    double* Quub = P.Quu ? P.Quu + b * (long long)T * M * M : nullptr;
+    double lims_lo[M], lims_hi[M];
+#pragma unroll
+    for (int a = 0; a < M; a++) { lims_lo[a] = use_qp ? P.lims[a] : 0.0; lims_hi[a] = use_qp ? P.lims[M + a] : 0.0; }
+
+    double V[N * N], Vx[N];            // V column-major: V[r + N c]
+    {
+        const double* cxN = tp(P.cx, b, T - 1);
+        const double* cxxN = tp(P.cxx, b, T - 1);
+        const double* cuuN = tp(P.cuu, b, T - 1);
+#pragma unroll
+        for (int e = 0; e < N; e++) { Vx[e] = cxN[e]; Vxb[(long long)(T - 1) * N + e] = Vx[e]; }
+#pragma unroll
+        for (int e = 0; e < N * N; e++) { V[e] = cxxN[e]; if (Vxxb) Vxxb[(long long)(T - 1) * N * N + e] = V[e]; }
+#pragma unroll
+        for (int e = 0; e < N * M; e++) Kb[(long long)(T - 1) * N * M + e] = 0.0;
+#pragma unroll
+        for (int e = 0; e < M; e++) kb[(long long)(T - 1) * M + e] = 0.0;
+        if (Quub)
+#pragma unroll
+            for (int e = 0; e < M * M; e++) Quub[(long long)(T - 1) * M * M + e] = cuuN[e];
+    }
+    double kw[M];
+#pragma unroll
+    for (int a = 0; a < M; a++) kw[a] = 0.0;
+    double dV0 = 0.0, dV1 = 0.0;
+    int diverge = 0;
+    StepIn<N, M> cur, nxt;
+    if (T >= 2) load_step<N, M>(cur, P, b, T - 2, use_qp);
+    for (int i = T - 2; i >= 0; i--) {
+        if (i > 0) load_step<N, M>(nxt, P, b, i - 1, use_qp);        // in flight during this step's arithmetic
+        const double* cxxi = tp(P.cxx, b, i);
+        const double* cxui = tp(P.cxu, b, i);
+        const double* cuui = tp(P.cuu, b, i);
+        // ---- W = V fx, Z = V fu
+        double W[N * N], Z[N * M];
+#pragma unroll
+        for (int c = 0; c < N; c++)
+#pragma unroll
+            for (int r = 0; r < N; r++) {
+                double acc = 0.0;
+#pragma unroll
+                for (int q = 0; q < N; q++) acc = fma(V[r + N * q], cur.fx[q + N * c], acc);
+                W[r + N * c] = acc;
+            }
+#pragma unroll
+        for (int c = 0; c < M; c++)
+#pragma unroll
+            for (int r = 0; r < N; r++) {
+                double acc = 0.0;
+#pragma unroll
+                for (int q = 0; q < N; q++) acc = fma(V[r + N * q], cur.fu[q + N * c], acc);
+                Z[r + N * c] = acc;
+            }
+        // ---- Q expansion (backward_pass.jl:240-247)
+        double Qxx[N * N], Qux[M * N], Quxr[M * N], Quu[M * M], QuuF[M * M], Qx[N], Qu[M];
+#pragma unroll
+        for (int c = 0; c < N; c++)
+#pragma unroll
+            for (int r = 0; r < N; r++) {
+                double acc = 0.0;
+#pragma unroll
+                for (int q = 0; q < N; q++) acc = fma(cur.fx[q + N * r], W[q + N * c], acc);
+                Qxx[r + N * c] = cxxi[r + N * c] + acc;
+            }
+#pragma unroll
+        for (int j = 0; j < N; j++)
+#pragma unroll
+            for (int a = 0; a < M; a++) {
+                double acc = 0.0, ff = 0.0;
+#pragma unroll
+                for (int q = 0; q < N; q++) { acc = fma(cur.fu[q + N * a], W[q + N * j], acc); ff = fma(cur.fu[q + N * a], cur.fx[q + N * j], ff); }
+                const double v = cxui[j + N * a] + acc;
+                Qux[a + M * j] = v;
+                Quxr[a + M * j] = reg2 ? v + lam * ff : v;
+            }
+#pragma unroll
+        for (int c = 0; c < M; c++)
+#pragma unroll
+            for (int a = 0; a < M; a++) {
+                double acc = 0.0, ff = 0.0;
+#pragma unroll
+                for (int q = 0; q < N; q++) { acc = fma(cur.fu[q + N * a], Z[q + N * c], acc); ff = fma(cur.fu[q + N * a], cur.fu[q + N * c], ff); }
+                const double v = cuui[a + M * c] + acc;
+                Quu[a + M * c] = v;
+                QuuF[a + M * c] = reg2 ? v + lam * ff : ((a == c) ? v + lam : v);
+            }
+#pragma unroll
+        for (int r = 0; r < N; r++) {
+            double acc = 0.0;
+#pragma unroll
+            for (int q = 0; q < N; q++) acc = fma(cur.fx[q + N * r], Vx[q], acc);
+            Qx[r] = cur.cx[r] + acc;
+        }
+#pragma unroll
+        for (int a = 0; a < M; a++) {
+            double acc = 0.0;
+#pragma unroll
+            for (int q = 0; q < N; q++) acc = fma(cur.fu[q + N * a], Vx[q], acc);
+            Qu[a] = cur.cu[a] + acc;
+        }
+        // ---- gains: Cholesky or box QP, in the oracle's arithmetic order
+        double ki[M], R[M * M], Ki[M * N];
+        unsigned fm = (1u << M) - 1u;
+        int nf = M;
+        bool failed = false;
+        if (!use_qp) {
+            int idx[M];
+#pragma unroll
+            for (int a = 0; a < M; a++) idx[a] = a;
+            if (!chol_upper_sub<M>(QuuF, M, idx, M, R, M)) failed = true;
+            else {
+#pragma unroll
+                for (int a = 0; a < M; a++) ki[a] = Qu[a];
+                chol_solve<M>(R, M, M, ki);
+#pragma unroll
+                for (int a = 0; a < M; a++) ki[a] = -ki[a];
+            }
+        } else {
+            double lo[M], up[M];
+#pragma unroll
+            for (int a = 0; a < M; a++) { lo[a] = lims_lo[a] - cur.u[a]; up[a] = lims_hi[a] - cur.u[a]; }      // :45-46
+            int nfac = 0;
+            const int res = boxqp_seq<M>(M, QuuF, M, Qu, lo, up, kw, P.qp, ki, R, M, &fm, &nfac);
+            if (res < 1) failed = true;                                                                  // :50-56
+            nf = __popc(fm);
+        }
+        if (failed) { diverge = i + 1; break; }
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+            double v[M];
+            int p = 0;
+#pragma unroll
+            for (int a = 0; a < M; a++)
+                if ((fm >> a) & 1u) v[p++] = Quxr[a + M * j];
+            if (nf > 0) chol_solve<M>(R, M, nf, v);
+            p = 0;
+#pragma unroll
+            for (int a = 0; a < M; a++) Ki[a + M * j] = ((fm >> a) & 1u) ? -v[p++] : 0.0;
+        }
+        // ---- value backup (:64-72)
+        double Quuk[M], QK[M * N];
+#pragma unroll
+        for (int a = 0; a < M; a++) {
+            double acc = 0.0;
+#pragma unroll
+            for (int c = 0; c < M; c++) acc = fma(Quu[a + M * c], ki[c], acc);
+            Quuk[a] = acc;
+        }
+        {
+            double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+            for (int a = 0; a < M; a++) { a0 = fma(ki[a], Qu[a], a0); a1 = fma(ki[a], Quuk[a], a1); }
+            dV0 += a0;
+            dV1 += 0.5 * a1;
+        }
+#pragma unroll
+        for (int j = 0; j < N; j++)
+#pragma unroll
+            for (int a = 0; a < M; a++) {
+                double acc = 0.0;
+#pragma unroll
+                for (int c = 0; c < M; c++) acc = fma(Quu[a + M * c], Ki[c + M * j], acc);
+                QK[a + M * j] = acc;
+            }
+#pragma unroll
+        for (int r = 0; r < N; r++) {
+            double t1 = 0.0, t2 = 0.0, t3 = 0.0;
+#pragma unroll
+            for (int a = 0; a < M; a++) {
+                t1 = fma(Ki[a + M * r], Quuk[a], t1);
+                t2 = fma(Ki[a + M * r], Qu[a], t2);
+                t3 = fma(Qux[a + M * r], ki[a], t3);
+            }
+            Vx[r] = ((Qx[r] + t1) + t2) + t3;
+        }
+#pragma unroll
+        for (int c = 0; c < N; c++)
+#pragma unroll
+            for (int r = 0; r < N; r++) {
+                double t1 = 0.0, t2 = 0.0, t3 = 0.0;
+#pragma unroll
+                for (int a = 0; a < M; a++) {
+                    t1 = fma(Ki[a + M * r], QK[a + M * c], t1);
+                    t2 = fma(Ki[a + M * r], Qux[a + M * c], t2);
+                    t3 = fma(Qux[a + M * r], Ki[a + M * c], t3);
+                }
+                W[r + N * c] = ((Qxx[r + N * c] + t1) + t2) + t3;
+            }
+#pragma unroll
+        for (int c = 0; c < N; c++)
+#pragma unroll
+            for (int r = 0; r < N; r++) V[r + N * c] = 0.5 * (W[r + N * c] + W[c + N * r]);
+        // ---- store
+#pragma unroll
+        for (int e = 0; e < N * M; e++) Kb[(long long)i * N * M + e] = Ki[e];
+#pragma unroll
+        for (int a = 0; a < M; a++) { kb[(long long)i * M + a] = ki[a]; kw[a] = ki[a]; }
+#pragma unroll
+        for (int r = 0; r < N; r++) Vxb[(long long)i * N + r] = Vx[r];
+        if (Vxxb)
+#pragma unroll
+            for (int e = 0; e < N * N; e++) Vxxb[(long long)i * N * N + e] = V[e];
+        if (Quub)
+#pragma unroll
+            for (int e = 0; e < M * M; e++) Quub[(long long)i * M * M + e] = Quu[e];
+        cur = nxt;
+    }
+    if (diverge > 0) {                               // outputs below the failed step stay zero (quirk Q10)
+        for (long long e = 0; e < (long long)diverge * N * M; e++) Kb[e] = 0.0;
+        for (long long e = 0; e < (long long)diverge * M; e++) kb[e] = 0.0;
+        for (long long e = 0; e < (long long)diverge * N; e++) Vxb[e] = 0.0;
+        if (Vxxb)
+            for (long long e = 0; e < (long long)diverge * N * N; e++) Vxxb[e] = 0.0;
+    }
+    if (P.Vxx1)
+#pragma unroll
+        for (int e = 0; e < N * N; e++) P.Vxx1[b * N * N + e] = (diverge > 0) ? 0.0 : V[e];
+    P.diverge[b] = diverge;
+    P.dV[2 * b] = dV0;
+    P.dV[2 * b + 1] = dV1;
+}
+
+template <int N, int M>
+int launch_small(ddp_handle_s* h, const BackParams& P) {
+    const unsigned grid = (unsigned)((P.B + 127) / 128);
+    bp_small_kernel<N, M><<<grid, 128, 0, h->stream>>>(P);
+    h->launches++;
+    return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+int launch_back_pass_small(ddp_handle_s* h, const BackParams& P, bool gps, bool* handled) {
+    *handled = false;
+    if (gps || P.T < 2) return 0;
+    int rc = 0;
+#define SMALL_CASE(NN, MM) if (P.n == NN && P.m == MM) { rc = launch_small<NN, MM>(h, P); *handled = true; return rc; }
+    SMALL_CASE(4, 1)
+    SMALL_CASE(2, 1)
+    SMALL_CASE(3, 1)
+    SMALL_CASE(4, 2)
+#undef SMALL_CASE
+    return rc;
+}

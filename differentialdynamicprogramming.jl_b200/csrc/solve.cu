@@ -341,6 +341,33 @@ int run_fwd(ddp_handle_s* h, const FwdParams& P) {
 
 extern "C" {
 
+// STEP 1 of iLQG.jl:225-229 for the built-in models: cx = Q(x - goal), cu = R u and, for the pendulum
+// on a cart, the ZoH-discretised Jacobians fx, fu (system_pendcart.jl:137-154).  For the linear model
+// the Jacobians are A and B themselves, so fx/fu must be NULL.
+int ddp_model_derivs_f64(ddp_handle_t h, const ddp_model* model, const double* x, const double* u, double* fx, double* fu,
+                         double* cx, double* cu) {
+    if (!h) return DDP_ERR_INVALID;
+    if (!model || !x || !u || !cx || !cu || !model->Q.ptr || !model->R.ptr) { h->err = "ddp_model_derivs_f64: missing argument"; return DDP_ERR_INVALID; }
+    const int n = h->n, m = h->m, T = h->T;
+    const long long B = h->B, wtot = B * T;
+    if (cudaSetDevice(h->device) != cudaSuccess) { h->err = "cudaSetDevice failed"; return DDP_ERR_CUDA; }
+    unsigned grid = (unsigned)std::min<long long>((wtot + 3) / 4, (long long)h->sm_count * 16);
+    df_cost_kernel<<<grid, 128, 0, h->stream>>>(n, m, T, B, x, u, mk(model->Q), mk(model->R), model->goal, nullptr, cx, cu);
+    h->launches++;
+    if (model->kind == DDP_MODEL_PENDCART) {
+        if (n != 4 || m != 1 || !fx || !fu) { h->err = "ddp_model_derivs_f64: pendcart needs n == 4, m == 1 and fx, fu outputs"; return DDP_ERR_INVALID; }
+        df_pendcart_kernel<<<(unsigned)((wtot + 127) / 128), 128, 0, h->stream>>>(T, B, x, u, model->p[0], model->p[1], model->p[2], model->p[3],
+                                                                                 nullptr, fx, fu);
+        h->launches++;
+    } else if (model->kind != DDP_MODEL_LINEAR) {
+        h->err = "ddp_model_derivs_f64: unknown model kind (no CPU fallback for host callbacks)";
+        return DDP_ERR_UNSUPPORTED;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { h->err = std::string("ddp_model_derivs_f64: ") + cudaGetErrorString(e); return DDP_ERR_CUDA; }
+    return DDP_OK;
+}
+
 int ddp_ilqg_solve_f64(ddp_handle_t h, const ddp_model* model, const ddp_ilqg_opts* opts, const double* x0, const double* u0,
                        double* x, double* u, double* K, double* k, double* Vx, double* Vxx1, ddp_ilqg_state* state,
                        int32_t* n_outer) {

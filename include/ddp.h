@@ -200,6 +200,12 @@ typedef struct ddp_forward_pass_args {
 
 DDP_API int ddp_forward_pass_f64(ddp_handle_t h, const ddp_model* model, const ddp_forward_pass_args* a);
 
+/* ---- derivatives of the built-in models (the reference's df callback, STEP 1 of iLQG.jl:225-229) ---- */
+/* x (n,T,B), u (m,T,B) -> cx = Q(x-goal) (n,T,B), cu = R u (m,T,B); pendcart also fx (4,4,T,B), fu (4,1,T,B)
+ * (ZoH Jacobians, system_pendcart.jl:137-154).  For the linear model fx/fu are A/B: pass NULL. */
+DDP_API int ddp_model_derivs_f64(ddp_handle_t h, const ddp_model* model, const double* x, const double* u, double* fx,
+                                 double* fu, double* cx, double* cu);
+
 /* ---- batch statistics: the vector a multi-GPU run all-reduces once per iteration --------- */
 /* stats[0]=Σcost_new, [1]=Σ(cost_old-cost_new), [2]=Σ expected reduction (α=alpha), [3]=#accepted
  * (ratio > 0), [4]=#diverged back passes, [5]=#active.  All doubles so one SUM all-reduce does. */

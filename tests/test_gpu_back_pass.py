@@ -113,3 +113,42 @@ def test_tile32x8_matches_generic_kernel(ddp):
     for a, b in ((r1[1].K, r2[1].K), (r1[1].k, r2[1].k), (r1[2], r2[2]), (r1[3], r2[3]), (r1[4], r2[4])):
         assert relerr(a, b) < 1e-10
     assert np.array_equal(r1[3], np.swapaxes(r1[3], -1, -2))          # Vxx exactly symmetric
+
+
+# ---- specialised small-system kernel (one thread per trajectory; config 3 is n=4, m=1 with lims) ----
+
+@pytest.mark.parametrize("n,m", [(4, 1), (2, 1), (3, 1), (4, 2)])
+@pytest.mark.parametrize("regType", [1, 2])
+def test_small_kernel_cholesky_and_qp(ddp, n, m, regType):
+    _check(ddp, 70, n, m, 33, regType, ltv=True, seed=40)
+    lims = np.tile(np.array([[-0.05, 0.05]]), (m, 1))
+    _check(ddp, 70, n, m, 33, regType, lims=lims, lam=1e-3, ltv=True, seed=41)
+    _check(ddp, 5, n, m, 20, regType, lims=lims, lam=1e-3, ltv=False, tv_cost=True, seed=42)
+
+
+def test_small_kernel_pendcart_lims_matches_oracle_and_generic(ddp):
+    """config 3 at test size: pendcart ZoH Jacobians, lims = +-5, regType 2 (system_pendcart.jl:197-206)."""
+    N, B = 150, 6
+    rng = np.random.default_rng(1)
+    om = O.PendcartModel()
+    lims = np.array([[-5.0, 5.0]])
+    xs, us, fxs, fus, cxs, cus = [], [], [], [], [], []
+    for b in range(B):
+        x0 = np.array([np.pi - 0.6 + 0.2 * rng.uniform(-1, 1), 0, 0, 0])
+        u = 6.0 * rng.standard_normal((N, 1))                       # large controls so that many steps clamp
+        x, un, _ = O.forward_pass(O.GaussianPolicy.empty(), x0, u, None, 1, om.f, om.costfun, lims)
+        fx, fu, _, _, _, cx, cu, cxx, cxu, cuu = om.df(x, un)
+        xs.append(x); us.append(un); fxs.append(fx); fus.append(fu); cxs.append(cx); cus.append(cu)
+    xs, us, fxs, fus, cxs, cus = map(np.array, (xs, us, fxs, fus, cxs, cus))
+    args = (cxs, cus, cxx, cxu, cuu, fxs, fus, 1.0, 2, lims, xs, us)
+    r1 = ddp.back_pass(*args)
+    r2 = ddp.back_pass(*args, force_generic=True)
+    nclamped = 0
+    for b in range(B):
+        d0, p0, Vx0, Vxx0, dV0 = O.back_pass(cxs[b], cus[b], cxx, cxu, cuu, fxs[b], fus[b], 1.0, 2, lims, xs[b], us[b])
+        for r in (r1, r2):
+            assert r[0][b] == d0 == 0
+            assert relerr(r[1].K[b], p0.K) < TOL and relerr(r[1].k[b], p0.k) < TOL and relerr(r[2][b], Vx0) < TOL and relerr(r[3][b], Vxx0) < TOL
+            assert np.array_equal(r[1].K[b] == 0, p0.K == 0)        # clamped steps have K = 0: the active sets agree exactly
+        nclamped += int(np.sum(np.all(p0.K[:-1] == 0, axis=(1, 2))))
+    assert nclamped > 0
