@@ -595,6 +595,94 @@ def iLQG(f, costfun, df, x0, u0, *, lims=None, alpha=None, tol_fun=1e-7, tol_gra
 
 
 # ---------------------------------------------------------------------------------------------
+# iLQGkl  (iLQGkl.jl:25-183, 238-252), single-KL-constraint branch
+# ---------------------------------------------------------------------------------------------
+
+
+def iLQGkl(dynamics, costfun, derivs, x0, traj_prev: GaussianPolicy, fx_model, R1, *, kl_step=1.0, lims=None, max_iter=50,
+           etabracket=(1e-8, 1.0, 1e16), del0=1e-4, cost=None, max_eta_retries=200, force_generic=False):
+    """``iLQGkl(dynamics,costfun,derivs,x0,traj_prev,model;kw...)`` -- iLQGkl.jl:25-183 + 238-252.
+
+    Every sweep runs on the device (``ddp_back_pass_gps_f64``, ``ddp_forward_pass_f64``, ``ddp_kl_div_f64``,
+    ``ddp_model_derivs_f64``); only the scalar η-bracket update of ``calc_η`` (klutils.jl:110-130) and the
+    loop control are host code.  ``fx_model``/``R1`` stand for the un-vendored ``model`` argument
+    (what ``df(model,x,u)`` and ``covariance(model,x,u)`` return, forward_pass.jl:38,42).  ``x0`` is the
+    pre-rolled trajectory (N,n) and ``cost`` its cost, as the reference requires (iLQGkl.jl:63-70).
+    Unbatched only (one trajectory), like the reference.
+    """
+    model = _model_of(dynamics, costfun)
+    u = np.array(traj_prev.k, dtype=np.float64)                     # :47
+    x = np.asarray(x0, dtype=np.float64)
+    N, m = u.shape
+    n = x.shape[1]
+    if x.ndim != 2 or x.shape[0] != N:
+        raise RuntimeError("pre-rolled initial trajectory must be of correct length (size(x0,2) == N)")
+    if cost is None:
+        raise RuntimeError("Initial trajectory supplied, initial cost must also be supplied")
+    eta = np.array(etabracket, dtype=np.float64)
+    prev0 = GaussianPolicy(N, n, m, traj_prev.K, np.zeros_like(traj_prev.k), traj_prev.Sigma, traj_prev.Sigmai)   # :52 k := 0
+    # derivatives once, outside the loop (:88, quirk Q9)
+    eng = Engine(n, m, N, 1, force_generic=force_generic)
+    M, keep = _pack_model(eng, model, 1, N, n, m)
+    dx, du = eng.upload(x[None]), eng.upload(u[None])
+    cxd, cud = eng.empty((1, N, n)), eng.empty((1, N, m))
+    fxd = eng.empty((1, N, n, n)) if model.kind == 2 else None
+    fud = eng.empty((1, N, n, m)) if model.kind == 2 else None
+    eng._ck(eng.lib.ddp_model_derivs_f64(eng.h, C.byref(M), dx.ptr, du.ptr, fxd.ptr if fxd else None, fud.ptr if fud else None,
+                                         cxd.ptr, cud.ptr))
+    eng.synchronize()
+    cx, cu = cxd.numpy()[0], cud.numpy()[0]
+    if model.kind == 2:
+        fx, fu = np.swapaxes(fxd.numpy()[0], -1, -2), np.swapaxes(fud.numpy()[0], -1, -2)
+    else:
+        fx, fu = np.asarray(model.A), np.asarray(model.B)
+    cxx, cuu, cxu = model.Q, model.R, np.zeros((n, m))
+    trace = {key: [] for key in ("cost", "improvement", "reduce_ratio", "divergence", "eta")}
+    trace["cost"].append((0, float(np.sum(cost))))
+    satisfied = False
+    traj_new = xnew = unew = costnew = Vx = Vxx = None
+    it = 0
+    for it in range(1, max_iter + 1):                               # :93
+        diverge, retries = 1, 0
+        while diverge > 0:                                          # :97
+            diverge, traj_new, Vx, Vxx, dV = back_pass_gps(cx, cu, cxx, cxu, cuu, fx, fu, lims, x, u, (prev0, eta),
+                                                           force_generic=force_generic)
+            if diverge > 0:
+                eta[1] += del0                                      # :104
+                del0 *= 2
+                retries += 1
+                if retries > max_eta_retries:
+                    raise RuntimeError("eta retry loop did not terminate")
+        xnew, unew, costnew = forward_pass(traj_new, x[0], u, x, 1.0, dynamics, costfun, lims, force_generic=force_generic)   # :134
+        kl_t, divergence = kl_div_wiki(xnew, x, fx_model, R1, traj_new, prev0)                                               # :135, :143
+        dcost = float(np.sum(cost) - costnew)
+        expected = -(dV[0] + dV[1])                                 # :138
+        # calc_η (klutils.jl:110-130)
+        if not (kl_step > 0):
+            satisfied, divergence = True, 0.0
+        else:
+            violation = divergence - kl_step
+            satisfied = abs(violation) < 0.1 * kl_step
+            if not satisfied:
+                if violation < 0:
+                    eta[2] = eta[1]
+                    eta[1] = max(math.sqrt(eta[0] * eta[2]), 0.1 * eta[2])
+                else:
+                    eta[0] = eta[1]
+                    eta[1] = min(math.sqrt(eta[0] * eta[2]), 10.0 * eta[0])
+        trace["improvement"].append((it, dcost))
+        trace["cost"].append((it, float(costnew)))
+        trace["reduce_ratio"].append((it, dcost / expected))
+        trace["divergence"].append((it, float(divergence)))
+        trace["eta"].append((it, float(eta[1])))
+        if satisfied or eta[1] > 0.999 * eta[2]:                    # :173-181
+            break
+    traj_new.k = unew.copy()                                        # :240-241 (quirk Q11)
+    trace.update(iters=it, satisfied=satisfied, etabracket=eta)
+    return xnew, unew, traj_new, Vx, Vxx, costnew, trace
+
+
+# ---------------------------------------------------------------------------------------------
 # one end-to-end iteration on host buffers (the bench's e2e path)
 # ---------------------------------------------------------------------------------------------
 

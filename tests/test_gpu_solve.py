@@ -98,3 +98,31 @@ def test_iter_host_matches_separate_calls(ddp):
     assert np.array_equal(it.bufs["xnew"], xn) and np.array_equal(it.bufs["unew"], un)
     assert np.array_equal(it.bufs["cost"], cn) and np.array_equal(it.bufs["dV"], dV)
     it.close()
+
+
+@pytest.mark.parametrize("kl_step", [1.0, 20.0])
+def test_ilqgkl_matches_oracle(ddp, kl_step):
+    """iLQGkl single-KL-constraint branch (iLQGkl.jl:93-183): same eta sequence, iteration count and result."""
+    from helpers import rollout
+    n, m, N = 6, 2, 40
+    rng = np.random.default_rng(31)
+    A, Bm, Q, R = make_lq(rng, n, m, h=0.1)
+    u = 0.1 * rng.standard_normal((N, m))
+    x = rollout(A, Bm, np.ones(n), u)
+    d, p, _, _, _ = O.back_pass(x @ Q.T, u @ R.T, Q, np.zeros((n, m)), R, A, Bm, 1.0, 1, None, x, u)
+    Sigi = p.Sigmai.copy()
+    Sig = np.array([np.linalg.inv(s) for s in Sigi])
+    R1 = 1e-3 * np.eye(n)
+    om = O.LinearModel(A, Bm, Q, R)
+    cost0 = om.costfun(x, u)
+    prev_o = O.GaussianPolicy(N, n, m, p.K.copy(), u.copy(), Sig.copy(), Sigi.copy())
+    ro = O.iLQGkl(om.f, om.costfun, lambda xx, uu: om.df(xx, uu, time_varying=True), x, prev_o, A, R1, kl_step=kl_step, cost=cost0)
+    model = ddp.LinearModel(A, Bm, Q, R)
+    prev_d = ddp.GaussianPolicy(N, n, m, p.K.copy(), u.copy(), Sig.copy(), Sigi.copy())
+    rd = ddp.iLQGkl(model.f, model.costfun, model.df, x, prev_d, A, R1, kl_step=kl_step, cost=cost0)
+    to, td = ro[6], rd[6]
+    assert td["iters"] == to["iters"] and td["satisfied"] == to["satisfied"]
+    assert np.allclose([e for _, e in td["eta"]], [e for _, e in to["eta"]], rtol=1e-9)
+    assert np.allclose([e for _, e in td["divergence"]], [e for _, e in to["divergence"]], rtol=1e-7)
+    assert relerr(rd[0], ro[0]) < 1e-7 and relerr(rd[1], ro[1]) < 1e-7 and abs(rd[5] - np.sum(ro[5])) < 1e-8 * abs(np.sum(ro[5]))
+    assert relerr(rd[2].K, ro[2].K) < 1e-7 and relerr(rd[2].Sigma, ro[2].Sigma) < 1e-7
