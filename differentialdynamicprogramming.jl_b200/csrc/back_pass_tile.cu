@@ -80,9 +80,33 @@ __device__ __forceinline__ double rcp_nr(double d) {
     return y;
 }
 
+// In-place Gauss-Jordan inverse of an 8 x 8 matrix held in the DMMA accumulator layout (lane (g,q) holds
+// A[g][2q], A[g][2q+1]); pivots and pivot rows/columns are broadcast by shuffles.  Returns false when a
+// pivot is <= 0 (or NaN): for a symmetric matrix these are the Cholesky pivots squared, i.e. the
+// reference's `cholesky` failure condition.
+__device__ __forceinline__ bool gj_inverse8(double& I0, double& I1, int lane, int g, int q) {
+    bool ok = true;
+#pragma unroll
+    for (int p = 0; p < 8; p++) {
+        const double own = (p & 1) ? I1 : I0;
+        const double d = shf(own, 4 * p + (p >> 1));             // A[p][p]
+        const double colp = shf(own, (lane & ~3) | (p >> 1));     // A[g][p]
+        const double rp0 = shf(I0, 4 * p + q), rp1 = shf(I1, 4 * p + q);   // A[p][2q], A[p][2q+1]
+        if (!(d > 0.0)) ok = false;
+        const double r = rcp_nr(d);
+        const double n0 = ((2 * q == p) ? 1.0 : rp0) * r, n1 = ((2 * q + 1 == p) ? 1.0 : rp1) * r;
+        if (g == p) { I0 = n0; I1 = n1; }
+        else {
+            I0 = fma(-colp, n0, (2 * q == p) ? 0.0 : I0);
+            I1 = fma(-colp, n1, (2 * q + 1 == p) ? 0.0 : I1);
+        }
+    }
+    return ok;
+}
+
 constexpr int gidx(int at, int bt) { return at * 5 - (at * (at - 1)) / 2 + (bt - at); }   // upper-tile index, 15 tiles
 
-template <bool LTV>
+template <bool LTV, bool GPS>
 __global__ void __launch_bounds__(WPB * 32, 2) bp_tile32x8_kernel(BackParams P) {
     extern __shared__ double smem_raw[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -105,8 +129,11 @@ __global__ void __launch_bounds__(WPB * 32, 2) bp_tile32x8_kernel(BackParams P) 
 
     for (long long b = (long long)blockIdx.x * WPB + w; b < P.B; b += warps_total) {
         if (P.active && !P.active[b]) continue;
-        const double lam = P.lambda[b];
-        const bool reg2 = (P.reg_type == 2);
+        const double lam = GPS ? 0.0 : P.lambda[b];
+        const bool reg2 = !GPS && (P.reg_type == 2);
+        const double eta = GPS ? P.eta[b] : 1.0, ieta = 1.0 / eta;
+        double* Quuib = (GPS && P.Quui) ? P.Quui + b * (long long)N * 64 : nullptr;
+        const bool has_kp = GPS && (P.kp.p != nullptr);
         double* Kb = P.K + b * (long long)N * 256;
         double* kb = P.k + b * (long long)N * 8;
         double* Vxb = P.Vx + b * (long long)N * 32;
@@ -131,7 +158,14 @@ __global__ void __launch_bounds__(WPB * 32, 2) bp_tile32x8_kernel(BackParams P) 
             }
             for (int c = lane; c < 128; c += 32) st2(Kb + (long long)(N - 1) * 256 + 2 * c, 0.0, 0.0);
             if (lane < 8) kb[(long long)(N - 1) * 8 + lane] = 0.0;
-            if (Quub) st2(Quub + (long long)(N - 1) * 64 + 2 * lane, cuuN[2 * lane], cuuN[2 * lane + 1]);
+            if (GPS) {                              // Quu(N) = cuu/eta + Sigma_i_prev(N), Sigma(N) = inv  (backward_pass.jl:282-283)
+                const double* SiN = tp(P.Sip, b, N - 1);
+                double T0 = cuuN[g + 8 * (2 * q)] / eta + SiN[g + 8 * (2 * q)];
+                double T1 = cuuN[g + 8 * (2 * q + 1)] / eta + SiN[g + 8 * (2 * q + 1)];
+                if (Quub) { Quub[(long long)(N - 1) * 64 + g + 8 * (2 * q)] = T0; Quub[(long long)(N - 1) * 64 + g + 8 * (2 * q + 1)] = T1; }
+                gj_inverse8(T0, T1, lane, g, q);
+                if (Quuib) { Quuib[(long long)(N - 1) * 64 + g + 8 * (2 * q)] = T0; Quuib[(long long)(N - 1) * 64 + g + 8 * (2 * q + 1)] = T1; }
+            } else if (Quub) st2(Quub + (long long)(N - 1) * 64 + 2 * lane, cuuN[2 * lane], cuuN[2 * lane + 1]);
         }
         int buf = 0;
         if (LTV) {
@@ -179,6 +213,18 @@ __global__ void __launch_bounds__(WPB * 32, 2) bp_tile32x8_kernel(BackParams P) 
             const double* cxxi = tp(P.cxx, b, i);
             const double* cxui = tp(P.cxu, b, i);
             const double* cuui = tp(P.cuu, b, i);
+            // KL terms: fragments of the previous policy, K_prev[2q..2q+1][8t+g], Sigma_i_prev[g][2q..2q+1]
+            double2 kpf[4];
+            double Sg0 = 0.0, Sg1 = 0.0, kp0 = 0.0, kp1 = 0.0;
+            if (GPS) {
+                const double* Kpi = tp(P.Kp, b, i) + 8 * g + 2 * q;
+#pragma unroll
+                for (int t = 0; t < 4; t++) kpf[t] = ld2(Kpi + 64 * t);
+                const double* Sii = tp(P.Sip, b, i);
+                Sg0 = Sii[g + 8 * (2 * q)];
+                Sg1 = Sii[g + 8 * (2 * q + 1)];
+                if (has_kp) { const double* kpi = tp(P.kp, b, i); kp0 = kpi[2 * q]; kp1 = kpi[2 * q + 1]; }
+            }
             // dump Vxx(i+1) history if requested (sV is stable here)
             if (Vxxb && i < N - 2) {
                 for (int c = lane; c < 512; c += 32) {
@@ -253,35 +299,58 @@ __global__ void __launch_bounds__(WPB * 32, 2) bp_tile32x8_kernel(BackParams P) 
 #pragma unroll
                     for (int bt = at; bt < 5; bt++) dmma(G[gidx(at, bt)][0], G[gidx(at, bt)][1], W[at][p][1], ff[bt].y);
             }
+            // ---- KL augmentation (backward_pass.jl:295-301): Q/eta + KL terms, formed in fragment layouts
+            double2 sf[4];
+            double Sik_own = 0.0, Sik0 = 0.0, Sik1 = 0.0;
+            if (GPS) {
+#pragma unroll
+                for (int t = 0; t < 15; t++) { G[t][0] *= ieta; G[t][1] *= ieta; }
+#pragma unroll
+                for (int t = 0; t < 4; t++) sf[t] = make_double2(0.0, 0.0);        // S = Sigma_i K_prev : sf[t] = S[2q..2q+1][8t+g]
+#pragma unroll
+                for (int t = 0; t < 4; t++) dmma(sf[t].x, sf[t].y, kpf[t].x, Sg0);
+#pragma unroll
+                for (int t = 0; t < 4; t++) dmma(sf[t].x, sf[t].y, kpf[t].y, Sg1);
+#pragma unroll
+                for (int at = 0; at < 4; at++)                                     // Qxx += K_prev' S
+#pragma unroll
+                    for (int bt = at; bt < 4; bt++) dmma(G[gidx(at, bt)][0], G[gidx(at, bt)][1], kpf[at].x, sf[bt].x);
+#pragma unroll
+                for (int at = 0; at < 4; at++)
+#pragma unroll
+                    for (int bt = at; bt < 4; bt++) dmma(G[gidx(at, bt)][0], G[gidx(at, bt)][1], kpf[at].y, sf[bt].y);
+                if (has_kp) {                                                      // Sigma_i k_prev, entry g per group
+                    double t = fma(Sg1, kp1, Sg0 * kp0);
+                    t += shx(t, 1);
+                    t += shx(t, 2);
+                    Sik_own = t;
+                    Sik0 = shf(Sik_own, c0src);
+                    Sik1 = shf(Sik_own, c1src);
+                }
+            }
             // ---- fragments straight from the accumulators:
             //      qf[t]  = Qux[2q..2q+1][8t+g]   (unregularised), qr[t] = Qux_reg, (U0,U1) = Quu[g][2q..2q+1]
             double2 qf[4], qr[4];
 #pragma unroll
             for (int t = 0; t < 4; t++) {
                 qf[t] = make_double2(G[gidx(t, 4)][0], G[gidx(t, 4)][1]);
+                if (GPS) { qf[t].x -= sf[t].x; qf[t].y -= sf[t].y; }              // cxukl = -Sigma_i K_prev
                 qr[t] = reg2 ? make_double2(fma(lam, FF[t][0], qf[t].x), fma(lam, FF[t][1], qf[t].y)) : qf[t];
             }
-            const double U0 = G[gidx(4, 4)][0], U1 = G[gidx(4, 4)][1];
+            double U0 = G[gidx(4, 4)][0], U1 = G[gidx(4, 4)][1];
+            if (GPS) {                                        // Quu/eta + Sigma_i, then 0.5 (Quu + Quu')  (:297, :301)
+                U0 += Sg0;
+                U1 += Sg1;
+                const int s0 = 4 * (2 * q) + (g >> 1), s1 = 4 * (2 * q + 1) + (g >> 1);
+                const double a00 = shf(U0, s0), a01 = shf(U1, s0), a10 = shf(U0, s1), a11 = shf(U1, s1);
+                U0 = 0.5 * (U0 + ((g & 1) ? a01 : a00));      // Quu[2q][g]
+                U1 = 0.5 * (U1 + ((g & 1) ? a11 : a10));      // Quu[2q+1][g]
+            }
             double I0, I1;                                   // QuuF, inverted in place below
             if (reg2) { I0 = fma(lam, FF[4][0], U0); I1 = fma(lam, FF[4][1], U1); }
             else { I0 = U0 + ((g == 2 * q) ? lam : 0.0); I1 = U1 + ((g == 2 * q + 1) ? lam : 0.0); }
             // ---- Gauss-Jordan inverse of QuuF in the accumulator layout; pivot p <= 0  <=>  Cholesky fails
-            bool ok = true;
-#pragma unroll
-            for (int p = 0; p < 8; p++) {
-                const double own = (p & 1) ? I1 : I0;
-                const double d = shf(own, 4 * p + (p >> 1));             // A[p][p]
-                const double colp = shf(own, (lane & ~3) | (p >> 1));     // A[g][p]
-                const double rp0 = shf(I0, 4 * p + q), rp1 = shf(I1, 4 * p + q);   // A[p][2q], A[p][2q+1]
-                if (!(d > 0.0)) ok = false;
-                const double r = rcp_nr(d);
-                const double n0 = ((2 * q == p) ? 1.0 : rp0) * r, n1 = ((2 * q + 1 == p) ? 1.0 : rp1) * r;
-                if (g == p) { I0 = n0; I1 = n1; }
-                else {
-                    I0 = fma(-colp, n0, (2 * q == p) ? 0.0 : I0);
-                    I1 = fma(-colp, n1, (2 * q + 1 == p) ? 0.0 : I1);
-                }
-            }
+            const bool ok = gj_inverse8(I0, I1, lane, g, q);
             if (!ok) { diverge = i + 1; break; }
             // ---- K' = -Qux_reg' Minv : kf[t] = K[2q..2q+1][8t+g]
             double2 kf[4];
@@ -294,7 +363,7 @@ __global__ void __launch_bounds__(WPB * 32, 2) bp_tile32x8_kernel(BackParams P) 
 #pragma unroll
             for (int t = 0; t < 4; t++) { kf[t].x = -kf[t].x; kf[t].y = -kf[t].y; }
             // ---- k = -Minv Qu, Quu k   (group g owns entry g; entries 2q, 2q+1 are fetched by shuffle)
-            const double Qu_own = cuv + fv[4];
+            const double Qu_own = GPS ? fma(cuv + fv[4], ieta, -Sik_own) : (cuv + fv[4]);     // Qu/eta + cukl, cukl = -Sigma_i k_prev
             const double Qu0 = shf(Qu_own, c0src), Qu1 = shf(Qu_own, c1src);
             double ks = fma(I1, Qu1, I0 * Qu0);
             ks += shx(ks, 1);
@@ -323,7 +392,17 @@ __global__ void __launch_bounds__(WPB * 32, 2) bp_tile32x8_kernel(BackParams P) 
                 sacc = fma(qf[t].y, k1, sacc);
                 sacc += shx(sacc, 1);
                 sacc += shx(sacc, 2);
-                vxn[t] = (cxv[t] + fv[t]) + sacc;
+                double qxv = cxv[t] + fv[t];
+                if (GPS) {                                    // Qx/eta + cxkl, cxkl = K_prev' Sigma_i k_prev
+                    qxv *= ieta;
+                    if (has_kp) {
+                        double c = fma(kpf[t].y, Sik1, kpf[t].x * Sik0);
+                        c += shx(c, 1);
+                        c += shx(c, 2);
+                        qxv += c;
+                    }
+                }
+                vxn[t] = qxv + sacc;
             }
             {
                 double d0 = k_own * Qu_own, d1 = k_own * Quuk_own;        // one term per group; sum over g
@@ -345,6 +424,10 @@ __global__ void __launch_bounds__(WPB * 32, 2) bp_tile32x8_kernel(BackParams P) 
                 if (Quub) {
                     Quub[(long long)i * 64 + g + 8 * (2 * q)] = U0;
                     Quub[(long long)i * 64 + g + 8 * (2 * q + 1)] = U1;
+                }
+                if (Quuib) {                                  // Sigma = inv(Quu)  (backward_pass.jl:346)
+                    Quuib[(long long)i * 64 + g + 8 * (2 * q)] = I0;
+                    Quuib[(long long)i * 64 + g + 8 * (2 * q + 1)] = I1;
                 }
             }
             // ---- step 4: Vxx = Qxx + K' M1 + Qux' K  (upper 10 tiles), all operands in registers
@@ -433,20 +516,27 @@ bool aligned16(const TensorD& t) { return ((uintptr_t)t.p % 16 == 0) && (t.sb % 
 
 int launch_back_pass_tile(ddp_handle_s* h, const BackParams& P, bool gps, bool* handled) {
     *handled = false;
-    if (gps || P.n != 32 || P.m != 8 || P.lims != nullptr || P.T < 2) return 0;
+    if (P.n != 32 || P.m != 8 || P.lims != nullptr || P.T < 2) return 0;
     if (!aligned16(P.fx) || !aligned16(P.fu) || !aligned16(P.cxx)) return 0;
     if (((uintptr_t)P.K % 16) || (P.Vxx && ((uintptr_t)P.Vxx % 16)) || (P.Vxx1 && ((uintptr_t)P.Vxx1 % 16))) return 0;
+    if (gps && !aligned16(P.Kp)) return 0;
     const bool ltv = (P.fx.st != 0 || P.fu.st != 0);
     const size_t bytes = (size_t)(ltv ? WARP_DOUBLES_LTV : WARP_DOUBLES) * sizeof(double) * WPB;
-    cudaError_t e;
-    if (ltv) e = cudaFuncSetAttribute(bp_tile32x8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    else e = cudaFuncSetAttribute(bp_tile32x8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    if (e != cudaSuccess) return (int)e;
     long long grid = (long long)h->sm_count * 2;
     long long need = (P.B + WPB - 1) / WPB;
     if (grid > need) grid = need;
-    if (ltv) bp_tile32x8_kernel<true><<<(unsigned)grid, WPB * 32, bytes, h->stream>>>(P);
-    else bp_tile32x8_kernel<false><<<(unsigned)grid, WPB * 32, bytes, h->stream>>>(P);
+    cudaError_t e = cudaSuccess;
+#define LAUNCH_TILE(L, G)                                                                                                \
+    do {                                                                                                                 \
+        e = cudaFuncSetAttribute(bp_tile32x8_kernel<L, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);     \
+        if (e == cudaSuccess) bp_tile32x8_kernel<L, G><<<(unsigned)grid, WPB * 32, bytes, h->stream>>>(P);               \
+    } while (0)
+    if (ltv && gps) LAUNCH_TILE(true, true);
+    else if (ltv) LAUNCH_TILE(true, false);
+    else if (gps) LAUNCH_TILE(false, true);
+    else LAUNCH_TILE(false, false);
+#undef LAUNCH_TILE
+    if (e != cudaSuccess) return (int)e;
     h->launches++;
     *handled = true;
     return (int)cudaGetLastError();

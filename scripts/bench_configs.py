@@ -83,7 +83,7 @@ def c4(B):
     gp = L.GpsArgs(); gp.K_prev, gp.Sigi_prev = tn(Kp, T * n * m, n * m), tn(Sip, T * m * m, m * m); gp.eta = eta.data_ptr(); gp.Quui = Quui.data_ptr()
     t_g = timeit(lambda: eng._ck(eng.lib.ddp_back_pass_gps_f64(eng.h, C.byref(ba), C.byref(gp))), reps=2)
     print(json.dumps(dict(config="C4 back_pass_gps on C2's system (eta=1)", batch=B, gps_back_ms=t_g, ms_scaled_to_65536=t_g * 65536 / B,
-                          diverged=int((dv > 0).sum().item()), note="KL-augmented sweep currently runs the generic (shared-memory) kernel")))
+                          diverged=int((dv > 0).sum().item()), variant=eng.kernel_variant)))
 
 
 if __name__ == "__main__":

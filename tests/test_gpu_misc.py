@@ -202,3 +202,25 @@ def test_forward_fast_pendcart(ddp):
         x0_, u0_, c0_ = O.forward_pass(pols[b][0], x0[b], us[b], xs[b], 0.7, om.f, om.costfun, lims)
         assert relerr(xn[b], x0_) < TOL and relerr(un[b], u0_) < TOL and relerr(ct[b], c0_) < TOL
         assert relerr(xg[b], x0_) < TOL and relerr(cg[b], c0_) < TOL
+
+
+@pytest.mark.parametrize("tv", [False, True])
+@pytest.mark.parametrize("with_kprev", [True, False])
+def test_back_pass_gps_tile32x8(ddp, tv, with_kprev):
+    """KL-augmented sweep on the n=32, m=8 DMMA kernel (LTI and LTV), vs the oracle and the generic kernel."""
+    n, m, N = 32, 8, 14
+    A, Bm, Q, R, x, u, cx, cu, prev = _prev_policy(n, m, N, 13)
+    if not with_kprev:
+        prev.k = np.zeros_like(prev.k)                       # what iLQGkl.jl:52 does
+    eta = np.array([1e-8, 1.7, 1e16])
+    rep = (lambda a: np.tile(a, (N, 1, 1))) if tv else (lambda a: a)
+    repo = lambda a: np.tile(a, (N, 1, 1))
+    d0, p0, Vx0, Vxx0, dV0 = O.back_pass_gps(cx, cu, repo(Q), repo(np.zeros((n, m))), repo(R), repo(A), repo(Bm), None, x, u,
+                                             (O.grad_kl(prev), eta))
+    gp = ddp.GaussianPolicy(N, n, m, prev.K, prev.k, prev.Sigma, prev.Sigmai)
+    for generic in (False, True):
+        d1, p1, Vx1, Vxx1, dV1 = ddp.back_pass_gps(cx, cu, rep(Q), rep(np.zeros((n, m))), rep(R), rep(A), rep(Bm), None, x, u,
+                                                   (gp, eta), force_generic=generic)
+        assert d0 == d1 == 0
+        for a, b in ((p1.K, p0.K), (p1.k, p0.k), (Vx1, Vx0), (Vxx1, Vxx0), (dV1, dV0), (p1.Sigmai, p0.Sigmai), (p1.Sigma, p0.Sigma)):
+            assert relerr(a, b) < TOL
