@@ -308,10 +308,10 @@ def main_gpu(args):
         # free the device-resident working set that the e2e path does not use
         eng_e = ddp.Engine(n, m, T, Be, device=local_rank)
         eng_e.set_stream(torch.cuda.current_stream().cuda_stream)
-        it = ddp.HostIteration(eng_e, np.zeros((n, n)), np.zeros((m, m)), reg_type=1, alpha=1.0, chunk=args.chunk)
+        it = ddp.HostIteration(eng_e, np.zeros((n, n)), np.zeros((m, m)), reg_type=1, alpha=1.0, chunk=args.chunk, device_derivs=True)
         it.Q[:] = Q.cpu().numpy(); it.R[:] = R.cpu().numpy()
         it.args.q_diagonal = 1
-        for name, src in (("fx", fx), ("fu", fu), ("cx", cx), ("cu", cu), ("x", x), ("u", u), ("lam", lam)):
+        for name, src in (("fx", fx), ("fu", fu), ("x", x), ("u", u), ("lam", lam)):
             it.bufs[name][...] = src[:Be].cpu().numpy()
         e_steps = max(1, min(args.steps, args.e2e_steps))
         it.run()                                       # warm-up (allocates the chunk pipeline)
@@ -332,7 +332,7 @@ def main_gpu(args):
             bool(np.allclose(it.bufs["cost"], cost[:Be].cpu().numpy(), rtol=1e-12, atol=0))
         e2e = dict(value=world * (Be / BATCH) * 1e3 / e_ms, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                    ms_per_step=e_ms, steps=e_steps, batch_per_gpu=Be, chunk=args.chunk or 4096,
-                   api="ddp_ilqg_iter_host_f64 (pinned host buffers in, results in host memory out; policy K stays on the device)",
+                   api="ddp_ilqg_iter_host_f64: x,u,fx,fu,lambda from pinned host memory -> df (cx=Qx, cu=Ru) + backward + forward on the device -> xnew,unew,cost,dV,diverge in host memory; policy K stays on the device",
                    matches_device_path=ok)
         it.close()
         eng_e.close()

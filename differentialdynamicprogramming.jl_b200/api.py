@@ -694,7 +694,7 @@ class HostIteration:
     FIELDS_IN = ("fx", "fu", "cx", "cu", "x", "u", "lam")
     FIELDS_OUT = ("xnew", "unew", "cost", "dV")
 
-    def __init__(self, eng: Engine, Q, R, cxu=None, reg_type=1, alpha=1.0, chunk=0):
+    def __init__(self, eng: Engine, Q, R, cxu=None, reg_type=1, alpha=1.0, chunk=0, device_derivs=False):
         self.eng = eng
         n, m, T, B = eng.n, eng.m, eng.T, eng.B
         shapes = dict(fx=(B, n, n), fu=(B, m, n), cx=(B, T, n), cu=(B, T, m), x=(B, T, n), u=(B, T, m), lam=(B,),
@@ -710,6 +710,8 @@ class HostIteration:
         self.args = L.IterHostArgs()
         for name in self.FIELDS_IN + self.FIELDS_OUT + ("diverge",):
             setattr(self.args, name, self.bufs[name].ctypes.data)
+        if device_derivs:            # cx = Qx, cu = Ru are formed on the device from x, u (the reference's df step)
+            self.args.cx = self.args.cu = None
         self.args.Q, self.args.R, self.args.cxu = self.Q.ctypes.data, self.R.ctypes.data, self.cxu.ctypes.data
         self.args.reg_type, self.args.alpha, self.args.chunk = reg_type, alpha, chunk
         self.args.q_diagonal = 1 if np.count_nonzero(self.Q - np.diag(np.diagonal(self.Q))) == 0 else 0

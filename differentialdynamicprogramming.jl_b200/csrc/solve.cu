@@ -578,7 +578,7 @@ extern "C" {
 
 int ddp_ilqg_iter_host_f64(ddp_handle_t h, ddp_iter_host_args* a) {
     if (!h) return DDP_ERR_INVALID;
-    if (!a || !a->fx || !a->fu || !a->cx || !a->cu || !a->x || !a->u || !a->lambda || !a->Q || !a->R || !a->cxu || !a->xnew ||
+    if (!a || !a->fx || !a->fu || ((a->cx == nullptr) != (a->cu == nullptr)) || !a->x || !a->u || !a->lambda || !a->Q || !a->R || !a->cxu || !a->xnew ||
         !a->unew || !a->cost || !a->dV || !a->diverge) {
         h->err = "ddp_ilqg_iter_host_f64: missing argument";
         return DDP_ERR_INVALID;
@@ -593,6 +593,7 @@ int ddp_ilqg_iter_host_f64(ddp_handle_t h, ddp_iter_host_args* a) {
     long long h2d = 0, d2h = 0;
     ModelD M{};
     IterCache* C = nullptr;
+    const bool host_derivs = (a->cx != nullptr);   // NULL: cx = Qx, cu = Ru are formed on the device (the reference's df step)
 
     CUS(cudaSetDevice(h->device));
     if (h->cache && static_cast<IterCache*>(h->cache)->chunk != chunk) { h->cache_free(h->cache); h->cache = nullptr; }
@@ -629,16 +630,25 @@ int ddp_ilqg_iter_host_f64(ddp_handle_t h, ddp_iter_host_args* a) {
             if (c >= NS) CUS(cudaStreamWaitEvent(s_in, ev_cp[si], 0));
             CUS(cudaMemcpyAsync(s.fx, a->fx + b0 * nn, nb * nn * 8, cudaMemcpyHostToDevice, s_in));
             CUS(cudaMemcpyAsync(s.fu, a->fu + b0 * nm, nb * nm * 8, cudaMemcpyHostToDevice, s_in));
-            CUS(cudaMemcpyAsync(s.cx, a->cx + b0 * Tn, nb * Tn * 8, cudaMemcpyHostToDevice, s_in));
-            CUS(cudaMemcpyAsync(s.cu, a->cu + b0 * Tm, nb * Tm * 8, cudaMemcpyHostToDevice, s_in));
+            if (host_derivs) {
+                CUS(cudaMemcpyAsync(s.cx, a->cx + b0 * Tn, nb * Tn * 8, cudaMemcpyHostToDevice, s_in));
+                CUS(cudaMemcpyAsync(s.cu, a->cu + b0 * Tm, nb * Tm * 8, cudaMemcpyHostToDevice, s_in));
+                h2d += (long long)nb * (long long)(Tn + Tm) * 8;
+            }
             CUS(cudaMemcpyAsync(s.x, a->x + b0 * Tn, nb * Tn * 8, cudaMemcpyHostToDevice, s_in));
             CUS(cudaMemcpyAsync(s.u, a->u + b0 * Tm, nb * Tm * 8, cudaMemcpyHostToDevice, s_in));
             CUS(cudaMemcpyAsync(s.lam, a->lambda + b0, nb * 8, cudaMemcpyHostToDevice, s_in));
-            h2d += (long long)nb * (long long)(nn + nm + 2 * Tn + 2 * Tm + 1) * 8;
+            h2d += (long long)nb * (long long)(nn + nm + Tn + Tm + 1) * 8;
             CUS(cudaEventRecord(ev_in[si], s_in));
             // kernels: outputs of this slot must have been copied out by the previous user
             CUS(cudaStreamWaitEvent(s_cp, ev_in[si], 0));
             if (c >= NS) CUS(cudaStreamWaitEvent(s_cp, ev_out[si], 0));
+            if (!host_derivs) {        // STEP 1 on the device: cx = Q x, cu = R u  (iLQG.jl:225-229, demo_linear.jl:38-39)
+                const long long wtot = nb * T;
+                const unsigned dgrid = (unsigned)std::min<long long>((wtot + 3) / 4, (long long)h->sm_count * 16);
+                df_cost_kernel<<<dgrid, 128, 0, s_cp>>>(n, m, T, nb, s.x, s.u, M.Q, M.R, nullptr, nullptr, s.cx, s.cu);
+                h->launches++;
+            }
             BackParams BP{};
             BP.n = n; BP.m = m; BP.T = T; BP.B = nb;
             BP.cx = TensorD{s.cx, (long long)Tn, n}; BP.cu = TensorD{s.cu, (long long)Tm, m};

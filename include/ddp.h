@@ -265,7 +265,8 @@ DDP_API int ddp_ilqg_solve_f64(ddp_handle_t h, const ddp_model* model, const ddp
  * (the headline workload), taking pinned HOST arrays: the batch is cut into chunks whose H2D
  * copies, kernels and D2H copies are pipelined on separate streams.  The policy (K,k) stays on the
  * device (the shim's GaussianPolicy holds it and downloads lazily).  Synchronous.
- * Host inputs:  fx (n,n,B), fu (n,m,B), cx (n,T,B), cu (m,T,B), x (n,T,B), u (m,T,B), lambda[B].
+ * Host inputs:  fx (n,n,B), fu (n,m,B), x (n,T,B), u (m,T,B), lambda[B], and cx (n,T,B), cu (m,T,B) -- or cx = cu = NULL,
+ *               in which case cx = Q x, cu = R u are formed on the device (STEP 1 of iLQG.jl:225-229 for this model).
  * Host outputs: xnew (n,T,B), unew (m,T,B), cost[B], dV (2,B), diverge[B].
  * Q (n,n), R (m,m), cxu (n,m) are small shared host matrices.                                     */
 typedef struct ddp_iter_host_args {

@@ -126,3 +126,21 @@ def test_ilqgkl_matches_oracle(ddp, kl_step):
     assert np.allclose([e for _, e in td["divergence"]], [e for _, e in to["divergence"]], rtol=1e-7)
     assert relerr(rd[0], ro[0]) < 1e-7 and relerr(rd[1], ro[1]) < 1e-7 and abs(rd[5] - np.sum(ro[5])) < 1e-8 * abs(np.sum(ro[5]))
     assert relerr(rd[2].K, ro[2].K) < 1e-7 and relerr(rd[2].Sigma, ro[2].Sigma) < 1e-7
+
+
+def test_iter_host_device_derivs(ddp):
+    """cx = cu = NULL: the derivative step runs on the device; results equal the host-derivative path."""
+    B, n, m, N = 21, 32, 8, 24
+    A, Bm, Q, R, x, u = make_batch_lq(19, B, n, m, N)
+    eng = ddp.Engine(n, m, N, B)
+    outs = []
+    for dd in (False, True):
+        it = ddp.HostIteration(eng, Q, R, reg_type=1, alpha=1.0, chunk=8, device_derivs=dd)
+        it.bufs["fx"][:] = np.swapaxes(A, -1, -2); it.bufs["fu"][:] = np.swapaxes(Bm, -1, -2)
+        it.bufs["cx"][:] = x @ Q.T; it.bufs["cu"][:] = u @ R.T; it.bufs["x"][:] = x; it.bufs["u"][:] = u; it.bufs["lam"][:] = 1.0
+        h2d, d2h = it.run()
+        outs.append((h2d, it.bufs["xnew"].copy(), it.bufs["unew"].copy(), it.bufs["cost"].copy(), it.bufs["diverge"].copy()))
+        it.close()
+    assert outs[1][0] < outs[0][0]
+    assert relerr(outs[1][1], outs[0][1]) < 1e-12 and relerr(outs[1][2], outs[0][2]) < 1e-12 and relerr(outs[1][3], outs[0][3]) < 1e-12
+    assert np.array_equal(outs[1][4], outs[0][4])
