@@ -38,6 +38,7 @@ constexpr int SVX = SF + 1280;               // Vx (32)
 constexpr int WARP_DOUBLES = SVX + 32;       // 2336 doubles = 18,688 B per warp
 constexpr int SF2 = WARP_DOUBLES;            // second F buffer (time-varying dynamics only)
 constexpr int WARP_DOUBLES_LTV = WARP_DOUBLES + 1280;
+constexpr int COST_DOUBLES = 15 * 32 * 2;    // per-CTA table of the cost tiles in accumulator (fragment) order
 
 // column-major 32-row matrices: element (i, c) lives at (i ^ s(c)) + 32 c with s(c) = ((c&1)<<3) | (((c>>1)&3)<<1).
 // 16-byte row pairs stay together, DMMA fragment loads (LDS.128) are bank-conflict free.
@@ -116,6 +117,30 @@ __global__ void __launch_bounds__(WPB * 32, 2) bp_tile32x8_kernel(BackParams P) 
     double* sVx = sm + SVX;
     const int N = P.T;
     const long long warps_total = (long long)gridDim.x * WPB;
+    // Cost Hessians shared by the batch and constant in time (the reference's LTI/QTIC methods): stage the
+    // symmetrised tiles once per CTA in accumulator order, so each step starts G with 15 conflict-free LDS.128.
+    double* sCost = smem_raw + (size_t)WPB * (LTV ? WARP_DOUBLES_LTV : WARP_DOUBLES);
+    const bool cost_shared = (P.cxx.sb == 0 && P.cxx.st == 0 && P.cxu.sb == 0 && P.cxu.st == 0 && P.cuu.sb == 0 && P.cuu.st == 0);
+    if (cost_shared) {
+        if (w == 0) {
+            const double* cxx0 = P.cxx.p;
+            const double* cxu0 = P.cxu.p;
+            const double* cuu0 = P.cuu.p;
+#pragma unroll
+            for (int at = 0; at < 4; at++) {
+                const int a = 8 * at + g;
+#pragma unroll
+                for (int bt = at; bt < 4; bt++) {
+                    const int b0 = 8 * bt + 2 * q;
+                    st2(&sCost[(gidx(at, bt) * 32 + lane) * 2], 0.5 * (cxx0[a * 32 + b0] + cxx0[b0 * 32 + a]),
+                        0.5 * (cxx0[a * 32 + b0 + 1] + cxx0[(b0 + 1) * 32 + a]));
+                }
+                st2(&sCost[(gidx(at, 4) * 32 + lane) * 2], cxu0[a + 32 * (2 * q)], cxu0[a + 32 * (2 * q + 1)]);
+            }
+            st2(&sCost[(gidx(4, 4) * 32 + lane) * 2], cuu0[g + 8 * (2 * q)], cuu0[g + 8 * (2 * q + 1)]);
+        }
+        __syncthreads();
+    }
     // lane constants of the swizzled addressing: swz(8p + 2q, 8t + g) = (p even ? LAe : LAo) + 8p + 256t,
     // swz(8at + g, 8bt + 2q + h) = LM + 8(at ^ h) + 32h + 256bt
     const int gg = (g >> 1) & 3, par = g & 1;
@@ -235,22 +260,31 @@ __global__ void __launch_bounds__(WPB * 32, 2) bp_tile32x8_kernel(BackParams P) 
             }
             // ---- G starts from the cost terms: their global loads are in flight during the tensor phase
             double G[15][2];
+            if (cost_shared) {
 #pragma unroll
-            for (int at = 0; at < 4; at++) {
-                const int a = 8 * at + g;
-#pragma unroll
-                for (int bt = at; bt < 4; bt++) {
-                    const int b0 = 8 * bt + 2 * q;
-                    double2 lo = ld2(cxxi + a * 32 + b0);                    // cxx[b0..b0+1][a]
-                    double u0 = cxxi[b0 * 32 + a], u1 = cxxi[(b0 + 1) * 32 + a];   // cxx[a][b0], cxx[a][b0+1]
-                    G[gidx(at, bt)][0] = 0.5 * (lo.x + u0);
-                    G[gidx(at, bt)][1] = 0.5 * (lo.y + u1);
+                for (int t = 0; t < 15; t++) {
+                    const double2 c = ld2(&sCost[(t * 32 + lane) * 2]);
+                    G[t][0] = c.x;
+                    G[t][1] = c.y;
                 }
-                G[gidx(at, 4)][0] = cxui[a + 32 * (2 * q)];                  // Qux[b'][a] = cxu[a][b'] + ...
-                G[gidx(at, 4)][1] = cxui[a + 32 * (2 * q + 1)];
+            } else {
+#pragma unroll
+                for (int at = 0; at < 4; at++) {
+                    const int a = 8 * at + g;
+#pragma unroll
+                    for (int bt = at; bt < 4; bt++) {
+                        const int b0 = 8 * bt + 2 * q;
+                        double2 lo = ld2(cxxi + a * 32 + b0);                    // cxx[b0..b0+1][a]
+                        double u0 = cxxi[b0 * 32 + a], u1 = cxxi[(b0 + 1) * 32 + a];   // cxx[a][b0], cxx[a][b0+1]
+                        G[gidx(at, bt)][0] = 0.5 * (lo.x + u0);
+                        G[gidx(at, bt)][1] = 0.5 * (lo.y + u1);
+                    }
+                    G[gidx(at, 4)][0] = cxui[a + 32 * (2 * q)];                  // Qux[b'][a] = cxu[a][b'] + ...
+                    G[gidx(at, 4)][1] = cxui[a + 32 * (2 * q + 1)];
+                }
+                G[gidx(4, 4)][0] = cuui[g + 8 * (2 * q)];
+                G[gidx(4, 4)][1] = cuui[g + 8 * (2 * q + 1)];
             }
-            G[gidx(4, 4)][0] = cuui[g + 8 * (2 * q)];
-            G[gidx(4, 4)][1] = cuui[g + 8 * (2 * q + 1)];
             // ---- step 1: W' = F' V.  The A fragments also give F'Vx: each lane sums its 8 rows, two shuffles finish it
             double W[5][4][2], fv[5];
 #pragma unroll
@@ -521,7 +555,7 @@ int launch_back_pass_tile(ddp_handle_s* h, const BackParams& P, bool gps, bool* 
     if (((uintptr_t)P.K % 16) || (P.Vxx && ((uintptr_t)P.Vxx % 16)) || (P.Vxx1 && ((uintptr_t)P.Vxx1 % 16))) return 0;
     if (gps && !aligned16(P.Kp)) return 0;
     const bool ltv = (P.fx.st != 0 || P.fu.st != 0);
-    const size_t bytes = (size_t)(ltv ? WARP_DOUBLES_LTV : WARP_DOUBLES) * sizeof(double) * WPB;
+    const size_t bytes = ((size_t)(ltv ? WARP_DOUBLES_LTV : WARP_DOUBLES) * WPB + COST_DOUBLES) * sizeof(double);
     long long grid = (long long)h->sm_count * 2;
     long long need = (P.B + WPB - 1) / WPB;
     if (grid > need) grid = need;
