@@ -35,7 +35,8 @@ constexpr int WPB = 4;                       // warps per CTA
 constexpr int SV = 0;                        // Vxx            32 x 32 swizzled
 constexpr int SF = SV + 1024;                // [fx fu]        32 x 40 swizzled
 constexpr int SVX = SF + 1280;               // Vx (32)
-constexpr int WARP_DOUBLES = SVX + 32;       // 2336 doubles = 18,688 B per warp
+constexpr int SCX = SVX + 32;                // this step's cx (32) and cu (8), landed by cp.async
+constexpr int WARP_DOUBLES = SCX + 48;       // 2384 doubles = 19,072 B per warp
 constexpr int SF2 = WARP_DOUBLES;            // second F buffer (time-varying dynamics only)
 constexpr int WARP_DOUBLES_LTV = WARP_DOUBLES + 1280;
 constexpr int COST_DOUBLES = 15 * 32 * 2;    // per-CTA table of the cost tiles in accumulator (fragment) order
@@ -57,6 +58,9 @@ __device__ __forceinline__ void cp_async16(double* dst_smem, const double* src) 
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src));
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
 
 // stage [fx fu] of one step into the swizzled buffer (16-byte chunks = 2 consecutive rows of a column)
 template <bool ASYNC>
@@ -115,6 +119,7 @@ __global__ void __launch_bounds__(WPB * 32, 2) bp_tile32x8_kernel(BackParams P) 
     double* sm = smem_raw + (size_t)w * (LTV ? WARP_DOUBLES_LTV : WARP_DOUBLES);
     double* sV = sm + SV;
     double* sVx = sm + SVX;
+    double* sCx = sm + SCX;
     const int N = P.T;
     const long long warps_total = (long long)gridDim.x * WPB;
     // Cost Hessians shared by the batch and constant in time (the reference's LTI/QTIC methods): stage the
@@ -226,18 +231,17 @@ __global__ void __launch_bounds__(WPB * 32, 2) bp_tile32x8_kernel(BackParams P) 
             if (LTV) {
                 cp_async_wait_all();
                 __syncwarp();
+            }
+            // this step's cost gradients -> shared memory (group A; no registers are held across the tensor phase)
+            if (lane < 16) cp_async16(&sCx[2 * lane], cxb + (long long)i * P.cx.st + 2 * lane);
+            else if (lane < 20) cp_async16(&sCx[2 * lane], cub + (long long)i * P.cu.st + 2 * (lane - 16));
+            cp_async_commit();
+            if (LTV) {                                       // next step's [fx fu] (group B)
                 if (i > 0) load_F<true>(sm + (buf ? SF : SF2), tp(P.fx, b, i - 1), tp(P.fu, b, i - 1), lane);
+                cp_async_commit();
                 if (reg2) compute_FF(sF);
             }
             // this step's cost gradients: lanes of group g own Qx[8t+g] (t = 0..3) and Qu[g]
-            const double* cxi = cxb + (long long)i * P.cx.st;
-            double cxv[4];
-#pragma unroll
-            for (int t = 0; t < 4; t++) cxv[t] = cxi[8 * t + g];
-            const double cuv = (cub + (long long)i * P.cu.st)[g];
-            const double* cxxi = tp(P.cxx, b, i);
-            const double* cxui = tp(P.cxu, b, i);
-            const double* cuui = tp(P.cuu, b, i);
             // KL terms: fragments of the previous policy, K_prev[2q..2q+1][8t+g], Sigma_i_prev[g][2q..2q+1]
             double2 kpf[4];
             double Sg0 = 0.0, Sg1 = 0.0, kp0 = 0.0, kp1 = 0.0;
@@ -268,6 +272,9 @@ __global__ void __launch_bounds__(WPB * 32, 2) bp_tile32x8_kernel(BackParams P) 
                     G[t][1] = c.y;
                 }
             } else {
+                const double* cxxi = tp(P.cxx, b, i);
+                const double* cxui = tp(P.cxu, b, i);
+                const double* cuui = tp(P.cuu, b, i);
 #pragma unroll
                 for (int at = 0; at < 4; at++) {
                     const int a = 8 * at + g;
@@ -333,6 +340,13 @@ __global__ void __launch_bounds__(WPB * 32, 2) bp_tile32x8_kernel(BackParams P) 
 #pragma unroll
                     for (int bt = at; bt < 5; bt++) dmma(G[gidx(at, bt)][0], G[gidx(at, bt)][1], W[at][p][1], ff[bt].y);
             }
+            // this step's cost gradients have landed long ago: lanes of group g own Qx[8t+g] (t = 0..3) and Qu[g]
+            if (LTV) cp_async_wait_group<1>(); else cp_async_wait_group<0>();      // group A has landed
+            __syncwarp();
+            double cxv[4];
+#pragma unroll
+            for (int t = 0; t < 4; t++) cxv[t] = sCx[8 * t + g];
+            const double cuv = sCx[32 + g];
             // ---- KL augmentation (backward_pass.jl:295-301): Q/eta + KL terms, formed in fragment layouts
             double2 sf[4];
             double Sik_own = 0.0, Sik0 = 0.0, Sik1 = 0.0;
@@ -554,6 +568,7 @@ int launch_back_pass_tile(ddp_handle_s* h, const BackParams& P, bool gps, bool* 
     if (!aligned16(P.fx) || !aligned16(P.fu) || !aligned16(P.cxx)) return 0;
     if (((uintptr_t)P.K % 16) || (P.Vxx && ((uintptr_t)P.Vxx % 16)) || (P.Vxx1 && ((uintptr_t)P.Vxx1 % 16))) return 0;
     if (gps && !aligned16(P.Kp)) return 0;
+    if (!aligned16(P.cx) || !aligned16(P.cu)) return 0;
     const bool ltv = (P.fx.st != 0 || P.fu.st != 0);
     const size_t bytes = ((size_t)(ltv ? WARP_DOUBLES_LTV : WARP_DOUBLES) * WPB + COST_DOUBLES) * sizeof(double);
     long long grid = (long long)h->sm_count * 2;
