@@ -331,7 +331,7 @@ def main_gpu(args):
         ok = bool(np.array_equal(it.bufs["diverge"], diverge[:Be].cpu().numpy())) and \
             bool(np.allclose(it.bufs["cost"], cost[:Be].cpu().numpy(), rtol=1e-12, atol=0))
         e2e = dict(value=world * (Be / BATCH) * 1e3 / e_ms, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                   ms_per_step=e_ms, steps=e_steps, batch_per_gpu=Be, chunk=args.chunk or 4096,
+                   ms_per_step=e_ms, steps=e_steps, batch_per_gpu=Be, chunk=(args.chunk or "ramped: 1,2,4,...,4,2,1 rounds of sm_count*8 trajectories"),
                    api="ddp_ilqg_iter_host_f64: x,u,fx,fu,lambda from pinned host memory -> df (cx=Qx, cu=Ru) + backward + forward on the device -> xnew,unew,cost,dV,diverge in host memory; policy K stays on the device",
                    matches_device_path=ok)
         it.close()

@@ -7,43 +7,96 @@
 // same sequential, FMA-free device functions as the generic kernel and the oracle (boxqp.cuh), so
 // the integer outcomes (diverge, clamped set, QP result) follow the oracle's branch decisions.
 //
-// This shape is HBM/latency bound (0.4 Mflop vs 245 KB per trajectory-iteration): a thread reads its
-// own 128-byte fx line per step, i.e. every sector fetched is fully used.
+// This shape is HBM/latency bound (0.4 Mflop vs 245 KB per trajectory-iteration).  The n x n block of
+// fx (128 bytes per trajectory-step at n = 4) is the dominant read: a thread fetching its own line with
+// eight 16-byte loads makes every load instruction touch 32 different lines (32 L1 wavefronts each),
+// which saturates the LSU long before HBM.  With STAGE the warp instead copies the 32 lines of the next
+// step with coalesced cp.async (lane -> (trajectory, 16-byte chunk): 4 whole lines per instruction) into
+// a padded, conflict-free shared-memory ring and every thread then reads its own row from there.
+#include <cstdlib>
 #include "boxqp.cuh"
 
 namespace {
 
 template <int N, int M>
 struct StepIn {
-    double fx[N * N], fu[N * M], cx[N], cu[M], u[M];
+    double fu[N * M], cx[N], cu[M], u[M];
 };
+
+__device__ __forceinline__ void cp_async16s(double* dst_smem, const double* src) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src));
+}
+
+template <int N>
+__device__ __forceinline__ void load_fx_direct(double* f, const BackParams& P, long long b, int i) {
+    const double* fx = tp(P.fx, b, i);
+#pragma unroll
+    for (int e = 0; e < N * N; e++) f[e] = fx[e];
+}
+
+// rows of the staging ring: N*N doubles + one 16-byte pad => a thread's 16-byte reads of its own row are
+// conflict-free (row stride 144 B at N = 4)
+template <int N>
+struct FxStage {
+    static constexpr int ROW = N * N + 2;
+    static constexpr int CH = (N * N) / 2;            // 16-byte chunks per row
+};
+
+template <int N>
+__device__ __forceinline__ void stage_fx(double* sbuf, const BackParams& P, long long b0, int i, int lane) {
+    constexpr int CH = FxStage<N>::CH, ROW = FxStage<N>::ROW;
+#pragma unroll
+    for (int k = 0; k < CH; k++) {
+        const int e = lane + 32 * k, row = e / CH, ch = e % CH;
+        const long long bb = b0 + row;
+        if (bb < P.B) cp_async16s(sbuf + row * ROW + 2 * ch, tp(P.fx, bb, i) + 2 * ch);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
 
 template <int N, int M>
 __device__ __forceinline__ void load_step(StepIn<N, M>& s, const BackParams& P, long long b, int i, bool use_qp) {
-    const double* fx = tp(P.fx, b, i);
     const double* fu = tp(P.fu, b, i);
     const double* cx = tp(P.cx, b, i);
     const double* cu = tp(P.cu, b, i);
-    if ((N * N) % 2 == 0 && ((uintptr_t)fx % 16) == 0) {
+    if ((N * M) % 2 == 0 && ((uintptr_t)fu % 16) == 0) {
 #pragma unroll
-        for (int e = 0; e < N * N; e += 2) { double2 t = *reinterpret_cast<const double2*>(fx + e); s.fx[e] = t.x; s.fx[e + 1] = t.y; }
+        for (int e = 0; e < N * M; e += 2) { double2 t = *reinterpret_cast<const double2*>(fu + e); s.fu[e] = t.x; s.fu[e + 1] = t.y; }
     } else {
 #pragma unroll
-        for (int e = 0; e < N * N; e++) s.fx[e] = fx[e];
+        for (int e = 0; e < N * M; e++) s.fu[e] = fu[e];
+    }
+    if (N % 2 == 0 && ((uintptr_t)cx % 16) == 0) {
+#pragma unroll
+        for (int e = 0; e < N; e += 2) { double2 t = *reinterpret_cast<const double2*>(cx + e); s.cx[e] = t.x; s.cx[e + 1] = t.y; }
+        goto cx_done;
     }
 #pragma unroll
-    for (int e = 0; e < N * M; e++) s.fu[e] = fu[e];
-#pragma unroll
     for (int e = 0; e < N; e++) s.cx[e] = cx[e];
+cx_done:
 #pragma unroll
     for (int e = 0; e < M; e++) { s.cu[e] = cu[e]; s.u[e] = use_qp ? tp(P.u, b, i)[e] : 0.0; }
 }
 
-template <int N, int M>
-__global__ void __launch_bounds__(128) bp_small_kernel(BackParams P) {
-    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= P.B) return;
-    if (P.active && !P.active[b]) return;
+template <int N, int M, int MINB, bool STAGE>
+__global__ void __launch_bounds__(128, MINB) bp_small_kernel(BackParams P) {
+    __shared__ __align__(16) double s_fx[STAGE ? 4 * 2 * 32 * FxStage<N>::ROW : 2];
+    // cost Hessians shared by the batch and constant in time (the usual case): one copy per CTA, read by broadcast
+    __shared__ double s_cost[N * N + N * M + M * M];
+    const bool cost_shared = (P.cxx.sb == 0 && P.cxx.st == 0 && P.cxu.sb == 0 && P.cxu.st == 0 && P.cuu.sb == 0 && P.cuu.st == 0);
+    if (cost_shared) {
+        for (int e = threadIdx.x; e < N * N + N * M + M * M; e += blockDim.x)
+            s_cost[e] = (e < N * N) ? P.cxx.p[e] : (e < N * N + N * M) ? P.cxu.p[e - N * N] : P.cuu.p[e - N * N - N * M];
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const long long b_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long b0 = b_raw - lane;                       // first trajectory of this warp
+    if (b0 >= P.B) return;                                   // warp-uniform
+    const bool valid = (b_raw < P.B) && !(P.active && !P.active[b_raw]);
+    const long long b = (b_raw < P.B) ? b_raw : P.B - 1;     // out-of-range lanes shadow the last trajectory, store nothing
+    double* sfx = s_fx + (STAGE ? wid * 2 * 32 * FxStage<N>::ROW : 0);
     const int T = P.T;
     const bool use_qp = (P.lims != nullptr) && !(P.lims[0] > P.lims[M]);     // backward_pass.jl:31
     const double lam = P.lambda[b];
@@ -53,6 +106,7 @@ __global__ void __launch_bounds__(128) bp_small_kernel(BackParams P) {
     double* Vxb = P.Vx + b * (long long)T * N;
     double* Vxxb = P.Vxx ? P.Vxx + b * (long long)T * N * N : nullptr;
     double* Quub = P.Quu ? P.Quu + b * (long long)T * M * M : nullptr;
+    const bool vec_out = ((uintptr_t)P.K % 16 == 0) && ((uintptr_t)P.Vx % 16 == 0);
     double lims_lo[M], lims_hi[M];
 #pragma unroll
     for (int a = 0; a < M; a++) { lims_lo[a] = use_qp ? P.lims[a] : 0.0; lims_hi[a] = use_qp ? P.lims[M + a] : 0.0; }
@@ -63,14 +117,16 @@ __global__ void __launch_bounds__(128) bp_small_kernel(BackParams P) {
         const double* cxxN = tp(P.cxx, b, T - 1);
         const double* cuuN = tp(P.cuu, b, T - 1);
 #pragma unroll
-        for (int e = 0; e < N; e++) { Vx[e] = cxN[e]; Vxb[(long long)(T - 1) * N + e] = Vx[e]; }
+        for (int e = 0; e < N; e++) { Vx[e] = cxN[e]; if (valid) Vxb[(long long)(T - 1) * N + e] = Vx[e]; }
 #pragma unroll
-        for (int e = 0; e < N * N; e++) { V[e] = cxxN[e]; if (Vxxb) Vxxb[(long long)(T - 1) * N * N + e] = V[e]; }
+        for (int e = 0; e < N * N; e++) { V[e] = cxxN[e]; if (valid && Vxxb) Vxxb[(long long)(T - 1) * N * N + e] = V[e]; }
+        if (valid) {
 #pragma unroll
-        for (int e = 0; e < N * M; e++) Kb[(long long)(T - 1) * N * M + e] = 0.0;
+            for (int e = 0; e < N * M; e++) Kb[(long long)(T - 1) * N * M + e] = 0.0;
 #pragma unroll
-        for (int e = 0; e < M; e++) kb[(long long)(T - 1) * M + e] = 0.0;
-        if (Quub)
+            for (int e = 0; e < M; e++) kb[(long long)(T - 1) * M + e] = 0.0;
+        }
+        if (valid && Quub)
 #pragma unroll
             for (int e = 0; e < M * M; e++) Quub[(long long)(T - 1) * M * M + e] = cuuN[e];
     }
@@ -80,12 +136,29 @@ __global__ void __launch_bounds__(128) bp_small_kernel(BackParams P) {
     double dV0 = 0.0, dV1 = 0.0;
     int diverge = 0;
     StepIn<N, M> cur, nxt;
-    if (T >= 2) load_step<N, M>(cur, P, b, T - 2, use_qp);
+    double cfx[N * N];
+    bool alive = valid;
+    if (T >= 2) {
+        load_step<N, M>(cur, P, b, T - 2, use_qp);
+        if (STAGE) stage_fx<N>(sfx + ((T - 2) & 1) * 32 * FxStage<N>::ROW, P, b0, T - 2, lane);
+    }
     for (int i = T - 2; i >= 0; i--) {
+        if (STAGE) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();                                            // the warp's copies of step i have landed
+            const double* row = sfx + (i & 1) * 32 * FxStage<N>::ROW + lane * FxStage<N>::ROW;
+#pragma unroll
+            for (int e = 0; e < N * N; e += 2) { double2 t = *reinterpret_cast<const double2*>(row + e); cfx[e] = t.x; cfx[e + 1] = t.y; }
+            // the other buffer was read in step i+1, before the __syncwarp above: refill it with step i-1
+            if (i > 0) stage_fx<N>(sfx + ((i - 1) & 1) * 32 * FxStage<N>::ROW, P, b0, i - 1, lane);
+        } else {
+            load_fx_direct<N>(cfx, P, b, i);
+        }
         if (i > 0) load_step<N, M>(nxt, P, b, i - 1, use_qp);        // in flight during this step's arithmetic
-        const double* cxxi = tp(P.cxx, b, i);
-        const double* cxui = tp(P.cxu, b, i);
-        const double* cuui = tp(P.cuu, b, i);
+        if (alive) {
+        const double* cxxi = cost_shared ? s_cost : tp(P.cxx, b, i);
+        const double* cxui = cost_shared ? s_cost + N * N : tp(P.cxu, b, i);
+        const double* cuui = cost_shared ? s_cost + N * N + N * M : tp(P.cuu, b, i);
         // ---- W = V fx, Z = V fu
         double W[N * N], Z[N * M];
 #pragma unroll
@@ -94,7 +167,7 @@ __global__ void __launch_bounds__(128) bp_small_kernel(BackParams P) {
             for (int r = 0; r < N; r++) {
                 double acc = 0.0;
 #pragma unroll
-                for (int q = 0; q < N; q++) acc = fma(V[r + N * q], cur.fx[q + N * c], acc);
+                for (int q = 0; q < N; q++) acc = fma(V[r + N * q], cfx[q + N * c], acc);
                 W[r + N * c] = acc;
             }
 #pragma unroll
@@ -114,7 +187,7 @@ __global__ void __launch_bounds__(128) bp_small_kernel(BackParams P) {
             for (int r = 0; r < N; r++) {
                 double acc = 0.0;
 #pragma unroll
-                for (int q = 0; q < N; q++) acc = fma(cur.fx[q + N * r], W[q + N * c], acc);
+                for (int q = 0; q < N; q++) acc = fma(cfx[q + N * r], W[q + N * c], acc);
                 Qxx[r + N * c] = cxxi[r + N * c] + acc;
             }
 #pragma unroll
@@ -123,7 +196,7 @@ __global__ void __launch_bounds__(128) bp_small_kernel(BackParams P) {
             for (int a = 0; a < M; a++) {
                 double acc = 0.0, ff = 0.0;
 #pragma unroll
-                for (int q = 0; q < N; q++) { acc = fma(cur.fu[q + N * a], W[q + N * j], acc); ff = fma(cur.fu[q + N * a], cur.fx[q + N * j], ff); }
+                for (int q = 0; q < N; q++) { acc = fma(cur.fu[q + N * a], W[q + N * j], acc); ff = fma(cur.fu[q + N * a], cfx[q + N * j], ff); }
                 const double v = cxui[j + N * a] + acc;
                 Qux[a + M * j] = v;
                 Quxr[a + M * j] = reg2 ? v + lam * ff : v;
@@ -143,7 +216,7 @@ __global__ void __launch_bounds__(128) bp_small_kernel(BackParams P) {
         for (int r = 0; r < N; r++) {
             double acc = 0.0;
 #pragma unroll
-            for (int q = 0; q < N; q++) acc = fma(cur.fx[q + N * r], Vx[q], acc);
+            for (int q = 0; q < N; q++) acc = fma(cfx[q + N * r], Vx[q], acc);
             Qx[r] = cur.cx[r] + acc;
         }
 #pragma unroll
@@ -179,7 +252,14 @@ __global__ void __launch_bounds__(128) bp_small_kernel(BackParams P) {
             if (res < 1) failed = true;                                                                  // :50-56
             nf = __popc(fm);
         }
-        if (failed) { diverge = i + 1; break; }
+        if (failed) { diverge = i + 1; alive = false; }
+        else {
+        if (M == 1) {
+            // scalar control: K = -Qux_reg / (R'R); one reciprocal of the factor instead of 2 divisions per column
+            const double rinv = (nf > 0) ? 1.0 / R[0] : 0.0;
+#pragma unroll
+            for (int j = 0; j < N; j++) Ki[j] = -((Quxr[j] * rinv) * rinv);
+        } else {
 #pragma unroll
         for (int j = 0; j < N; j++) {
             double v[M];
@@ -191,6 +271,7 @@ __global__ void __launch_bounds__(128) bp_small_kernel(BackParams P) {
             p = 0;
 #pragma unroll
             for (int a = 0; a < M; a++) Ki[a + M * j] = ((fm >> a) & 1u) ? -v[p++] : 0.0;
+        }
         }
         // ---- value backup (:64-72)
         double Quuk[M], QK[M * N];
@@ -246,20 +327,30 @@ __global__ void __launch_bounds__(128) bp_small_kernel(BackParams P) {
 #pragma unroll
             for (int r = 0; r < N; r++) V[r + N * c] = 0.5 * (W[r + N * c] + W[c + N * r]);
         // ---- store
+        if (vec_out && (N * M) % 2 == 0 && N % 2 == 0) {
 #pragma unroll
-        for (int e = 0; e < N * M; e++) Kb[(long long)i * N * M + e] = Ki[e];
+            for (int e = 0; e < N * M; e += 2) *reinterpret_cast<double2*>(Kb + (long long)i * N * M + e) = make_double2(Ki[e], Ki[e + 1]);
+#pragma unroll
+            for (int r = 0; r < N; r += 2) *reinterpret_cast<double2*>(Vxb + (long long)i * N + r) = make_double2(Vx[r], Vx[r + 1]);
+        } else {
+#pragma unroll
+            for (int e = 0; e < N * M; e++) Kb[(long long)i * N * M + e] = Ki[e];
+#pragma unroll
+            for (int r = 0; r < N; r++) Vxb[(long long)i * N + r] = Vx[r];
+        }
 #pragma unroll
         for (int a = 0; a < M; a++) { kb[(long long)i * M + a] = ki[a]; kw[a] = ki[a]; }
-#pragma unroll
-        for (int r = 0; r < N; r++) Vxb[(long long)i * N + r] = Vx[r];
         if (Vxxb)
 #pragma unroll
             for (int e = 0; e < N * N; e++) Vxxb[(long long)i * N * N + e] = V[e];
         if (Quub)
 #pragma unroll
             for (int e = 0; e < M * M; e++) Quub[(long long)i * M * M + e] = Quu[e];
+        }
+        }
         cur = nxt;
     }
+    if (!valid) return;
     if (diverge > 0) {                               // outputs below the failed step stay zero (quirk Q10)
         for (long long e = 0; e < (long long)diverge * N * M; e++) Kb[e] = 0.0;
         for (long long e = 0; e < (long long)diverge * M; e++) kb[e] = 0.0;
@@ -278,7 +369,14 @@ __global__ void __launch_bounds__(128) bp_small_kernel(BackParams P) {
 template <int N, int M>
 int launch_small(ddp_handle_s* h, const BackParams& P) {
     const unsigned grid = (unsigned)((P.B + 127) / 128);
-    bp_small_kernel<N, M><<<grid, 128, 0, h->stream>>>(P);
+    static int minb = -1;
+    if (minb < 0) { const char* ev = getenv("DDP_SMALL_MINB"); minb = ev ? atoi(ev) : 2; }
+    const bool stage = ((N * N) % 2 == 0) && ((uintptr_t)P.fx.p % 16 == 0) && (P.fx.sb % 2 == 0) && (P.fx.st % 2 == 0) &&
+                       !(getenv("DDP_SMALL_NOSTAGE"));
+    if (stage) {
+        if (minb == 3) bp_small_kernel<N, M, 3, true><<<grid, 128, 0, h->stream>>>(P);
+        else bp_small_kernel<N, M, 2, true><<<grid, 128, 0, h->stream>>>(P);
+    } else bp_small_kernel<N, M, 2, false><<<grid, 128, 0, h->stream>>>(P);
     h->launches++;
     return (int)cudaGetLastError();
 }

@@ -27,6 +27,7 @@
 //
 // Restrictions (anything else dispatches to the generic kernel): Cholesky branch only (lims ==
 // NULL), 16-byte aligned fx/fu/cxx with even strides, symmetric cxx (it is a Hessian).
+#include <cstdlib>
 #include "ddp_common.cuh"
 
 namespace {
@@ -109,6 +110,8 @@ __device__ __forceinline__ bool gj_inverse8(double& I0, double& I1, int lane, in
     return ok;
 }
 
+__device__ unsigned g_sm_ticket[1024];     // per-SM arrival counter: consecutive CTAs on one SM get different parities
+
 constexpr int gidx(int at, int bt) { return at * 5 - (at * (at - 1)) / 2 + (bt - at); }   // upper-tile index, 15 tiles
 
 template <bool LTV, bool GPS>
@@ -154,6 +157,22 @@ __global__ void __launch_bounds__(WPB * 32, 2) bp_tile32x8_kernel(BackParams P) 
     const int LM = (g ^ (2 * q)) + 64 * q;
 #define FRAG(p, t) (((p) & 1 ? LAo : LAe) + 8 * (p) + 256 * (t))
 #define MIRR(at, bt, h) (LM + 8 * ((at) ^ (h)) + 32 * (h) + 256 * (bt))
+    // The two warps that share an SM sub-partition would otherwise run in phase (both in the tensor phase,
+    // then both in the latency-bound pivot/shuffle phase): delay the second resident CTA by part of a step
+    // so that one warp's serial phase overlaps the other's DMMA phase.
+    if (P.stagger > 0) {
+        __shared__ unsigned s_ticket;
+        if (threadIdx.x == 0) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            s_ticket = atomicAdd(&g_sm_ticket[smid & 1023], 1u);
+        }
+        __syncthreads();
+        if (s_ticket & 1u) {
+            const long long t0 = clock64();
+            while (clock64() - t0 < P.stagger) { }
+        }
+    }
     const bool up0 = (2 * q >= g), st0 = (2 * q > g), up1 = (2 * q + 1 >= g), st1 = (2 * q + 1 > g);
     const int c0src = 8 * q, c1src = 8 * q + 4;        // a lane of the group that owns entry 2q / 2q+1
 
@@ -574,11 +593,17 @@ int launch_back_pass_tile(ddp_handle_s* h, const BackParams& P, bool gps, bool* 
     long long grid = (long long)h->sm_count * 2;
     long long need = (P.B + WPB - 1) / WPB;
     if (grid > need) grid = need;
+    BackParams Ps = P;
+    {
+        static int stagger = -1;
+        if (stagger < 0) { const char* ev = getenv("DDP_BP_STAGGER"); stagger = ev ? atoi(ev) : 0; }
+        Ps.stagger = stagger;
+    }
     cudaError_t e = cudaSuccess;
 #define LAUNCH_TILE(L, G)                                                                                                \
     do {                                                                                                                 \
         e = cudaFuncSetAttribute(bp_tile32x8_kernel<L, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);     \
-        if (e == cudaSuccess) bp_tile32x8_kernel<L, G><<<(unsigned)grid, WPB * 32, bytes, h->stream>>>(P);               \
+        if (e == cudaSuccess) bp_tile32x8_kernel<L, G><<<(unsigned)grid, WPB * 32, bytes, h->stream>>>(Ps);              \
     } while (0)
     if (ltv && gps) LAUNCH_TILE(true, true);
     else if (ltv) LAUNCH_TILE(true, false);

@@ -207,7 +207,29 @@ __global__ void __launch_bounds__(FW_WPB * 32, 2) fwd_lin32x8_kernel(FwdParams P
 }
 
 // ---------------------------------------------------------------------------------------------
-// pendulum on a cart: one thread per trajectory, everything in registers
+// pendulum on a cart: one thread per trajectory, everything in registers.  The rollout is a serial
+// chain per trajectory (load -> control -> sincos -> next state), so the operands of the next PEND_PF
+// steps are kept in flight in a register ring: the kernel is HBM-bound only if enough loads are pending.
+constexpr int PEND_PF = 4;
+struct PendIn {
+    double2 K01, K23, x01, x23;
+    double k, u;
+};
+template <bool POLICY>
+__device__ __forceinline__ void pend_load(PendIn& r, const FwdParams& P, long long b, int t) {
+    const int N = P.T;
+    r.u = tp(P.u, b, t)[0];
+    if (POLICY) {
+        const double* Kt = P.K + (b * N + t) * 4;
+        const double* xo = tp(P.x, b, t);
+        r.K01 = ldg2(Kt);
+        r.K23 = ldg2(Kt + 2);
+        r.x01 = ldg2(xo);
+        r.x23 = ldg2(xo + 2);
+        r.k = P.k[b * N + t];
+    }
+}
+
 template <bool POLICY>
 __global__ void __launch_bounds__(128) fwd_pend_kernel(FwdParams P) {
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -228,50 +250,59 @@ __global__ void __launch_bounds__(128) fwd_pend_kernel(FwdParams P) {
     double* xnb = P.xnew + b * (long long)N * 4;
     double* unb = P.unew + b * (long long)N;
     double ctot = 0.0, clast = 0.0;
-    for (int t = 0; t < N; t++) {
-        double un = tp(P.u, b, t)[0] * P.u_scale;
-        if (POLICY) {
-            const double2 K01 = ldg2(P.K + (b * N + t) * 4), K23 = ldg2(P.K + (b * N + t) * 4 + 2);
-            const double* xo = tp(P.x, b, t);
-            const double2 xo01 = ldg2(xo), xo23 = ldg2(xo + 2);
-            un = un + P.k[b * N + t] * alpha;
-            double acc = K01.x * (x[0] - xo01.x);
-            acc = fma(K01.y, x[1] - xo01.y, acc);
-            acc = fma(K23.x, x[2] - xo23.x, acc);
-            acc = fma(K23.y, x[3] - xo23.y, acc);
-            un = un + acc;
-        }
-        if (has_lims) un = fmin(fmax(un, lo), hi);
-        if (un != un) un = 0.0;
-        stg2(xnb + (long long)t * 4, x[0], x[1]);
-        stg2(xnb + (long long)t * 4 + 2, x[2], x[3]);
-        unb[t] = un;
-        double d[4], qd[4];
+    PendIn ring[PEND_PF];
 #pragma unroll
-        for (int i = 0; i < 4; i++) d[i] = x[i] - goal[i];
-        double cs = 0.0;
+    for (int d = 0; d < PEND_PF; d++)
+        if (d < N) pend_load<POLICY>(ring[d], P, b, d);
+    for (int t0 = 0; t0 < N; t0 += PEND_PF) {
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            qd[i] = 0.0;
+        for (int d = 0; d < PEND_PF; d++) {
+            const int t = t0 + d;
+            if (t < N) {
+                const PendIn c = ring[d];
+                if (t + PEND_PF < N) pend_load<POLICY>(ring[d], P, b, t + PEND_PF);
+                double un = c.u * P.u_scale;
+                if (POLICY) {
+                    un = un + c.k * alpha;
+                    double acc = c.K01.x * (x[0] - c.x01.x);
+                    acc = fma(c.K01.y, x[1] - c.x01.y, acc);
+                    acc = fma(c.K23.x, x[2] - c.x23.x, acc);
+                    acc = fma(c.K23.y, x[3] - c.x23.y, acc);
+                    un = un + acc;
+                }
+                if (has_lims) un = fmin(fmax(un, lo), hi);
+                if (un != un) un = 0.0;
+                stg2(xnb + (long long)t * 4, x[0], x[1]);
+                stg2(xnb + (long long)t * 4 + 2, x[2], x[3]);
+                unb[t] = un;
+                double dlt[4], qd[4];
 #pragma unroll
-            for (int j = 0; j < 4; j++) qd[i] = fma(Q[i + 4 * j], d[j], qd[i]);
-            cs = fma(0.5 * d[i], qd[i], cs);
-        }
-        clast = cs;
-        const double ru = Rv * un;
-        const double cstep = fma(0.5 * un, ru, cs);
-        if (P.cx) { stg2(P.cx + (b * N + t) * 4, qd[0], qd[1]); stg2(P.cx + (b * N + t) * 4 + 2, qd[2], qd[3]); }
-        if (P.cu) P.cu[b * N + t] = ru;
-        if (P.cost_t) P.cost_t[b * (N + P.model.terminal_cost) + t] = cstep;
-        ctot += cstep;
-        if (t < N - 1) {
-            double sn, cs2;
-            sincos(x[0], &sn, &cs2);
-            const double x0n = x[0] + h * x[1];
-            const double x1n = x[1] + h * (-gg / l * sn + un / l * cs2 - dd * x[1]);
-            const double x2n = x[2] + h * x[3];
-            const double x3n = x[3] + h * un;
-            x[0] = x0n; x[1] = x1n; x[2] = x2n; x[3] = x3n;
+                for (int i = 0; i < 4; i++) dlt[i] = x[i] - goal[i];
+                double cs = 0.0;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    qd[i] = 0.0;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) qd[i] = fma(Q[i + 4 * j], dlt[j], qd[i]);
+                    cs = fma(0.5 * dlt[i], qd[i], cs);
+                }
+                clast = cs;
+                const double ru = Rv * un;
+                const double cstep = fma(0.5 * un, ru, cs);
+                if (P.cx) { stg2(P.cx + (b * N + t) * 4, qd[0], qd[1]); stg2(P.cx + (b * N + t) * 4 + 2, qd[2], qd[3]); }
+                if (P.cu) P.cu[b * N + t] = ru;
+                if (P.cost_t) P.cost_t[b * (N + P.model.terminal_cost) + t] = cstep;
+                ctot += cstep;
+                if (t < N - 1) {
+                    double sn, cs2;
+                    sincos(x[0], &sn, &cs2);
+                    const double x0n = x[0] + h * x[1];
+                    const double x1n = x[1] + h * (-gg / l * sn + un / l * cs2 - dd * x[1]);
+                    const double x2n = x[2] + h * x[3];
+                    const double x3n = x[3] + h * un;
+                    x[0] = x0n; x[1] = x1n; x[2] = x2n; x[3] = x3n;
+                }
+            }
         }
     }
     if (P.model.terminal_cost) {

@@ -517,7 +517,7 @@ fail:
 }  // extern "C"
 
 namespace {
-constexpr int NS = 3;     // chunk slots in flight
+constexpr int NS = 4;     // chunk slots in flight
 struct Slot { double *fx, *fu, *cx, *cu, *x, *u, *lam, *K, *k, *Vx, *xnew, *unew, *cost, *dV; int* div; };
 struct IterCache {
     DevBuf mem;
@@ -585,8 +585,25 @@ int ddp_ilqg_iter_host_f64(ddp_handle_t h, ddp_iter_host_args* a) {
     }
     const int n = h->n, m = h->m, T = h->T;
     const long long B = h->B;
-    long long chunk = a->chunk > 0 ? a->chunk : 4096;
-    if (chunk > B) chunk = B;
+    // Chunk schedule.  Default: chunks are whole "rounds" of the resident warp set of the sweep kernels
+    // (sm_count x 8 warps, one trajectory each), so no launch ends with a partly filled round; the first and
+    // last chunks are short (1 and 2 rounds) to shorten the fill (first H2D) and drain (last D2H) of the pipeline.
+    std::vector<long long> sizes;
+    long long chunk;
+    if (a->chunk > 0) {
+        chunk = std::min<long long>(a->chunk, B);
+        for (long long b0 = 0; b0 < B; b0 += chunk) sizes.push_back(std::min<long long>(chunk, B - b0));
+    } else {
+        const long long unit = (long long)h->sm_count * 8;
+        chunk = std::min<long long>(4 * unit, B);
+        long long left = B;
+        auto take = [&](long long rounds) { long long nb = std::min<long long>(rounds * unit, left); if (nb > 0) { sizes.push_back(nb); left -= nb; } };
+        const long long R = (B + unit - 1) / unit;
+        if (R >= 12) { take(1); take(2); }
+        while (left > (R >= 12 ? 3 : 0) * unit) take(4);
+        take(2);
+        take(1);
+    }
     cudaError_t err = cudaSuccess;
     cudaStream_t saved = h->stream;
     const size_t nn = (size_t)n * n, nm = (size_t)n * m, Tn = (size_t)T * n, Tm = (size_t)T * m;
@@ -621,9 +638,9 @@ int ddp_ilqg_iter_host_f64(ddp_handle_t h, ddp_iter_host_args* a) {
     M.Q = TensorD{dQ, 0, 0}; M.R = TensorD{dR, 0, 0};
 
     {
-        int c = 0;
-        for (long long b0 = 0; b0 < B; b0 += chunk, c++) {
-            const long long nb = std::min<long long>(chunk, B - b0);
+        long long b0 = 0;
+        for (int c = 0; c < (int)sizes.size(); b0 += sizes[c], c++) {
+            const long long nb = sizes[c];
             const int si = c % NS;
             Slot& s = sl[si];
             // inputs may be overwritten once the kernels of the chunk that used this slot are done
