@@ -68,6 +68,25 @@ class IlqgState(C.Structure):       # ddp_ilqg_state
                 ("accepted_iter", C.c_int32), ("status", C.c_int32), ("pad", C.c_int32)]
 
 
+class IlqgklOpts(C.Structure):      # ddp_ilqgkl_opts
+    _fields_ = [("kl_step", C.c_double), ("max_iter", C.c_int32), ("eta_bracket", C.c_double * 3),
+                ("del0", C.c_double), ("max_eta_retries", C.c_int32), ("lims", C.c_void_p)]
+
+
+class IlqgklState(C.Structure):     # ddp_ilqgkl_state
+    _fields_ = [("eta_min", C.c_double), ("eta", C.c_double), ("eta_max", C.c_double), ("del0", C.c_double),
+                ("divergence", C.c_double), ("dcost", C.c_double), ("expected", C.c_double), ("cost", C.c_double),
+                ("iter", C.c_int32), ("status", C.c_int32), ("retries", C.c_int32), ("pad", C.c_int32)]
+
+
+class IlqgklArgs(C.Structure):      # ddp_ilqgkl_args
+    _fields_ = [("x", C.c_void_p), ("u", C.c_void_p), ("cost", C.c_void_p),
+                ("K_prev", Tensor), ("Sig_prev", Tensor), ("Sigi_prev", Tensor), ("fx_model", Tensor), ("R1", Tensor),
+                ("xnew", C.c_void_p), ("unew", C.c_void_p), ("K", C.c_void_p), ("k", C.c_void_p),
+                ("Sig", C.c_void_p), ("Sigi", C.c_void_p), ("Vx", C.c_void_p), ("Vxx1", C.c_void_p),
+                ("costnew", C.c_void_p), ("state", C.c_void_p)]
+
+
 class IterHostArgs(C.Structure):    # ddp_iter_host_args
     _fields_ = [("fx", C.c_void_p), ("fu", C.c_void_p), ("cx", C.c_void_p), ("cu", C.c_void_p),
                 ("x", C.c_void_p), ("u", C.c_void_p), ("lam", C.c_void_p),
@@ -105,6 +124,8 @@ SYMBOLS = [
     ("ddp_model_derivs_f64", C.c_int, [C.c_void_p, C.POINTER(Model)] + [C.c_void_p] * 6),
     ("ddp_ilqg_solve_f64", C.c_int, [C.c_void_p, C.POINTER(Model), C.POINTER(IlqgOpts)] + [C.c_void_p] * 9 +
      [C.POINTER(C.c_int32)]),
+    ("ddp_ilqgkl_solve_f64", C.c_int, [C.c_void_p, C.POINTER(Model), C.POINTER(IlqgklOpts), C.POINTER(IlqgklArgs),
+                                       C.POINTER(C.c_int32)]),
     ("ddp_ilqg_iter_host_f64", C.c_int, [C.c_void_p, C.POINTER(IterHostArgs)]),
 ]
 

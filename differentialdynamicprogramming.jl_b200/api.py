@@ -682,6 +682,78 @@ def iLQGkl(dynamics, costfun, derivs, x0, traj_prev: GaussianPolicy, fx_model, R
     return xnew, unew, traj_new, Vx, Vxx, costnew, trace
 
 
+KL_STATUS = {-1: "running", 0: "KL constraint satisfied", 1: "eta > 0.999 eta_max", 3: "EXIT: Maximum iterations reached",
+             5: "eta-retry limit reached"}
+
+
+def iLQGkl_device(dynamics, costfun, derivs, x0, traj_prev: GaussianPolicy, fx_model, R1, *, kl_step=1.0, lims=None, max_iter=50,
+                  etabracket=(1e-8, 1.0, 1e16), del0=1e-4, cost=None, max_eta_retries=200, force_generic=False,
+                  engine: Engine = None):
+    """Whole ``iLQGkl`` outer loop on the device for one trajectory or a batch (``ddp_ilqgkl_solve_f64``):
+    iLQGkl.jl:93-183 with ``calc_eta`` (klutils.jl:110-130) as per-trajectory state machines.
+
+    ``x0`` is the pre-rolled trajectory ``(N,n)`` / ``(B,N,n)``, ``traj_prev`` holds ``K (…,N,m,n)``, ``k (…,N,m)``,
+    ``Sigma``/``Sigmai (…,N,m,m)``, ``cost`` the total (or per-step) cost of ``x0``.  Returns
+    ``(xnew, unew, traj_new, Vx, Vxx1, costnew, trace)``; ``trace`` holds the per-trajectory final
+    ``status, iter, eta bracket, divergence, dcost, expected, retries`` (no per-iteration history: nothing is
+    read back inside the loop except two counters).
+    """
+    model = _model_of(dynamics, costfun)
+    x = np.asarray(x0, dtype=np.float64)
+    batched = x.ndim == 3
+    if not batched:
+        x = x[None]
+    B, N, n = x.shape
+    u = np.array(traj_prev.k, dtype=np.float64).reshape(B, N, -1)               # iLQGkl.jl:47
+    m = u.shape[-1]
+    if cost is None:
+        raise RuntimeError("Initial trajectory supplied, initial cost must also be supplied")
+    cost = np.asarray(cost, dtype=np.float64)
+    cost = cost.reshape(B, -1).sum(axis=1) if cost.size != B else cost.reshape(B)
+    eng = engine or Engine(n, m, N, B, force_generic=force_generic)
+    M, keep = _pack_model(eng, model, B, N, n, m)
+    o = L.IlqgklOpts()
+    o.kl_step, o.max_iter, o.del0, o.max_eta_retries = float(kl_step), int(max_iter), float(del0), int(max_eta_retries)
+    for i in range(3):
+        o.eta_bracket[i] = float(etabracket[i])
+    ld = _lims_dev(eng, lims, m)
+    if ld is not None:
+        keep.append(ld)
+        o.lims = ld.ptr
+    a = L.IlqgklArgs()
+    dx, du, dc = eng.upload(x), eng.upload(u), eng.upload(cost)
+    a.x, a.u, a.cost = dx.ptr, du.ptr, dc.ptr
+    dev, a.K_prev = _pack_mat(eng, np.asarray(traj_prev.K).reshape(B, N, m, n), B, N, m, n, "K_prev"); keep.append(dev)
+    dev, a.Sig_prev = _pack_mat(eng, np.asarray(traj_prev.Sigma).reshape(B, N, m, m), B, N, m, m, "Sig_prev"); keep.append(dev)
+    dev, a.Sigi_prev = _pack_mat(eng, np.asarray(traj_prev.Sigmai).reshape(B, N, m, m), B, N, m, m, "Sigi_prev"); keep.append(dev)
+    dev, a.fx_model = _pack_mat(eng, fx_model, B, N, n, n, "fx_model"); keep.append(dev)
+    dev, a.R1 = _pack_mat(eng, R1, B, 1, n, n, "R1"); keep.append(dev)
+    xnew, unew, K, k = eng.empty((B, N, n)).zero(), eng.empty((B, N, m)).zero(), eng.empty((B, N, n, m)).zero(), eng.empty((B, N, m)).zero()
+    Sig, Sigi, Vx, Vxx1 = eng.empty((B, N, m, m)).zero(), eng.empty((B, N, m, m)).zero(), eng.empty((B, N, n)).zero(), eng.empty((B, n, n)).zero()
+    cnew = eng.empty((B,)).zero()
+    st = eng.empty((B, C.sizeof(L.IlqgklState)), np.uint8)
+    a.xnew, a.unew, a.K, a.k, a.Sig, a.Sigi, a.Vx, a.Vxx1, a.costnew, a.state = (xnew.ptr, unew.ptr, K.ptr, k.ptr, Sig.ptr, Sigi.ptr,
+                                                                              Vx.ptr, Vxx1.ptr, cnew.ptr, st.ptr)
+    n_outer = C.c_int32(0)
+    eng._ck(eng.lib.ddp_ilqgkl_solve_f64(eng.h, C.byref(M), C.byref(o), C.byref(a), C.byref(n_outer)))
+    states = np.frombuffer(st.numpy().tobytes(), dtype=np.dtype(
+        [("eta_min", "f8"), ("eta", "f8"), ("eta_max", "f8"), ("del0", "f8"), ("divergence", "f8"), ("dcost", "f8"),
+         ("expected", "f8"), ("cost", "f8"), ("iter", "i4"), ("status", "i4"), ("retries", "i4"), ("pad", "i4")]))
+    trace = {key: states[key].copy() for key in ("status", "iter", "eta_min", "eta", "eta_max", "del0", "divergence", "dcost",
+                                                 "expected", "retries")}
+    trace["satisfied"] = trace["status"] == 0
+    trace["n_outer"] = int(n_outer.value)
+    pol = GaussianPolicy(N, n, m, np.swapaxes(K.numpy(), -1, -2), k.numpy(), np.swapaxes(Sig.numpy(), -1, -2),
+                         np.swapaxes(Sigi.numpy(), -1, -2))
+    out = (xnew.numpy(), unew.numpy(), pol, Vx.numpy(), np.swapaxes(Vxx1.numpy(), -1, -2), cnew.numpy(), trace)
+    del keep
+    if batched:
+        return out
+    pol1 = GaussianPolicy(N, n, m, pol.K[0], pol.k[0], pol.Sigma[0], pol.Sigmai[0])
+    tr1 = {key: (v[0] if isinstance(v, np.ndarray) else v) for key, v in trace.items()}
+    return out[0][0], out[1][0], pol1, out[3][0], out[4][0], float(out[5][0]), tr1
+
+
 # ---------------------------------------------------------------------------------------------
 # one end-to-end iteration on host buffers (the bench's e2e path)
 # ---------------------------------------------------------------------------------------------

@@ -283,7 +283,7 @@ int ddp_kl_div_f64(ddp_handle_t h, const ddp_kl_args* a) {
     P.n = h->n; P.m = h->m; P.T = h->T; P.B = h->B;
     P.fx = mk(a->fx); P.R1 = mk(a->R1); P.Kp = mk(a->K_prev); P.kp = mk(a->k_prev); P.Sp = mk(a->Sig_prev); P.Sip = mk(a->Sigi_prev);
     P.xnew = a->xnew; P.xold = a->xold; P.Kn = a->K_new; P.kn = a->k_new; P.Sn = a->Sig_new;
-    P.kl_t = a->kl_t; P.kl_mean = a->kl_mean;
+    P.kl_t = a->kl_t; P.kl_mean = a->kl_mean; P.active = nullptr;
     CU(h, cudaSetDevice(h->device));
     int rc = launch_kl_div(h, P);
     if (rc != 0) return cuda_fail(h, (cudaError_t)rc, "kl_div launch");

@@ -64,6 +64,7 @@ struct KlParams {
     TensorD fx, R1, Kp, kp, Sp, Sip;
     const double *xnew, *xold, *Kn, *kn, *Sn;
     double *kl_t, *kl_mean;
+    const unsigned char* active;     // [B] or nullptr
 };
 
 struct ddp_handle_s {

@@ -12,6 +12,7 @@
 //
 // Replaces forward_pass of src/forward_pass.jl:9-33 (+ f/costfun of demo_linear.jl:35-50 and
 // system_pendcart.jl:83-106).  Anything else dispatches to forward_generic.cu.
+#include <cstdlib>
 #include "ddp_common.cuh"
 
 namespace {
@@ -312,6 +313,186 @@ __global__ void __launch_bounds__(128) fwd_pend_kernel(FwdParams P) {
     P.cost[b] = ctot;
 }
 
+// ---------------------------------------------------------------------------------------------
+// pendulum on a cart, time-blocked staging (the fast path).  A thread walking its own trajectory touches
+// one 32-byte sector per tensor per step, so every load/store instruction of a warp hits 32 different
+// lines (32 L1 wavefronts): the LSU, not HBM, bounds fwd_pend_kernel.  Here a warp moves whole 128-byte
+// lines instead: for each block of 4 steps the next K / x blocks (32 trajectories x 128 B) and k / u blocks
+// (32 x 32 B) are copied with coalesced cp.async into a double-buffered shared-memory ring (rows padded to
+// 144 B => conflict-free 16-byte row reads), the threads read their own rows, write xnew / unew (and cx, cu)
+// back into the rows, and the block is written out with coalesced 16-byte stores.
+constexpr int PS_W = 2;                                   // warps per CTA
+constexpr int PS_R = 18;                                  // padded row of 16 doubles
+constexpr int PS_WARP_DOUBLES = 2 * 32 * PS_R * 2 + 2 * 32 * 4 * 2 + 32 * PS_R + 32 * 4;   // K,X ring; k,u ring; cx; cu
+
+__device__ __forceinline__ void cp16(double* dst_smem, const double* src) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src));
+}
+
+template <bool POLICY>
+__global__ void __launch_bounds__(PS_W * 32) fwd_pend_staged_kernel(FwdParams P) {
+    extern __shared__ __align__(16) double ps_smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const long long b0 = ((long long)blockIdx.x * PS_W + wid) * 32;
+    if (b0 >= P.B) return;
+    const long long b_raw = b0 + lane;
+    const bool valid = (b_raw < P.B) && !(P.active && !P.active[b_raw]);
+    const unsigned amask = __ballot_sync(0xffffffffu, valid);
+    const long long b = (b_raw < P.B) ? b_raw : P.B - 1;
+    double* sm = ps_smem + (size_t)wid * PS_WARP_DOUBLES;
+    double* sK = sm;                          // [2][32][18]
+    double* sX = sK + 2 * 32 * PS_R;          // [2][32][18]   x of the old trajectory in, xnew out (in place)
+    double* sk = sX + 2 * 32 * PS_R;          // [2][32][4]
+    double* su = sk + 2 * 32 * 4;             // [2][32][4]    u in, unew out (in place)
+    double* scx = su + 2 * 32 * 4;            // [32][18]
+    double* scu = scx + 32 * PS_R;            // [32][4]
+    const int N = P.T;
+    const double alpha = P.alpha ? P.alpha[b] : P.alpha_scalar;
+    const double gg = P.model.p[0], l = P.model.p[1], h = P.model.p[2], dd = P.model.p[3];
+    const double* Qm = P.model.Q.p + b * P.model.Q.sb;
+    const double Rv = (P.model.R.p + b * P.model.R.sb)[0];
+    double Q[16], goal[4], x[4];
+#pragma unroll
+    for (int i = 0; i < 16; i++) Q[i] = Qm[i];
+#pragma unroll
+    for (int i = 0; i < 4; i++) { goal[i] = P.model.goal ? P.model.goal[i] : 0.0; x[i] = (P.x0.p + b * P.x0.sb)[i]; }
+    const bool has_lims = P.lims != nullptr;
+    const double lo = has_lims ? P.lims[0] : 0.0, hi = has_lims ? P.lims[1] : 0.0;
+    const bool want_c = (P.cx != nullptr), want_cu = (P.cu != nullptr);
+    // lane -> (row, 16-byte chunk) maps of the coalesced copies
+    const int r8 = lane >> 3, c8 = lane & 7;              // 128-byte rows: 4 rows per instruction, 8 instructions
+    const int r2 = lane >> 1, c2 = lane & 1;              // 32-byte rows: 16 rows per instruction, 2 instructions
+    auto stage = [&](int j, int p) {
+        const int t0 = 4 * j;
+        if (t0 + (c8 >> 1) < N) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int row = r8 + 4 * k;
+                const long long bb = b0 + row;
+                if (bb < P.B) {
+                    if (POLICY) {
+                        cp16(sK + (p * 32 + row) * PS_R + 2 * c8, P.K + (bb * N + t0) * 4 + 2 * c8);
+                        cp16(sX + (p * 32 + row) * PS_R + 2 * c8, tp(P.x, bb, t0) + 2 * c8);
+                    }
+                }
+            }
+        }
+        if (t0 + 2 * c2 < N) {
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const int row = r2 + 16 * k;
+                const long long bb = b0 + row;
+                if (bb < P.B) {
+                    if (POLICY) cp16(sk + (p * 32 + row) * 4 + 2 * c2, P.k + bb * N + t0 + 2 * c2);
+                    cp16(su + (p * 32 + row) * 4 + 2 * c2, tp(P.u, bb, t0) + 2 * c2);
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    double ctot = 0.0, clast = 0.0;
+    const int nblk = (N + 3) >> 2;
+    stage(0, 0);
+    for (int j = 0; j < nblk; j++) {
+        const int p = j & 1, t0 = 4 * j;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        if (j + 1 < nblk) stage(j + 1, p ^ 1);
+        double* rK = sK + (p * 32 + lane) * PS_R;
+        double* rX = sX + (p * 32 + lane) * PS_R;
+        double* rk = sk + (p * 32 + lane) * 4;
+        double* ru_ = su + (p * 32 + lane) * 4;
+#pragma unroll
+        for (int s_ = 0; s_ < 4; s_++) {
+            const int t = t0 + s_;
+            if (t < N) {
+                double un = ru_[s_] * P.u_scale;
+                if (POLICY) {
+                    const double2 K01 = ldg2(rK + 4 * s_), K23 = ldg2(rK + 4 * s_ + 2);
+                    const double2 xo01 = ldg2(rX + 4 * s_), xo23 = ldg2(rX + 4 * s_ + 2);
+                    un = un + rk[s_] * alpha;
+                    double acc = K01.x * (x[0] - xo01.x);
+                    acc = fma(K01.y, x[1] - xo01.y, acc);
+                    acc = fma(K23.x, x[2] - xo23.x, acc);
+                    acc = fma(K23.y, x[3] - xo23.y, acc);
+                    un = un + acc;
+                }
+                if (has_lims) un = fmin(fmax(un, lo), hi);
+                if (un != un) un = 0.0;
+                stg2(rX + 4 * s_, x[0], x[1]);
+                stg2(rX + 4 * s_ + 2, x[2], x[3]);
+                ru_[s_] = un;
+                double dlt[4], qd[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) dlt[i] = x[i] - goal[i];
+                double cs = 0.0;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    qd[i] = 0.0;
+#pragma unroll
+                    for (int jj = 0; jj < 4; jj++) qd[i] = fma(Q[i + 4 * jj], dlt[jj], qd[i]);
+                    cs = fma(0.5 * dlt[i], qd[i], cs);
+                }
+                clast = cs;
+                const double ru = Rv * un;
+                const double cstep = fma(0.5 * un, ru, cs);
+                if (want_c) { stg2(scx + lane * PS_R + 4 * s_, qd[0], qd[1]); stg2(scx + lane * PS_R + 4 * s_ + 2, qd[2], qd[3]); }
+                if (want_cu) scu[lane * 4 + s_] = ru;
+                if (P.cost_t && valid) P.cost_t[b * (N + P.model.terminal_cost) + t] = cstep;
+                ctot += cstep;
+                if (t < N - 1) {
+                    double sn, cs2;
+                    sincos(x[0], &sn, &cs2);
+                    const double x0n = x[0] + h * x[1];
+                    const double x1n = x[1] + h * (-gg / l * sn + un / l * cs2 - dd * x[1]);
+                    const double x2n = x[2] + h * x[3];
+                    const double x3n = x[3] + h * un;
+                    x[0] = x0n; x[1] = x1n; x[2] = x2n; x[3] = x3n;
+                }
+            }
+        }
+        __syncwarp();
+        // coalesced write-out of the block
+        if (t0 + (c8 >> 1) < N) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int row = r8 + 4 * k;
+                const long long bb = b0 + row;
+                if ((amask >> row) & 1u) {
+                    const double2 v = ldg2(sX + (p * 32 + row) * PS_R + 2 * c8);
+                    stg2(P.xnew + (bb * N + t0) * 4 + 2 * c8, v.x, v.y);
+                    if (want_c) {
+                        const double2 c = ldg2(scx + row * PS_R + 2 * c8);
+                        stg2(P.cx + (bb * N + t0) * 4 + 2 * c8, c.x, c.y);
+                    }
+                }
+            }
+        }
+        if (t0 + 2 * c2 < N) {
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const int row = r2 + 16 * k;
+                const long long bb = b0 + row;
+                if ((amask >> row) & 1u) {
+                    const double2 v = ldg2(su + (p * 32 + row) * 4 + 2 * c2);
+                    stg2(P.unew + bb * N + t0 + 2 * c2, v.x, v.y);
+                    if (want_cu) {
+                        const double2 c = ldg2(scu + row * 4 + 2 * c2);
+                        stg2(P.cu + bb * N + t0 + 2 * c2, c.x, c.y);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (P.model.terminal_cost) {
+        if (P.cost_t && valid) P.cost_t[b * (N + 1) + N] = clast;
+        ctot += clast;
+    }
+    if (valid) P.cost[b] = ctot;
+}
+
 bool al16(const void* p) { return ((uintptr_t)p % 16) == 0; }
 
 }  // namespace
@@ -341,6 +522,25 @@ int launch_forward_fast(ddp_handle_s* h, const FwdParams& P, bool* handled) {
     if (P.model.kind == DDP_MODEL_PENDCART && P.n == 4 && P.m == 1) {
         if (!al16(P.xnew) || (policy && (!al16(P.K) || !al16(P.x.p) || (P.x.sb % 2) || (P.x.st % 2)))) return 0;
         if (P.cx && !al16(P.cx)) return 0;
+        // staged path: whole-line traffic; needs time-contiguous, 16-byte aligned rows (T even for the scalar rows)
+        const bool staged = (P.T % 2 == 0) && al16(P.unew) && al16(P.u.p) && (P.u.sb % 2 == 0) && P.u.st == 1 &&
+                            (!policy || (P.x.st == 4 && al16(P.k))) && (!P.cu || al16(P.cu)) && !getenv("DDP_PEND_NOSTAGE");
+        if (staged) {
+            const size_t bytes = (size_t)PS_W * PS_WARP_DOUBLES * sizeof(double);
+            const unsigned sgrid = (unsigned)((P.B + 32 * PS_W - 1) / (32 * PS_W));
+            cudaError_t e;
+            if (policy) {
+                e = cudaFuncSetAttribute(fwd_pend_staged_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+                if (e == cudaSuccess) fwd_pend_staged_kernel<true><<<sgrid, PS_W * 32, bytes, h->stream>>>(P);
+            } else {
+                e = cudaFuncSetAttribute(fwd_pend_staged_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+                if (e == cudaSuccess) fwd_pend_staged_kernel<false><<<sgrid, PS_W * 32, bytes, h->stream>>>(P);
+            }
+            if (e != cudaSuccess) return (int)e;
+            h->launches++;
+            *handled = true;
+            return (int)cudaGetLastError();
+        }
         unsigned grid = (unsigned)((P.B + 127) / 128);
         if (policy) fwd_pend_kernel<true><<<grid, 128, 0, h->stream>>>(P);
         else fwd_pend_kernel<false><<<grid, 128, 0, h->stream>>>(P);

@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(KT) kl_div_kernel(KlParams P) {
     double* scal = red + KT;            // 4
     const long long nn = (long long)n * n, mn = (long long)m * n, mm = (long long)m * m;
     for (long long b = blockIdx.x; b < P.B; b += gridDim.x) {
+        if (P.active && !P.active[b]) continue;          // block-uniform
         __syncthreads();
         const double* R1 = P.R1.p + b * P.R1.sb;
         for (int e = tid; e < n * n; e += KT) Sg[(e % n) + ldn * (e / n)] = R1[e];       // Σ_1 = R1

@@ -716,3 +716,224 @@ fail:
 }
 
 }  // extern "C"
+
+// =============================================================================================
+// ddp_ilqgkl_solve_f64: the iLQGkl outer loop (src/iLQGkl.jl:93-183) + calc_eta (src/klutils.jl:110-130)
+// for a whole batch, device resident.  Per trajectory: eta bracket (3), del0, retry count, status.
+namespace {
+
+struct KlSolveState {
+    double *eta3, *eta, *del0, *div, *dcost, *expected, *dV, *klmean;
+    int *iter, *status, *retries, *diverge;
+    unsigned char *active, *need_bp;
+    int* counters;          // [0] back passes to retry, [1] trajectories still iterating
+};
+
+__global__ void kl_init_kernel(long long B, KlSolveState s, double e0, double e1, double e2, double del0) {
+    long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    s.eta3[3 * b] = e0; s.eta3[3 * b + 1] = e1; s.eta3[3 * b + 2] = e2; s.eta[b] = e1; s.del0[b] = del0;
+    s.div[b] = 0.0; s.dcost[b] = 0.0; s.expected[b] = 0.0; s.dV[2 * b] = s.dV[2 * b + 1] = 0.0; s.klmean[b] = 0.0;
+    s.iter[b] = 0; s.status[b] = -1; s.retries[b] = 0; s.diverge[b] = 0; s.active[b] = 1; s.need_bp[b] = 1;
+}
+
+// after a KL-augmented backward launch: iLQGkl.jl:97-124 -- on failure eta += del0, del0 *= 2 and try again
+__global__ void kl_retry_kernel(long long B, KlSolveState s, int max_retries) {
+    long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B || !s.need_bp[b]) return;
+    if (s.diverge[b] > 0) {
+        const double d0 = s.del0[b];
+        const double e = s.eta3[3 * b + 1] + d0;          // :104
+        s.eta3[3 * b + 1] = e;
+        s.eta[b] = e;
+        s.del0[b] = 2.0 * d0;                             // :105
+        const int r = s.retries[b] + 1;
+        s.retries[b] = r;
+        if (r > max_retries) { s.need_bp[b] = 0; s.active[b] = 0; s.status[b] = 5; }
+        else atomicAdd(&s.counters[0], 1);
+    } else {
+        s.need_bp[b] = 0;
+    }
+}
+
+// after forward pass + KL evaluation: expected / actual improvement (iLQGkl.jl:137-139), calc_eta
+// (klutils.jl:110-130) and the two exits (iLQGkl.jl:173-181)
+__global__ void kl_eta_kernel(long long B, KlSolveState s, const double* __restrict__ cost, const double* __restrict__ costnew,
+                              double kl_step, int it, int max_iter) {
+    long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B || !s.active[b]) return;
+    s.iter[b] = it;
+    s.dcost[b] = cost[b] - costnew[b];
+    s.expected[b] = -(s.dV[2 * b] + s.dV[2 * b + 1]);     // :138
+    double e0 = s.eta3[3 * b], e1 = s.eta3[3 * b + 1], e2 = s.eta3[3 * b + 2];
+    bool satisfied;
+    double divergence;
+    if (!(kl_step > 0.0)) {                               // klutils.jl:111
+        satisfied = true;
+        divergence = 0.0;
+    } else {
+        divergence = s.klmean[b];
+        const double violation = divergence - kl_step;
+        satisfied = fabs(violation) < 0.1 * kl_step;      // :115
+        if (!satisfied) {
+            if (violation < 0.0) {                        // KL too small: eta is an upper bound (:119-122)
+                e2 = e1;
+                e1 = fmax(sqrt(e0 * e2), 0.1 * e2);
+            } else {                                      // KL too big: eta is a lower bound (:123-126)
+                e0 = e1;
+                e1 = fmin(sqrt(e0 * e2), 10.0 * e0);
+            }
+        }
+    }
+    s.div[b] = divergence;
+    s.eta3[3 * b] = e0; s.eta3[3 * b + 1] = e1; s.eta3[3 * b + 2] = e2; s.eta[b] = e1;
+    if (satisfied) { s.status[b] = 0; s.active[b] = 0; }
+    else if (e1 > 0.999 * e2) { s.status[b] = 1; s.active[b] = 0; }       // iLQGkl.jl:178
+    else if (it >= max_iter) { s.status[b] = 3; s.active[b] = 0; }
+    else { s.need_bp[b] = 1; atomicAdd(&s.counters[1], 1); }
+}
+
+__global__ void kl_export_kernel(long long B, KlSolveState s, const double* __restrict__ costnew, ddp_ilqgkl_state* out) {
+    long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    ddp_ilqgkl_state r;
+    r.eta_min = s.eta3[3 * b]; r.eta = s.eta3[3 * b + 1]; r.eta_max = s.eta3[3 * b + 2];
+    r.del0 = s.del0[b]; r.divergence = s.div[b]; r.dcost = s.dcost[b]; r.expected = s.expected[b]; r.cost = costnew[b];
+    r.iter = s.iter[b]; r.status = s.status[b]; r.retries = s.retries[b]; r.pad = 0;
+    out[b] = r;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ddp_ilqgkl_solve_f64(ddp_handle_t h, const ddp_model* model, const ddp_ilqgkl_opts* opts, const ddp_ilqgkl_args* a,
+                         int32_t* n_outer) {
+    if (!h) return DDP_ERR_INVALID;
+    if (!model || !opts || !a || !a->x || !a->u || !a->cost || !a->K_prev.ptr || !a->Sig_prev.ptr || !a->Sigi_prev.ptr ||
+        !a->fx_model.ptr || !a->R1.ptr || !a->xnew || !a->unew || !a->K || !a->k || !a->Sig || !a->Sigi || !a->Vx || !a->costnew ||
+        !a->state) {
+        h->err = "ddp_ilqgkl_solve_f64: missing argument";
+        return DDP_ERR_INVALID;
+    }
+    if (model->kind != DDP_MODEL_LINEAR && model->kind != DDP_MODEL_PENDCART) {
+        h->err = "ddp_ilqgkl_solve_f64: unknown model kind (arbitrary host callbacks cannot run on the device; no CPU fallback)";
+        return DDP_ERR_UNSUPPORTED;
+    }
+    if (model->kind == DDP_MODEL_PENDCART && (h->n != 4 || h->m != 1)) { h->err = "pendcart model needs n == 4, m == 1"; return DDP_ERR_INVALID; }
+    if (model->kind == DDP_MODEL_LINEAR && (!model->A.ptr || !model->Bm.ptr)) { h->err = "linear model needs A and B"; return DDP_ERR_INVALID; }
+    if (!model->Q.ptr || !model->R.ptr) { h->err = "model needs Q and R"; return DDP_ERR_INVALID; }
+    const int n = h->n, m = h->m, T = h->T;
+    const long long B = h->B;
+    const int max_iter = opts->max_iter > 0 ? opts->max_iter : 50;
+    const int max_retries = opts->max_eta_retries > 0 ? opts->max_eta_retries : 200;
+    cudaError_t err = cudaSuccess;
+    DevBuf mem;
+    KlSolveState s{};
+    double *cx = nullptr, *cu = nullptr, *fxb = nullptr, *fub = nullptr, *zeros = nullptr;
+    int hc[2];
+    int it = 0;
+    const unsigned gB = (unsigned)((B + 255) / 256);
+    cudaStream_t st = h->stream;
+    ModelD M;
+    BackParams BP{};
+    FwdParams FP{};
+    KlParams KP{};
+
+    CUS(cudaSetDevice(h->device));
+    CUS(mem.alloc(&s.eta3, 3 * B)); CUS(mem.alloc(&s.eta, B)); CUS(mem.alloc(&s.del0, B)); CUS(mem.alloc(&s.div, B));
+    CUS(mem.alloc(&s.dcost, B)); CUS(mem.alloc(&s.expected, B)); CUS(mem.alloc(&s.dV, 2 * B)); CUS(mem.alloc(&s.klmean, B));
+    CUS(mem.alloc(&s.iter, B)); CUS(mem.alloc(&s.status, B)); CUS(mem.alloc(&s.retries, B)); CUS(mem.alloc(&s.diverge, B));
+    CUS(mem.alloc(&s.active, B)); CUS(mem.alloc(&s.need_bp, B)); CUS(mem.alloc(&s.counters, 2));
+    CUS(mem.alloc(&cx, (size_t)B * T * n)); CUS(mem.alloc(&cu, (size_t)B * T * m));
+    CUS(mem.alloc(&zeros, (size_t)n * m));
+    CUS(cudaMemsetAsync(zeros, 0, sizeof(double) * n * m, st));
+    if (model->kind == DDP_MODEL_PENDCART) { CUS(mem.alloc(&fxb, (size_t)B * T * 16)); CUS(mem.alloc(&fub, (size_t)B * T * 4)); }
+
+    M.kind = model->kind; M.A = mk(model->A); M.Bm = mk(model->Bm); M.Q = mk(model->Q); M.R = mk(model->R); M.goal = model->goal;
+    for (int i = 0; i < 8; i++) M.p[i] = model->p[i];
+    M.terminal_cost = model->terminal_cost ? 1 : 0;
+    M.flags = model->flags;
+
+    kl_init_kernel<<<gB, 256, 0, st>>>(B, s, opts->eta_bracket[0], opts->eta_bracket[1], opts->eta_bracket[2], opts->del0);
+    h->launches++;
+
+    // derivatives once, before the loop (iLQGkl.jl:88, quirk Q9)
+    {
+        const long long wtot = B * T;
+        const unsigned dgrid = (unsigned)std::min<long long>((wtot + 3) / 4, (long long)h->sm_count * 16);
+        df_cost_kernel<<<dgrid, 128, 0, st>>>(n, m, T, B, a->x, a->u, M.Q, M.R, M.goal, nullptr, cx, cu);
+        h->launches++;
+        if (model->kind == DDP_MODEL_PENDCART) {
+            df_pendcart_kernel<<<(unsigned)((wtot + 127) / 128), 128, 0, st>>>(T, B, a->x, a->u, M.p[0], M.p[1], M.p[2], M.p[3], nullptr, fxb, fub);
+            h->launches++;
+        }
+    }
+    BP.n = n; BP.m = m; BP.T = T; BP.B = B;
+    BP.cx = TensorD{cx, (long long)T * n, n}; BP.cu = TensorD{cu, (long long)T * m, m};
+    BP.cxx = M.Q; BP.cuu = M.R; BP.cxu = TensorD{zeros, 0, 0};
+    if (model->kind == DDP_MODEL_PENDCART) {
+        BP.fx = TensorD{fxb, (long long)T * 16, 16}; BP.fu = TensorD{fub, (long long)T * 4, 4};
+    } else {
+        BP.fx = M.A; BP.fu = M.Bm;
+    }
+    BP.u = TensorD{a->u, (long long)T * m, m};
+    BP.lambda = nullptr; BP.reg_type = 0; BP.lims = opts->lims; BP.active = s.need_bp;
+    BP.Kp = mk(a->K_prev); BP.kp = TensorD{nullptr, 0, 0};          // k_prev := 0 (iLQGkl.jl:52)
+    BP.Sip = mk(a->Sigi_prev); BP.eta = s.eta; BP.Quui = a->Sig;
+    BP.diverge = s.diverge; BP.K = a->K; BP.k = a->k; BP.Vx = a->Vx; BP.Vxx = nullptr; BP.Vxx1 = a->Vxx1; BP.Quu = a->Sigi; BP.dV = s.dV;
+    BP.qp = QPOpts{100, 1e-8, 1e-8, 0.6, 1e-22, 0.1};
+
+    FP.n = n; FP.m = m; FP.T = T; FP.B = B; FP.model = M;
+    FP.K = a->K; FP.k = a->k;
+    FP.x0 = TensorD{a->x, (long long)T * n, 0};
+    FP.x = TensorD{a->x, (long long)T * n, n}; FP.u = TensorD{a->u, (long long)T * m, m};
+    FP.alpha = nullptr; FP.alpha_scalar = 1.0; FP.u_scale = 1.0;                       // forward pass with alpha = 1 (:134)
+    FP.lims = opts->lims; FP.active = s.active;
+    FP.xnew = a->xnew; FP.unew = a->unew; FP.cost = a->costnew; FP.cost_t = nullptr; FP.cx = nullptr; FP.cu = nullptr;
+
+    KP.n = n; KP.m = m; KP.T = T; KP.B = B;
+    KP.fx = mk(a->fx_model); KP.R1 = mk(a->R1); KP.Kp = mk(a->K_prev); KP.kp = TensorD{nullptr, 0, 0};
+    KP.Sp = mk(a->Sig_prev); KP.Sip = mk(a->Sigi_prev);
+    KP.xnew = a->xnew; KP.xold = a->x; KP.Kn = a->K; KP.kn = a->k; KP.Sn = a->Sig;
+    KP.kl_t = nullptr; KP.kl_mean = s.klmean; KP.active = s.active;
+
+    for (it = 1; it <= max_iter; it++) {
+        // KL-augmented backward sweep with the eta-retry loop (iLQGkl.jl:97-124)
+        for (;;) {
+            CUS(cudaMemsetAsync(s.counters, 0, 2 * sizeof(int), st));
+            {
+                bool handled = false;
+                int rc = 0;
+                if (!(h->flags & 1u)) rc = launch_back_pass_tile(h, BP, true, &handled);
+                if (!handled && rc == 0) rc = launch_back_pass_generic(h, BP, true);
+                CUS((cudaError_t)rc);
+            }
+            kl_retry_kernel<<<gB, 256, 0, st>>>(B, s, max_retries);
+            h->launches++;
+            CUS(cudaMemcpyAsync(hc, s.counters, sizeof(hc), cudaMemcpyDeviceToHost, st));
+            CUS(cudaStreamSynchronize(st));
+            if (hc[0] == 0) break;
+        }
+        CUS((cudaError_t)run_fwd(h, FP));
+        if (opts->kl_step > 0.0) CUS((cudaError_t)launch_kl_div(h, KP));
+        CUS(cudaMemsetAsync(s.counters, 0, 2 * sizeof(int), st));
+        kl_eta_kernel<<<gB, 256, 0, st>>>(B, s, a->cost, a->costnew, opts->kl_step, it, max_iter);
+        h->launches++;
+        CUS(cudaMemcpyAsync(hc, s.counters, sizeof(hc), cudaMemcpyDeviceToHost, st));
+        CUS(cudaStreamSynchronize(st));
+        if (hc[1] == 0) break;
+    }
+    // traj_new.k = copy(u) (iLQGkl.jl:240-241, quirk Q11)
+    CUS(cudaMemcpyAsync(a->k, a->unew, sizeof(double) * (size_t)B * T * m, cudaMemcpyDeviceToDevice, st));
+    kl_export_kernel<<<gB, 256, 0, st>>>(B, s, a->costnew, a->state);
+    h->launches++;
+    CUS(cudaStreamSynchronize(st));
+    if (n_outer) *n_outer = std::min(it, max_iter);
+    return DDP_OK;
+fail:
+    h->err = std::string("ddp_ilqgkl_solve_f64: ") + cudaGetErrorString(err);
+    return DDP_ERR_CUDA;
+}
+
+}  // extern "C"

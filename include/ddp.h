@@ -15,6 +15,7 @@
  *   ddp_kl_div_f64         <- forward_covariance + kl_div_wiki
  *                             src/forward_pass.jl:37-56, src/klutils.jl:70-100
  *   ddp_ilqg_solve_f64     <- iLQG(f,costfun,df,x0,u0;kw...)           src/iLQG.jl:143-341
+ *   ddp_ilqgkl_solve_f64   <- iLQGkl outer loop + calc_eta (src/iLQGkl.jl:93-183, src/klutils.jl:110-130)
  *   ddp_ilqg_iter_host_f64 <- one back_pass + forward_pass (α given) on HOST buffers, chunked
  *                             and overlapped with the PCIe copies (the end-to-end path)
  *
@@ -259,6 +260,52 @@ typedef struct ddp_ilqg_state {
 DDP_API int ddp_ilqg_solve_f64(ddp_handle_t h, const ddp_model* model, const ddp_ilqg_opts* opts, const double* x0,
                        const double* u0, double* x, double* u, double* K, double* k, double* Vx,
                        double* Vxx1, ddp_ilqg_state* state, int32_t* n_outer);
+
+/* ---- whole iLQGkl solve (single-KL-constraint branch), device resident --------------------- */
+/* Replaces the outer loop of iLQGkl (src/iLQGkl.jl:25-183, 238-252) with calc_eta (src/klutils.jl:110-130)
+ * for a whole batch: every trajectory carries its own eta bracket, del0 and iteration count; the
+ * KL-augmented backward sweep, the forward rollout (alpha = 1) and the KL evaluation run over the batch
+ * with activity masks.  The derivatives are computed once, before the loop (iLQGkl.jl:88, quirk Q9). */
+typedef struct ddp_ilqgkl_opts {        /* defaults: iLQGkl.jl:25-42 */
+    double kl_step;                     /* 1.0; <= 0 => satisfied at once (klutils.jl:111)            */
+    int32_t max_iter;                   /* 50                                                         */
+    double eta_bracket[3];              /* {1e-8, 1, 1e16}                                            */
+    double del0;                        /* 1e-4                                                       */
+    int32_t max_eta_retries;            /* bounds the reference's unbounded eta-retry loop (iLQGkl.jl:97); 0 => 200 */
+    const double* lims;                 /* DEVICE (m,2) or NULL                                       */
+} ddp_ilqgkl_opts;
+
+typedef struct ddp_ilqgkl_state {
+    double eta_min, eta, eta_max;       /* the bracket at exit                                        */
+    double del0, divergence, dcost, expected, cost;
+    int32_t iter;                       /* iterations executed (1-based, as the reference's `iter`)   */
+    int32_t status;                     /* -1 running, 0 KL constraint satisfied, 1 eta > 0.999 eta_max (iLQGkl.jl:178),
+                                           3 max_iter, 5 eta-retry limit                              */
+    int32_t retries, pad;
+} ddp_ilqgkl_state;
+
+typedef struct ddp_ilqgkl_args {
+    /* inputs (device) */
+    const double* x;                    /* (n,T,B) pre-rolled trajectory (iLQGkl.jl:63-70)            */
+    const double* u;                    /* (m,T,B) = traj_prev.k (iLQGkl.jl:47)                       */
+    const double* cost;                 /* [B] total cost of (x,u)                                    */
+    ddp_tensor K_prev;                  /* (m,n,T,B) traj_prev.K                                      */
+    ddp_tensor Sig_prev;                /* (m,m,T,B) traj_prev.Σ                                      */
+    ddp_tensor Sigi_prev;               /* (m,m,T,B) traj_prev.Σi                                     */
+    ddp_tensor fx_model;                /* (n,n[,T][,B]) what df(model,x,u) returns (forward_pass.jl:38) */
+    ddp_tensor R1;                      /* (n,n[,B])     what covariance(model,x,u) returns (forward_pass.jl:42) */
+    /* outputs (device) */
+    double *xnew, *unew;                /* (n,T,B), (m,T,B)                                           */
+    double *K, *k;                      /* new policy; k = unew on return (quirk Q11, iLQGkl.jl:241)  */
+    double *Sig, *Sigi;                 /* (m,m,T,B) new policy Σ = inv(Quu), Σi = Quu                */
+    double* Vx;                         /* (n,T,B)                                                    */
+    double* Vxx1;                       /* (n,n,B) or NULL                                            */
+    double* costnew;                    /* [B]                                                        */
+    ddp_ilqgkl_state* state;            /* [B]                                                        */
+} ddp_ilqgkl_args;
+
+DDP_API int ddp_ilqgkl_solve_f64(ddp_handle_t h, const ddp_model* model, const ddp_ilqgkl_opts* opts,
+                                 const ddp_ilqgkl_args* a, int32_t* n_outer);
 
 /* ---- end-to-end iteration on HOST buffers ------------------------------------------------ */
 /* One backward sweep + one forward rollout for a linear model with per-trajectory LTI dynamics

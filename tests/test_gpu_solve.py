@@ -128,6 +128,53 @@ def test_ilqgkl_matches_oracle(ddp, kl_step):
     assert relerr(rd[2].K, ro[2].K) < 1e-7 and relerr(rd[2].Sigma, ro[2].Sigma) < 1e-7
 
 
+@pytest.mark.parametrize("n,m", [(6, 2), (32, 8)])
+def test_ilqgkl_device_batch_matches_oracle(ddp, n, m):
+    """ddp_ilqgkl_solve_f64: the whole iLQGkl loop (iLQGkl.jl:93-183, klutils.jl:110-130) device resident for a batch of
+    different problems with different kl_step-to-divergence regimes; every trajectory ends with the oracle's iteration
+    count, status and eta bracket (integers exact, eta <= 1e-9 rel) and its trajectories/policy within 1e-7."""
+    from helpers import rollout
+    B, N = 5, 24
+    rng = np.random.default_rng(77)
+    xs, us, Ks, Sigs, Sigis, costs, As, Bs = [], [], [], [], [], [], [], []
+    Q = R = None
+    for b in range(B):
+        A, Bm, Q, R = make_lq(rng, n, m, h=0.1)
+        u = (0.05 + 0.1 * b) * rng.standard_normal((N, m))
+        x = rollout(A, Bm, np.ones(n), u)
+        d, p, _, _, _ = O.back_pass(x @ Q.T, u @ R.T, Q, np.zeros((n, m)), R, A, Bm, 1.0, 1, None, x, u)
+        assert d == 0
+        Sigi = p.Sigmai.copy()
+        xs.append(x); us.append(u); Ks.append(p.K.copy()); Sigis.append(Sigi); Sigs.append(np.array([np.linalg.inv(s_) for s_ in Sigi]))
+        As.append(A); Bs.append(Bm)
+        costs.append(O.LinearModel(A, Bm, Q, R).costfun(x, u))
+    R1 = 1e-3 * np.eye(n)
+    kl_step = 2.0
+    ref = []
+    for b in range(B):
+        om = O.LinearModel(As[b], Bs[b], Q, R)
+        prev = O.GaussianPolicy(N, n, m, Ks[b].copy(), us[b].copy(), Sigs[b].copy(), Sigis[b].copy())
+        ref.append(O.iLQGkl(om.f, om.costfun, lambda xx, uu, om=om: om.df(xx, uu, time_varying=True), xs[b], prev, As[b], R1,
+                            kl_step=kl_step, cost=costs[b]))
+    A4, B4 = np.stack(As)[:, None], np.stack(Bs)[:, None]
+    model = ddp.LinearModel(A4, B4, Q, R)
+    prev_d = ddp.GaussianPolicy(N, n, m, np.stack(Ks), np.stack(us), np.stack(Sigs), np.stack(Sigis))
+    rd = ddp.iLQGkl_device(model.f, model.costfun, model.df, np.stack(xs), prev_d, A4, R1, kl_step=kl_step,
+                           cost=np.array([np.sum(c) for c in costs]))
+    tr = rd[6]
+    iters = [r[6]["iters"] for r in ref]
+    assert len(set(iters)) > 1 or B == 1, "the batch should exercise different iteration counts"
+    for b in range(B):
+        to = ref[b][6]
+        assert tr["iter"][b] == to["iters"] and bool(tr["satisfied"][b]) == bool(to["satisfied"])
+        assert np.allclose([tr["eta_min"][b], tr["eta"][b], tr["eta_max"][b]], to["etabracket"], rtol=1e-9)
+        assert abs(tr["divergence"][b] - to["divergence"][-1][1]) <= 1e-7 * max(1.0, abs(to["divergence"][-1][1]))
+        assert relerr(rd[0][b], ref[b][0]) < 1e-7 and relerr(rd[1][b], ref[b][1]) < 1e-7
+        assert abs(rd[5][b] - np.sum(ref[b][5])) < 1e-8 * abs(np.sum(ref[b][5]))
+        assert relerr(rd[2].K[b], ref[b][2].K) < 1e-7 and relerr(rd[2].Sigma[b], ref[b][2].Sigma) < 1e-7
+        assert relerr(rd[2].k[b], ref[b][1]) < 1e-7                      # quirk Q11: k = u on return
+
+
 def test_iter_host_device_derivs(ddp):
     """cx = cu = NULL: the derivative step runs on the device; results equal the host-derivative path."""
     B, n, m, N = 21, 32, 8, 24
