@@ -124,6 +124,8 @@ SYMBOLS = [
     ("ddp_model_derivs_f64", C.c_int, [C.c_void_p, C.POINTER(Model)] + [C.c_void_p] * 6),
     ("ddp_ilqg_solve_f64", C.c_int, [C.c_void_p, C.POINTER(Model), C.POINTER(IlqgOpts)] + [C.c_void_p] * 9 +
      [C.POINTER(C.c_int32)]),
+    ("ddp_forward_costs_multi_f64", C.c_int, [C.c_void_p, C.POINTER(Model), C.POINTER(ForwardPassArgs), C.c_int32,
+                                              C.POINTER(C.c_double), C.c_void_p]),
     ("ddp_ilqgkl_solve_f64", C.c_int, [C.c_void_p, C.POINTER(Model), C.POINTER(IlqgklOpts), C.POINTER(IlqgklArgs),
                                        C.POINTER(C.c_int32)]),
     ("ddp_ilqg_iter_host_f64", C.c_int, [C.c_void_p, C.POINTER(IterHostArgs)]),

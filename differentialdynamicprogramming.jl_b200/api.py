@@ -476,6 +476,44 @@ def forward_pass(traj_new: GaussianPolicy, x0, u, x, alpha, f, costfun, lims, di
     return xn, un, cn
 
 
+def forward_costs(traj_new: GaussianPolicy, x0, u, x, alphas, f, costfun, lims, *, force_generic=False, engine: Engine = None):
+    """Total cost of ``forward_pass(traj_new,x0,u,x,α,…)`` for every ``α`` in ``alphas`` in one call
+    (``ddp_forward_costs_multi_f64``): the serial backtracking of iLQG.jl:267-281 with the policy gains read once.
+    Returns an array ``(len(alphas),)`` / ``(len(alphas), B)``."""
+    model = _model_of(f, costfun)
+    u = np.asarray(u, dtype=np.float64)
+    batched = u.ndim == 3
+    B = u.shape[0] if batched else 1
+    N, m = u.shape[-2:]
+    x0 = np.asarray(x0, dtype=np.float64)
+    n = x0.shape[-1]
+    eng = engine or Engine(n, m, N, B, force_generic=force_generic)
+    M, keep = _pack_model(eng, model, B, N, n, m)
+    a = L.ForwardPassArgs()
+    x0b = np.broadcast_to(x0.reshape(-1, n), (B, n)) if x0.ndim <= 1 or x0.shape[0] != B else x0
+    dx0 = eng.upload(x0b); keep.append(dx0)
+    a.x0 = _tensor(dx0.ptr, n, 0)
+    du, a.u = _pack_vec(eng, u, B, N, m, "u"); keep.append(du)
+    dK = eng.upload(np.swapaxes(np.asarray(traj_new.K, dtype=np.float64).reshape(B, N, m, n), -1, -2)); keep.append(dK)
+    dk = eng.upload(np.asarray(traj_new.k, dtype=np.float64).reshape(B, N, m)); keep.append(dk)
+    a.K, a.k = dK.ptr, dk.ptr
+    dx, a.x = _pack_vec(eng, x, B, N, n, "x"); keep.append(dx)
+    a.u_scale = 1.0
+    ld = _lims_dev(eng, lims, m)
+    if ld is not None:
+        keep.append(ld)
+        a.lims = ld.ptr
+    xnew, unew, cost = eng.empty((B, N, n)), eng.empty((B, N, m)), eng.empty((B,))
+    a.xnew, a.unew, a.cost = xnew.ptr, unew.ptr, cost.ptr
+    al = np.ascontiguousarray(np.asarray(alphas, dtype=np.float64).reshape(-1))
+    out = eng.empty((len(al), B))
+    eng._ck(eng.lib.ddp_forward_costs_multi_f64(eng.h, C.byref(M), C.byref(a), len(al), al.ctypes.data_as(L.c_double_p), out.ptr))
+    eng.synchronize()
+    res = out.numpy()
+    del keep
+    return res if batched else res[:, 0]
+
+
 # ---------------------------------------------------------------------------------------------
 # KL divergence (forward_covariance + kl_div_wiki)
 # ---------------------------------------------------------------------------------------------

@@ -265,6 +265,37 @@ int ddp_forward_pass_f64(ddp_handle_t h, const ddp_model* model, const ddp_forwa
     return DDP_OK;
 }
 
+int ddp_forward_costs_multi_f64(ddp_handle_t h, const ddp_model* model, const ddp_forward_pass_args* a, int32_t n_alpha,
+                                const double* alpha, double* cost_out) {
+    if (!h) return DDP_ERR_INVALID;
+    if (!a || !alpha || !cost_out || n_alpha < 1) return fail(h, DDP_ERR_INVALID, "ddp_forward_costs_multi_f64: args, alpha, cost_out are required");
+    FwdParams P;
+    std::string why;
+    if (!fill_model(h, model, P.model, why)) return fail(h, model && model->kind > 2 ? DDP_ERR_UNSUPPORTED : DDP_ERR_INVALID, "ddp_forward_costs_multi_f64: " + why);
+    if (!a->K || !a->k || !a->x.ptr || !a->x0.ptr || !a->u.ptr) return fail(h, DDP_ERR_INVALID, "ddp_forward_costs_multi_f64: K, k, x0, x, u are required");
+    P.n = h->n; P.m = h->m; P.T = h->T; P.B = h->B;
+    P.K = a->K; P.k = a->k; P.x0 = mk(a->x0); P.x = mk(a->x); P.u = mk(a->u);
+    P.alpha = nullptr; P.alpha_scalar = 1.0; P.u_scale = (a->u_scale == 0.0) ? 1.0 : a->u_scale;
+    P.lims = a->lims; P.active = a->active;
+    P.xnew = a->xnew; P.unew = a->unew; P.cost = a->cost; P.cost_t = nullptr; P.cx = nullptr; P.cu = nullptr;
+    CU(h, cudaSetDevice(h->device));
+    bool handled = false;
+    int rc = 0;
+    if (!(h->flags & 1u)) rc = launch_forward_multi(h, P, n_alpha, alpha, cost_out, &handled);
+    if (!handled && rc == 0) {
+        if (!a->xnew || !a->unew) return fail(h, DDP_ERR_INVALID, "ddp_forward_costs_multi_f64: xnew, unew scratch are required for this shape");
+        for (int i = 0; i < n_alpha && rc == 0; i++) {
+            P.alpha_scalar = alpha[i];
+            P.cost = cost_out + (long long)i * h->B;
+            bool hd = false;
+            if (!(h->flags & 1u)) rc = launch_forward_fast(h, P, &hd);
+            if (!hd && rc == 0) rc = launch_forward_generic(h, P);
+        }
+    }
+    if (rc != 0) return cuda_fail(h, (cudaError_t)rc, "forward_costs_multi launch");
+    return DDP_OK;
+}
+
 int ddp_batch_stats_f64(ddp_handle_t h, const double* cost_old, const double* cost_new, const double* dV, const double* alpha,
                         double alpha_scalar, const int32_t* diverge, const uint8_t* active, double* stats8) {
     if (!h || !stats8) return DDP_ERR_INVALID;

@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(FW_WPB * 32, 2) fwd_lin32x8_kernel(FwdParams P
             xnb[(long long)t * 32 + lane] = x;
             __syncwarp();
             // 2. controls: u + alpha k + K dx   (lane holds K[2q..2q+1][g + 8i], i = 0..3)
-            double un0 = uu.x * P.u_scale, un1 = uu.y * P.u_scale;
+            double un0 = __dmul_rn(uu.x, P.u_scale), un1 = __dmul_rn(uu.y, P.u_scale);
             if (POLICY) {
                 const double d0 = sdx[g], d1 = sdx[g + 8], d2 = sdx[g + 16], d3 = sdx[g + 24];
                 double p0 = fma(K3.x, d3, fma(K2.x, d2, fma(K1.x, d1, K0.x * d0)));
@@ -113,8 +113,8 @@ __global__ void __launch_bounds__(FW_WPB * 32, 2) fwd_lin32x8_kernel(FwdParams P
                     p0 += __shfl_xor_sync(0xffffffffu, p0, o);
                     p1 += __shfl_xor_sync(0xffffffffu, p1, o);
                 }
-                un0 = (un0 + kk.x * alpha) + p0;          // forward_pass.jl:18,20: two separate roundings
-                un1 = (un1 + kk.y * alpha) + p1;
+                un0 = __dadd_rn(__dadd_rn(un0, __dmul_rn(kk.x, alpha)), p0);   // forward_pass.jl:18,20: separate roundings, no FMA
+                un1 = __dadd_rn(__dadd_rn(un1, __dmul_rn(kk.y, alpha)), p1);
             }
             if (has_lims) { un0 = fmin(fmax(un0, lo0), hi0); un1 = fmin(fmax(un1, lo1), hi1); }
             if (un0 != un0) un0 = 0.0;
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(FW_WPB * 32, 2) fwd_lin32x8_kernel(FwdParams P
                 for (int o = 16; o > 0; o >>= 1) ct += __shfl_xor_sync(0xffffffffu, ct, o);
                 if (lane == 0) P.cost_t[b * (N + P.model.terminal_cost) + t] = ct;
             }
-            cpart += cstep;
+            cpart = __dadd_rn(cpart, cstep);
             if (t < N - 1) x = ((ax0 + ax1) + (ax2 + ax3)) + bu;
             __syncwarp();
         };
@@ -191,18 +191,183 @@ __global__ void __launch_bounds__(FW_WPB * 32, 2) fwd_lin32x8_kernel(FwdParams P
 #pragma unroll
                 for (int j = 0; j < 32; j++) qd = fma(sQ[lane + 32 * j], sv[j], qd);
             }
-            double cterm = 0.5 * (x - goal) * qd;
+            double cterm = __dmul_rn(0.5 * (x - goal), qd);
             if (P.cost_t) {
                 double ct = cterm;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) ct += __shfl_xor_sync(0xffffffffu, ct, o);
                 if (lane == 0) P.cost_t[b * (N + 1) + N] = ct;
             }
-            cpart += cterm;
+            cpart = __dadd_rn(cpart, cterm);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) cpart += __shfl_xor_sync(0xffffffffu, cpart, o);
         if (lane == 0) P.cost[b] = cpart;
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Multi-alpha line-search rollout for the headline shape: the total cost of the rollout
+// for up to FM_NA step sizes in ONE pass over the policy, i.e. K (512 KB per trajectory, the dominant read of
+// a forward pass) is streamed once instead of once per backtracking step of iLQG.jl:267-281.  Only costs are
+// produced; the accepted step size is then rolled out by fwd_lin32x8_kernel, whose per-lane arithmetic
+// (operation order, FMA placement, reduction trees) this kernel repeats exactly, so the costs agree bit for bit.
+constexpr int FM_NA = 10;
+constexpr int FM_WARP_DOUBLES = FM_NA * (32 + 32 + 32 + 8);
+struct MultiAlpha {
+    int na;
+    double a[16];
+};
+
+template <int QMODE>
+__global__ void __launch_bounds__(FW_WPB * 32, 2) fwd_lin32x8_multi_kernel(FwdParams P, MultiAlpha MA, double* __restrict__ cost_out) {
+    extern __shared__ double fm_smem[];
+    __shared__ double sQ[QMODE == 1 ? 1024 : 1];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    double* sx = fm_smem + w * FM_WARP_DOUBLES;          // [a][32]
+    double* sdx = sx + FM_NA * 32;
+    double* sd = sdx + FM_NA * 32;
+    double* su = sd + FM_NA * 32;                         // [a][8]
+    const int N = P.T, na = MA.na;
+    const bool has_goal = (P.model.goal != nullptr);
+    const bool has_lims = (P.lims != nullptr);
+    const long long warps_total = (long long)gridDim.x * FW_WPB;
+    if (QMODE == 1) {
+        for (int e = threadIdx.x; e < 1024; e += FW_WPB * 32) sQ[e] = P.model.Q.p[e];
+        __syncthreads();
+    }
+    for (long long b = (long long)blockIdx.x * FW_WPB + w; b < P.B; b += warps_total) {
+        if (P.active && !P.active[b]) continue;
+        double Ar[32], Br[8], Rr[8];
+        double qdiag = 0.0;
+        {
+            const double* A = P.model.A.p + b * P.model.A.sb;
+            const double* Bm = P.model.Bm.p + b * P.model.Bm.sb;
+            const double* R = P.model.R.p + b * P.model.R.sb;
+#pragma unroll
+            for (int j = 0; j < 32; j++) Ar[j] = A[lane + 32 * j];
+#pragma unroll
+            for (int c = 0; c < 8; c++) { Br[c] = Bm[lane + 32 * c]; Rr[c] = R[(lane & 7) + 8 * c]; }
+            if (QMODE == 0) qdiag = (P.model.Q.p + b * P.model.Q.sb)[lane * 33];
+        }
+        const double goal = has_goal ? P.model.goal[lane] : 0.0;
+        double lo0 = 0, lo1 = 0, hi0 = 0, hi1 = 0;
+        if (has_lims) { lo0 = P.lims[2 * q]; lo1 = P.lims[2 * q + 1]; hi0 = P.lims[8 + 2 * q]; hi1 = P.lims[8 + 2 * q + 1]; }
+        double x[FM_NA], cpart[FM_NA];
+        {
+            const double x0 = (P.x0.p + b * P.x0.sb)[lane];
+#pragma unroll
+            for (int a = 0; a < FM_NA; a++) { x[a] = x0; cpart[a] = 0.0; }
+        }
+        Pre pa, pb;
+        prefetch<true>(pa, P, b, 0, lane, q);
+        if (N > 1) prefetch<true>(pb, P, b, 1, lane, q);
+        auto step = [&](int t, Pre& p) {
+            const double2 K0 = p.K0, K1 = p.K1, K2 = p.K2, K3 = p.K3, uu = p.u, kk = p.k;
+            const double xo = p.xo;
+            if (t + 2 < N) prefetch<true>(p, P, b, t + 2, lane, q);
+#pragma unroll
+            for (int a = 0; a < FM_NA; a++)
+                if (a < na) {
+                    sx[a * 32 + lane] = x[a];
+                    sdx[a * 32 + lane] = x[a] - xo;
+                    if (has_goal && QMODE == 1) sd[a * 32 + lane] = x[a] - goal;
+                }
+            __syncwarp();
+#pragma unroll
+            for (int a = 0; a < FM_NA; a++)
+                if (a < na) {
+                    double un0 = __dmul_rn(uu.x, P.u_scale), un1 = __dmul_rn(uu.y, P.u_scale);
+                    const double* dxa = sdx + a * 32;
+                    const double d0 = dxa[g], d1 = dxa[g + 8], d2 = dxa[g + 16], d3 = dxa[g + 24];
+                    double p0 = fma(K3.x, d3, fma(K2.x, d2, fma(K1.x, d1, K0.x * d0)));
+                    double p1 = fma(K3.y, d3, fma(K2.y, d2, fma(K1.y, d1, K0.y * d0)));
+#pragma unroll
+                    for (int o = 4; o < 32; o <<= 1) {
+                        p0 += __shfl_xor_sync(0xffffffffu, p0, o);
+                        p1 += __shfl_xor_sync(0xffffffffu, p1, o);
+                    }
+                    un0 = __dadd_rn(__dadd_rn(un0, __dmul_rn(kk.x, MA.a[a])), p0);
+                    un1 = __dadd_rn(__dadd_rn(un1, __dmul_rn(kk.y, MA.a[a])), p1);
+                    if (has_lims) { un0 = fmin(fmax(un0, lo0), hi0); un1 = fmin(fmax(un1, lo1), hi1); }
+                    if (un0 != un0) un0 = 0.0;
+                    if (un1 != un1) un1 = 0.0;
+                    if (g == 0) stg2(&su[a * 8 + 2 * q], un0, un1);
+                }
+            __syncwarp();
+#pragma unroll
+            for (int a = 0; a < FM_NA; a++)
+                if (a < na) {
+                    const double* sxa = sx + a * 32;
+                    const double* sda = sd + a * 32;
+                    const double* sua = su + a * 8;
+                    const double d = x[a] - goal;
+                    double ax0 = 0.0, ax1 = 0.0, ax2 = 0.0, ax3 = 0.0, qd0 = 0.0, qd1 = 0.0;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const double2 xa = *reinterpret_cast<const double2*>(&sxa[j]);
+                        const double2 xb = *reinterpret_cast<const double2*>(&sxa[j + 2]);
+                        ax0 = fma(Ar[j], xa.x, ax0);
+                        ax1 = fma(Ar[j + 1], xa.y, ax1);
+                        ax2 = fma(Ar[j + 2], xb.x, ax2);
+                        ax3 = fma(Ar[j + 3], xb.y, ax3);
+                        if (QMODE == 1) {
+                            if (!has_goal) {
+                                qd0 = fma(sQ[lane + 32 * j], xa.x, qd0);
+                                qd1 = fma(sQ[lane + 32 * (j + 1)], xa.y, qd1);
+                                qd0 = fma(sQ[lane + 32 * (j + 2)], xb.x, qd0);
+                                qd1 = fma(sQ[lane + 32 * (j + 3)], xb.y, qd1);
+                            } else {
+                                const double2 da = *reinterpret_cast<const double2*>(&sda[j]);
+                                const double2 db = *reinterpret_cast<const double2*>(&sda[j + 2]);
+                                qd0 = fma(sQ[lane + 32 * j], da.x, qd0);
+                                qd1 = fma(sQ[lane + 32 * (j + 1)], da.y, qd1);
+                                qd0 = fma(sQ[lane + 32 * (j + 2)], db.x, qd0);
+                                qd1 = fma(sQ[lane + 32 * (j + 3)], db.y, qd1);
+                            }
+                        }
+                    }
+                    double bu = 0.0, ru = 0.0;
+#pragma unroll
+                    for (int c = 0; c < 8; c += 2) {
+                        const double2 uv = *reinterpret_cast<const double2*>(&sua[c]);
+                        bu = fma(Br[c], uv.x, bu);
+                        bu = fma(Br[c + 1], uv.y, bu);
+                        ru = fma(Rr[c], uv.x, ru);
+                        ru = fma(Rr[c + 1], uv.y, ru);
+                    }
+                    const double qd = (QMODE == 0) ? qdiag * d : (qd0 + qd1);
+                    double cstep = 0.5 * d * qd;
+                    if (lane < 8) cstep = fma(0.5 * sua[lane], ru, cstep);
+                    cpart[a] = __dadd_rn(cpart[a], cstep);
+                    if (t < N - 1) x[a] = ((ax0 + ax1) + (ax2 + ax3)) + bu;
+                }
+            __syncwarp();
+        };
+        for (int t = 0; t < N; t += 2) {
+            step(t, pa);
+            if (t + 1 < N) step(t + 1, pb);
+        }
+#pragma unroll
+        for (int a = 0; a < FM_NA; a++)
+            if (a < na) {
+                double c = cpart[a];
+                if (P.model.terminal_cost) {
+                    double qd = 0.0;
+                    if (QMODE == 0) qd = qdiag * (x[a] - goal);
+                    else {
+                        const double* sv = has_goal ? (sd + a * 32) : (sx + a * 32);
+#pragma unroll
+                        for (int j = 0; j < 32; j++) qd = fma(sQ[lane + 32 * j], sv[j], qd);
+                    }
+                    c = __dadd_rn(c, __dmul_rn(0.5 * (x[a] - goal), qd));
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+                if (lane == 0) cost_out[(long long)a * P.B + b] = c;
+            }
         __syncwarp();
     }
 }
@@ -549,4 +714,33 @@ int launch_forward_fast(ddp_handle_s* h, const FwdParams& P, bool* handled) {
         return (int)cudaGetLastError();
     }
     return 0;
+}
+
+// costs of the rollouts for na step sizes, cost_out (na, B) (row a = alpha[a]); *handled = false when the shape is
+// not the headline one (the caller then loops over ddp_forward_pass launches)
+int launch_forward_multi(ddp_handle_s* h, const FwdParams& P, int na, const double* alpha, double* cost_out, bool* handled) {
+    *handled = false;
+    if (!(P.model.kind == DDP_MODEL_LINEAR && P.n == 32 && P.m == 8 && P.model.A.st == 0 && P.model.Bm.st == 0)) return 0;
+    if (P.K == nullptr || na < 1) return 0;
+    if (!al16(P.u.p) || (P.u.sb % 2) || (P.u.st % 2) || !al16(P.K) || !al16(P.k)) return 0;
+    const bool qdiag = (P.model.flags & 1) != 0;
+    if (!qdiag && P.model.Q.sb != 0) return 0;
+    long long grid = (long long)h->sm_count * 2;
+    long long need = (P.B + FW_WPB - 1) / FW_WPB;
+    if (grid > need) grid = need;
+    const size_t bytes = (size_t)FW_WPB * FM_WARP_DOUBLES * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(fwd_lin32x8_multi_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(fwd_lin32x8_multi_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return (int)e;
+    for (int a0 = 0; a0 < na; a0 += FM_NA) {
+        MultiAlpha MA;
+        MA.na = (na - a0 < FM_NA) ? (na - a0) : FM_NA;
+        for (int i = 0; i < 16; i++) MA.a[i] = (i < MA.na) ? alpha[a0 + i] : 0.0;
+        double* out = cost_out + (long long)a0 * P.B;
+        if (qdiag) fwd_lin32x8_multi_kernel<0><<<(unsigned)grid, FW_WPB * 32, bytes, h->stream>>>(P, MA, out);
+        else fwd_lin32x8_multi_kernel<1><<<(unsigned)grid, FW_WPB * 32, bytes, h->stream>>>(P, MA, out);
+        h->launches++;
+    }
+    *handled = true;
+    return (int)cudaGetLastError();
 }

@@ -9,6 +9,7 @@
 // ddp_ilqg_iter_host_f64 runs one backward + forward sweep on pinned HOST arrays, cutting the
 // batch into chunks whose H2D copies, kernels and D2H copies overlap on three streams.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 #include "ddp_common.cuh"
 
@@ -206,6 +207,33 @@ __global__ void linesearch_kernel(long long B, SolveState s, SolveOpts o) {
     }
 }
 
+// the same serial test over the costs of ALL remaining step sizes (one multi-alpha launch): the first alpha in
+// order with ratio > reduce_ratio_min wins, exactly as the loop of iLQG.jl:267-281 would find it
+__global__ void linesearch_multi_kernel(long long B, SolveState s, SolveOpts o, const double* __restrict__ costs /* (n_alpha-1, B) */) {
+    long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B || !s.need_fwd[b]) return;
+    bool found = false;
+    for (int ai = 1; ai < o.n_alpha; ai++) {
+        const double a = o.alpha[ai];
+        const double dcost = s.cost[b] - costs[(long long)(ai - 1) * B + b];
+        const double expected = -a * (s.dV[2 * b] + a * s.dV[2 * b + 1]);
+        double ratio;
+        if (expected > 0) ratio = dcost / expected;
+        else ratio = (dcost > 0) ? 1.0 : ((dcost < 0) ? -1.0 : dcost);
+        s.last_dcost[b] = dcost;
+        s.aidx[b] = ai;
+        s.alpha[b] = a;
+        if (ratio > o.reduce_ratio_min) { found = true; break; }
+    }
+    if (found) { s.accepted[b] = 1; atomicAdd(&s.counters[1], 1); }     // need_fwd stays set: the accepted step is rolled out next
+    else s.need_fwd[b] = 0;                                             // line search exhausted
+}
+
+__global__ void clear_flags_kernel(long long B, unsigned char* f) {
+    long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) f[b] = 0;
+}
+
 // STEP 4 (iLQG.jl:293-323) scalars; the array copies are done by copy_accepted_kernel
 __global__ void accept_kernel(long long B, SolveState s, SolveOpts o) {
     long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -386,6 +414,10 @@ int ddp_ilqg_solve_f64(ddp_handle_t h, const ddp_model* model, const ddp_ilqg_op
     SolveState s{};
     SolveOpts o{};
     double *cx = nullptr, *cu = nullptr, *xnew = nullptr, *unew = nullptr, *fxb = nullptr, *fub = nullptr, *zeros = nullptr;
+    double* multi_costs = nullptr;
+    // multi-alpha line search (headline shape only): after a rejected alpha[0] all remaining step sizes are evaluated in one launch
+    const bool use_multi = (model->kind == DDP_MODEL_LINEAR && h->n == 32 && h->m == 8 && model->A.stride_t == 0 && model->Bm.stride_t == 0 &&
+                            !(h->flags & 1u) && !getenv("DDP_NO_MULTI_ALPHA"));
     int hc[4];
     int outer = 0;
     const unsigned gB = (unsigned)((B + 255) / 256), gW = (unsigned)((B * 32 + 127) / 128);
@@ -411,6 +443,7 @@ int ddp_ilqg_solve_f64(ddp_handle_t h, const ddp_model* model, const ddp_ilqg_op
     CUS(mem.alloc(&zeros, (size_t)n * m));
     CUS(cudaMemsetAsync(zeros, 0, sizeof(double) * n * m, st));
     if (model->kind == DDP_MODEL_PENDCART) { CUS(mem.alloc(&fxb, (size_t)B * T * 16)); CUS(mem.alloc(&fub, (size_t)B * T * 4)); }
+    if (use_multi) CUS(mem.alloc(&multi_costs, (size_t)B * 16));
 
     M.kind = model->kind; M.A = mk(model->A); M.Bm = mk(model->Bm); M.Q = mk(model->Q); M.R = mk(model->R); M.goal = model->goal;
     for (int i = 0; i < 8; i++) M.p[i] = model->p[i];
@@ -491,6 +524,25 @@ int ddp_ilqg_solve_f64(ddp_handle_t h, const ddp_model* model, const ddp_ilqg_op
                 CUS(cudaMemcpyAsync(hc, s.counters, sizeof(hc), cudaMemcpyDeviceToHost, st));
                 CUS(cudaStreamSynchronize(st));
                 if (hc[1] == 0) break;
+                if (ai == 0 && use_multi && o.n_alpha > 2) {
+                    // someone rejected alpha[0]: evaluate ALL remaining step sizes in one pass over K (multi-alpha
+                    // rollout, costs only), pick the first acceptable one per trajectory, then roll that one out
+                    bool handled = false;
+                    FwdParams FM = FP;
+                    FM.alpha = nullptr;
+                    CUS((cudaError_t)launch_forward_multi(h, FM, o.n_alpha - 1, o.alpha + 1, multi_costs, &handled));
+                    if (handled) {
+                        CUS(cudaMemsetAsync(s.counters, 0, 4 * sizeof(int), st));
+                        linesearch_multi_kernel<<<gB, 256, 0, st>>>(B, s, o, multi_costs);
+                        h->launches++;
+                        CUS(cudaMemcpyAsync(hc, s.counters, sizeof(hc), cudaMemcpyDeviceToHost, st));
+                        CUS(cudaStreamSynchronize(st));
+                        if (hc[1] > 0) CUS((cudaError_t)run_fwd(h, FP));          // per-trajectory accepted alpha, masked by need_fwd
+                        clear_flags_kernel<<<gB, 256, 0, st>>>(B, s.need_fwd);
+                        h->launches++;
+                        break;
+                    }
+                }
             }
             // STEP 4: accept / reject
             CUS(cudaMemsetAsync(s.counters, 0, 4 * sizeof(int), st));

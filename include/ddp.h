@@ -201,6 +201,15 @@ typedef struct ddp_forward_pass_args {
 
 DDP_API int ddp_forward_pass_f64(ddp_handle_t h, const ddp_model* model, const ddp_forward_pass_args* a);
 
+/* Multi-alpha line-search helper (the serial backtracking of iLQG.jl:267-281 evaluated in one pass): the total
+ * cost of the rollout for each of n_alpha step sizes, cost_out (n_alpha,B) row-major (row i = alpha[i], HOST array
+ * of step sizes).  For the headline shape (n=32, m=8, per-trajectory LTI linear model) the policy gains K are
+ * streamed ONCE for up to 10 step sizes and the costs are bit-identical to ddp_forward_pass_f64's; other shapes
+ * run one rollout per step size.  a->alpha is ignored; a->xnew, a->unew, a->cost are scratch (contents undefined
+ * on return); roll out the accepted step size with ddp_forward_pass_f64. */
+DDP_API int ddp_forward_costs_multi_f64(ddp_handle_t h, const ddp_model* model, const ddp_forward_pass_args* a,
+                                        int32_t n_alpha, const double* alpha, double* cost_out);
+
 /* ---- derivatives of the built-in models (the reference's df callback, STEP 1 of iLQG.jl:225-229) ---- */
 /* x (n,T,B), u (m,T,B) -> cx = Q(x-goal) (n,T,B), cu = R u (m,T,B); pendcart also fx (4,4,T,B), fu (4,1,T,B)
  * (ZoH Jacobians, system_pendcart.jl:137-154).  For the linear model fx/fu are A/B: pass NULL. */

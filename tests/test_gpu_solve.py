@@ -32,6 +32,64 @@ def test_ilqg_lq_batch(ddp, n, m, N, generic):
         assert relerr(Vxx[b], Vxx0[0]) < 1e-7
 
 
+@pytest.mark.parametrize("lims", [None, 0.35])
+def test_ilqg_multi_alpha_linesearch(ddp, monkeypatch, lims):
+    """Multi-alpha line search (all remaining step sizes in one pass over K after a rejected alpha[0]) finds exactly the
+    step the serial backtracking of iLQG.jl:267-281 finds: integer outcomes and trajectories identical to the serial
+    device path, and equal to the oracle's.  alpha[0] = 10^0.6 overshoots a quadratic, so it is always rejected."""
+    n, m, N, B = 32, 8, 30, 6
+    rng = np.random.default_rng(5)
+    As, Bs, x0s, u0s = [], [], [], []
+    for b in range(B):
+        A, Bm, Q, R = make_lq(rng, n, m, h=0.05)
+        As.append(A); Bs.append(Bm); x0s.append(np.ones(n) * (1 + 0.2 * b)); u0s.append(0.1 * rng.standard_normal((N, m)))
+    As, Bs, x0s, u0s = map(np.array, (As, Bs, x0s, u0s))
+    alpha = 10.0 ** np.linspace(0.6, -3, 8)
+    lim = None if lims is None else np.tile(np.array([[-lims, lims]]), (m, 1))
+    kw = dict(alpha=alpha, max_iter=8, lims=lim)
+    model = ddp.LinearModel(As[:, None], Bs[:, None], Q, R)
+    monkeypatch.delenv("DDP_NO_MULTI_ALPHA", raising=False)
+    rm = ddp.iLQG(model.f, model.costfun, model.df, x0s, u0s, **kw)
+    monkeypatch.setenv("DDP_NO_MULTI_ALPHA", "1")
+    rs = ddp.iLQG(model.f, model.costfun, model.df, x0s, u0s, **kw)
+    monkeypatch.delenv("DDP_NO_MULTI_ALPHA", raising=False)
+    tm, ts = rm[6], rs[6]
+    for key in ("status", "iter", "accepted_iter", "last_alpha", "lam"):
+        assert np.array_equal(tm[key], ts[key]), key
+    assert np.array_equal(rm[0], rs[0]) and np.array_equal(rm[1], rs[1]) and np.array_equal(rm[5], rs[5])
+    assert np.all(tm["last_alpha"] < alpha[0])                   # the multi-alpha branch ran for every trajectory
+    if lims is None:
+        for b in range(B):
+            om = O.LinearModel(As[b], Bs[b], Q, R)
+            x0_, u0_, p0, Vx0, Vxx0, c0, t0 = O.iLQG(om.f, om.costfun, om.df, x0s[b], u0s[b], alpha=alpha, max_iter=8)
+            assert tm["status"][b] == t0["status"] and tm["iter"][b] == t0["iters"]
+            assert relerr(rm[0][b], x0_) < 1e-7 and relerr(rm[1][b], u0_) < 1e-7
+
+
+@pytest.mark.parametrize("n,m,lims,dense_q", [(32, 8, None, False), (32, 8, 0.2, True), (6, 2, None, False)])
+def test_forward_costs_multi(ddp, n, m, lims, dense_q):
+    """ddp_forward_costs_multi_f64: the cost of every step size from one pass over K equals forward_pass's, bit for bit."""
+    B, N = 7, 33 if n == 6 else 26
+    A, Bm, Q, R, x, u = make_batch_lq(3, B, n, m, N, h=0.05)
+    if dense_q:
+        rng = np.random.default_rng(1)
+        W = rng.standard_normal((n, n)); Q = 0.01 * (W @ W.T) / n + Q
+    pol = None
+    Ks, ks = [], []
+    for b in range(B):
+        d, p, _, _, _ = O.back_pass(x[b] @ Q.T, u[b] @ R.T, Q, np.zeros((n, m)), R, A[b], Bm[b], 1.0, 1, None, x[b], u[b])
+        Ks.append(p.K); ks.append(p.k)
+    pol = ddp.GaussianPolicy(N, n, m, np.array(Ks), np.array(ks))
+    model = ddp.LinearModel(A[:, None], Bm[:, None], Q, R)
+    lim = None if lims is None else np.tile(np.array([[-lims, lims]]), (m, 1))
+    alphas = 10.0 ** np.linspace(0.3, -3, 12)                    # 12 > 10: two launches of the multi kernel
+    costs = ddp.forward_costs(pol, x[:, 0], u, x, alphas, model.f, model.costfun, lim)
+    assert costs.shape == (len(alphas), B)
+    for i, a in enumerate(alphas):
+        _, _, c = ddp.forward_pass(pol, x[:, 0], u, x, float(a), model.f, model.costfun, lim)
+        assert np.array_equal(costs[i], c), (i, np.max(np.abs(costs[i] - c)))
+
+
 def test_ilqg_thresholds_of_test_readme(ddp):
     """test/test_readme.jl:82-84 on fresh instances of its problem distribution (n=10, m=2, T=1000)."""
     rng = np.random.default_rng(0)
