@@ -110,11 +110,9 @@ __device__ __forceinline__ bool gj_inverse8(double& I0, double& I1, int lane, in
     return ok;
 }
 
-__device__ unsigned g_sm_ticket[1024];     // per-SM arrival counter: consecutive CTAs on one SM get different parities
-
 constexpr int gidx(int at, int bt) { return at * 5 - (at * (at - 1)) / 2 + (bt - at); }   // upper-tile index, 15 tiles
 
-template <bool LTV, bool GPS>
+template <bool LTV, bool GPS, bool REG2>
 __global__ void __launch_bounds__(WPB * 32, 2) bp_tile32x8_kernel(BackParams P) {
     extern __shared__ double smem_raw[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -157,29 +155,13 @@ __global__ void __launch_bounds__(WPB * 32, 2) bp_tile32x8_kernel(BackParams P) 
     const int LM = (g ^ (2 * q)) + 64 * q;
 #define FRAG(p, t) (((p) & 1 ? LAo : LAe) + 8 * (p) + 256 * (t))
 #define MIRR(at, bt, h) (LM + 8 * ((at) ^ (h)) + 32 * (h) + 256 * (bt))
-    // The two warps that share an SM sub-partition would otherwise run in phase (both in the tensor phase,
-    // then both in the latency-bound pivot/shuffle phase): delay the second resident CTA by part of a step
-    // so that one warp's serial phase overlaps the other's DMMA phase.
-    if (P.stagger > 0) {
-        __shared__ unsigned s_ticket;
-        if (threadIdx.x == 0) {
-            unsigned smid;
-            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-            s_ticket = atomicAdd(&g_sm_ticket[smid & 1023], 1u);
-        }
-        __syncthreads();
-        if (s_ticket & 1u) {
-            const long long t0 = clock64();
-            while (clock64() - t0 < P.stagger) { }
-        }
-    }
     const bool up0 = (2 * q >= g), st0 = (2 * q > g), up1 = (2 * q + 1 >= g), st1 = (2 * q + 1 > g);
     const int c0src = 8 * q, c1src = 8 * q + 4;        // a lane of the group that owns entry 2q / 2q+1
 
     for (long long b = (long long)blockIdx.x * WPB + w; b < P.B; b += warps_total) {
         if (P.active && !P.active[b]) continue;
         const double lam = GPS ? 0.0 : P.lambda[b];
-        const bool reg2 = !GPS && (P.reg_type == 2);
+        constexpr bool reg2 = REG2 && !GPS;
         const double eta = GPS ? P.eta[b] : 1.0, ieta = 1.0 / eta;
         double* Quuib = (GPS && P.Quui) ? P.Quui + b * (long long)N * 64 : nullptr;
         const bool has_kp = GPS && (P.kp.p != nullptr);
@@ -311,53 +293,131 @@ __global__ void __launch_bounds__(WPB * 32, 2) bp_tile32x8_kernel(BackParams P) 
                 G[gidx(4, 4)][0] = cuui[g + 8 * (2 * q)];
                 G[gidx(4, 4)][1] = cuui[g + 8 * (2 * q + 1)];
             }
-            // ---- step 1: W' = F' V.  The A fragments also give F'Vx: each lane sums its 8 rows, two shuffles finish it
-            double W[5][4][2], fv[5];
+            // ---- tensor phase, by row blocks of W' = F'V so that only 1-2 row blocks (not all 5) are live:
+            //      block 4 (fu'V) first => Quu = G(4,4) is complete after 40 DMMAs and its Gauss-Jordan inverse (a long
+            //      latency-bound chain of shuffles and FMAs) is interleaved, pivot by pivot, with the DMMAs of blocks 0,1.
+            double fv[5];
+            auto w_block1 = [&](const int a0, double (&Wa)[4][2], double& fva) {
 #pragma unroll
-            for (int at = 0; at < 5; at++) {
-                fv[at] = 0.0;
+                for (int jt = 0; jt < 4; jt++) Wa[jt][0] = Wa[jt][1] = 0.0;
+                fva = 0.0;
 #pragma unroll
-                for (int jt = 0; jt < 4; jt++) W[at][jt][0] = W[at][jt][1] = 0.0;
+                for (int p = 0; p < 4; p++) {
+                    const double2 fa0 = ld2(&sF[FRAG(p, a0)]);
+                    double2 fb[4];
+#pragma unroll
+                    for (int jt = 0; jt < 4; jt++) fb[jt] = ld2(&sV[FRAG(p, jt)]);
+                    const double2 vx = ld2(&sVx[8 * p + 2 * q]);
+#pragma unroll
+                    for (int jt = 0; jt < 4; jt++) dmma(Wa[jt][0], Wa[jt][1], fa0.x, fb[jt].x);
+                    fva = fma(fa0.y, vx.y, fma(fa0.x, vx.x, fva));
+#pragma unroll
+                    for (int jt = 0; jt < 4; jt++) dmma(Wa[jt][0], Wa[jt][1], fa0.y, fb[jt].y);
+                }
+            };
+            double I0 = 0.0, I1 = 0.0, U0, U1;
+            bool ok = true;
+            auto gj_step = [&](const int p) {                 // one pivot of the in-place inverse (see gj_inverse8)
+                const double own = (p & 1) ? I1 : I0;
+                const double d = shf(own, 4 * p + (p >> 1));
+                const double colp = shf(own, (lane & ~3) | (p >> 1));
+                const double rp0 = shf(I0, 4 * p + q), rp1 = shf(I1, 4 * p + q);
+                if (!(d > 0.0)) ok = false;
+                const double r = rcp_nr(d);
+                const double n0 = ((2 * q == p) ? 1.0 : rp0) * r, n1 = ((2 * q + 1 == p) ? 1.0 : rp1) * r;
+                if (g == p) { I0 = n0; I1 = n1; }
+                else {
+                    I0 = fma(-colp, n0, (2 * q == p) ? 0.0 : I0);
+                    I1 = fma(-colp, n1, (2 * q + 1 == p) ? 0.0 : I1);
+                }
+            };
+            auto w_block0123 = [&](double (&W)[4][4][2]) {      // rows 0..3 of W' (fx'V), the 8 Gauss-Jordan pivots in between
+#pragma unroll
+                for (int at = 0; at < 4; at++) {
+                    fv[at] = 0.0;
+#pragma unroll
+                    for (int jt = 0; jt < 4; jt++) W[at][jt][0] = W[at][jt][1] = 0.0;
+                }
+#pragma unroll
+                for (int p = 0; p < 4; p++) {
+                    double2 fa[4], fb[4];
+#pragma unroll
+                    for (int at = 0; at < 4; at++) fa[at] = ld2(&sF[FRAG(p, at)]);
+#pragma unroll
+                    for (int jt = 0; jt < 4; jt++) fb[jt] = ld2(&sV[FRAG(p, jt)]);
+                    const double2 vx = ld2(&sVx[8 * p + 2 * q]);
+#pragma unroll
+                    for (int at = 0; at < 4; at++)
+#pragma unroll
+                        for (int jt = 0; jt < 4; jt++) dmma(W[at][jt][0], W[at][jt][1], fa[at].x, fb[jt].x);
+                    gj_step(2 * p);
+#pragma unroll
+                    for (int at = 0; at < 4; at++) fv[at] = fma(fa[at].y, vx.y, fma(fa[at].x, vx.x, fv[at]));
+#pragma unroll
+                    for (int at = 0; at < 4; at++)
+#pragma unroll
+                        for (int jt = 0; jt < 4; jt++) dmma(W[at][jt][0], W[at][jt][1], fa[at].y, fb[jt].y);
+                    gj_step(2 * p + 1);
+                }
+            };
+            // G(a, a..4) += W'[a,:] F[:, a..4]
+            auto g_block1 = [&](const int a0, double (&Wa)[4][2]) {
+#pragma unroll
+                for (int p = 0; p < 4; p++) {
+                    double2 ff[5];
+#pragma unroll
+                    for (int bt = a0; bt < 5; bt++) ff[bt] = ld2(&sF[FRAG(p, bt)]);
+#pragma unroll
+                    for (int bt = a0; bt < 5; bt++) dmma(G[gidx(a0, bt)][0], G[gidx(a0, bt)][1], Wa[p][0], ff[bt].x);
+#pragma unroll
+                    for (int bt = a0; bt < 5; bt++) dmma(G[gidx(a0, bt)][0], G[gidx(a0, bt)][1], Wa[p][1], ff[bt].y);
+                }
+            };
+            auto g_block0123 = [&](double (&W)[4][4][2]) {
+#pragma unroll
+                for (int p = 0; p < 4; p++) {
+                    double2 ff[5];
+#pragma unroll
+                    for (int bt = 0; bt < 5; bt++) ff[bt] = ld2(&sF[FRAG(p, bt)]);
+#pragma unroll
+                    for (int at = 0; at < 4; at++)
+#pragma unroll
+                        for (int bt = at; bt < 5; bt++) dmma(G[gidx(at, bt)][0], G[gidx(at, bt)][1], W[at][p][0], ff[bt].x);
+#pragma unroll
+                    for (int at = 0; at < 4; at++)
+#pragma unroll
+                        for (int bt = at; bt < 5; bt++) dmma(G[gidx(at, bt)][0], G[gidx(at, bt)][1], W[at][p][1], ff[bt].y);
+                }
+            };
+            {
+                double Wa[4][2];
+                // block 4: fu'V, Quu
+                w_block1(4, Wa, fv[4]);
+                g_block1(4, Wa);
+                // (U0,U1) = Quu[g][2q..2q+1]; QuuF in (I0,I1)
+                U0 = G[gidx(4, 4)][0];
+                U1 = G[gidx(4, 4)][1];
+                if (GPS) {                                    // Quu/eta + Sigma_i, then 0.5 (Quu + Quu')  (:297, :301)
+                    U0 = fma(U0, ieta, Sg0);
+                    U1 = fma(U1, ieta, Sg1);
+                    const int s0 = 4 * (2 * q) + (g >> 1), s1 = 4 * (2 * q + 1) + (g >> 1);
+                    const double a00 = shf(U0, s0), a01 = shf(U1, s0), a10 = shf(U0, s1), a11 = shf(U1, s1);
+                    U0 = 0.5 * (U0 + ((g & 1) ? a01 : a00));  // Quu[2q][g]
+                    U1 = 0.5 * (U1 + ((g & 1) ? a11 : a10));  // Quu[2q+1][g]
+                }
+                if (reg2) { I0 = fma(lam, FF[4][0], U0); I1 = fma(lam, FF[4][1], U1); }
+                else { I0 = U0 + ((g == 2 * q) ? lam : 0.0); I1 = U1 + ((g == 2 * q + 1) ? lam : 0.0); }
             }
-#pragma unroll
-            for (int p = 0; p < 4; p++) {
-                double2 fa[5], fb[4];
-#pragma unroll
-                for (int at = 0; at < 5; at++) fa[at] = ld2(&sF[FRAG(p, at)]);
-#pragma unroll
-                for (int jt = 0; jt < 4; jt++) fb[jt] = ld2(&sV[FRAG(p, jt)]);
-                const double2 vx = ld2(&sVx[8 * p + 2 * q]);
-                // consecutive DMMAs go to different accumulator tiles (a tile is revisited 20 issues later)
-#pragma unroll
-                for (int at = 0; at < 5; at++)
-#pragma unroll
-                    for (int jt = 0; jt < 4; jt++) dmma(W[at][jt][0], W[at][jt][1], fa[at].x, fb[jt].x);
-#pragma unroll
-                for (int at = 0; at < 5; at++) fv[at] = fma(fa[at].y, vx.y, fma(fa[at].x, vx.x, fv[at]));
-#pragma unroll
-                for (int at = 0; at < 5; at++)
-#pragma unroll
-                    for (int jt = 0; jt < 4; jt++) dmma(W[at][jt][0], W[at][jt][1], fa[at].y, fb[jt].y);
+            {
+                // blocks 0..3 with the Gauss-Jordan pivots in between; pivot p <= 0  <=>  Cholesky fails
+                double W[4][4][2];
+                w_block0123(W);
+                g_block0123(W);
             }
 #pragma unroll
             for (int at = 0; at < 5; at++) {
                 fv[at] += shx(fv[at], 1);
                 fv[at] += shx(fv[at], 2);
-            }
-            // ---- step 2: G = W' F  (upper tiles)
-#pragma unroll
-            for (int p = 0; p < 4; p++) {
-                double2 ff[5];
-#pragma unroll
-                for (int bt = 0; bt < 5; bt++) ff[bt] = ld2(&sF[FRAG(p, bt)]);
-#pragma unroll
-                for (int at = 0; at < 5; at++)
-#pragma unroll
-                    for (int bt = at; bt < 5; bt++) dmma(G[gidx(at, bt)][0], G[gidx(at, bt)][1], W[at][p][0], ff[bt].x);
-#pragma unroll
-                for (int at = 0; at < 5; at++)
-#pragma unroll
-                    for (int bt = at; bt < 5; bt++) dmma(G[gidx(at, bt)][0], G[gidx(at, bt)][1], W[at][p][1], ff[bt].y);
             }
             // this step's cost gradients have landed long ago: lanes of group g own Qx[8t+g] (t = 0..3) and Qu[g]
             if (LTV) cp_async_wait_group<1>(); else cp_async_wait_group<0>();      // group A has landed
@@ -371,7 +431,7 @@ __global__ void __launch_bounds__(WPB * 32, 2) bp_tile32x8_kernel(BackParams P) 
             double Sik_own = 0.0, Sik0 = 0.0, Sik1 = 0.0;
             if (GPS) {
 #pragma unroll
-                for (int t = 0; t < 15; t++) { G[t][0] *= ieta; G[t][1] *= ieta; }
+                for (int t = 0; t < 14; t++) { G[t][0] *= ieta; G[t][1] *= ieta; }      // tile (4,4) was scaled into (U0,U1) above
 #pragma unroll
                 for (int t = 0; t < 4; t++) sf[t] = make_double2(0.0, 0.0);        // S = Sigma_i K_prev : sf[t] = S[2q..2q+1][8t+g]
 #pragma unroll
@@ -396,7 +456,7 @@ __global__ void __launch_bounds__(WPB * 32, 2) bp_tile32x8_kernel(BackParams P) 
                 }
             }
             // ---- fragments straight from the accumulators:
-            //      qf[t]  = Qux[2q..2q+1][8t+g]   (unregularised), qr[t] = Qux_reg, (U0,U1) = Quu[g][2q..2q+1]
+            //      qf[t]  = Qux[2q..2q+1][8t+g]   (unregularised), qr[t] = Qux_reg
             double2 qf[4], qr[4];
 #pragma unroll
             for (int t = 0; t < 4; t++) {
@@ -404,20 +464,6 @@ __global__ void __launch_bounds__(WPB * 32, 2) bp_tile32x8_kernel(BackParams P) 
                 if (GPS) { qf[t].x -= sf[t].x; qf[t].y -= sf[t].y; }              // cxukl = -Sigma_i K_prev
                 qr[t] = reg2 ? make_double2(fma(lam, FF[t][0], qf[t].x), fma(lam, FF[t][1], qf[t].y)) : qf[t];
             }
-            double U0 = G[gidx(4, 4)][0], U1 = G[gidx(4, 4)][1];
-            if (GPS) {                                        // Quu/eta + Sigma_i, then 0.5 (Quu + Quu')  (:297, :301)
-                U0 += Sg0;
-                U1 += Sg1;
-                const int s0 = 4 * (2 * q) + (g >> 1), s1 = 4 * (2 * q + 1) + (g >> 1);
-                const double a00 = shf(U0, s0), a01 = shf(U1, s0), a10 = shf(U0, s1), a11 = shf(U1, s1);
-                U0 = 0.5 * (U0 + ((g & 1) ? a01 : a00));      // Quu[2q][g]
-                U1 = 0.5 * (U1 + ((g & 1) ? a11 : a10));      // Quu[2q+1][g]
-            }
-            double I0, I1;                                   // QuuF, inverted in place below
-            if (reg2) { I0 = fma(lam, FF[4][0], U0); I1 = fma(lam, FF[4][1], U1); }
-            else { I0 = U0 + ((g == 2 * q) ? lam : 0.0); I1 = U1 + ((g == 2 * q + 1) ? lam : 0.0); }
-            // ---- Gauss-Jordan inverse of QuuF in the accumulator layout; pivot p <= 0  <=>  Cholesky fails
-            const bool ok = gj_inverse8(I0, I1, lane, g, q);
             if (!ok) { diverge = i + 1; break; }
             // ---- K' = -Qux_reg' Minv : kf[t] = K[2q..2q+1][8t+g]
             double2 kf[4];
@@ -593,22 +639,19 @@ int launch_back_pass_tile(ddp_handle_s* h, const BackParams& P, bool gps, bool* 
     long long grid = (long long)h->sm_count * 2;
     long long need = (P.B + WPB - 1) / WPB;
     if (grid > need) grid = need;
-    BackParams Ps = P;
-    {
-        static int stagger = -1;
-        if (stagger < 0) { const char* ev = getenv("DDP_BP_STAGGER"); stagger = ev ? atoi(ev) : 0; }
-        Ps.stagger = stagger;
-    }
     cudaError_t e = cudaSuccess;
-#define LAUNCH_TILE(L, G)                                                                                                \
+#define LAUNCH_TILE(L, G, R2)                                                                                            \
     do {                                                                                                                 \
-        e = cudaFuncSetAttribute(bp_tile32x8_kernel<L, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);     \
-        if (e == cudaSuccess) bp_tile32x8_kernel<L, G><<<(unsigned)grid, WPB * 32, bytes, h->stream>>>(Ps);              \
+        e = cudaFuncSetAttribute(bp_tile32x8_kernel<L, G, R2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); \
+        if (e == cudaSuccess) bp_tile32x8_kernel<L, G, R2><<<(unsigned)grid, WPB * 32, bytes, h->stream>>>(P);            \
     } while (0)
-    if (ltv && gps) LAUNCH_TILE(true, true);
-    else if (ltv) LAUNCH_TILE(true, false);
-    else if (gps) LAUNCH_TILE(false, true);
-    else LAUNCH_TILE(false, false);
+    const bool r2 = !gps && (P.reg_type == 2);
+    if (ltv && gps) LAUNCH_TILE(true, true, false);
+    else if (ltv && r2) LAUNCH_TILE(true, false, true);
+    else if (ltv) LAUNCH_TILE(true, false, false);
+    else if (gps) LAUNCH_TILE(false, true, false);
+    else if (r2) LAUNCH_TILE(false, false, true);
+    else LAUNCH_TILE(false, false, false);
 #undef LAUNCH_TILE
     if (e != cudaSuccess) return (int)e;
     h->launches++;

@@ -33,7 +33,6 @@ struct BackParams {
     int* diverge;
     double *K, *k, *Vx, *Vxx, *Vxx1, *Quu, *dV;
     QPOpts qp;
-    int stagger;                 // tile kernel: start delay (clocks) of the second co-resident warp set
 };
 
 struct ModelD {
