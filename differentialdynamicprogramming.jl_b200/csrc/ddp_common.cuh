@@ -93,6 +93,7 @@ int launch_boxqp(ddp_handle_s* h, long long B, int m, const double* H, const dou
                  const double* upper, const double* x0, QPOpts o, double* x, int* result, double* Hfree,
                  unsigned* free_mask, int* nfactor);
 int launch_kl_div(ddp_handle_s* h, const KlParams& P);
+int launch_kl_div_tile(ddp_handle_s* h, const KlParams& P, bool* handled);
 int launch_batch_stats(ddp_handle_s* h, long long B, const double* cost_old, const double* cost_new, const double* dV,
                        const double* alpha, double alpha_scalar, const int* diverge, const unsigned char* active,
                        double* stats8);

@@ -1,0 +1,280 @@
+// KL evaluation for n = 32, m = 8 on FP64 tensor tiles: ONE WARP PER TRAJECTORY.
+//
+// Replaces forward_covariance (src/forward_pass.jl:37-56, state block only: the reference propagates
+// Sigma_{t+1} = fx Sigma_t fx' + R1 with the open-loop Jacobian, independent of the policy) and
+// kl_div_wiki (src/klutils.jl:70-100) for the headline shape; anything else runs kl_div_kernel
+// (misc_kernels.cu).  Per step (DMMA = mma.sync.m8n8k4.f64, as in back_pass_tile.cu):
+//
+//   F   = fx'                 32 x 32    shared memory, transposed once per trajectory (time-invariant fx)
+//   W'  = F' Sigma            32 x 32    128 DMMA  (Sigma symmetric, shared memory, swizzled)
+//   P   = dK Sigma            8 x 32      32 DMMA  (shares the Sigma fragments of W')
+//   S+  = W' F + R1           upper 10 tiles, 80 DMMA, mirrored back => exactly symmetric
+//   M   = Sigma_i_prev dK     8 x 32       8 DMMA ;  tr(dK' Sigma_i dK Sigma_t) = sum(M o P)
+//   logdet(Sigma_prev) - logdet(Sigma_new) = log(prod pivots / prod pivots): two 8 x 8 eliminations in the
+//   accumulator layout (shuffles), one log per step
+//   the vector terms (dK mu, Sigma_i dk, ...) are a few FMAs per lane plus shuffles.
+//
+//   kl_t = max(0, 1/2(tr(Sip Sn) + dk'Sip dk - m + logdet Sp - logdet Sn)
+//                 + 1/2(mu'dK'Sip dK mu + tr(dK'Sip dK S_t)) + dk'Sip dK mu)          (klutils.jl:75-91, 98)
+//
+// 248 DMMA per step; 16.6 KB of shared memory per warp, 12 warps per SM.
+#include "ddp_common.cuh"
+
+namespace {
+
+constexpr int KW = 4;                        // warps per CTA
+constexpr int KSV = 0;                       // Sigma_t  32 x 32 swizzled
+constexpr int KSF = 1024;                    // F = fx'  32 x 32 swizzled
+constexpr int KWARP_DOUBLES = 2048;
+constexpr int KTAB_DOUBLES = 10 * 32 * 2;    // R1 tiles in accumulator order (per CTA)
+
+__device__ __forceinline__ int swz(int i, int c) { return (i ^ (((c & 1) << 3) | (((c >> 1) & 3) << 1))) + 32 * c; }
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+__device__ __forceinline__ void st2(double* p, double a, double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
+__device__ __forceinline__ double shf(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ double shx(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+__device__ __forceinline__ double rcp_nr(double d) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    double e = fma(-d, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-d, y, 1.0);
+    y = fma(y, e, y);
+    return y;
+}
+constexpr int uidx(int at, int bt) { return at * 4 - (at * (at - 1)) / 2 + (bt - at); }   // upper-tile index of a 4 x 4 tiling, 10 tiles
+
+__global__ void __launch_bounds__(KW * 32, 3) kl_tile32x8_kernel(KlParams P) {
+    extern __shared__ double ksm[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    double* sV = ksm + (size_t)w * KWARP_DOUBLES + KSV;
+    double* sF = ksm + (size_t)w * KWARP_DOUBLES + KSF;
+    double* sTab = ksm + (size_t)KW * KWARP_DOUBLES;
+    const int N = P.T;
+    // R1 (shared by the batch) in accumulator order, symmetrised (it is a covariance)
+    if (w == 0) {
+        const double* R1 = P.R1.p;
+#pragma unroll
+        for (int at = 0; at < 4; at++) {
+            const int a = 8 * at + g;
+#pragma unroll
+            for (int bt = at; bt < 4; bt++) {
+                const int b0 = 8 * bt + 2 * q;
+                st2(&sTab[(uidx(at, bt) * 32 + lane) * 2], 0.5 * (R1[a + 32 * b0] + R1[b0 + 32 * a]),
+                    0.5 * (R1[a + 32 * (b0 + 1)] + R1[(b0 + 1) + 32 * a]));
+            }
+        }
+    }
+    __syncthreads();
+    const int gg = (g >> 1) & 3, par = g & 1;
+    const int LA = 2 * (q ^ gg) + 32 * g;
+    const int LAe = LA + 8 * par, LAo = LA - 8 * par;
+    const int LM = (g ^ (2 * q)) + 64 * q;
+#define FRAG(p, t) (((p) & 1 ? LAo : LAe) + 8 * (p) + 256 * (t))
+#define MIRR(at, bt, h) (LM + 8 * ((at) ^ (h)) + 32 * (h) + 256 * (bt))
+    const bool up0 = (2 * q >= g), st0 = (2 * q > g), up1 = (2 * q + 1 >= g), st1 = (2 * q + 1 > g);
+    const int c0src = 8 * q, c1src = 8 * q + 4;
+    const long long warps_total = (long long)gridDim.x * KW;
+
+    for (long long b = (long long)blockIdx.x * KW + w; b < P.B; b += warps_total) {
+        if (P.active && !P.active[b]) continue;
+        __syncwarp();
+        {   // Sigma_0 = R1 ; F = fx' (time-invariant)
+            const double* R1 = P.R1.p;
+            for (int c = lane; c < 512; c += 32) {
+                const int col = c >> 4, i = (c & 15) << 1;
+                st2(&sV[swz(i, col)], 0.5 * (R1[i + 32 * col] + R1[col + 32 * i]), 0.5 * (R1[i + 1 + 32 * col] + R1[col + 32 * (i + 1)]));
+            }
+            const double* fx = P.fx.p + b * P.fx.sb;
+            for (int e = lane; e < 1024; e += 32) {
+                const int c = e & 31, i = e >> 5;             // F(i, c) = fx[c][i] = fx[c + 32 i]
+                sF[swz(i, c)] = fx[e];
+            }
+        }
+        __syncwarp();
+        double klsum = 0.0;
+        for (int t = 0; t < N; t++) {
+            // ---- operands of the KL terms (global; consumed after / inside the tensor phase)
+            const double* Kn = P.Kn + (b * N + t) * 256;
+            const double* Kp = tp(P.Kp, b, t);
+            double2 dKa[4], dKb[4], mu2[4];
+#pragma unroll
+            for (int p = 0; p < 4; p++) {
+                const int o = (8 * p + 2 * q) * 8 + g;
+                dKa[p] = make_double2(Kp[o] - Kn[o], Kp[o + 8] - Kn[o + 8]);                 // dK[g][8p+2q], dK[g][8p+2q+1]
+                const double2 kp2 = ld2(Kp + (8 * p + g) * 8 + 2 * q), kn2 = ld2(Kn + (8 * p + g) * 8 + 2 * q);
+                dKb[p] = make_double2(kp2.x - kn2.x, kp2.y - kn2.y);                         // dK[2q..2q+1][8p+g]
+                const double2 xn = ld2(P.xnew + (b * N + t) * 32 + 8 * p + 2 * q), xo = ld2(P.xold + (b * N + t) * 32 + 8 * p + 2 * q);
+                mu2[p] = make_double2(xn.x - xo.x, xn.y - xo.y);
+            }
+            const double* Sipm = tp(P.Sip, b, t);
+            const double S0 = Sipm[g + 8 * (2 * q)], S1 = Sipm[g + 8 * (2 * q + 1)];         // Sip[g][2q..2q+1]
+            const double2 Sn2 = ld2(P.Sn + (b * N + t) * 64 + 8 * g + 2 * q);                // Sn[2q..2q+1][g]
+            const double2 Sp2 = ld2(tp(P.Sp, b, t) + 8 * g + 2 * q);                         // Sp[2q..2q+1][g]
+            const double* knm = P.kn + (b * N + t) * 8;
+            double dk_own = -knm[g], dk0 = -knm[2 * q], dk1 = -knm[2 * q + 1];
+            if (P.kp.p) { const double* kpm = tp(P.kp, b, t); dk_own += kpm[g]; dk0 += kpm[2 * q]; dk1 += kpm[2 * q + 1]; }
+            // ---- tensor phase: W' = F' Sigma and P = dK Sigma share the Sigma fragments
+            double W[4][4][2], Pt[4][2];
+#pragma unroll
+            for (int at = 0; at < 4; at++) {
+                Pt[at][0] = Pt[at][1] = 0.0;
+#pragma unroll
+                for (int jt = 0; jt < 4; jt++) W[at][jt][0] = W[at][jt][1] = 0.0;
+            }
+            const bool prop = (t < N - 1);
+#pragma unroll
+            for (int p = 0; p < 4; p++) {
+                double2 fa[4], fb[4];
+#pragma unroll
+                for (int jt = 0; jt < 4; jt++) fb[jt] = ld2(&sV[FRAG(p, jt)]);
+#pragma unroll
+                for (int jt = 0; jt < 4; jt++) dmma(Pt[jt][0], Pt[jt][1], dKa[p].x, fb[jt].x);
+                if (prop) {
+#pragma unroll
+                    for (int at = 0; at < 4; at++) fa[at] = ld2(&sF[FRAG(p, at)]);
+#pragma unroll
+                    for (int at = 0; at < 4; at++)
+#pragma unroll
+                        for (int jt = 0; jt < 4; jt++) dmma(W[at][jt][0], W[at][jt][1], fa[at].x, fb[jt].x);
+                }
+#pragma unroll
+                for (int jt = 0; jt < 4; jt++) dmma(Pt[jt][0], Pt[jt][1], dKa[p].y, fb[jt].y);
+                if (prop) {
+#pragma unroll
+                    for (int at = 0; at < 4; at++)
+#pragma unroll
+                        for (int jt = 0; jt < 4; jt++) dmma(W[at][jt][0], W[at][jt][1], fa[at].y, fb[jt].y);
+                }
+            }
+            // ---- M = Sip dK ; trace term
+            double tr2 = 0.0;
+            {
+                double Mt[4][2];
+#pragma unroll
+                for (int jt = 0; jt < 4; jt++) Mt[jt][0] = Mt[jt][1] = 0.0;
+#pragma unroll
+                for (int jt = 0; jt < 4; jt++) dmma(Mt[jt][0], Mt[jt][1], S0, dKb[jt].x);
+#pragma unroll
+                for (int jt = 0; jt < 4; jt++) dmma(Mt[jt][0], Mt[jt][1], S1, dKb[jt].y);
+#pragma unroll
+                for (int jt = 0; jt < 4; jt++) tr2 = fma(Mt[jt][1], Pt[jt][1], fma(Mt[jt][0], Pt[jt][0], tr2));
+            }
+            // ---- pivots of Sp' and Sn' (determinant of the transpose = determinant): accumulator layout, shuffles
+            double pdp = 1.0, pdn = 1.0;
+            bool pos = true;
+            {
+                double A0 = Sp2.x, A1 = Sp2.y, B0 = Sn2.x, B1 = Sn2.y;
+#pragma unroll
+                for (int p = 0; p < 8; p++) {
+                    const double ownA = (p & 1) ? A1 : A0, ownB = (p & 1) ? B1 : B0;
+                    const double dA = shf(ownA, 4 * p + (p >> 1)), dB = shf(ownB, 4 * p + (p >> 1));
+                    const double cA = shf(ownA, (lane & ~3) | (p >> 1)), cB = shf(ownB, (lane & ~3) | (p >> 1));
+                    const double rA0 = shf(A0, 4 * p + q), rA1 = shf(A1, 4 * p + q), rB0 = shf(B0, 4 * p + q), rB1 = shf(B1, 4 * p + q);
+                    if (!(dA > 0.0) || !(dB > 0.0)) pos = false;
+                    pdp *= dA;
+                    pdn *= dB;
+                    const double fA = cA * rcp_nr(dA), fB = cB * rcp_nr(dB);
+                    if (g != p) {                         // rows below (and above, harmlessly) the pivot row
+                        A0 = fma(-fA, rA0, A0); A1 = fma(-fA, rA1, A1);
+                        B0 = fma(-fB, rB0, B0); B1 = fma(-fB, rB1, B1);
+                    }
+                }
+            }
+            // ---- vector terms
+            double vs = 0.0;
+#pragma unroll
+            for (int p = 0; p < 4; p++) vs = fma(dKa[p].y, mu2[p].y, fma(dKa[p].x, mu2[p].x, vs));
+            vs += shx(vs, 1);
+            vs += shx(vs, 2);                             // v[g] = (dK mu)[g]
+            const double v0 = shf(vs, c0src), v1 = shf(vs, c1src);
+            double ws = fma(S1, v1, S0 * v0), zs = fma(S1, dk1, S0 * dk0);
+            ws += shx(ws, 1); zs += shx(zs, 1);
+            ws += shx(ws, 2); zs += shx(zs, 2);          // (Sip v)[g], (Sip dk)[g]
+            double part = (q == 0) ? (0.5 * vs * ws + dk_own * ws + 0.5 * dk_own * zs) : 0.0;
+            part = fma(0.5, fma(S1, Sn2.y, S0 * Sn2.x), part);       // 1/2 tr(Sip Sn)
+            part = fma(0.5, tr2, part);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) part += shx(part, o);
+            {
+                double v = part + 0.5 * (-8.0 + log(pdp / pdn));
+                if (!pos) v = nan("");
+                v = fmax(0.0, v);
+                if (v != v) v = INFINITY;                  // the reference returns Inf when logdet throws
+                if (P.kl_t && lane == 0) P.kl_t[b * N + t] = v;
+                klsum += v;
+            }
+            // ---- Sigma_{t+1} = F' Sigma F + R1 (upper tiles), mirrored back into shared memory
+            if (prop) {
+                double G[10][2];
+#pragma unroll
+                for (int u = 0; u < 10; u++) {
+                    const double2 c = ld2(&sTab[(u * 32 + lane) * 2]);
+                    G[u][0] = c.x;
+                    G[u][1] = c.y;
+                }
+#pragma unroll
+                for (int p = 0; p < 4; p++) {
+                    double2 ff[4];
+#pragma unroll
+                    for (int bt = 0; bt < 4; bt++) ff[bt] = ld2(&sF[FRAG(p, bt)]);
+#pragma unroll
+                    for (int at = 0; at < 4; at++)
+#pragma unroll
+                        for (int bt = at; bt < 4; bt++) dmma(G[uidx(at, bt)][0], G[uidx(at, bt)][1], W[at][p][0], ff[bt].x);
+#pragma unroll
+                    for (int at = 0; at < 4; at++)
+#pragma unroll
+                        for (int bt = at; bt < 4; bt++) dmma(G[uidx(at, bt)][0], G[uidx(at, bt)][1], W[at][p][1], ff[bt].y);
+                }
+                __syncwarp();          // every lane is past its reads of sV for this step
+#pragma unroll
+                for (int at = 0; at < 4; at++) {
+#pragma unroll
+                    for (int bt = at; bt < 4; bt++) {
+                        const double v0_ = G[uidx(at, bt)][0], v1_ = G[uidx(at, bt)][1];
+                        if (bt > at) {
+                            st2(&sV[FRAG(bt, at)], v0_, v1_);
+                            sV[MIRR(at, bt, 0)] = v0_;
+                            sV[MIRR(at, bt, 1)] = v1_;
+                        } else {
+                            if (up0) sV[FRAG(at, at)] = v0_;
+                            if (st0) sV[MIRR(at, at, 0)] = v0_;
+                            if (up1) sV[FRAG(at, at) + 1] = v1_;
+                            if (st1) sV[MIRR(at, at, 1)] = v1_;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        if (lane == 0) P.kl_mean[b] = klsum / (double)N;
+    }
+#undef FRAG
+#undef MIRR
+}
+
+bool al16t(const TensorD& t) { return ((uintptr_t)t.p % 16 == 0) && (t.sb % 2 == 0) && (t.st % 2 == 0); }
+
+}  // namespace
+
+int launch_kl_div_tile(ddp_handle_s* h, const KlParams& P, bool* handled) {
+    *handled = false;
+    if (P.n != 32 || P.m != 8 || P.T < 1) return 0;
+    if (P.fx.st != 0 || P.R1.sb != 0 || P.R1.st != 0) return 0;          // time-invariant model Jacobian, shared noise covariance
+    if (!al16t(P.Kp) || !al16t(P.Sp) || ((uintptr_t)P.Kn % 16) || ((uintptr_t)P.Sn % 16) || ((uintptr_t)P.xnew % 16) || ((uintptr_t)P.xold % 16)) return 0;
+    const size_t bytes = ((size_t)KW * KWARP_DOUBLES + KTAB_DOUBLES) * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(kl_tile32x8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return (int)e;
+    long long grid = (long long)h->sm_count * 3;
+    const long long need = (P.B + KW - 1) / KW;
+    if (grid > need) grid = need;
+    kl_tile32x8_kernel<<<(unsigned)grid, KW * 32, bytes, h->stream>>>(P);
+    h->launches++;
+    *handled = true;
+    return (int)cudaGetLastError();
+}

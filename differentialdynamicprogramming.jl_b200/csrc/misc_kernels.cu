@@ -246,6 +246,11 @@ int launch_boxqp(ddp_handle_s* h, long long B, int m, const double* H, const dou
 }
 
 int launch_kl_div(ddp_handle_s* h, const KlParams& P) {
+    if (!(h->flags & 1u)) {               // headline shape: FP64 tensor-tile kernel (kl_tile.cu)
+        bool handled = false;
+        int rc = launch_kl_div_tile(h, P, &handled);
+        if (rc != 0 || handled) return rc;
+    }
     size_t bytes = kl_smem_doubles(P.n, P.m) * sizeof(double);
     if ((long long)bytes > h->max_smem_optin) return (int)cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(kl_div_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);

@@ -82,8 +82,34 @@ def c4(B):
     eta = torch.ones(B, dtype=f64, device=dev)
     gp = L.GpsArgs(); gp.K_prev, gp.Sigi_prev = tn(Kp, T * n * m, n * m), tn(Sip, T * m * m, m * m); gp.eta = eta.data_ptr(); gp.Quui = Quui.data_ptr()
     t_g = timeit(lambda: eng._ck(eng.lib.ddp_back_pass_gps_f64(eng.h, C.byref(ba), C.byref(gp))), reps=2)
-    print(json.dumps(dict(config="C4 back_pass_gps on C2's system (eta=1)", batch=B, gps_back_ms=t_g, ms_scaled_to_65536=t_g * 65536 / B,
-                          diverged=int((dv > 0).sum().item()), variant=eng.kernel_variant)))
+    # forward rollout (alpha = 1) with the new policy and the KL evaluation (forward_covariance + kl_div_wiki), iLQGkl.jl:134-143
+    x0 = 1.0 + 0.1 * torch.randn(B, n, dtype=f64, device=dev, generator=g)
+    u = 0.1 * torch.randn(B, T, m, dtype=f64, device=dev, generator=g)
+    x, xnew, unew, cnew = E(B, T, n), E(B, T, n), E(B, T, m), E(B)
+    M = L.Model(); M.kind = 1; M.A, M.Bm = tn(fx, n * n, 0), tn(fu, n * m, 0); M.Q, M.R = tn(Q, 0, 0), tn(R, 0, 0); M.flags = 1
+    f0 = L.ForwardPassArgs(); f0.x0, f0.u = tn(x0, n, 0), tn(u, T * m, m); f0.alpha_scalar = f0.u_scale = 1.0
+    f0.xnew, f0.unew, f0.cost = x.data_ptr(), unew.data_ptr(), cnew.data_ptr()
+    eng._ck(eng.lib.ddp_forward_pass_f64(eng.h, C.byref(M), C.byref(f0)))
+    f2 = L.ForwardPassArgs(); f2.K, f2.k = K.data_ptr(), k.data_ptr(); f2.x0, f2.x, f2.u = tn(x0, n, 0), tn(x, T * n, n), tn(u, T * m, m)
+    f2.alpha_scalar = f2.u_scale = 1.0; f2.xnew, f2.unew, f2.cost = xnew.data_ptr(), unew.data_ptr(), cnew.data_ptr()
+    t_f = timeit(lambda: eng._ck(eng.lib.ddp_forward_pass_f64(eng.h, C.byref(M), C.byref(f2))))
+    Sp = torch.linalg.inv(Sip).contiguous()
+    R1 = (1e-4 * torch.eye(n, dtype=f64, device=dev)).contiguous()
+    klm = E(B)
+    ka = L.KlArgs(); ka.fx, ka.R1 = tn(fx, n * n, 0), tn(R1, 0, 0); ka.xnew, ka.xold = xnew.data_ptr(), x.data_ptr()
+    ka.K_new, ka.k_new, ka.Sig_new = K.data_ptr(), k.data_ptr(), Quui.data_ptr()
+    ka.K_prev, ka.Sig_prev, ka.Sigi_prev = tn(Kp, T * n * m, n * m), tn(Sp, T * m * m, m * m), tn(Sip, T * m * m, m * m)
+    ka.kl_mean = klm.data_ptr()
+    t_k = timeit(lambda: eng._ck(eng.lib.ddp_kl_div_f64(eng.h, C.byref(ka))), reps=2)
+    # multi-alpha line-search costs: 10 step sizes in one pass over K
+    al = (C.c_double * 10)(*[10.0 ** (-0.3 * i) for i in range(10)])
+    mc = E(10, B)
+    t_m = timeit(lambda: eng._ck(eng.lib.ddp_forward_costs_multi_f64(eng.h, C.byref(M), C.byref(f2), 10, al, mc.data_ptr())), reps=2)
+    sc = 65536 / B
+    print(json.dumps(dict(config="C4 KL-augmented sweep + forward + KL evaluation on C2's system (eta=1)", batch=B, gps_back_ms=t_g, fwd_ms=t_f,
+                          kl_div_ms=t_k, multi_alpha10_ms=t_m, iter_ms_scaled_to_65536=(t_g + t_f + t_k) * sc,
+                          gps_back_ms_scaled=t_g * sc, kl_div_ms_scaled=t_k * sc, multi_alpha10_ms_scaled=t_m * sc,
+                          kl_mean=float(klm.mean().item()), diverged=int((dv > 0).sum().item()), variant=eng.kernel_variant)))
 
 
 if __name__ == "__main__":

@@ -130,8 +130,10 @@ def test_back_pass_gps(ddp, n, m, N, lims):
         assert relerr(a, b) < TOL
 
 
-def test_kl_div(ddp):
-    n, m, N = 8, 2, 30
+@pytest.mark.parametrize("n,m,N,dense_r1", [(8, 2, 30, False), (32, 8, 20, False), (32, 8, 9, True)])
+def test_kl_div(ddp, n, m, N, dense_r1):
+    """forward_covariance + kl_div_wiki (forward_pass.jl:37-56, klutils.jl:70-100): generic kernel and, for n=32, m=8,
+    the FP64 tensor-tile kernel (kl_tile.cu), per-step divergence vs the oracle."""
     A, Bm, Q, R, x, u, cx, cu, prev = _prev_policy(n, m, N, 21)
     rep = lambda a: np.tile(a, (N, 1, 1))
     d0, pnew, _, _, _ = O.back_pass_gps(cx, cu, rep(Q), rep(np.zeros((n, m))), rep(R), rep(A), rep(Bm), None, x, u,
@@ -139,6 +141,9 @@ def test_kl_div(ddp):
     om = O.LinearModel(A, Bm, Q, R)
     xnew, unew, _ = O.forward_pass(pnew, x[0], u, x, 1, om.f, om.costfun, None)
     R1 = 1e-4 * np.eye(n)
+    if dense_r1:
+        Wn = np.random.default_rng(3).standard_normal((n, n))
+        R1 = R1 + 1e-4 * (Wn @ Wn.T) / n
     sig = O.forward_covariance(A, R1, pnew)
     kl0 = O.kl_div_wiki(xnew, x, sig, pnew, prev)
     gpn = ddp.GaussianPolicy(N, n, m, pnew.K, pnew.k, pnew.Sigma, pnew.Sigmai)
