@@ -36,7 +36,8 @@ N_X, M_U, T_H = 32, 8, 256
 BATCH = 65536
 H_STEP = 0.01
 # algorithmic work per trajectory-iteration, SURVEY.md section 8(d) / DESIGN.md
-FLOPS_BACK_STEP = 213419.0            # per backward timestep at n=32, m=8 (reference formulation)
+FLOPS_BACK_STEP = 213419.0            # per backward timestep at n=32, m=8 (reference formulation, SURVEY.md 8d)
+FLOPS_BACK_STEP_SYM = 336 * 512.0     # the same step with symmetric products counted once = what the tile kernel issues
 FLOPS_FWD_STEP = 5264.0
 BYTES_BACK = 92168.0 + 606228.0       # backward read + write per trajectory
 BYTES_FWD = 632832.0 + 81928.0        # forward read + write per trajectory
@@ -342,13 +343,17 @@ def main_gpu(args):
     if rank == 0:
         peaks, peak_kind = measured_peaks()
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        flops_back = FLOPS_BACK_STEP * (T - 1) * B
+        flops_back = FLOPS_BACK_STEP_SYM * (T - 1) * B
         ach_tf = flops_back / (bk * 1e-3) * 1e-12
+        ref_tf = FLOPS_BACK_STEP * (T - 1) * B / (bk * 1e-3) * 1e-12
         roofline = dict(
             bound="tensor", kernel="bp_tile32x8_kernel (backward sweep, FP64 mma.sync m8n8k4 tiles)",
             achieved=ach_tf, peak=FP64_TENSOR_PEAK_TFLOPS, unit="TFLOP/s", frac=ach_tf / FP64_TENSOR_PEAK_TFLOPS,
             peak_source="FP64 tensor (DMMA) peak measured on this pool's B200 by profiles/microbench (MEASURED_PEAKS.json has no FP64 figure); "
-                        "algorithmic flops = 213419/step x 255 steps x 65536 trajectories (SURVEY.md 8d)",
+                        "algorithmic flops = 172032/step (the symmetric halves of F'VF and of the Vxx update counted once: 336 m8n8k4 "
+                        "tiles) x 255 steps x 65536 trajectories; SURVEY.md 8d's reference formulation (213419/step, full products) is "
+                        "reported as reference_formulation_tflops and would read 1.0+ of the peak",
+            reference_formulation_tflops=ref_tf, reference_formulation_frac=ref_tf / FP64_TENSOR_PEAK_TFLOPS,
             fp64_dfma_frac=ach_tf / FP64_DFMA_PEAK_TFLOPS,
             kernel_ms=bk, share_of_step=bk / ms_per_step,
             hbm=dict(achieved=BYTES_BACK * B / (bk * 1e-3) * 1e-9, peak=hbm_peak, unit="GB/s",

@@ -43,14 +43,16 @@ struct FxStage {
     static constexpr int CH = (N * N) / 2;            // 16-byte chunks per row
 };
 
+// Coalesced copy of the warp's 32 fx blocks of step i into the ring: lane -> (row = lane / CH + (32 / CH) k, chunk = lane % CH).
+// The per-lane source pointer (row, chunk) and the row validity mask are formed once per trajectory set; per step the
+// address work is one 64-bit multiply-add plus one add per instruction.
 template <int N>
-__device__ __forceinline__ void stage_fx(double* sbuf, const BackParams& P, long long b0, int i, int lane) {
-    constexpr int CH = FxStage<N>::CH, ROW = FxStage<N>::ROW;
+__device__ __forceinline__ void stage_fx(double* sdst_lane, const double* src_lane, long long rowstep, unsigned rowmask) {
+    constexpr int CH = FxStage<N>::CH, ROW = FxStage<N>::ROW, RPI = 32 / CH;    // rows per instruction
 #pragma unroll
     for (int k = 0; k < CH; k++) {
-        const int e = lane + 32 * k, row = e / CH, ch = e % CH;
-        const long long bb = b0 + row;
-        if (bb < P.B) cp_async16s(sbuf + row * ROW + 2 * ch, tp(P.fx, bb, i) + 2 * ch);
+        if ((rowmask >> k) & 1u) cp_async16s(sdst_lane + k * RPI * ROW, src_lane);
+        src_lane += rowstep;
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
@@ -98,6 +100,16 @@ __global__ void __launch_bounds__(128, MINB) bp_small_kernel(BackParams P) {
     const long long b = (b_raw < P.B) ? b_raw : P.B - 1;     // out-of-range lanes shadow the last trajectory, store nothing
     double* sfx = s_fx + (STAGE ? wid * 2 * 32 * FxStage<N>::ROW : 0);
     const int T = P.T;
+    // staging maps (see stage_fx)
+    constexpr int S_CH = FxStage<N>::CH, S_RPI = 32 / (S_CH > 0 ? S_CH : 1);
+    const int s_row = lane / S_CH, s_ch = lane % S_CH;
+    const double* fx_lane = P.fx.p + (b0 + s_row) * P.fx.sb + 2 * s_ch;
+    const long long fx_rowstep = (long long)S_RPI * P.fx.sb;
+    unsigned fx_rowmask = 0;
+#pragma unroll
+    for (int k = 0; k < S_CH; k++)
+        if (b0 + s_row + (long long)S_RPI * k < P.B) fx_rowmask |= 1u << k;
+    double* sfx_lane = sfx + s_row * FxStage<N>::ROW + 2 * s_ch;
     const bool use_qp = (P.lims != nullptr) && !(P.lims[0] > P.lims[M]);     // backward_pass.jl:31
     const double lam = P.lambda[b];
     const bool reg2 = (P.reg_type == 2);
@@ -140,7 +152,7 @@ __global__ void __launch_bounds__(128, MINB) bp_small_kernel(BackParams P) {
     bool alive = valid;
     if (T >= 2) {
         load_step<N, M>(cur, P, b, T - 2, use_qp);
-        if (STAGE) stage_fx<N>(sfx + ((T - 2) & 1) * 32 * FxStage<N>::ROW, P, b0, T - 2, lane);
+        if (STAGE) stage_fx<N>(sfx_lane + ((T - 2) & 1) * 32 * FxStage<N>::ROW, fx_lane + (long long)(T - 2) * P.fx.st, fx_rowstep, fx_rowmask);
     }
     for (int i = T - 2; i >= 0; i--) {
         if (STAGE) {
@@ -150,7 +162,7 @@ __global__ void __launch_bounds__(128, MINB) bp_small_kernel(BackParams P) {
 #pragma unroll
             for (int e = 0; e < N * N; e += 2) { double2 t = *reinterpret_cast<const double2*>(row + e); cfx[e] = t.x; cfx[e + 1] = t.y; }
             // the other buffer was read in step i+1, before the __syncwarp above: refill it with step i-1
-            if (i > 0) stage_fx<N>(sfx + ((i - 1) & 1) * 32 * FxStage<N>::ROW, P, b0, i - 1, lane);
+            if (i > 0) stage_fx<N>(sfx_lane + ((i - 1) & 1) * 32 * FxStage<N>::ROW, fx_lane + (long long)(i - 1) * P.fx.st, fx_rowstep, fx_rowmask);
         } else {
             load_fx_direct<N>(cfx, P, b, i);
         }
@@ -371,7 +383,7 @@ int launch_small(ddp_handle_s* h, const BackParams& P) {
     const unsigned grid = (unsigned)((P.B + 127) / 128);
     static int minb = -1;
     if (minb < 0) { const char* ev = getenv("DDP_SMALL_MINB"); minb = ev ? atoi(ev) : 2; }
-    const bool stage = ((N * N) % 2 == 0) && ((uintptr_t)P.fx.p % 16 == 0) && (P.fx.sb % 2 == 0) && (P.fx.st % 2 == 0) &&
+    const bool stage = ((N * N) % 2 == 0) && (32 % ((N * N) / 2) == 0) && ((uintptr_t)P.fx.p % 16 == 0) && (P.fx.sb % 2 == 0) && (P.fx.st % 2 == 0) &&
                        !(getenv("DDP_SMALL_NOSTAGE"));
     if (stage) {
         if (minb == 3) bp_small_kernel<N, M, 3, true><<<grid, 128, 0, h->stream>>>(P);

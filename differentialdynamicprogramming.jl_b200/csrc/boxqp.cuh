@@ -144,7 +144,10 @@ __device__ int boxqp_seq(int m, const double* H, int ldh, const double* g, const
         }
         double gs = 0.0;
         for (int p = 0; p < nf; p++) gs = DADD(gs, DMUL(grad[idx[p]], grad[idx[p]]));   // norm(grad[free]) :120
-        if (__dsqrt_rn(gs) < o.min_grad) {
+        // One free variable: sqrt(fl(g*g)) == |g| exactly in binary floating point with round-to-nearest as long as g*g
+        // neither underflows nor overflows, so the (expensive) square root is skipped without changing a single bit.
+        const double gnorm = (MM == 1 && nf == 1 && gs > 1e-280 && gs < 1e280) ? fabs(grad[idx[0]]) : __dsqrt_rn(gs);
+        if (gnorm < o.min_grad) {
             result = 5;
             break;
         }

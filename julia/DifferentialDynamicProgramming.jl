@@ -16,7 +16,7 @@
 module DifferentialDynamicProgramming
 
 using LinearAlgebra
-export iLQG, boxQP, GaussianPolicy, LinearModel, PendcartModel, back_pass, forward_pass
+export iLQG, iLQGkl, boxQP, GaussianPolicy, LinearModel, PendcartModel, back_pass, forward_pass
 
 const libddp = get(ENV, "LIBDDP", joinpath(@__DIR__, "..", "differentialdynamicprogramming.jl_b200", "libddp.so"))
 
@@ -81,6 +81,27 @@ end
 struct DdpIlqgState
     lambda::Float64; dlambda::Float64; cost::Float64; g_norm::Float64; last_dcost::Float64; last_alpha::Float64
     iter::Int32; accepted_iter::Int32; status::Int32; pad::Int32
+end
+
+struct DdpIlqgklOpts                      # ddp_ilqgkl_opts (defaults: iLQGkl.jl:25-42)
+    kl_step::Float64
+    max_iter::Int32
+    eta_bracket::NTuple{3,Float64}
+    del0::Float64
+    max_eta_retries::Int32
+    lims::Ptr{Float64}
+end
+
+struct DdpIlqgklState
+    eta_min::Float64; eta::Float64; eta_max::Float64; del0::Float64; divergence::Float64; dcost::Float64; expected::Float64; cost::Float64
+    iter::Int32; status::Int32; retries::Int32; pad::Int32
+end
+
+struct DdpIlqgklArgs
+    x::Ptr{Float64}; u::Ptr{Float64}; cost::Ptr{Float64}
+    K_prev::DdpTensor; Sig_prev::DdpTensor; Sigi_prev::DdpTensor; fx_model::DdpTensor; R1::DdpTensor
+    xnew::Ptr{Float64}; unew::Ptr{Float64}; K::Ptr{Float64}; k::Ptr{Float64}; Sig::Ptr{Float64}; Sigi::Ptr{Float64}
+    Vx::Ptr{Float64}; Vxx1::Ptr{Float64}; costnew::Ptr{Float64}; state::Ptr{DdpIlqgklState}
 end
 
 # ---- handle + device memory -------------------------------------------------------------------
@@ -220,6 +241,49 @@ function iLQG(f::DeviceModel, costfun::DeviceModel, df::DeviceModel, x0, u0;
         return x[:, :, 1], u[:, :, 1], GaussianPolicy(N, n, m, K[:, :, :, 1], k[:, :, 1], zeros(m, m, 0), zeros(m, m, 0)), Vx[:, :, 1], Vxx1[:, :, 1], st[1].cost, st
     end
     return x, u, (K, k), Vx, Vxx1, [s.cost for s in st], st
+end
+
+# ---- iLQGkl(dynamics,costfun,derivs,x0,traj_prev,model; kw...)   iLQGkl.jl:25 --------------------
+# Whole outer loop on the device (ddp_ilqgkl_solve_f64).  `model` of the reference (LinearTimeVaryingModelsBase) is
+# replaced by what it is used for: `fx_model` = df(model,x,u)[1] and `R1` = covariance(model,x,u) (forward_pass.jl:38,42).
+# x0 is the pre-rolled trajectory (n,N[,B]); traj_prev = (K (m,n,N[,B]), k (m,N[,B]), Σ (m,m,N[,B]), Σi (m,m,N[,B])).
+function iLQGkl(dynamics::DeviceModel, costfun::DeviceModel, derivs::DeviceModel, x0, traj_prev, fx_model, R1;
+                cost = nothing, kl_step = 1.0, lims = [], max_iter = 50, ηbracket = [1e-8, 1.0, 1e16], del0 = 1e-4, kwargs...)
+    dynamics === costfun === derivs || error("dynamics, costfun and derivs must be one device model descriptor")
+    cost === nothing && error("Initial trajectory supplied, initial cost must also be supplied")         # iLQGkl.jl:66-68
+    model = dynamics
+    Kp, kp, Σp, Σip = traj_prev
+    n, N = size(x0, 1), size(x0, 2); m = size(kp, 1); B = size(x0, 3)
+    e = Engine(n, m, N, B)
+    keep = Ptr{Cvoid}[]
+    up(a) = (p = upload(e, Array{Float64}(a)); push!(keep, p); p)
+    Q, R = model.Q, model.R
+    qdiag = Int32(isdiag(Q) ? 1 : 0)
+    md = if model isa LinearModel
+        DdpModel(1, tensor(up(model.A), model.A, N, B), tensor(up(model.B), model.B, N, B), DdpTensor(up(Q), 0, 0), DdpTensor(up(R), 0, 0),
+                 C_NULL, ntuple(_ -> 0.0, 8), 0, qdiag)
+    else
+        DdpModel(2, DdpTensor(), DdpTensor(), DdpTensor(up(Q), 0, 0), DdpTensor(up(R), 0, 0), Ptr{Float64}(up(model.goal)),
+                 (model.g, model.l, model.h, model.d, 0.0, 0.0, 0.0, 0.0), 1, qdiag)
+    end
+    limsd = isempty(lims) ? C_NULL : up(lims)
+    opts = DdpIlqgklOpts(kl_step, max_iter, (ηbracket[1], ηbracket[2], ηbracket[3]), del0, 200, Ptr{Float64}(limsd))
+    costs = B == 1 ? [sum(cost)] : vec(sum(reshape(Array{Float64}(cost), :, B), dims = 1))
+    xnew = zeros(n, N, B); unew = zeros(m, N, B); K = zeros(m, n, N, B); k = zeros(m, N, B); Σ = zeros(m, m, N, B); Σi = zeros(m, m, N, B)
+    Vx = zeros(n, N, B); Vxx1 = zeros(n, n, B); cnew = zeros(B); st = Vector{DdpIlqgklState}(undef, B)
+    outs = (xnew, unew, K, k, Σ, Σi, Vx, Vxx1, cnew, st)
+    dptr = [dmalloc(e, sizeof(a)) for a in outs]
+    args = DdpIlqgklArgs(up(x0), up(kp), up(costs),                                                       # u = traj_prev.k (iLQGkl.jl:47)
+                         tensor(up(Kp), Kp, N, B), tensor(up(Σp), Σp, N, B), tensor(up(Σip), Σip, N, B),
+                         tensor(up(fx_model), fx_model, N, B), tensor(up(R1), R1, 1, B), dptr...)
+    nouter = Ref{Int32}(0)
+    check(e, ccall((:ddp_ilqgkl_solve_f64, libddp), Cint, (Ptr{Cvoid}, Ref{DdpModel}, Ref{DdpIlqgklOpts}, Ref{DdpIlqgklArgs}, Ref{Int32}),
+                   e.h, md, opts, args, nouter))
+    for (a, p) in zip(outs, dptr); download!(e, a, p); dfree(e, p); end
+    foreach(p -> dfree(e, p), keep)
+    B == 1 && return xnew[:, :, 1], unew[:, :, 1], GaussianPolicy(N, n, m, K[:, :, :, 1], k[:, :, 1], Σ[:, :, :, 1], Σi[:, :, :, 1]),
+                     Vx[:, :, 1], Vxx1[:, :, 1], cnew[1], st
+    return xnew, unew, (K, k, Σ, Σi), Vx, Vxx1, cnew, st
 end
 
 iLQG(f, costfun, df, x0, u0; kwargs...) = error("iLQG: f/costfun/df must be a device model descriptor (LinearModel, PendcartModel); " *
