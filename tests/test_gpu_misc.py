@@ -182,8 +182,11 @@ def test_forward_fast_lin32x8(ddp, lims, goal):
         assert relerr(xg[b], x0_) < TOL and abs(cg[b] - c0_.sum()) < TOL * abs(c0_.sum())
 
 
-def test_forward_fast_pendcart(ddp):
-    N, B = 120, 37
+@pytest.mark.parametrize("N", [120, 30, 31, 2])
+def test_forward_fast_pendcart(ddp, N):
+    """N = 120: whole 4-step blocks of the staged kernel; 30: ragged last block; 31: odd horizon (rows are not 16-byte
+    aligned => the unstaged kernel); 2: shorter than one block.  B = 37 leaves a ragged warp."""
+    B = 37
     rng = np.random.default_rng(8)
     x0 = np.stack([np.array([np.pi - 0.6 + 0.2 * rng.uniform(-1, 1), 0, 0, 0]) for _ in range(B)])
     u = rng.standard_normal((B, N, 1))
@@ -201,12 +204,14 @@ def test_forward_fast_pendcart(ddp):
         pols.append((p, xo, uo))
     pol = ddp.GaussianPolicy(N, 4, 1, np.array([p[0].K for p in pols]), np.array([p[0].k for p in pols]))
     xs, us = np.array([p[1] for p in pols]), np.array([p[2] for p in pols])
-    xn, un, ct = ddp.forward_pass(pol, x0, us, xs, 0.7, pm.f, pm.costfun, lims, per_step_cost=True)
+    xn, un, ct, (cxn, cun) = ddp.forward_pass(pol, x0, us, xs, 0.7, pm.f, pm.costfun, lims, per_step_cost=True, want_derivs=True)
     xg, ug, cg = ddp.forward_pass(pol, x0, us, xs, 0.7, pm.f, pm.costfun, lims, per_step_cost=True, force_generic=True)
     for b in range(B):
         x0_, u0_, c0_ = O.forward_pass(pols[b][0], x0[b], us[b], xs[b], 0.7, om.f, om.costfun, lims)
         assert relerr(xn[b], x0_) < TOL and relerr(un[b], u0_) < TOL and relerr(ct[b], c0_) < TOL
         assert relerr(xg[b], x0_) < TOL and relerr(cg[b], c0_) < TOL
+        dcx = om.df(x0_, u0_)
+        assert relerr(cxn[b], dcx[5]) < TOL and relerr(cun[b], dcx[6]) < TOL       # fused df outputs cx = Q(x - goal), cu = R u
 
 
 @pytest.mark.parametrize("tv", [False, True])
