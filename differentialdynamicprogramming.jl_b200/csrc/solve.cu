@@ -54,62 +54,166 @@ __global__ void __launch_bounds__(128) df_cost_kernel(int n, int m, int T, long 
     }
 }
 
-__device__ __forceinline__ void mat5_mul(const double* A, const double* Bm, double* C) {
+// Same result for cost matrices shared by the batch (the usual case): Q and R are staged once per CTA in shared memory
+// (QDIAG: only the diagonal of Q is read, e.g. Q = h*I of demo_linear.jl:18), so the per-(b,t) work is n FMAs per lane
+// on operands that never leave the SM.  One warp per (b,t).
+template <bool QDIAG>
+__global__ void __launch_bounds__(256) df_cost_shared_kernel(int n, int m, int T, long long B, const double* __restrict__ x,
+                                                             const double* __restrict__ u, const double* __restrict__ Q,
+                                                             const double* __restrict__ R, const double* __restrict__ goal,
+                                                             const unsigned char* __restrict__ mask, double* __restrict__ cx,
+                                                             double* __restrict__ cu) {
+    extern __shared__ double dsm[];
+    double* sQ = dsm;                                   // n x n (or n diagonal entries)
+    double* sR = sQ + (QDIAG ? n : n * n);              // m x m
+    double* sg = sR + m * m;                            // goal (n)
+    double* sd = sg + n;                                // per warp: d (n) | u (m)
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int e = threadIdx.x; e < (QDIAG ? n : n * n); e += blockDim.x) sQ[e] = QDIAG ? Q[e * (n + 1)] : Q[e];
+    for (int e = threadIdx.x; e < m * m; e += blockDim.x) sR[e] = R[e];
+    for (int e = threadIdx.x; e < n; e += blockDim.x) sg[e] = goal ? goal[e] : 0.0;
+    __syncthreads();
+    double* d = sd + w * (n + m);
+    const long long total = B * T;
+    for (long long bt = (long long)blockIdx.x * nw + w; bt < total; bt += (long long)gridDim.x * nw) {
+        if (mask && !mask[bt / T]) continue;
+        __syncwarp();
+        for (int i = lane; i < n; i += 32) d[i] = x[bt * n + i] - sg[i];
+        for (int a = lane; a < m; a += 32) d[n + a] = u[bt * m + a];
+        __syncwarp();
+        for (int i = lane; i < n; i += 32) {
+            double s = 0.0;
+            if (QDIAG) s = sQ[i] * d[i];
+            else
+                for (int j = 0; j < n; j++) s = fma(sQ[i + n * j], d[j], s);
+            cx[bt * n + i] = s;
+        }
+        for (int a = lane; a < m; a += 32) {
+            double s = 0.0;
+            for (int c = 0; c < m; c++) s = fma(sR[a + m * c], d[n + c], s);
+            cu[bt * m + a] = s;
+        }
+    }
+}
+
+// Small systems (n <= 8): one THREAD per output element; a warp-per-(b,t) mapping would leave 32 - n lanes idle.
+__global__ void __launch_bounds__(256) df_cost_small_kernel(int n, int m, int T, long long B, const double* __restrict__ x,
+                                                            const double* __restrict__ u, const double* __restrict__ Q,
+                                                            const double* __restrict__ R, const double* __restrict__ goal,
+                                                            const unsigned char* __restrict__ mask, double* __restrict__ cx,
+                                                            double* __restrict__ cu) {
+    __shared__ double sQ[64], sR[64], sg[8];
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) sQ[e] = Q[e];
+    for (int e = threadIdx.x; e < m * m; e += blockDim.x) sR[e] = R[e];
+    for (int e = threadIdx.x; e < n; e += blockDim.x) sg[e] = goal ? goal[e] : 0.0;
+    __syncthreads();
+    const long long nx = B * T * n, nu = B * T * m, stride = (long long)gridDim.x * blockDim.x;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < nx; idx += stride) {
+        const long long bt = idx / n;
+        const int i = (int)(idx - bt * n);
+        if (mask && !mask[bt / T]) continue;
+        double s = 0.0;
+        for (int j = 0; j < n; j++) s = fma(sQ[i + n * j], x[bt * n + j] - sg[j], s);
+        cx[idx] = s;
+    }
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < nu; idx += stride) {
+        const long long bt = idx / m;
+        const int a = (int)(idx - bt * m);
+        if (mask && !mask[bt / T]) continue;
+        double s = 0.0;
+        for (int c = 0; c < m; c++) s = fma(sR[a + m * c], u[bt * m + c], s);
+        cu[idx] = s;
+    }
+}
+
+__device__ __forceinline__ void mat3_mul(const double* A, const double* Bm, double* C) {
 #pragma unroll
-    for (int i = 0; i < 5; i++)
+    for (int i = 0; i < 3; i++)
 #pragma unroll
-        for (int j = 0; j < 5; j++) {
+        for (int j = 0; j < 3; j++) {
             double s = 0.0;
 #pragma unroll
-            for (int k = 0; k < 5; k++) s = fma(A[i * 5 + k], Bm[k * 5 + j], s);
-            C[i * 5 + j] = s;
+            for (int k = 0; k < 3; k++) s = fma(A[i * 3 + k], Bm[k * 3 + j], s);
+            C[i * 3 + j] = s;
         }
 }
 
 // ZoH-discretised Jacobians of the pendulum on a cart: [fx fu; 0 1] = exp(h [fxc fuc; 0 0])
-// (system_pendcart.jl:137-151).  Scaling-and-squaring with a degree-10 Taylor polynomial: the
-// scaled norm is < 0.02, so the truncation error is below 1e-20.  One thread per (b,t).
+// (system_pendcart.jl:137-151).  The 5 x 5 generator is block diagonal up to the shared input column:
+//   (x1, x2, u):  h [0 1 0; a -d b; 0 0 0],  a = -g/l cos x1 - u/l sin x1,  b = cos x1 / l
+//   (x3, x4, u):  h [0 1 0; 0 0 1; 0 0 0]    nilpotent: exp = [1 h h^2/2; 0 1 h; 0 0 1] exactly
+// so only a 3 x 3 exponential is computed: scaling-and-squaring (2^-4) with a degree-10 Taylor polynomial; the scaled
+// norm is < 0.02, so the truncation error is below 1e-20.  One thread per (b,t).
 __global__ void __launch_bounds__(128) df_pendcart_kernel(int T, long long B, const double* __restrict__ x,
                                                           const double* __restrict__ u, double g, double l, double h, double d,
                                                           const unsigned char* __restrict__ mask, double* __restrict__ fx,
                                                           double* __restrict__ fu) {
-    const long long bt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (bt >= B * T) return;
-    if (mask && !mask[bt / T]) return;
+    const long long bt_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (bt_raw - (threadIdx.x & 31) >= B * T) return;               // whole warp out of range
+    const bool inrange = bt_raw < B * T;
+    const long long bt = inrange ? bt_raw : B * T - 1;              // tail lanes shadow the last item: the write-out below is cooperative
+    const bool act = inrange && !(mask && !mask[bt / T]);
     double sn, cs;
     sincos(x[bt * 4], &sn, &cs);
     const double uu = u[bt];
-    double M[25], P[25], S[25], Tm[25];
+    double M[9], P[9], S[9], Tm[9];
 #pragma unroll
-    for (int i = 0; i < 25; i++) M[i] = 0.0;
+    for (int i = 0; i < 9; i++) M[i] = 0.0;
     const double sc = h / 16.0;
-    M[0 * 5 + 1] = sc;                                   // fxc[1,2] = 1
-    M[1 * 5 + 0] = sc * (-g / l * cs - uu / l * sn);     // fxc[2,1]
-    M[1 * 5 + 1] = sc * (-d);                            // fxc[2,2]
-    M[2 * 5 + 3] = sc;                                   // fxc[3,4] = 1
-    M[1 * 5 + 4] = sc * (cs / l);                        // fuc[2]
-    M[3 * 5 + 4] = sc;                                   // fuc[4] = 1
+    M[0 * 3 + 1] = sc;                                   // fxc[1,2] = 1
+    M[1 * 3 + 0] = sc * (-g / l * cs - uu / l * sn);     // fxc[2,1]
+    M[1 * 3 + 1] = sc * (-d);                            // fxc[2,2]
+    M[1 * 3 + 2] = sc * (cs / l);                        // fuc[2]
     // S = I + M + M^2/2! + ... + M^10/10!
 #pragma unroll
-    for (int i = 0; i < 25; i++) { S[i] = M[i] + ((i % 6 == 0) ? 1.0 : 0.0); P[i] = M[i]; }
+    for (int i = 0; i < 9; i++) { S[i] = M[i] + ((i % 4 == 0) ? 1.0 : 0.0); P[i] = M[i]; }
+#pragma unroll
     for (int k = 2; k <= 10; k++) {
-        mat5_mul(P, M, Tm);
+        mat3_mul(P, M, Tm);
         const double inv = 1.0 / (double)k;
 #pragma unroll
-        for (int i = 0; i < 25; i++) { P[i] = Tm[i] * inv; S[i] += P[i]; }
+        for (int i = 0; i < 9; i++) { P[i] = Tm[i] * inv; S[i] += P[i]; }
     }
+#pragma unroll
     for (int s = 0; s < 4; s++) {
-        mat5_mul(S, S, Tm);
+        mat3_mul(S, S, Tm);
 #pragma unroll
-        for (int i = 0; i < 25; i++) S[i] = Tm[i];
+        for (int i = 0; i < 9; i++) S[i] = Tm[i];
     }
-    // column-major outputs: fx[i + 4 j] = S[i][j], fu[i] = S[i][4]
+    // column-major outputs fx[i + 4 j], fu[i]: the warp's 32 blocks are one contiguous 4 KB (fx) / 1 KB (fu) run of
+    // global memory, so they go through padded shared-memory rows and leave as fully coalesced 16-byte stores
+    // (a thread storing its own 128-byte block makes every store instruction touch 32 lines).
+    __shared__ __align__(16) double s_out[4][32 * 18 + 32 * 4];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    double* row = s_out[w] + lane * 18;
+    double* frow = s_out[w] + 32 * 18 + lane * 4;
+    auto put2 = [](double* p, double a, double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); };
+    put2(row + 0, S[0], S[3]);   put2(row + 2, 0.0, 0.0);        // column 1: (S00, S10, 0, 0)
+    put2(row + 4, S[1], S[4]);   put2(row + 6, 0.0, 0.0);        // column 2: (S01, S11, 0, 0)
+    put2(row + 8, 0.0, 0.0);     put2(row + 10, 1.0, 0.0);       // column 3: (0, 0, 1, 0)
+    put2(row + 12, 0.0, 0.0);    put2(row + 14, h, 1.0);         // column 4: (0, 0, h, 1)
+    put2(frow, S[2], S[5]);      put2(frow + 2, 0.5 * h * h, h);
+    __syncwarp();
+    const long long bt0 = bt_raw - lane;                          // first (b,t) of the warp
+    const bool vec = (((uintptr_t)fx % 16) == 0) && (((uintptr_t)fu % 16) == 0) && (mask == nullptr);
+    if (vec) {
+        const long long total = B * T;
 #pragma unroll
-    for (int j = 0; j < 4; j++)
+        for (int k = 0; k < 8; k++) {
+            const int e = k * 32 + lane, r = e >> 3, c = e & 7;
+            if (bt0 + r < total) *reinterpret_cast<double2*>(fx + bt0 * 16 + 2 * e) = *reinterpret_cast<const double2*>(s_out[w] + r * 18 + 2 * c);
+        }
 #pragma unroll
-        for (int i = 0; i < 4; i++) fx[bt * 16 + i + 4 * j] = S[i * 5 + j];
+        for (int k = 0; k < 2; k++) {
+            const int e = k * 32 + lane, r = e >> 1, c = e & 1;
+            if (bt0 + r < total) *reinterpret_cast<double2*>(fu + bt0 * 4 + 2 * e) = *reinterpret_cast<const double2*>(s_out[w] + 32 * 18 + r * 4 + 2 * c);
+        }
+    } else if (act) {
 #pragma unroll
-    for (int i = 0; i < 4; i++) fu[bt * 4 + i] = S[i * 5 + 4];
+        for (int i = 0; i < 16; i++) fx[bt * 16 + i] = row[i];
+#pragma unroll
+        for (int i = 0; i < 4; i++) fu[bt * 4 + i] = frow[i];
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -346,6 +450,26 @@ struct DevBuf {
     ~DevBuf() { for (void* p : ptrs) cudaFree(p); }
 };
 
+// cx = Q (x - goal), cu = R u over the batch: shared-matrix kernel when Q, R are shared by the batch, else the general one
+void launch_df_cost(ddp_handle_s* h, cudaStream_t st, int n, int m, int T, long long B, const double* x, const double* u, const TensorD& Q,
+                    const TensorD& R, const double* goal, const unsigned char* mask, double* cx, double* cu, bool qdiag) {
+    const long long wtot = B * T;
+    if (Q.sb == 0 && R.sb == 0 && n <= 8 && m <= 8) {
+        const unsigned grid = (unsigned)std::min<long long>((wtot * n + 255) / 256, (long long)h->sm_count * 16);
+        df_cost_small_kernel<<<grid, 256, 0, st>>>(n, m, T, B, x, u, Q.p, R.p, goal, mask, cx, cu);
+    } else if (Q.sb == 0 && R.sb == 0) {
+        const int nw = 8;
+        const size_t bytes = ((size_t)(qdiag ? n : n * n) + (size_t)m * m + n + (size_t)nw * (n + m)) * sizeof(double);
+        const unsigned grid = (unsigned)std::min<long long>((wtot + nw - 1) / nw, (long long)h->sm_count * 8);
+        if (qdiag) df_cost_shared_kernel<true><<<grid, nw * 32, bytes, st>>>(n, m, T, B, x, u, Q.p, R.p, goal, mask, cx, cu);
+        else df_cost_shared_kernel<false><<<grid, nw * 32, bytes, st>>>(n, m, T, B, x, u, Q.p, R.p, goal, mask, cx, cu);
+    } else {
+        const unsigned grid = (unsigned)std::min<long long>((wtot + 3) / 4, (long long)h->sm_count * 16);
+        df_cost_kernel<<<grid, 128, 0, st>>>(n, m, T, B, x, u, Q, R, goal, mask, cx, cu);
+    }
+    h->launches++;
+}
+
 int run_back(ddp_handle_s* h, const BackParams& P) {
     bool handled = false;
     int rc = 0;
@@ -379,9 +503,7 @@ int ddp_model_derivs_f64(ddp_handle_t h, const ddp_model* model, const double* x
     const int n = h->n, m = h->m, T = h->T;
     const long long B = h->B, wtot = B * T;
     if (cudaSetDevice(h->device) != cudaSuccess) { h->err = "cudaSetDevice failed"; return DDP_ERR_CUDA; }
-    unsigned grid = (unsigned)std::min<long long>((wtot + 3) / 4, (long long)h->sm_count * 16);
-    df_cost_kernel<<<grid, 128, 0, h->stream>>>(n, m, T, B, x, u, mk(model->Q), mk(model->R), model->goal, nullptr, cx, cu);
-    h->launches++;
+    launch_df_cost(h, h->stream, n, m, T, B, x, u, mk(model->Q), mk(model->R), model->goal, nullptr, cx, cu, (model->flags & DDP_MODEL_Q_DIAGONAL) != 0);
     if (model->kind == DDP_MODEL_PENDCART) {
         if (n != 4 || m != 1 || !fx || !fu) { h->err = "ddp_model_derivs_f64: pendcart needs n == 4, m == 1 and fx, fu outputs"; return DDP_ERR_INVALID; }
         df_pendcart_kernel<<<(unsigned)((wtot + 127) / 128), 128, 0, h->stream>>>(T, B, x, u, model->p[0], model->p[1], model->p[2], model->p[3],
@@ -492,9 +614,7 @@ int ddp_ilqg_solve_f64(ddp_handle_t h, const ddp_model* model, const ddp_ilqg_op
             // STEP 1: derivatives along the trajectories whose x,u changed (need_bp marks exactly those here)
             {
                 long long wtot = B * T;
-                unsigned grid = (unsigned)std::min<long long>((wtot + 3) / 4, (long long)h->sm_count * 16);
-                df_cost_kernel<<<grid, 128, 0, st>>>(n, m, T, B, x, u, M.Q, M.R, M.goal, s.need_bp, cx, cu);
-                h->launches++;
+                launch_df_cost(h, st, n, m, T, B, x, u, M.Q, M.R, M.goal, s.need_bp, cx, cu, (M.flags & DDP_MODEL_Q_DIAGONAL) != 0);
                 if (model->kind == DDP_MODEL_PENDCART) {
                     df_pendcart_kernel<<<(unsigned)((wtot + 127) / 128), 128, 0, st>>>(T, B, x, u, M.p[0], M.p[1], M.p[2], M.p[3],
                                                                                        s.need_bp, fxb, fub);
@@ -713,10 +833,7 @@ int ddp_ilqg_iter_host_f64(ddp_handle_t h, ddp_iter_host_args* a) {
             CUS(cudaStreamWaitEvent(s_cp, ev_in[si], 0));
             if (c >= NS) CUS(cudaStreamWaitEvent(s_cp, ev_out[si], 0));
             if (!host_derivs) {        // STEP 1 on the device: cx = Q x, cu = R u  (iLQG.jl:225-229, demo_linear.jl:38-39)
-                const long long wtot = nb * T;
-                const unsigned dgrid = (unsigned)std::min<long long>((wtot + 3) / 4, (long long)h->sm_count * 16);
-                df_cost_kernel<<<dgrid, 128, 0, s_cp>>>(n, m, T, nb, s.x, s.u, M.Q, M.R, nullptr, nullptr, s.cx, s.cu);
-                h->launches++;
+                launch_df_cost(h, s_cp, n, m, T, nb, s.x, s.u, M.Q, M.R, nullptr, nullptr, s.cx, s.cu, a->q_diagonal != 0);
             }
             BackParams BP{};
             BP.n = n; BP.m = m; BP.T = T; BP.B = nb;
@@ -913,9 +1030,7 @@ int ddp_ilqgkl_solve_f64(ddp_handle_t h, const ddp_model* model, const ddp_ilqgk
     // derivatives once, before the loop (iLQGkl.jl:88, quirk Q9)
     {
         const long long wtot = B * T;
-        const unsigned dgrid = (unsigned)std::min<long long>((wtot + 3) / 4, (long long)h->sm_count * 16);
-        df_cost_kernel<<<dgrid, 128, 0, st>>>(n, m, T, B, a->x, a->u, M.Q, M.R, M.goal, nullptr, cx, cu);
-        h->launches++;
+        launch_df_cost(h, st, n, m, T, B, a->x, a->u, M.Q, M.R, M.goal, nullptr, cx, cu, (M.flags & DDP_MODEL_Q_DIAGONAL) != 0);
         if (model->kind == DDP_MODEL_PENDCART) {
             df_pendcart_kernel<<<(unsigned)((wtot + 127) / 128), 128, 0, st>>>(T, B, a->x, a->u, M.p[0], M.p[1], M.p[2], M.p[3], nullptr, fxb, fub);
             h->launches++;
