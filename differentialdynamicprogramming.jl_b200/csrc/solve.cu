@@ -438,16 +438,41 @@ __global__ void export_state_kernel(long long B, SolveState s, ddp_ilqg_state* o
     out[b] = r;
 }
 
+// Device scratch of one call.  With a handle, allocations are bump-allocated from the handle's workspace arena, which
+// is kept between calls (cudaMalloc/cudaFree of two dozen buffers cost several hundred ms per solve otherwise); what
+// does not fit falls back to cudaMalloc and the arena is grown for the next call.
 struct DevBuf {
     std::vector<void*> ptrs;
+    ddp_handle_s* h = nullptr;
+    size_t off = 0, need = 0;
+    DevBuf() = default;
+    explicit DevBuf(ddp_handle_s* handle) : h(handle) {}
+    cudaError_t reserve(size_t bytes) {                  // make the arena at least this large before the first alloc
+        if (!h || bytes <= h->ws_cap) return cudaSuccess;
+        if (h->ws) { cudaFree(h->ws); h->ws = nullptr; h->ws_cap = 0; }
+        cudaError_t e = cudaMalloc(&h->ws, bytes);
+        if (e == cudaSuccess) h->ws_cap = bytes;
+        else cudaGetLastError();                         // not fatal: alloc() falls back to cudaMalloc
+        return cudaSuccess;
+    }
     template <typename T>
     cudaError_t alloc(T** p, size_t count) {
+        const size_t bytes = (std::max<size_t>(count * sizeof(T), 16) + 255) & ~(size_t)255;
+        need += bytes;
+        if (h && h->ws && off + bytes <= h->ws_cap) {
+            *p = (T*)((char*)h->ws + off);
+            off += bytes;
+            return cudaSuccess;
+        }
         void* q = nullptr;
-        cudaError_t e = cudaMalloc(&q, std::max<size_t>(count * sizeof(T), 16));
+        cudaError_t e = cudaMalloc(&q, bytes);
         if (e == cudaSuccess) { ptrs.push_back(q); *p = (T*)q; }
         return e;
     }
-    ~DevBuf() { for (void* p : ptrs) cudaFree(p); }
+    ~DevBuf() {
+        for (void* p : ptrs) cudaFree(p);
+        if (h && need > h->ws_cap) reserve(need);
+    }
 };
 
 // cx = Q (x - goal), cu = R u over the batch: shared-matrix kernel when Q, R are shared by the batch, else the general one
@@ -532,7 +557,7 @@ int ddp_ilqg_solve_f64(ddp_handle_t h, const ddp_model* model, const ddp_ilqg_op
     const int n = h->n, m = h->m, T = h->T;
     const long long B = h->B;
     cudaError_t err = cudaSuccess;
-    DevBuf mem;
+    DevBuf mem(h);
     SolveState s{};
     SolveOpts o{};
     double *cx = nullptr, *cu = nullptr, *xnew = nullptr, *unew = nullptr, *fxb = nullptr, *fub = nullptr, *zeros = nullptr;
@@ -554,6 +579,7 @@ int ddp_ilqg_solve_f64(ddp_handle_t h, const ddp_model* model, const ddp_ilqg_op
     o.lam_min = opts->lambda_min; o.reduce_ratio_min = opts->reduce_ratio_min; o.max_iter = opts->max_iter;
 
     CUS(cudaSetDevice(h->device));
+    CUS(mem.reserve((size_t)B * 8 * 40 + (size_t)B * T * (n + m) * 16 + (model->kind == DDP_MODEL_PENDCART ? (size_t)B * T * 160 : 0) + (size_t)B * 128 + (1 << 16)));
     CUS(mem.alloc(&s.lambda, B)); CUS(mem.alloc(&s.dlambda, B)); CUS(mem.alloc(&s.cost, B)); CUS(mem.alloc(&s.costnew, B));
     CUS(mem.alloc(&s.alpha, B)); CUS(mem.alloc(&s.gnorm, B)); CUS(mem.alloc(&s.dV, 2 * B)); CUS(mem.alloc(&s.last_dcost, B));
     CUS(mem.alloc(&s.aidx, B)); CUS(mem.alloc(&s.status, B)); CUS(mem.alloc(&s.iter, B)); CUS(mem.alloc(&s.acc, B));
@@ -997,7 +1023,7 @@ int ddp_ilqgkl_solve_f64(ddp_handle_t h, const ddp_model* model, const ddp_ilqgk
     const int max_iter = opts->max_iter > 0 ? opts->max_iter : 50;
     const int max_retries = opts->max_eta_retries > 0 ? opts->max_eta_retries : 200;
     cudaError_t err = cudaSuccess;
-    DevBuf mem;
+    DevBuf mem(h);
     KlSolveState s{};
     double *cx = nullptr, *cu = nullptr, *fxb = nullptr, *fub = nullptr, *zeros = nullptr;
     int hc[2];
@@ -1010,6 +1036,7 @@ int ddp_ilqgkl_solve_f64(ddp_handle_t h, const ddp_model* model, const ddp_ilqgk
     KlParams KP{};
 
     CUS(cudaSetDevice(h->device));
+    CUS(mem.reserve((size_t)B * 8 * 40 + (size_t)B * T * (n + m) * 8 + (model->kind == DDP_MODEL_PENDCART ? (size_t)B * T * 160 : 0) + (1 << 16)));
     CUS(mem.alloc(&s.eta3, 3 * B)); CUS(mem.alloc(&s.eta, B)); CUS(mem.alloc(&s.del0, B)); CUS(mem.alloc(&s.div, B));
     CUS(mem.alloc(&s.dcost, B)); CUS(mem.alloc(&s.expected, B)); CUS(mem.alloc(&s.dV, 2 * B)); CUS(mem.alloc(&s.klmean, B));
     CUS(mem.alloc(&s.iter, B)); CUS(mem.alloc(&s.status, B)); CUS(mem.alloc(&s.retries, B)); CUS(mem.alloc(&s.diverge, B));

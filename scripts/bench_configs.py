@@ -112,9 +112,66 @@ def c4(B):
                           kl_mean=float(klm.mean().item()), diverged=int((dv > 0).sum().item()), variant=eng.kernel_variant)))
 
 
+def solve(which, B):
+    """Whole device-resident iLQG solves (ddp_ilqg_solve_f64): wall time, outer iterations, final status histogram."""
+    import time
+    if which == "c2":
+        n, m, T, h = 32, 8, 256, 0.01
+        g = torch.Generator(device=dev); g.manual_seed(0)
+        G = torch.randn(B, n, n, dtype=f64, device=dev, generator=g)
+        A = torch.linalg.matrix_exp(h * (G - G.transpose(1, 2))); Bm = h * torch.randn(B, n, m, dtype=f64, device=dev, generator=g)
+        fx, fu = A.transpose(1, 2).contiguous(), Bm.transpose(1, 2).contiguous()
+        Q = (h * torch.eye(n, dtype=f64, device=dev)).contiguous(); R = (0.1 * h * torch.eye(m, dtype=f64, device=dev)).contiguous()
+        M = L.Model(); M.kind = 1; M.A, M.Bm = tn(fx, n * n, 0), tn(fu, n * m, 0); M.Q, M.R = tn(Q, 0, 0), tn(R, 0, 0); M.flags = 1
+        x0 = 1.0 + 0.1 * torch.randn(B, n, dtype=f64, device=dev, generator=g)
+        u0 = 0.1 * torch.randn(B, T, m, dtype=f64, device=dev, generator=g)
+        alpha = [10.0 ** (-3.0 * i / 10) for i in range(11)]
+        o = L.IlqgOpts(); o.tol_fun, o.tol_grad, o.max_iter = 1e-7, 1e-4, 500; o.reg_type = 1
+        o.lam, o.dlam, o.lam_factor, o.lam_max, o.lam_min = 1.0, 1.0, 1.6, 1e10, 1e-6
+        keep = (fx, fu, Q, R)
+    else:
+        n, m, T = 4, 1, 600
+        g = torch.Generator(device=dev); g.manual_seed(1)
+        x0 = torch.zeros(B, n, dtype=f64, device=dev)
+        x0[:, 0] = np.pi - 0.6 + 0.2 * (2 * torch.rand(B, dtype=f64, device=dev, generator=g) - 1)
+        u0 = torch.zeros(B, T, m, dtype=f64, device=dev)
+        Q = torch.diag(torch.tensor([10.0, 1, 2, 1], dtype=f64, device=dev)).contiguous(); R = torch.ones(1, 1, dtype=f64, device=dev)
+        goal = torch.tensor([np.pi, 0, 0, 0], dtype=f64, device=dev)
+        lims = torch.tensor([-5.0, 5.0], dtype=f64, device=dev)
+        M = L.Model(); M.kind = 2; M.Q, M.R = tn(Q, 0, 0), tn(R, 0, 0); M.goal = goal.data_ptr(); M.terminal_cost = 1
+        for i, v in enumerate((9.82, 0.35, 0.01, 0.99)): M.p[i] = v
+        alpha = [10.0 ** (0.2 - 3.2 * i / 5) for i in range(6)]                    # system_pendcart.jl:197-206
+        o = L.IlqgOpts(); o.tol_fun, o.tol_grad, o.max_iter = 1e-8, 1e-8, int(os.environ.get("C3_MAX_ITER", "30")); o.reg_type = 2
+        o.lam, o.dlam, o.lam_factor, o.lam_max, o.lam_min = 1.0, 1.0, 1.6, 1e15, 1e-6
+        o.lims = lims.data_ptr()
+        keep = (Q, R, goal, lims)
+    o.n_alpha = len(alpha)
+    for i, v in enumerate(alpha): o.alpha[i] = v
+    E = lambda *s_: torch.zeros(*s_, dtype=f64, device=dev)
+    x, u, K, k, Vx, Vxx1 = E(B, T, n), E(B, T, m), E(B, T, n, m), E(B, T, m), E(B, T, n), E(B, n, n)
+    st = torch.zeros(B, C.sizeof(L.IlqgState), dtype=torch.uint8, device=dev)
+    eng = ddp.Engine(n, m, T, B); eng.set_stream(torch.cuda.current_stream().cuda_stream)
+    nouter = C.c_int32(0)
+    walls = []
+    for rep in range(2):                                  # the second call re-uses the handle's workspace arena
+        torch.cuda.synchronize(); l0 = eng.launch_count; t0 = time.perf_counter()
+        eng._ck(eng.lib.ddp_ilqg_solve_f64(eng.h, C.byref(M), C.byref(o), x0.data_ptr(), u0.data_ptr(), x.data_ptr(), u.data_ptr(), K.data_ptr(),
+                                           k.data_ptr(), Vx.data_ptr(), Vxx1.data_ptr(), st.data_ptr(), C.byref(nouter)))
+        torch.cuda.synchronize(); dt = time.perf_counter() - t0
+        walls.append(dt)
+    sa = np.frombuffer(st.cpu().numpy().tobytes(), dtype=np.dtype([("lam", "f8"), ("dlam", "f8"), ("cost", "f8"), ("g_norm", "f8"), ("last_dcost", "f8"),
+                                                                   ("last_alpha", "f8"), ("iter", "i4"), ("accepted_iter", "i4"), ("status", "i4"), ("pad", "i4")]))
+    hist = {int(s_): int((sa["status"] == s_).sum()) for s_ in np.unique(sa["status"])}
+    print(json.dumps(dict(config=f"whole iLQG solve ({which}), device resident", batch=B, wall_s=dt, wall_s_first_call=walls[0], n_outer=int(nouter.value), launches=eng.launch_count - l0,
+                          status_hist=hist, iter_mean=float(sa["iter"].mean()), iter_max=int(sa["iter"].max()), cost_mean=float(sa["cost"].mean()),
+                          trajectory_iterations_per_s=float(sa["iter"].sum() / dt))))
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "c3"
     if which == "c3":
         c3(int(sys.argv[2]) if len(sys.argv) > 2 else 262144)
+    elif which == "solve":
+        solve(sys.argv[2], int(sys.argv[3]))
     else:
         c4(int(sys.argv[2]) if len(sys.argv) > 2 else 4096)
