@@ -18,6 +18,7 @@
 //                 + 1/2(mu'dK'Sip dK mu + tr(dK'Sip dK S_t)) + dk'Sip dK mu)          (klutils.jl:75-91, 98)
 //
 // 248 DMMA per step; 16.6 KB of shared memory per warp, 8 warps per SM (255 registers).
+#include <type_traits>
 #include "ddp_common.cuh"
 
 namespace {
@@ -45,6 +46,7 @@ __device__ __forceinline__ double rcp_nr(double d) {
     y = fma(y, e, y);
     return y;
 }
+__device__ const double kl_zero8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 constexpr int uidx(int at, int bt) { return at * 4 - (at * (at - 1)) / 2 + (bt - at); }   // upper-tile index of a 4 x 4 tiling, 10 tiles
 
 __global__ void __launch_bounds__(KW * 32, 2) kl_tile32x8_kernel(KlParams P) {
@@ -97,7 +99,10 @@ __global__ void __launch_bounds__(KW * 32, 2) kl_tile32x8_kernel(KlParams P) {
         }
         __syncwarp();
         double klsum = 0.0;
-        for (int t = 0; t < N; t++) {
+        // One step; PROP (compile time) = also propagate Sigma.  The body is branch-free straight-line code so that the
+        // scheduler can interleave the pivot chains and the vector terms with the DMMA stream.
+        auto step = [&](const int t, auto prop_tag) {
+            constexpr bool prop = decltype(prop_tag)::value;
             // ---- operands of the KL terms (global; consumed after / inside the tensor phase)
             const double* Kn = P.Kn + (b * N + t) * 256;
             const double* Kp = tp(P.Kp, b, t);
@@ -116,8 +121,25 @@ __global__ void __launch_bounds__(KW * 32, 2) kl_tile32x8_kernel(KlParams P) {
             const double2 Sn2 = ld2(P.Sn + (b * N + t) * 64 + 8 * g + 2 * q);                // Sn[2q..2q+1][g]
             const double2 Sp2 = ld2(tp(P.Sp, b, t) + 8 * g + 2 * q);                         // Sp[2q..2q+1][g]
             const double* knm = P.kn + (b * N + t) * 8;
-            double dk_own = -knm[g], dk0 = -knm[2 * q], dk1 = -knm[2 * q + 1];
-            if (P.kp.p) { const double* kpm = tp(P.kp, b, t); dk_own += kpm[g]; dk0 += kpm[2 * q]; dk1 += kpm[2 * q + 1]; }
+            const double* kpm = P.kp.p ? tp(P.kp, b, t) : kl_zero8;
+            const double dk_own = kpm[g] - knm[g], dk0 = kpm[2 * q] - knm[2 * q], dk1 = kpm[2 * q + 1] - knm[2 * q + 1];
+            // ---- pivots of Sp' and Sn' (determinant of the transpose = determinant): accumulator layout, shuffles; one pivot
+            //      of both matrices per call, interleaved with the DMMAs below
+            double pdp = 1.0, pdn = 1.0;
+            bool pos = true;
+            double A0 = Sp2.x, A1 = Sp2.y, B0 = Sn2.x, B1 = Sn2.y;
+            auto piv_step = [&](const int p) {
+                const double ownA = (p & 1) ? A1 : A0, ownB = (p & 1) ? B1 : B0;
+                const double dA = shf(ownA, 4 * p + (p >> 1)), dB = shf(ownB, 4 * p + (p >> 1));
+                const double cA = shf(ownA, (lane & ~3) | (p >> 1)), cB = shf(ownB, (lane & ~3) | (p >> 1));
+                const double rA0 = shf(A0, 4 * p + q), rA1 = shf(A1, 4 * p + q), rB0 = shf(B0, 4 * p + q), rB1 = shf(B1, 4 * p + q);
+                if (!(dA > 0.0) || !(dB > 0.0)) pos = false;
+                pdp *= dA;
+                pdn *= dB;
+                const double fA = (g != p) ? cA * rcp_nr(dA) : 0.0, fB = (g != p) ? cB * rcp_nr(dB) : 0.0;   // the pivot row stays
+                A0 = fma(-fA, rA0, A0); A1 = fma(-fA, rA1, A1);
+                B0 = fma(-fB, rB0, B0); B1 = fma(-fB, rB1, B1);
+            };
             // ---- tensor phase: W' = F' Sigma and P = dK Sigma share the Sigma fragments
             double W[4][4][2], Pt[4][2];
 #pragma unroll
@@ -126,7 +148,6 @@ __global__ void __launch_bounds__(KW * 32, 2) kl_tile32x8_kernel(KlParams P) {
 #pragma unroll
                 for (int jt = 0; jt < 4; jt++) W[at][jt][0] = W[at][jt][1] = 0.0;
             }
-            const bool prop = (t < N - 1);
 #pragma unroll
             for (int p = 0; p < 4; p++) {
                 double2 fa[4], fb[4];
@@ -142,6 +163,7 @@ __global__ void __launch_bounds__(KW * 32, 2) kl_tile32x8_kernel(KlParams P) {
 #pragma unroll
                         for (int jt = 0; jt < 4; jt++) dmma(W[at][jt][0], W[at][jt][1], fa[at].x, fb[jt].x);
                 }
+                piv_step(2 * p);
 #pragma unroll
                 for (int jt = 0; jt < 4; jt++) dmma(Pt[jt][0], Pt[jt][1], dKa[p].y, fb[jt].y);
                 if (prop) {
@@ -150,6 +172,7 @@ __global__ void __launch_bounds__(KW * 32, 2) kl_tile32x8_kernel(KlParams P) {
 #pragma unroll
                         for (int jt = 0; jt < 4; jt++) dmma(W[at][jt][0], W[at][jt][1], fa[at].y, fb[jt].y);
                 }
+                piv_step(2 * p + 1);
             }
             // ---- M = Sip dK ; trace term
             double tr2 = 0.0;
@@ -163,27 +186,6 @@ __global__ void __launch_bounds__(KW * 32, 2) kl_tile32x8_kernel(KlParams P) {
                 for (int jt = 0; jt < 4; jt++) dmma(Mt[jt][0], Mt[jt][1], S1, dKb[jt].y);
 #pragma unroll
                 for (int jt = 0; jt < 4; jt++) tr2 = fma(Mt[jt][1], Pt[jt][1], fma(Mt[jt][0], Pt[jt][0], tr2));
-            }
-            // ---- pivots of Sp' and Sn' (determinant of the transpose = determinant): accumulator layout, shuffles
-            double pdp = 1.0, pdn = 1.0;
-            bool pos = true;
-            {
-                double A0 = Sp2.x, A1 = Sp2.y, B0 = Sn2.x, B1 = Sn2.y;
-#pragma unroll
-                for (int p = 0; p < 8; p++) {
-                    const double ownA = (p & 1) ? A1 : A0, ownB = (p & 1) ? B1 : B0;
-                    const double dA = shf(ownA, 4 * p + (p >> 1)), dB = shf(ownB, 4 * p + (p >> 1));
-                    const double cA = shf(ownA, (lane & ~3) | (p >> 1)), cB = shf(ownB, (lane & ~3) | (p >> 1));
-                    const double rA0 = shf(A0, 4 * p + q), rA1 = shf(A1, 4 * p + q), rB0 = shf(B0, 4 * p + q), rB1 = shf(B1, 4 * p + q);
-                    if (!(dA > 0.0) || !(dB > 0.0)) pos = false;
-                    pdp *= dA;
-                    pdn *= dB;
-                    const double fA = cA * rcp_nr(dA), fB = cB * rcp_nr(dB);
-                    if (g != p) {                         // rows below (and above, harmlessly) the pivot row
-                        A0 = fma(-fA, rA0, A0); A1 = fma(-fA, rA1, A1);
-                        B0 = fma(-fB, rB0, B0); B1 = fma(-fB, rB1, B1);
-                    }
-                }
             }
             // ---- vector terms
             double vs = 0.0;
@@ -251,7 +253,9 @@ __global__ void __launch_bounds__(KW * 32, 2) kl_tile32x8_kernel(KlParams P) {
                 }
                 __syncwarp();
             }
-        }
+        };
+        for (int t = 0; t < N - 1; t++) step(t, std::true_type{});
+        step(N - 1, std::false_type{});
         if (lane == 0) P.kl_mean[b] = klsum / (double)N;
     }
 #undef FRAG
