@@ -22,6 +22,7 @@ __device__ __forceinline__ void stg2(double* p, double a, double b) { *reinterpr
 
 constexpr int FW_WPB = 4;
 constexpr int FW_WARP_DOUBLES = 32 + 32 + 32 + 8;   // sx, sdx, sd, su  (per warp)
+constexpr int FW_KD = 4;                            // depth of the cp.async ring of K_t (2 KB per step per warp)
 
 struct Pre {
     double2 K0, K1, K2, K3;
@@ -29,15 +30,17 @@ struct Pre {
     double xo;
 };
 
-template <bool POLICY>
+template <bool POLICY, bool WITHK = true>
 __device__ __forceinline__ void prefetch(Pre& p, const FwdParams& P, long long b, int t, int lane, int q) {
     const int N = P.T;
     if (POLICY) {
-        const double* Kt = P.K + (b * N + t) * 256 + 2 * lane;
-        p.K0 = ldg2(Kt);
-        p.K1 = ldg2(Kt + 64);
-        p.K2 = ldg2(Kt + 128);
-        p.K3 = ldg2(Kt + 192);
+        if (WITHK) {
+            const double* Kt = P.K + (b * N + t) * 256 + 2 * lane;
+            p.K0 = ldg2(Kt);
+            p.K1 = ldg2(Kt + 64);
+            p.K2 = ldg2(Kt + 128);
+            p.K3 = ldg2(Kt + 192);
+        }
         p.k = ldg2(P.k + (b * N + t) * 8 + 2 * q);
         p.xo = tp(P.x, b, t)[lane];
     }
@@ -50,8 +53,10 @@ template <bool POLICY, int QMODE>
 __global__ void __launch_bounds__(FW_WPB * 32, 2) fwd_lin32x8_kernel(FwdParams P) {
     __shared__ double smem[FW_WPB * FW_WARP_DOUBLES];
     __shared__ double sQ[QMODE == 1 ? 1024 : 1];
+    __shared__ __align__(16) double sKring[POLICY ? FW_WPB * FW_KD * 256 : 2];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int g = lane >> 2, q = lane & 3;
+    double* kring = sKring + (POLICY ? w * FW_KD * 256 : 0) + 2 * lane;      // this lane's 16-byte cells: + 64 i + 256 slot
     double* sx = smem + w * FW_WARP_DOUBLES;
     double* sdx = sx + 32;
     double* sd = sdx + 32;
@@ -91,10 +96,33 @@ __global__ void __launch_bounds__(FW_WPB * 32, 2) fwd_lin32x8_kernel(FwdParams P
 
         // `p` holds the operands of step t; they are copied out and `p` is refilled for step t+2 at once,
         // so two steps' worth of loads (~5 KB per warp) are always in flight and stay in registers.
+        // K_t (2 KB per step) goes through a cp.async ring FW_KD steps deep: no registers are held while it is in flight,
+        // and every lane reads back exactly the 16-byte cells it copied itself (no cross-lane hand-over).
+        auto issue_K = [&](int t) {
+            if (POLICY) {
+                if (t < N) {
+                    const double* Kt = P.K + (b * N + t) * 256 + 2 * lane;
+                    double* dst = kring + (t % FW_KD) * 256;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const unsigned d = (unsigned)__cvta_generic_to_shared(dst + 64 * i);
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(Kt + 64 * i));
+                    }
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");      // one group per step, empty past the horizon
+            }
+        };
         auto step = [&](int t, Pre& p) {
-            const double2 K0 = p.K0, K1 = p.K1, K2 = p.K2, K3 = p.K3, uu = p.u, kk = p.k;
+            const double2 uu = p.u, kk = p.k;
             const double xo = p.xo;
-            if (t + 2 < N) prefetch<POLICY>(p, P, b, t + 2, lane, q);
+            if (t + 2 < N) prefetch<POLICY, false>(p, P, b, t + 2, lane, q);
+            double2 K0 = make_double2(0.0, 0.0), K1 = K0, K2 = K0, K3 = K0;
+            if (POLICY) {
+                issue_K(t + FW_KD - 1);
+                asm volatile("cp.async.wait_group %0;" ::"n"(FW_KD - 1) : "memory");   // K_t has landed
+                const double* src = kring + (t % FW_KD) * 256;
+                K0 = ldg2(src); K1 = ldg2(src + 64); K2 = ldg2(src + 128); K3 = ldg2(src + 192);
+            }
             // 1. publish x (and dx, d) to the warp
             const double d = x - goal;
             sx[lane] = x;
@@ -176,12 +204,15 @@ __global__ void __launch_bounds__(FW_WPB * 32, 2) fwd_lin32x8_kernel(FwdParams P
         };
 
         Pre pa, pb;
-        prefetch<POLICY>(pa, P, b, 0, lane, q);
-        if (N > 1) prefetch<POLICY>(pb, P, b, 1, lane, q);
+        prefetch<POLICY, false>(pa, P, b, 0, lane, q);
+        if (N > 1) prefetch<POLICY, false>(pb, P, b, 1, lane, q);
+#pragma unroll
+        for (int t = 0; t < FW_KD - 1; t++) issue_K(t);
         for (int t = 0; t < N; t += 2) {
             step(t, pa);
             if (t + 1 < N) step(t + 1, pb);
         }
+        if (POLICY) asm volatile("cp.async.wait_group 0;" ::: "memory");
         if (P.model.terminal_cost) {
             // ½ d'Qd at the last state once more (system_pendcart.jl:104)
             double qd = 0.0;

@@ -56,6 +56,36 @@ def ilqg_case():
                         cost_trace=np.array([c for _, c in tr["cost"]]), alpha_trace=np.array([a for _, a in tr["alpha"]]))
 
 
+def ilqgkl_case():
+    """KL-constrained path at the headline shape (n=32, m=8): one KL-augmented sweep, the KL evaluation and a whole iLQGkl solve."""
+    from helpers import rollout
+    n, m, N = 32, 8, 16
+    rng = np.random.default_rng(9)
+    A, Bm, Q, R = make_lq(rng, n, m, h=0.1)
+    u = 0.1 * rng.standard_normal((N, m))
+    x = rollout(A, Bm, np.ones(n), u)
+    d, p, _, _, _ = O.back_pass(x @ Q.T, u @ R.T, Q, np.zeros((n, m)), R, A, Bm, 1.0, 1, None, x, u)
+    Sigi = p.Sigmai.copy()
+    Sig = np.array([np.linalg.inv(s) for s in Sigi])
+    R1 = 1e-3 * np.eye(n)
+    om = O.LinearModel(A, Bm, Q, R)
+    cost0 = om.costfun(x, u)
+    rep = lambda a: np.tile(a, (N, 1, 1))
+    prev0 = O.GaussianPolicy(N, n, m, p.K.copy(), np.zeros((N, m)), Sig.copy(), Sigi.copy())
+    eta = np.array([1e-8, 1.3, 1e16])
+    dg, pg, Vxg, Vxxg, dVg = O.back_pass_gps(x @ Q.T, u @ R.T, rep(Q), rep(np.zeros((n, m))), rep(R), rep(A), rep(Bm), None, x, u, (O.grad_kl(prev0), eta))
+    xn, un, cn = O.forward_pass(pg, x[0], u, x, 1, om.f, om.costfun, None)
+    kl = O.kl_div_wiki(xn, x, O.forward_covariance(A, R1, pg), pg, prev0)
+    prev = O.GaussianPolicy(N, n, m, p.K.copy(), u.copy(), Sig.copy(), Sigi.copy())
+    r = O.iLQGkl(om.f, om.costfun, lambda xx, uu: om.df(xx, uu, time_varying=True), x, prev, A, R1, kl_step=1.5, cost=cost0)
+    tr = r[6]
+    np.savez_compressed(os.path.join(HERE, "ilqgkl_n32_m8.npz"), A=A, Bm=Bm, Q=Q, R=R, x=x, u=u, K_prev=p.K, Sig_prev=Sig, Sigi_prev=Sigi, R1=R1,
+                        cost0=np.sum(cost0), eta=eta, gps_K=pg.K, gps_k=pg.k, gps_Sigma=pg.Sigma, gps_Sigmai=pg.Sigmai, gps_Vx=Vxg, gps_dV=dVg,
+                        gps_diverge=dg, fwd_x=xn, fwd_u=un, kl_t=kl, kl_step=1.5, sol_x=r[0], sol_u=r[1], sol_K=r[2].K, sol_cost=np.sum(r[5]),
+                        sol_iters=tr["iters"], sol_satisfied=tr["satisfied"], sol_etabracket=tr["etabracket"],
+                        sol_divergence=tr["divergence"][-1][1])
+
+
 if __name__ == "__main__":
     back_pass_case("back_pass_n10_m2_chol", 10, 2, 40, 1, None, 1.0, 101)
     back_pass_case("back_pass_n32_m8_reg2", 32, 8, 16, 2, None, 0.5, 102)
@@ -63,4 +93,5 @@ if __name__ == "__main__":
     back_pass_case("back_pass_n6_m3_lims", 6, 3, 30, 1, 0.05, 1e-3, 104)
     boxqp_case()
     ilqg_case()
+    ilqgkl_case()
     print(sorted(f for f in os.listdir(HERE) if f.endswith(".npz")))
