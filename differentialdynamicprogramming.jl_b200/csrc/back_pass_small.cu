@@ -381,14 +381,11 @@ __global__ void __launch_bounds__(128, MINB) bp_small_kernel(BackParams P) {
 template <int N, int M>
 int launch_small(ddp_handle_s* h, const BackParams& P) {
     const unsigned grid = (unsigned)((P.B + 127) / 128);
-    static int minb = -1;
-    if (minb < 0) { const char* ev = getenv("DDP_SMALL_MINB"); minb = ev ? atoi(ev) : 2; }
     const bool stage = ((N * N) % 2 == 0) && (32 % ((N * N) / 2) == 0) && ((uintptr_t)P.fx.p % 16 == 0) && (P.fx.sb % 2 == 0) && (P.fx.st % 2 == 0) &&
                        !(getenv("DDP_SMALL_NOSTAGE"));
-    if (stage) {
-        if (minb == 3) bp_small_kernel<N, M, 3, true><<<grid, 128, 0, h->stream>>>(P);
-        else bp_small_kernel<N, M, 2, true><<<grid, 128, 0, h->stream>>>(P);
-    } else bp_small_kernel<N, M, 2, false><<<grid, 128, 0, h->stream>>>(P);
+    // 2 CTAs (8 warps) per SM: 168- and 128-register builds (3 / 4 CTAs) spill and measured 24-41 ms against 12 ms
+    if (stage) bp_small_kernel<N, M, 2, true><<<grid, 128, 0, h->stream>>>(P);
+    else bp_small_kernel<N, M, 2, false><<<grid, 128, 0, h->stream>>>(P);
     h->launches++;
     return (int)cudaGetLastError();
 }

@@ -152,3 +152,25 @@ def test_small_kernel_pendcart_lims_matches_oracle_and_generic(ddp):
             assert np.array_equal(r[1].K[b] == 0, p0.K == 0)        # clamped steps have K = 0: the active sets agree exactly
         nclamped += int(np.sum(np.all(p0.K[:-1] == 0, axis=(1, 2))))
     assert nclamped > 0
+
+
+def test_small_kernel_staged_equals_direct_loads(ddp, monkeypatch):
+    """The cp.async-staged fx ring of bp_small_kernel changes where operands come from, not the arithmetic: the staged and
+    the direct-load build (diagnostic switch DDP_SMALL_NOSTAGE) agree bit for bit, also on a ragged batch (B % 32 != 0)."""
+    rng = np.random.default_rng(3)
+    B, n, m, N = 45, 4, 1, 37
+    fx = np.eye(n) + 0.05 * rng.standard_normal((B, N, n, n)); fu = 0.1 * rng.standard_normal((B, N, n, m))
+    x = rng.standard_normal((B, N, n)); u = 0.3 * rng.standard_normal((B, N, m))
+    Q, R = np.diag([10.0, 1, 2, 1]), np.eye(m)
+    cx, cu = x @ Q.T, u @ R.T
+    lims = np.array([[-0.4, 0.4]])
+    args = (cx, cu, Q, np.zeros((n, m)), R, fx, fu, 0.7, 2, lims, x, u)
+    monkeypatch.delenv("DDP_SMALL_NOSTAGE", raising=False)
+    r1 = ddp.back_pass(*args)
+    monkeypatch.setenv("DDP_SMALL_NOSTAGE", "1")
+    r2 = ddp.back_pass(*args)
+    monkeypatch.delenv("DDP_SMALL_NOSTAGE", raising=False)
+    assert np.array_equal(r1[0], r2[0])
+    for a, b in ((r1[1].K, r2[1].K), (r1[1].k, r2[1].k), (r1[2], r2[2]), (r1[3], r2[3]), (r1[4], r2[4])):
+        assert np.array_equal(a, b)
+    assert np.any(np.all(r1[1].K[:, :-1] == 0, axis=(2, 3)))        # some steps are clamped

@@ -234,3 +234,27 @@ def test_back_pass_gps_tile32x8(ddp, tv, with_kprev):
         assert d0 == d1 == 0
         for a, b in ((p1.K, p0.K), (p1.k, p0.k), (Vx1, Vx0), (Vxx1, Vxx0), (dV1, dV0), (p1.Sigmai, p0.Sigmai), (p1.Sigma, p0.Sigma)):
             assert relerr(a, b) < TOL
+
+
+def test_forward_pendcart_staged_equals_unstaged(ddp, monkeypatch):
+    """fwd_pend_staged_kernel (time-blocked cp.async ring) and fwd_pend_kernel (diagnostic switch DDP_PEND_NOSTAGE) run
+    the same per-trajectory arithmetic: identical bits, ragged batch and ragged last block."""
+    N, B = 38, 75
+    rng = np.random.default_rng(12)
+    x0 = np.stack([np.array([np.pi - 0.6 + 0.2 * rng.uniform(-1, 1), 0, 0, 0]) for _ in range(B)])
+    u = rng.standard_normal((B, N, 1))
+    pm = ddp.PendcartModel()
+    lims = np.array([[-5.0, 5.0]])
+    xr, ur, _ = ddp.forward_pass(ddp.GaussianPolicy.empty(), x0, u, None, 1.0, pm.f, pm.costfun, lims)
+    pol = ddp.GaussianPolicy(N, 4, 1, 0.3 * rng.standard_normal((B, N, 1, 4)), 0.2 * rng.standard_normal((B, N, 1)))
+    outs = []
+    for flag in (None, "1"):
+        if flag is None:
+            monkeypatch.delenv("DDP_PEND_NOSTAGE", raising=False)
+        else:
+            monkeypatch.setenv("DDP_PEND_NOSTAGE", flag)
+        outs.append(ddp.forward_pass(pol, x0, ur, xr, 0.5, pm.f, pm.costfun, lims, per_step_cost=True, want_derivs=True))
+    monkeypatch.delenv("DDP_PEND_NOSTAGE", raising=False)
+    a, b = outs
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    assert np.array_equal(a[3][0], b[3][0]) and np.array_equal(a[3][1], b[3][1])
