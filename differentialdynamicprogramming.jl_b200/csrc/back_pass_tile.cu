@@ -32,14 +32,15 @@
 
 namespace {
 
-constexpr int WPB = 4;                       // warps per CTA
+constexpr int WPB_LTI = 4;                   // warps per CTA, time-invariant dynamics: 2 CTAs x 4 warps x 18.7 KB per SM
+constexpr int WPB_LTV = 4;                   // time-varying: same residency; the single [fx fu] buffer is refilled for the next step right after its last read
+constexpr int wpb(bool ltv) { return ltv ? WPB_LTV : WPB_LTI; }
 constexpr int SV = 0;                        // Vxx            32 x 32 swizzled
 constexpr int SF = SV + 1024;                // [fx fu]        32 x 40 swizzled
 constexpr int SVX = SF + 1280;               // Vx (32)
 constexpr int SCX = SVX + 32;                // this step's cx (32) and cu (8), landed by cp.async
 constexpr int WARP_DOUBLES = SCX + 48;       // 2384 doubles = 19,072 B per warp
-constexpr int SF2 = WARP_DOUBLES;            // second F buffer (time-varying dynamics only)
-constexpr int WARP_DOUBLES_LTV = WARP_DOUBLES + 1280;
+constexpr int WARP_DOUBLES_LTV = WARP_DOUBLES;  // (a second [fx fu] buffer would cost 10 KB per warp and halve the residency: measured 113-134 ms)
 constexpr int COST_DOUBLES = 15 * 32 * 2;    // per-CTA table of the cost tiles in accumulator (fragment) order
 
 // column-major 32-row matrices: element (i, c) lives at (i ^ s(c)) + 32 c with s(c) = ((c&1)<<3) | (((c>>1)&3)<<1).
@@ -63,15 +64,23 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N_>
 __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
 
-// stage [fx fu] of one step into the swizzled buffer (16-byte chunks = 2 consecutive rows of a column)
+// stage [fx fu] of one step into the swizzled buffer (16-byte chunks = 2 consecutive rows of a column).
+// Chunk c = lane + 32 k (k = 0..19) is column (lane >> 4) + 2k, rows i = 2 (lane & 15): per lane the row pair and the parity
+// of the column are constants, so with k unrolled the swizzled destination is (i ^ s) + 32 col with s known up to a per-lane
+// constant -- two integer instructions per chunk instead of a dozen.
 template <bool ASYNC>
 __device__ __forceinline__ void load_F(double* sF, const double* fx, const double* fu, int lane) {
-#pragma unroll 4
-    for (int c = lane; c < 640; c += 32) {
-        int col = c >> 4, i = (c & 15) << 1;
-        const double* src = (col < 32) ? (fx + col * 32 + i) : (fu + (col - 32) * 32 + i);
-        if (ASYNC) cp_async16(&sF[swz(i, col)], src);
-        else st2(&sF[swz(i, col)], src[0], src[1]);
+    const int cb = lane >> 4, i = (lane & 15) << 1;
+    const int i8 = i ^ (cb << 3);                       // (c & 1) << 3 with c & 1 == cb
+    const double* sx = fx + cb * 32 + i;                // column cb + 2k of fx: + 64 k
+    const double* su = fu + cb * 32 + i;                // column cb + 2 (k - 16) of fu
+    double* d0 = sF + 32 * cb;
+#pragma unroll
+    for (int k = 0; k < 20; k++) {
+        const double* src = (k < 16) ? (sx + 64 * k) : (su + 64 * (k - 16));
+        double* dst = d0 + (i8 ^ ((k & 3) << 1)) + 64 * k;          // ((c >> 1) & 3) == (k & 3)
+        if (ASYNC) cp_async16(dst, src);
+        else st2(dst, src[0], src[1]);
     }
 }
 
@@ -113,7 +122,8 @@ __device__ __forceinline__ bool gj_inverse8(double& I0, double& I1, int lane, in
 constexpr int gidx(int at, int bt) { return at * 5 - (at * (at - 1)) / 2 + (bt - at); }   // upper-tile index, 15 tiles
 
 template <bool LTV, bool GPS, bool REG2>
-__global__ void __launch_bounds__(WPB * 32, 2) bp_tile32x8_kernel(BackParams P) {
+__global__ void __launch_bounds__(wpb(LTV) * 32, 2) bp_tile32x8_kernel(BackParams P) {
+    constexpr int WPB = wpb(LTV);
     extern __shared__ double smem_raw[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int g = lane >> 2, q = lane & 3;
@@ -198,7 +208,6 @@ __global__ void __launch_bounds__(WPB * 32, 2) bp_tile32x8_kernel(BackParams P) 
                 if (Quuib) { Quuib[(long long)(N - 1) * 64 + g + 8 * (2 * q)] = T0; Quuib[(long long)(N - 1) * 64 + g + 8 * (2 * q + 1)] = T1; }
             } else if (Quub) st2(Quub + (long long)(N - 1) * 64 + 2 * lane, cuuN[2 * lane], cuuN[2 * lane + 1]);
         }
-        int buf = 0;
         if (LTV) {
             if (N >= 2) load_F<true>(sm + SF, tp(P.fx, b, N - 2), tp(P.fu, b, N - 2), lane);
         } else {
@@ -228,7 +237,7 @@ __global__ void __launch_bounds__(WPB * 32, 2) bp_tile32x8_kernel(BackParams P) 
         double dV0 = 0.0, dV1 = 0.0;
         int diverge = 0;
         for (int i = N - 2; i >= 0; i--) {
-            const double* sF = sm + (LTV ? (buf ? SF2 : SF) : SF);
+            const double* sF = sm + SF;
             if (LTV) {
                 cp_async_wait_all();
                 __syncwarp();
@@ -237,11 +246,7 @@ __global__ void __launch_bounds__(WPB * 32, 2) bp_tile32x8_kernel(BackParams P) 
             if (lane < 16) cp_async16(&sCx[2 * lane], cxb + (long long)i * P.cx.st + 2 * lane);
             else if (lane < 20) cp_async16(&sCx[2 * lane], cub + (long long)i * P.cu.st + 2 * (lane - 16));
             cp_async_commit();
-            if (LTV) {                                       // next step's [fx fu] (group B)
-                if (i > 0) load_F<true>(sm + (buf ? SF : SF2), tp(P.fx, b, i - 1), tp(P.fu, b, i - 1), lane);
-                cp_async_commit();
-                if (reg2) compute_FF(sF);
-            }
+            if (LTV && reg2) compute_FF(sF);
             // this step's cost gradients: lanes of group g own Qx[8t+g] (t = 0..3) and Qu[g]
             // KL terms: fragments of the previous policy, K_prev[2q..2q+1][8t+g], Sigma_i_prev[g][2q..2q+1]
             double2 kpf[4];
@@ -414,6 +419,11 @@ __global__ void __launch_bounds__(WPB * 32, 2) bp_tile32x8_kernel(BackParams P) 
                 w_block0123(W);
                 g_block0123(W);
             }
+            if (LTV) {                                       // [fx fu] was read for the last time in this step: refill it for the
+                __syncwarp();                                // next one (group B); it lands during the non-tensor tail of the step
+                if (i > 0) load_F<true>(sm + SF, tp(P.fx, b, i - 1), tp(P.fu, b, i - 1), lane);
+                cp_async_commit();
+            }
 #pragma unroll
             for (int at = 0; at < 5; at++) {
                 fv[at] += shx(fv[at], 1);
@@ -579,7 +589,6 @@ __global__ void __launch_bounds__(WPB * 32, 2) bp_tile32x8_kernel(BackParams P) 
 #pragma unroll
                 for (int t = 0; t < 4; t++) sVx[8 * t + g] = vxn[t];
             }
-            if (LTV) buf ^= 1;
             __syncwarp();
         }
         if (LTV) { cp_async_wait_all(); }
@@ -635,6 +644,7 @@ int launch_back_pass_tile(ddp_handle_s* h, const BackParams& P, bool gps, bool* 
     if (gps && !aligned16(P.Kp)) return 0;
     if (!aligned16(P.cx) || !aligned16(P.cu)) return 0;
     const bool ltv = (P.fx.st != 0 || P.fu.st != 0);
+    const int WPB = wpb(ltv);
     const size_t bytes = ((size_t)(ltv ? WARP_DOUBLES_LTV : WARP_DOUBLES) * WPB + COST_DOUBLES) * sizeof(double);
     long long grid = (long long)h->sm_count * 2;
     long long need = (P.B + WPB - 1) / WPB;

@@ -7,6 +7,7 @@ import ddp_b200 as ddp
 from ddp_b200 import _lib as L
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
+LTV = len(sys.argv) > 2 and sys.argv[2] == "ltv"          # time-varying dynamics: fx, fu materialised as [B,T,.,.]
 n, m, T = 32, 8, 256
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
@@ -33,7 +34,11 @@ a = L.BackPassArgs()
 t = lambda x, sb, st: L.Tensor(x.data_ptr(), sb, st)
 a.cx, a.cu = t(cx, T * n, n), t(cu, T * m, m)
 a.cxx, a.cxu, a.cuu = t(Q, 0, 0), t(cxu, 0, 0), t(R, 0, 0)
-a.fx, a.fu = t(fx, n * n, 0), t(fu, n * m, 0)
+if LTV:
+    fx = fx[:, None].expand(B, T, n, n).contiguous(); fu = fu[:, None].expand(B, T, m, n).contiguous()
+    a.fx, a.fu = t(fx, T * n * n, n * n), t(fu, T * n * m, n * m)
+else:
+    a.fx, a.fu = t(fx, n * n, 0), t(fu, n * m, 0)
 a.lam, a.reg_type = lam.data_ptr(), 1
 a.diverge, a.K, a.k, a.Vx, a.dV = dv.data_ptr(), K.data_ptr(), k.data_ptr(), Vx.data_ptr(), dV.data_ptr()
 print("variant", eng.kernel_variant)
@@ -44,4 +49,4 @@ for rep in range(3):
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     flops = 213419.0 * (T - 1) * B
-    print(f"back_pass B={B}: {ms:.2f} ms  -> {flops / ms * 1e-9:.2f} TFLOP/s algorithmic; full-batch(65536) est {ms * 65536 / B:.1f} ms; diverged {int((dv>0).sum())}")
+    print(f"back_pass {'LTV ' if LTV else ''}B={B}: {ms:.2f} ms  -> {flops / ms * 1e-9:.2f} TFLOP/s algorithmic; full-batch(65536) est {ms * 65536 / B:.1f} ms; diverged {int((dv>0).sum())}")
