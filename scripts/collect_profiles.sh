@@ -10,6 +10,10 @@ timeout 600 python bench.py > $o/${tag}_bench.json 2> $o/${tag}_bench.err
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $o/${tag}_bench_ref.json 2> $o/${tag}_bench_ref.err
 timeout 300 python scripts/bench_configs.py c3 > $o/${tag}_c3.json 2>&1
 timeout 300 python scripts/bench_configs.py c4 17760 > $o/${tag}_c4.json 2>&1
+timeout 120 python __graft_entry__.py --smoke > $o/${tag}_smoke.log 2>&1
+timeout 200 python scripts/perf_probe.py 9472 ltv > $o/${tag}_ltv.log 2>&1
+timeout 300 python scripts/bench_configs.py solve c2 16384 > $o/${tag}_solve_c2.json 2>&1
+timeout 300 python scripts/bench_configs.py solve c3 65536 > $o/${tag}_solve_c3.json 2>&1
 ./profiles/microbench/dmma_occ > $o/${tag}_dmma_occ.txt 2>&1
 python scripts/pcie_probe.py > $o/${tag}_pcie.json 2>&1
 # launch list of the bench command (kernel share of the step)
