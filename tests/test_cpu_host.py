@@ -34,9 +34,10 @@ def test_struct_sizes_match_the_header(ddp):
     src = r'''
 #include <stdio.h>
 #include "ddp.h"
-int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(ddp_tensor), sizeof(ddp_boxqp_opts),
+int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(ddp_tensor), sizeof(ddp_boxqp_opts),
   sizeof(ddp_back_pass_args), sizeof(ddp_gps_args), sizeof(ddp_model), sizeof(ddp_forward_pass_args), sizeof(ddp_kl_args),
-  sizeof(ddp_ilqg_opts), sizeof(ddp_ilqg_state), sizeof(ddp_iter_host_args)); return 0; }
+  sizeof(ddp_ilqg_opts), sizeof(ddp_ilqg_state), sizeof(ddp_iter_host_args), sizeof(ddp_ilqgkl_opts), sizeof(ddp_ilqgkl_state),
+  sizeof(ddp_ilqgkl_args)); return 0; }
 '''
     import tempfile
     with tempfile.TemporaryDirectory() as td:
@@ -45,7 +46,8 @@ int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(ddp_
         subprocess.check_call(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
         sizes = list(map(int, subprocess.check_output([exe]).split()))
     L = ddp._lib
-    mirror = [L.Tensor, L.BoxQPOpts, L.BackPassArgs, L.GpsArgs, L.Model, L.ForwardPassArgs, L.KlArgs, L.IlqgOpts, L.IlqgState, L.IterHostArgs]
+    mirror = [L.Tensor, L.BoxQPOpts, L.BackPassArgs, L.GpsArgs, L.Model, L.ForwardPassArgs, L.KlArgs, L.IlqgOpts, L.IlqgState, L.IterHostArgs,
+              L.IlqgklOpts, L.IlqgklState, L.IlqgklArgs]
     assert sizes == [ctypes.sizeof(t) for t in mirror]
 
 

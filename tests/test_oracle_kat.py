@@ -179,3 +179,41 @@ def test_pendcart_model_matches_closed_form_jacobian():
     assert cuu.shape == (1, 1) and cxu.shape == (4, 1) and np.allclose(cx[1], 0)
     c = om.costfun(x, u)
     assert c.shape == (3,) and abs(c[-1] - 0.5 * (x[-1] - om.goal) @ om.Q @ (x[-1] - om.goal)) < 1e-15
+
+
+def test_kl_div_is_the_expected_gaussian_kl_and_covariance_is_lyapunov():
+    """kl_div_wiki (klutils.jl:70-100) is E_x[ KL( N(Kn x + kn, Sn) || N(Kp x + kp, Sp) ) ] for x ~ N(mu, St): checked against
+    the textbook Gaussian KL evaluated by Monte Carlo-free algebra written independently (means and covariances of the two
+    control distributions), and forward_covariance (forward_pass.jl:47-54) converges to the discrete Lyapunov solution."""
+    rng = np.random.default_rng(4)
+    n, m, N = 5, 2, 6
+    def spd(k):
+        W = rng.standard_normal((k, k)); return W @ W.T / k + 0.5 * np.eye(k)
+    Kp, Kn = rng.standard_normal((N, m, n)), rng.standard_normal((N, m, n))
+    kp, kn = rng.standard_normal((N, m)), rng.standard_normal((N, m))
+    Sp, Sn = np.array([spd(m) for _ in range(N)]), np.array([spd(m) for _ in range(N)])
+    prev = O.GaussianPolicy(N, n, m, Kp, kp, Sp, np.array([np.linalg.inv(s) for s in Sp]))
+    new = O.GaussianPolicy(N, n, m, Kn, kn, Sn, np.array([np.linalg.inv(s) for s in Sn]))
+    xold, xnew = rng.standard_normal((N, n)), rng.standard_normal((N, n))
+    sig = np.zeros((N, n + m, n + m))
+    for t in range(N):
+        sig[t, :n, :n] = spd(n)
+    got = O.kl_div_wiki(xnew, xold, sig, new, prev)
+    for t in range(N):
+        mu, St = xnew[t] - xold[t], sig[t, :n, :n]
+        Sip = np.linalg.inv(Sp[t])
+        # KL(N(a, Sn) || N(b, Sp)) = 1/2 [tr(Sp^-1 Sn) + (b - a)' Sp^-1 (b - a) - m + ln det Sp - ln det Sn]; here b - a = dk + dK x is
+        # itself Gaussian in x, so the quadratic term's expectation is its value at the mean plus tr(dK' Sp^-1 dK St)
+        dK, dk = Kp[t] - Kn[t], kp[t] - kn[t]
+        e = dk + dK @ mu
+        want = 0.5 * (np.trace(Sip @ Sn[t]) + e @ Sip @ e + np.trace(dK.T @ Sip @ dK @ St) - m
+                      + np.linalg.slogdet(Sp[t])[1] - np.linalg.slogdet(Sn[t])[1])
+        assert abs(got[t] - max(0.0, want)) <= 1e-10 * max(1.0, abs(want))
+    # covariance propagation: Sigma_{t+1} = fx Sigma_t fx' + R1 from Sigma_1 = R1 tends to the discrete Lyapunov solution
+    fx = 0.8 * sla.expm(0.3 * (lambda G: G - G.T)(rng.standard_normal((n, n))))
+    R1 = spd(n)
+    T = 200
+    pol = O.GaussianPolicy(T, n, m, np.zeros((T, m, n)), np.zeros((T, m)), np.tile(np.eye(m), (T, 1, 1)), np.tile(np.eye(m), (T, 1, 1)))
+    sg = O.forward_covariance(fx, R1, pol)
+    assert np.allclose(sg[0, :n, :n], R1)
+    assert np.allclose(sg[-1, :n, :n], sla.solve_discrete_lyapunov(fx, R1), rtol=1e-9, atol=1e-12)
