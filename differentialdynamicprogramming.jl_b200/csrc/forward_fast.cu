@@ -407,6 +407,45 @@ __global__ void __launch_bounds__(FW_WPB * 32, 2) fwd_lin32x8_multi_kernel(FwdPa
 // pendulum on a cart: one thread per trajectory, everything in registers.  The rollout is a serial
 // chain per trajectory (load -> control -> sincos -> next state), so the operands of the next PEND_PF
 // steps are kept in flight in a register ring: the kernel is HBM-bound only if enough loads are pending.
+// The control law and the Euler step of the pendulum on a cart, shared by the three rollout kernels below.  Every rounding
+// is explicit (no FMA contraction), as in the reference's Julia arithmetic (forward_pass.jl:18-20, system_pendcart.jl:51-54),
+// so the kernels agree with each other bit for bit whatever the compiler hoists or fuses around them.
+__device__ __forceinline__ double pend_policy_control(double u_scaled, double kk, double alpha, double2 K01, double2 K23, double2 xo01,
+                                                      double2 xo23, const double* x) {
+    double un = __dadd_rn(u_scaled, __dmul_rn(kk, alpha));
+    double acc = __dmul_rn(K01.x, x[0] - xo01.x);
+    acc = __dadd_rn(acc, __dmul_rn(K01.y, x[1] - xo01.y));
+    acc = __dadd_rn(acc, __dmul_rn(K23.x, x[2] - xo23.x));
+    acc = __dadd_rn(acc, __dmul_rn(K23.y, x[3] - xo23.y));
+    return __dadd_rn(un, acc);
+}
+__device__ __forceinline__ void pend_euler_step(double* x, double un, double gg, double l, double h, double dd) {
+    double sn, cs2;
+    sincos(x[0], &sn, &cs2);
+    const double acc = __dsub_rn(__dadd_rn(__dmul_rn(-gg / l, sn), __dmul_rn(un / l, cs2)), __dmul_rn(dd, x[1]));
+    const double x0n = __dadd_rn(x[0], __dmul_rn(h, x[1]));
+    const double x1n = __dadd_rn(x[1], __dmul_rn(h, acc));
+    const double x2n = __dadd_rn(x[2], __dmul_rn(h, x[3]));
+    const double x3n = __dadd_rn(x[3], __dmul_rn(h, un));
+    x[0] = x0n; x[1] = x1n; x[2] = x2n; x[3] = x3n;
+}
+// stage cost 1/2 d'Qd (+ 1/2 R u^2): qd = Q d is also the cost gradient cx
+__device__ __forceinline__ double pend_state_cost(const double* x, const double* goal, const double* Q, double* qd) {
+    double dlt[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) dlt[i] = x[i] - goal[i];
+    double cs = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) s = __dadd_rn(s, __dmul_rn(Q[i + 4 * j], dlt[j]));
+        qd[i] = s;
+        cs = __dadd_rn(cs, __dmul_rn(__dmul_rn(0.5, dlt[i]), s));
+    }
+    return cs;
+}
+
 constexpr int PEND_PF = 4;
 struct PendIn {
     double2 K01, K23, x01, x23;
@@ -458,47 +497,23 @@ __global__ void __launch_bounds__(128) fwd_pend_kernel(FwdParams P) {
             if (t < N) {
                 const PendIn c = ring[d];
                 if (t + PEND_PF < N) pend_load<POLICY>(ring[d], P, b, t + PEND_PF);
-                double un = c.u * P.u_scale;
-                if (POLICY) {
-                    un = un + c.k * alpha;
-                    double acc = c.K01.x * (x[0] - c.x01.x);
-                    acc = fma(c.K01.y, x[1] - c.x01.y, acc);
-                    acc = fma(c.K23.x, x[2] - c.x23.x, acc);
-                    acc = fma(c.K23.y, x[3] - c.x23.y, acc);
-                    un = un + acc;
-                }
+                double un = __dmul_rn(c.u, P.u_scale);
+                if (POLICY) un = pend_policy_control(un, c.k, alpha, c.K01, c.K23, c.x01, c.x23, x);
                 if (has_lims) un = fmin(fmax(un, lo), hi);
                 if (un != un) un = 0.0;
                 stg2(xnb + (long long)t * 4, x[0], x[1]);
                 stg2(xnb + (long long)t * 4 + 2, x[2], x[3]);
                 unb[t] = un;
-                double dlt[4], qd[4];
-#pragma unroll
-                for (int i = 0; i < 4; i++) dlt[i] = x[i] - goal[i];
-                double cs = 0.0;
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    qd[i] = 0.0;
-#pragma unroll
-                    for (int j = 0; j < 4; j++) qd[i] = fma(Q[i + 4 * j], dlt[j], qd[i]);
-                    cs = fma(0.5 * dlt[i], qd[i], cs);
-                }
+                double qd[4];
+                const double cs = pend_state_cost(x, goal, Q, qd);
                 clast = cs;
-                const double ru = Rv * un;
-                const double cstep = fma(0.5 * un, ru, cs);
+                const double ru = __dmul_rn(Rv, un);
+                const double cstep = __dadd_rn(cs, __dmul_rn(__dmul_rn(0.5, un), ru));
                 if (P.cx) { stg2(P.cx + (b * N + t) * 4, qd[0], qd[1]); stg2(P.cx + (b * N + t) * 4 + 2, qd[2], qd[3]); }
                 if (P.cu) P.cu[b * N + t] = ru;
                 if (P.cost_t) P.cost_t[b * (N + P.model.terminal_cost) + t] = cstep;
-                ctot += cstep;
-                if (t < N - 1) {
-                    double sn, cs2;
-                    sincos(x[0], &sn, &cs2);
-                    const double x0n = x[0] + h * x[1];
-                    const double x1n = x[1] + h * (-gg / l * sn + un / l * cs2 - dd * x[1]);
-                    const double x2n = x[2] + h * x[3];
-                    const double x3n = x[3] + h * un;
-                    x[0] = x0n; x[1] = x1n; x[2] = x2n; x[3] = x3n;
-                }
+                ctot = __dadd_rn(ctot, cstep);
+                if (t < N - 1) pend_euler_step(x, un, gg, l, h, dd);
             }
         }
     }
@@ -603,49 +618,27 @@ __global__ void __launch_bounds__(PS_W * 32) fwd_pend_staged_kernel(FwdParams P)
         for (int s_ = 0; s_ < 4; s_++) {
             const int t = t0 + s_;
             if (t < N) {
-                double un = ru_[s_] * P.u_scale;
+                double un = __dmul_rn(ru_[s_], P.u_scale);
                 if (POLICY) {
                     const double2 K01 = ldg2(rK + 4 * s_), K23 = ldg2(rK + 4 * s_ + 2);
                     const double2 xo01 = ldg2(rX + 4 * s_), xo23 = ldg2(rX + 4 * s_ + 2);
-                    un = un + rk[s_] * alpha;
-                    double acc = K01.x * (x[0] - xo01.x);
-                    acc = fma(K01.y, x[1] - xo01.y, acc);
-                    acc = fma(K23.x, x[2] - xo23.x, acc);
-                    acc = fma(K23.y, x[3] - xo23.y, acc);
-                    un = un + acc;
+                    un = pend_policy_control(un, rk[s_], alpha, K01, K23, xo01, xo23, x);
                 }
                 if (has_lims) un = fmin(fmax(un, lo), hi);
                 if (un != un) un = 0.0;
                 stg2(rX + 4 * s_, x[0], x[1]);
                 stg2(rX + 4 * s_ + 2, x[2], x[3]);
                 ru_[s_] = un;
-                double dlt[4], qd[4];
-#pragma unroll
-                for (int i = 0; i < 4; i++) dlt[i] = x[i] - goal[i];
-                double cs = 0.0;
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    qd[i] = 0.0;
-#pragma unroll
-                    for (int jj = 0; jj < 4; jj++) qd[i] = fma(Q[i + 4 * jj], dlt[jj], qd[i]);
-                    cs = fma(0.5 * dlt[i], qd[i], cs);
-                }
+                double qd[4];
+                const double cs = pend_state_cost(x, goal, Q, qd);
                 clast = cs;
-                const double ru = Rv * un;
-                const double cstep = fma(0.5 * un, ru, cs);
+                const double ru = __dmul_rn(Rv, un);
+                const double cstep = __dadd_rn(cs, __dmul_rn(__dmul_rn(0.5, un), ru));
                 if (want_c) { stg2(scx + lane * PS_R + 4 * s_, qd[0], qd[1]); stg2(scx + lane * PS_R + 4 * s_ + 2, qd[2], qd[3]); }
                 if (want_cu) scu[lane * 4 + s_] = ru;
                 if (P.cost_t && valid) P.cost_t[b * (N + P.model.terminal_cost) + t] = cstep;
-                ctot += cstep;
-                if (t < N - 1) {
-                    double sn, cs2;
-                    sincos(x[0], &sn, &cs2);
-                    const double x0n = x[0] + h * x[1];
-                    const double x1n = x[1] + h * (-gg / l * sn + un / l * cs2 - dd * x[1]);
-                    const double x2n = x[2] + h * x[3];
-                    const double x3n = x[3] + h * un;
-                    x[0] = x0n; x[1] = x1n; x[2] = x2n; x[3] = x3n;
-                }
+                ctot = __dadd_rn(ctot, cstep);
+                if (t < N - 1) pend_euler_step(x, un, gg, l, h, dd);
             }
         }
         __syncwarp();
@@ -687,6 +680,119 @@ __global__ void __launch_bounds__(PS_W * 32) fwd_pend_staged_kernel(FwdParams P)
         ctot += clast;
     }
     if (valid) P.cost[b] = ctot;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pendulum on a cart, multi-alpha line-search rollout: the total cost for up to PM_NA step sizes in one pass over the
+// policy (K, k) and the old trajectory, staged like fwd_pend_staged_kernel (no outputs but the costs).  The per-step
+// expressions are the ones of fwd_pend_kernel / fwd_pend_staged_kernel, so the costs agree bit for bit with a rollout of
+// the single step size.
+constexpr int PM_NA = 8;
+constexpr int PM_WARP_DOUBLES = 2 * 32 * PS_R * 2 + 2 * 32 * 4 * 2;      // K, X ring; k, u ring
+
+__global__ void __launch_bounds__(PS_W * 32) fwd_pend_multi_kernel(FwdParams P, MultiAlpha MA, double* __restrict__ cost_out) {
+    extern __shared__ __align__(16) double pm_smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const long long b0 = ((long long)blockIdx.x * PS_W + wid) * 32;
+    if (b0 >= P.B) return;
+    const long long b_raw = b0 + lane;
+    const bool valid = (b_raw < P.B) && !(P.active && !P.active[b_raw]);
+    const long long b = (b_raw < P.B) ? b_raw : P.B - 1;
+    double* sm = pm_smem + (size_t)wid * PM_WARP_DOUBLES;
+    double* sK = sm;
+    double* sX = sK + 2 * 32 * PS_R;
+    double* sk = sX + 2 * 32 * PS_R;
+    double* su = sk + 2 * 32 * 4;
+    const int N = P.T, na = MA.na;
+    const double gg = P.model.p[0], l = P.model.p[1], h = P.model.p[2], dd = P.model.p[3];
+    const double* Qm = P.model.Q.p + b * P.model.Q.sb;
+    const double Rv = (P.model.R.p + b * P.model.R.sb)[0];
+    double Q[16], goal[4], x[PM_NA][4], ctot[PM_NA], clast[PM_NA];
+#pragma unroll
+    for (int i = 0; i < 16; i++) Q[i] = Qm[i];
+#pragma unroll
+    for (int i = 0; i < 4; i++) goal[i] = P.model.goal ? P.model.goal[i] : 0.0;
+#pragma unroll
+    for (int a = 0; a < PM_NA; a++) {
+        ctot[a] = 0.0; clast[a] = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) x[a][i] = (P.x0.p + b * P.x0.sb)[i];
+    }
+    const bool has_lims = P.lims != nullptr;
+    const double lo = has_lims ? P.lims[0] : 0.0, hi = has_lims ? P.lims[1] : 0.0;
+    const int r8 = lane >> 3, c8 = lane & 7, r2 = lane >> 1, c2 = lane & 1;
+    auto stage = [&](int j, int p) {
+        const int t0 = 4 * j;
+        if (t0 + (c8 >> 1) < N) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int row = r8 + 4 * k;
+                const long long bb = b0 + row;
+                if (bb < P.B) {
+                    cp16(sK + (p * 32 + row) * PS_R + 2 * c8, P.K + (bb * N + t0) * 4 + 2 * c8);
+                    cp16(sX + (p * 32 + row) * PS_R + 2 * c8, tp(P.x, bb, t0) + 2 * c8);
+                }
+            }
+        }
+        if (t0 + 2 * c2 < N) {
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const int row = r2 + 16 * k;
+                const long long bb = b0 + row;
+                if (bb < P.B) {
+                    cp16(sk + (p * 32 + row) * 4 + 2 * c2, P.k + bb * N + t0 + 2 * c2);
+                    cp16(su + (p * 32 + row) * 4 + 2 * c2, tp(P.u, bb, t0) + 2 * c2);
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    const int nblk = (N + 3) >> 2;
+    stage(0, 0);
+    for (int j = 0; j < nblk; j++) {
+        const int p = j & 1, t0 = 4 * j;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        if (j + 1 < nblk) stage(j + 1, p ^ 1);
+        const double* rK = sK + (p * 32 + lane) * PS_R;
+        const double* rX = sX + (p * 32 + lane) * PS_R;
+        const double* rk = sk + (p * 32 + lane) * 4;
+        const double* ru_ = su + (p * 32 + lane) * 4;
+#pragma unroll
+        for (int s_ = 0; s_ < 4; s_++) {
+            const int t = t0 + s_;
+            if (t < N) {
+                const double2 K01 = ldg2(rK + 4 * s_), K23 = ldg2(rK + 4 * s_ + 2);
+                const double2 xo01 = ldg2(rX + 4 * s_), xo23 = ldg2(rX + 4 * s_ + 2);
+                const double kk = rk[s_], uu = ru_[s_];
+#pragma unroll
+                for (int a = 0; a < PM_NA; a++)
+                    if (a < na) {
+                        const double alpha = MA.a[a];
+                        double un = pend_policy_control(__dmul_rn(uu, P.u_scale), kk, alpha, K01, K23, xo01, xo23, x[a]);
+                        if (has_lims) un = fmin(fmax(un, lo), hi);
+                        if (un != un) un = 0.0;
+                        double qd[4];
+                        const double cs = pend_state_cost(x[a], goal, Q, qd);
+                        clast[a] = cs;
+                        const double ru = __dmul_rn(Rv, un);
+                        const double cstep = __dadd_rn(cs, __dmul_rn(__dmul_rn(0.5, un), ru));
+                        ctot[a] = __dadd_rn(ctot[a], cstep);
+                        if (t < N - 1) pend_euler_step(x[a], un, gg, l, h, dd);
+                    }
+            }
+        }
+        __syncwarp();
+    }
+    if (valid) {
+#pragma unroll
+        for (int a = 0; a < PM_NA; a++)
+            if (a < na) {
+                double c = ctot[a];
+                if (P.model.terminal_cost) c = __dadd_rn(c, clast[a]);
+                cost_out[(long long)a * P.B + b] = c;
+            }
+    }
 }
 
 bool al16(const void* p) { return ((uintptr_t)p % 16) == 0; }
@@ -751,6 +857,24 @@ int launch_forward_fast(ddp_handle_s* h, const FwdParams& P, bool* handled) {
 // not the headline one (the caller then loops over ddp_forward_pass launches)
 int launch_forward_multi(ddp_handle_s* h, const FwdParams& P, int na, const double* alpha, double* cost_out, bool* handled) {
     *handled = false;
+    if (P.model.kind == DDP_MODEL_PENDCART && P.n == 4 && P.m == 1 && P.K != nullptr && na >= 1) {
+        // same view requirements as the staged single-alpha kernel
+        if (!((P.T % 2 == 0) && al16(P.u.p) && (P.u.sb % 2 == 0) && P.u.st == 1 && P.x.st == 4 && al16(P.k) && al16(P.K) && al16(P.x.p) &&
+              (P.x.sb % 2 == 0))) return 0;
+        const size_t bytes = (size_t)PS_W * PM_WARP_DOUBLES * sizeof(double);
+        cudaError_t e = cudaFuncSetAttribute(fwd_pend_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return (int)e;
+        const unsigned sgrid = (unsigned)((P.B + 32 * PS_W - 1) / (32 * PS_W));
+        for (int a0 = 0; a0 < na; a0 += PM_NA) {
+            MultiAlpha MA;
+            MA.na = (na - a0 < PM_NA) ? (na - a0) : PM_NA;
+            for (int i = 0; i < 16; i++) MA.a[i] = (i < MA.na) ? alpha[a0 + i] : 0.0;
+            fwd_pend_multi_kernel<<<sgrid, PS_W * 32, bytes, h->stream>>>(P, MA, cost_out + (long long)a0 * P.B);
+            h->launches++;
+        }
+        *handled = true;
+        return (int)cudaGetLastError();
+    }
     if (!(P.model.kind == DDP_MODEL_LINEAR && P.n == 32 && P.m == 8 && P.model.A.st == 0 && P.model.Bm.st == 0)) return 0;
     if (P.K == nullptr || na < 1) return 0;
     if (!al16(P.u.p) || (P.u.sb % 2) || (P.u.st % 2) || !al16(P.K) || !al16(P.k)) return 0;

@@ -563,8 +563,9 @@ int ddp_ilqg_solve_f64(ddp_handle_t h, const ddp_model* model, const ddp_ilqg_op
     double *cx = nullptr, *cu = nullptr, *xnew = nullptr, *unew = nullptr, *fxb = nullptr, *fub = nullptr, *zeros = nullptr;
     double* multi_costs = nullptr;
     // multi-alpha line search (headline shape only): after a rejected alpha[0] all remaining step sizes are evaluated in one launch
-    const bool use_multi = (model->kind == DDP_MODEL_LINEAR && h->n == 32 && h->m == 8 && model->A.stride_t == 0 && model->Bm.stride_t == 0 &&
-                            !(h->flags & 1u) && !getenv("DDP_NO_MULTI_ALPHA"));
+    const bool use_multi = ((model->kind == DDP_MODEL_LINEAR && h->n == 32 && h->m == 8 && model->A.stride_t == 0 && model->Bm.stride_t == 0) ||
+                            (model->kind == DDP_MODEL_PENDCART && h->T % 2 == 0)) &&
+                           !(h->flags & 1u) && !getenv("DDP_NO_MULTI_ALPHA");
     int hc[4];
     int outer = 0;
     const unsigned gB = (unsigned)((B + 255) / 256), gW = (unsigned)((B * 32 + 127) / 128);

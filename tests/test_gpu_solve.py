@@ -90,6 +90,41 @@ def test_forward_costs_multi(ddp, n, m, lims, dense_q):
         assert np.array_equal(costs[i], c), (i, np.max(np.abs(costs[i] - c)))
 
 
+def test_forward_costs_multi_pendcart(ddp):
+    """Pendulum-on-a-cart multi-alpha rollout (fwd_pend_multi_kernel): costs bit-identical to one rollout per step size."""
+    N, B = 46, 41
+    rng = np.random.default_rng(2)
+    x0 = np.stack([np.array([np.pi - 0.6 + 0.2 * rng.uniform(-1, 1), 0, 0, 0]) for _ in range(B)])
+    pm = ddp.PendcartModel()
+    lims = np.array([[-5.0, 5.0]])
+    xr, ur, _ = ddp.forward_pass(ddp.GaussianPolicy.empty(), x0, rng.standard_normal((B, N, 1)), None, 1.0, pm.f, pm.costfun, lims)
+    pol = ddp.GaussianPolicy(N, 4, 1, 0.3 * rng.standard_normal((B, N, 1, 4)), 0.2 * rng.standard_normal((B, N, 1)))
+    alphas = 10.0 ** np.linspace(0.2, -3, 11)                   # 11 > 8: two launches
+    costs = ddp.forward_costs(pol, x0, ur, xr, alphas, pm.f, pm.costfun, lims)
+    for i, a in enumerate(alphas):
+        _, _, c = ddp.forward_pass(pol, x0, ur, xr, float(a), pm.f, pm.costfun, lims)
+        assert np.array_equal(costs[i], c), (i, np.max(np.abs(costs[i] - c)))
+
+
+def test_ilqg_pendcart_multi_alpha_equals_serial(ddp, monkeypatch):
+    """demo_pendcart's settings: the multi-alpha line search and the serial one take identical decisions and trajectories."""
+    N, B = 100, 9
+    rng = np.random.default_rng(6)
+    x0 = np.stack([np.array([np.pi - 0.6 + 0.3 * rng.uniform(-1, 1), 0.1 * rng.standard_normal(), 0, 0]) for _ in range(B)])
+    u0 = np.zeros((B, N, 1))
+    kw = dict(lims=np.array([[-5.0, 5.0]]), regType=2, alpha=10.0 ** np.linspace(0.2, -3, 6), lammax=1e15, tol_fun=1e-8, tol_grad=1e-8, max_iter=8)
+    pm = ddp.PendcartModel()
+    monkeypatch.delenv("DDP_NO_MULTI_ALPHA", raising=False)
+    rm = ddp.iLQG(pm.f, pm.costfun, pm.df, x0, u0, **kw)
+    monkeypatch.setenv("DDP_NO_MULTI_ALPHA", "1")
+    rs = ddp.iLQG(pm.f, pm.costfun, pm.df, x0, u0, **kw)
+    monkeypatch.delenv("DDP_NO_MULTI_ALPHA", raising=False)
+    for key in ("status", "iter", "accepted_iter", "last_alpha", "lam"):
+        assert np.array_equal(rm[6][key], rs[6][key]), key
+    assert np.array_equal(rm[0], rs[0]) and np.array_equal(rm[1], rs[1]) and np.array_equal(rm[5], rs[5])
+    assert np.any(rm[6]["last_alpha"] < kw["alpha"][0])          # some line searches went past alpha[0]
+
+
 def test_ilqg_thresholds_of_test_readme(ddp):
     """test/test_readme.jl:82-84 on fresh instances of its problem distribution (n=10, m=2, T=1000)."""
     rng = np.random.default_rng(0)
