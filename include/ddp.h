@@ -203,9 +203,9 @@ DDP_API int ddp_forward_pass_f64(ddp_handle_t h, const ddp_model* model, const d
 
 /* Multi-alpha line-search helper (the serial backtracking of iLQG.jl:267-281 evaluated in one pass): the total
  * cost of the rollout for each of n_alpha step sizes, cost_out (n_alpha,B) row-major (row i = alpha[i], HOST array
- * of step sizes).  For the headline shape (n=32, m=8, per-trajectory LTI linear model) the policy gains K are
- * streamed ONCE for up to 10 step sizes and the costs are bit-identical to ddp_forward_pass_f64's; other shapes
- * run one rollout per step size.  a->alpha is ignored; a->xnew, a->unew, a->cost are scratch (contents undefined
+ * of step sizes).  For the headline shape (n=32, m=8, per-trajectory LTI linear model; up to 10 step sizes per pass) and for
+ * the pendulum-on-a-cart model (up to 8 per pass) the policy gains K are streamed ONCE and the costs are bit-identical to
+ * ddp_forward_pass_f64's; other shapes run one rollout per step size.  a->alpha is ignored; a->xnew, a->unew, a->cost are scratch (contents undefined
  * on return); roll out the accepted step size with ddp_forward_pass_f64. */
 DDP_API int ddp_forward_costs_multi_f64(ddp_handle_t h, const ddp_model* model, const ddp_forward_pass_args* a,
                                         int32_t n_alpha, const double* alpha, double* cost_out);
