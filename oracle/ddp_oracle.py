@@ -8,12 +8,14 @@ THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only ``tests/``, ``__graft_entry
 Pinning status: the reference ships NO golden vectors, known-answer tests or fixtures for this
 path (test/runtests.jl:7-12 are assertion-free smoke runs) and Julia is not installed in the build
 container, so the reference itself cannot be executed here.  BIT-LEVEL PARITY WITH JULIA IS
-THEREFORE UNPINNED.  What pins this oracle instead (tests/test_oracle_*.py):
+THEREFORE UNPINNED (status: "parity unpinned").  What pins this oracle instead (tests/test_oracle_*.py):
   * the reference's only assertions, the statistical cost thresholds of test/test_readme.jl:82-84,
     re-run on fresh instances of the same problem distribution;
   * analytic known answers the reference's maths implies: LQ backward pass == discrete Riccati
     recursion (and its long-horizon limit == scipy's DARE), boxQP == KKT / bounded least squares,
-    one-step convergence of iLQG on LQ problems, forced non-PD ``cuu`` => ``diverge == N-1``.
+    one-step convergence of iLQG on LQ problems, forced non-PD ``cuu`` => ``diverge == N-1``,
+    kl_div_wiki == the expected Gaussian KL written independently, forward_covariance -> discrete Lyapunov;
+  * committed fixtures of its own outputs (tests/golden/, generator beside them), reproduced bit for bit.
 
 Conventions.  Time is 0-based here; the reference (Julia) is 1-based.  ``diverge`` is returned as the
 reference's 1-based timestep index (0 == success) so values compare equal to the reference's.
