@@ -257,11 +257,29 @@ def main_gpu(args):
         e2.record()
         eng._ck(eng.lib.ddp_batch_stats_f64(eng.h, cost0.data_ptr(), cost.data_ptr(), dV.data_ptr(), None, 1.0,
                                             diverge.data_ptr(), None, stats.data_ptr()))
-        if world > 1:
-            dist.all_reduce(stats)                    # the line-search cost reduction: 64 bytes over NVLink
+        if world > 1:                                 # the line-search cost reduction: 64 bytes over NVLink
+            if lib_comm:
+                eng.allreduce_stats(stats.data_ptr())  # ncclAllReduce inside libddp (ddp_comm_allreduce_stats_f64), on the handle's stream
+            else:
+                dist.all_reduce(stats)
         if timed:
             back_ms.append((e0, e1)); fwd_ms.append((e1, e2))
 
+    # the library's own communicator for the one collective of the path; torch.distributed carries the 128-byte id
+    lib_comm = False
+    if world > 1:
+        try:
+            idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+            if rank == 0:
+                idt.copy_(torch.frombuffer(bytearray(eng.comm_unique_id()), dtype=torch.uint8))
+            dist.broadcast(idt, 0)
+            eng.comm_init(world, rank, bytes(idt.cpu().numpy().tobytes()))
+            lib_comm = True
+        except Exception as exc:                      # fall back to torch.distributed's all-reduce
+            sys.stderr.write(f"[bench] ddp_comm_init unavailable ({exc}); using torch.distributed.all_reduce\n")
+        flag = torch.tensor([1.0 if lib_comm else 0.0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        lib_comm = bool(flag.item() > 0.5)
     for _ in range(args.warmup):
         step(False)
     torch.cuda.synchronize()
@@ -381,7 +399,8 @@ def main_gpu(args):
                     config=dict(workload="C2: batched LTI linear dynamics n=32 m=8 T=256, 65536 trajectories per GPU, lambda=1 regType=1 "
                                          "no lims, alpha=1 (BASELINE.json configs[1])",
                                 batch_per_gpu=B, l2="inputs (~56 GB working set) are larger than the 126 MB L2: no flush needed",
-                                parallelism=f"batch sharded over {world} GPU(s); one 64-byte NCCL all-reduce per step" if world > 1
+                                parallelism=(f"batch sharded over {world} GPU(s); one 64-byte NCCL all-reduce per step "
+                                             f"({'inside libddp: ddp_comm_allreduce_stats_f64' if lib_comm else 'torch.distributed'})") if world > 1
                                 else "single GPU", kernel_variant=eng.kernel_variant),
                     clocks=clocks, e2e=e2e, gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu_baseline,
                     check=dict(diverged=n_div, mean_cost_new=float(stats_h[0] / max(stats_h[5], 1)),

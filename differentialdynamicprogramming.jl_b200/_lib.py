@@ -126,6 +126,10 @@ SYMBOLS = [
      [C.POINTER(C.c_int32)]),
     ("ddp_forward_costs_multi_f64", C.c_int, [C.c_void_p, C.POINTER(Model), C.POINTER(ForwardPassArgs), C.c_int32,
                                               C.POINTER(C.c_double), C.c_void_p]),
+    ("ddp_comm_unique_id", C.c_int, [C.c_void_p]),
+    ("ddp_comm_init", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    ("ddp_comm_allreduce_stats_f64", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("ddp_comm_destroy", C.c_int, [C.c_void_p]),
     ("ddp_ilqgkl_solve_f64", C.c_int, [C.c_void_p, C.POINTER(Model), C.POINTER(IlqgklOpts), C.POINTER(IlqgklArgs),
                                        C.POINTER(C.c_int32)]),
     ("ddp_ilqg_iter_host_f64", C.c_int, [C.c_void_p, C.POINTER(IterHostArgs)]),

@@ -112,6 +112,19 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.ddp_launch_count(self.h))
 
+    # ---- multi-GPU: the statistics all-reduce inside the library (ddp_comm_*; NCCL resolved at run time)
+    def comm_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        self._ck(self.lib.ddp_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, nranks: int, rank: int, unique_id: bytes):
+        assert len(unique_id) == 128
+        self._ck(self.lib.ddp_comm_init(self.h, nranks, rank, C.create_string_buffer(unique_id, 128)))
+
+    def allreduce_stats(self, stats_ptr: int):
+        self._ck(self.lib.ddp_comm_allreduce_stats_f64(self.h, C.c_void_p(stats_ptr)))
+
     def empty(self, shape, dtype=np.float64) -> DevArray:
         return DevArray(self, shape, dtype)
 

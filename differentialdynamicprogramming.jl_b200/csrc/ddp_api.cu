@@ -102,6 +102,7 @@ int ddp_destroy(ddp_handle_t h) {
     if (!h) return DDP_OK;
     cudaSetDevice(h->device);
     if (h->cache && h->cache_free) h->cache_free(h->cache);
+    if (h->comm) ddp_comm_destroy(h);
     if (h->ws) cudaFree(h->ws);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;

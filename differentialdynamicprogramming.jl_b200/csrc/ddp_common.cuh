@@ -78,6 +78,7 @@ struct ddp_handle_s {
     std::string err;
     void* cache = nullptr;               // lazily created pipeline state (solve.cu)
     void (*cache_free)(void*) = nullptr;
+    void* comm = nullptr;                // ncclComm_t (comm.cu)
     void* ws = nullptr;                  // workspace arena of the solve drivers, kept between calls (solve.cu)
     size_t ws_cap = 0;
     // scratch for the solve driver / host-iteration pipeline is allocated lazily by those entry points

@@ -223,6 +223,18 @@ DDP_API int ddp_batch_stats_f64(ddp_handle_t h, const double* cost_old, const do
                         const double* alpha, double alpha_scalar, const int32_t* diverge,
                         const uint8_t* active, double* stats8 /* device, 8 doubles */);
 
+/* ---- multi-GPU: the one collective of the path ----------------------------- */
+/* Trajectories are independent, so a batch shards over GPUs with no data-path exchange; what the ranks share per
+ * iteration is the 64-byte statistics vector of ddp_batch_stats_f64 (the line-search cost reduction).  These entry points
+ * let a host without any CUDA/NCCL binding of its own (the Julia shim) do that all-reduce: rank 0 calls
+ * ddp_comm_unique_id and hands the 128 bytes to the other ranks by whatever channel it has, every rank calls
+ * ddp_comm_init, then ddp_comm_allreduce_stats_f64 sums stats8 in place (on the handle's stream) over NCCL / NVLink.
+ * libnccl.so.2 is loaded at run time (dlopen); DDP_ERR_UNSUPPORTED if it is not present. */
+DDP_API int ddp_comm_unique_id(void* id128 /* out: 128 bytes */);
+DDP_API int ddp_comm_init(ddp_handle_t h, int32_t nranks, int32_t rank, const void* id128);
+DDP_API int ddp_comm_allreduce_stats_f64(ddp_handle_t h, double* stats8 /* device, 8 doubles, in place */);
+DDP_API int ddp_comm_destroy(ddp_handle_t h);
+
 /* ---- KL divergence between the new and previous policy ----------------------------------- */
 typedef struct ddp_kl_args {
     ddp_tensor fx;               /* (n,n[,T][,B]) model Jacobian used by forward_covariance       */

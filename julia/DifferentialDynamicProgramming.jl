@@ -243,6 +243,11 @@ function iLQG(f::DeviceModel, costfun::DeviceModel, df::DeviceModel, x0, u0;
     return x, u, (K, k), Vx, Vxx1, [s.cost for s in st], st
 end
 
+# ---- multi-GPU: one process per GPU, the batch sharded by contiguous ranges; the only exchange is the statistics all-reduce
+comm_unique_id() = (id = zeros(UInt8, 128); ccall((:ddp_comm_unique_id, libddp), Cint, (Ptr{UInt8},), id) == 0 || error("libddp: NCCL not available"); id)
+comm_init(e::Engine, nranks, rank, id::Vector{UInt8}) = check(e, ccall((:ddp_comm_init, libddp), Cint, (Ptr{Cvoid}, Int32, Int32, Ptr{UInt8}), e.h, nranks, rank, id))
+allreduce_stats!(e::Engine, stats8_dev::Ptr{Cvoid}) = check(e, ccall((:ddp_comm_allreduce_stats_f64, libddp), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), e.h, stats8_dev))
+
 # ---- iLQGkl(dynamics,costfun,derivs,x0,traj_prev,model; kw...)   iLQGkl.jl:25 --------------------
 # Whole outer loop on the device (ddp_ilqgkl_solve_f64).  `model` of the reference (LinearTimeVaryingModelsBase) is
 # replaced by what it is used for: `fx_model` = df(model,x,u)[1] and `R1` = covariance(model,x,u) (forward_pass.jl:38,42).

@@ -258,3 +258,18 @@ def test_forward_pendcart_staged_equals_unstaged(ddp, monkeypatch):
     a, b = outs
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
     assert np.array_equal(a[3][0], b[3][0]) and np.array_equal(a[3][1], b[3][1])
+
+
+def test_library_communicator_single_rank(ddp):
+    """ddp_comm_unique_id / ddp_comm_init / ddp_comm_allreduce_stats_f64 (NCCL resolved at run time) on a world of one rank:
+    the all-reduce is the identity and runs on the handle's stream."""
+    eng = ddp.Engine(4, 1, 8, 3)
+    uid = eng.comm_unique_id()
+    assert len(uid) == 128 and any(uid)
+    eng.comm_init(1, 0, uid)
+    st = eng.upload(np.arange(8, dtype=np.float64) + 0.5)
+    n0 = eng.launch_count
+    eng.allreduce_stats(st.ptr)
+    eng.synchronize()
+    assert np.array_equal(st.numpy(), np.arange(8) + 0.5) and eng.launch_count == n0 + 1
+    eng.close()
