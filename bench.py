@@ -44,6 +44,8 @@ BYTES_FWD = 632832.0 + 81928.0        # forward read + write per trajectory
 FP64_TENSOR_PEAK_TFLOPS = 37.08       # measured: profiles/microbench/ubench_r01_b200.txt (DMMA m8n8k4)
 FP64_DFMA_PEAK_TFLOPS = 34.14         # measured, same file (DFMA pipe, sustained)
 METRIC = "iLQG iters/sec (backward+forward), batch=65536 n=32 m=8 T=256"
+WORKLOAD = ("C2: batched LTI linear dynamics n=32 m=8 T=256, 65536 trajectories per GPU, lambda=1 regType=1 "
+            "no lims, alpha=1 (BASELINE.json configs[1])")
 UNIT = "iters/s (1 iter = backward+forward sweep over 65536 trajectories, FP64)"
 
 
@@ -113,7 +115,7 @@ def main_reference(args):
     line = dict(impl="reference", metric=METRIC, value=cb["value"], unit=UNIT, n_gpus=args.gpus, steps=steps,
                 warmup=min(args.warmup, 2), ms_per_step=1e3 / cb["value"], higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="f64", data="synthetic",
-                config=dict(workload="C2: batched LTI linear dynamics n=32 m=8 T=256 batch=65536, lambda=1 regType=1 no lims, alpha=1",
+                config=dict(workload=WORKLOAD,
                             impl_note="restated reference (C++/OpenMP port of back_pass + forward_pass), all host threads"),
                 cpu_baseline=cb,
                 e2e=dict(value=cb["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
@@ -396,8 +398,7 @@ def main_gpu(args):
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
                     data="synthetic",
-                    config=dict(workload="C2: batched LTI linear dynamics n=32 m=8 T=256, 65536 trajectories per GPU, lambda=1 regType=1 "
-                                         "no lims, alpha=1 (BASELINE.json configs[1])",
+                    config=dict(workload=WORKLOAD,
                                 batch_per_gpu=B, l2="inputs (~56 GB working set) are larger than the 126 MB L2: no flush needed",
                                 parallelism=(f"batch sharded over {world} GPU(s); one 64-byte NCCL all-reduce per step "
                                              f"({'inside libddp: ddp_comm_allreduce_stats_f64' if lib_comm else 'torch.distributed'})") if world > 1
