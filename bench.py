@@ -173,6 +173,33 @@ class ClockSampler:
                     reasons=sorted(reasons))
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this process to the CPUs next to its GPU (sysfs local_cpulist of the GPU's PCI device) before any pinned host
+    buffer is allocated, so that the e2e path's host memory sits on the GPU's NUMA node.  Returns the CPU set or None."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local_rank)],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if not bus:
+            return None
+        bus = bus[-12:] if len(bus) > 12 else bus            # 00000000:1b:00.0 -> 0000:1b:00.0
+        with open(f"/sys/bus/pci/devices/{bus}/local_cpulist") as f:
+            txt = f.read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return sorted(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def main_gpu(args):
     import torch
     import torch.distributed as dist
@@ -184,6 +211,8 @@ def main_gpu(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- this arm has no CPU fallback (use --impl reference for the CPU arm)")
+    all_cpus = os.sched_getaffinity(0)
+    numa_cpus = bind_to_gpu_numa_node(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -354,7 +383,7 @@ def main_gpu(args):
         e2e = dict(value=world * (Be / BATCH) * 1e3 / e_ms, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                    ms_per_step=e_ms, steps=e_steps, batch_per_gpu=Be, chunk=(args.chunk or "ramped: 1,2,4,...,4,2,1 rounds of sm_count*8 trajectories"),
                    api="ddp_ilqg_iter_host_f64: x,u,fx,fu,lambda from pinned host memory -> df (cx=Qx, cu=Ru) + backward + forward on the device -> xnew,unew,cost,dV,diverge in host memory; policy K stays on the device",
-                   matches_device_path=ok)
+                   matches_device_path=ok, host_cpus_bound_to_gpu_numa_node=(len(numa_cpus) if numa_cpus else None))
         it.close()
         eng_e.close()
     except Exception as exc:                           # report, never fake
@@ -389,6 +418,10 @@ def main_gpu(args):
             except Exception:
                 pass
         cpu_baseline = None
+        try:
+            os.sched_setaffinity(0, all_cpus)              # the CPU baseline uses every host core again
+        except Exception:
+            pass
         if world == 1 and not args.no_cpu_baseline:
             try:
                 cpu_baseline, _ = run_cpu_baseline(args.cpu_sample, 2, 1)
