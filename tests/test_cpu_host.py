@@ -148,3 +148,30 @@ def test_batch_sharding_world_size_2_gloo(tmp_path):
                           "--master-port", "29613", str(script), ROOT], capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "SHARD_OK" in out.stdout
+
+
+def _build_c_host(tmp_path):
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "c_host")
+    libdir = os.path.join(root, "differentialdynamicprogramming.jl_b200")
+    r = subprocess.run(["gcc", "-O2", "-Wall", "-Werror", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "c_host.c"),
+                        "-L", libdir, "-lddp", "-lm", "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe, libdir
+
+
+def test_plain_c_host_compiles_and_links(tmp_path):
+    """examples/c_host.c: a C (not C++) program that includes include/ddp.h and links libddp.so -- the boundary has no C++
+    or torch types in it."""
+    _build_c_host(tmp_path)
+
+
+@pytest.mark.gpu
+def test_plain_c_host_runs(tmp_path):
+    import subprocess
+    exe, libdir = _build_c_host(tmp_path)
+    env = dict(os.environ, LD_LIBRARY_PATH=libdir + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    r = subprocess.run([exe], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "0 diverged back passes" in r.stdout and "kernel variant: tile32x8" in r.stdout
