@@ -342,6 +342,41 @@ def main_gpu(args):
     stats_h = stats.cpu().numpy()
     n_div = int((diverge > 0).sum().item())
 
+    # ---- size-independent properties of the full-size result (outside the timed region; never fatal)
+    props = {}
+    try:
+        expected = -(dV[:, 0] + dV[:, 1])                         # iLQG.jl:271 at alpha = 1
+        ratio = (cost0 - cost) / expected
+        props["ratio_min"], props["ratio_max"] = float(ratio.min().item()), float(ratio.max().item())
+        props["terminal_Vx_is_cx"] = bool(torch.equal(Vx[:, T - 1], cx[:, T - 1]))          # backward_pass.jl:21
+        props["terminal_gains_zero"] = bool((K[:, T - 1] == 0).all().item() and (k[:, T - 1] == 0).all().item())   # quirk Q7
+        props["xnew0_is_x0"] = bool(torch.equal(xnew[:, 0], x0))                            # forward_pass.jl:13
+        # batch independence: the first S trajectories alone (another grid, another warp <-> trajectory map) give the same bits
+        S = 1000
+        eng_s = ddp.Engine(n, m, T, S, device=local_rank)
+        eng_s.set_stream(torch.cuda.current_stream().cuda_stream)
+        K_s, k_s, Vx_s, dV_s = empty(S, T, n, m), empty(S, T, m), empty(S, T, n), empty(S, 2)
+        xn_s, un_s, c_s = empty(S, T, n), empty(S, T, m), empty(S)
+        dv_s = torch.empty(S, dtype=torch.int32, device=dev)
+        bs = L.BackPassArgs()
+        for name in ("cx", "cu", "cxx", "cxu", "cuu", "fx", "fu", "lam", "reg_type"):
+            setattr(bs, name, getattr(ba, name))
+        bs.diverge, bs.K, bs.k, bs.Vx, bs.dV = dv_s.data_ptr(), K_s.data_ptr(), k_s.data_ptr(), Vx_s.data_ptr(), dV_s.data_ptr()
+        fs = L.ForwardPassArgs()
+        fs.K, fs.k = K_s.data_ptr(), k_s.data_ptr()
+        fs.x0, fs.x, fs.u = fa.x0, fa.x, fa.u
+        fs.alpha_scalar, fs.u_scale = 1.0, 1.0
+        fs.xnew, fs.unew, fs.cost = xn_s.data_ptr(), un_s.data_ptr(), c_s.data_ptr()
+        eng_s._ck(eng_s.lib.ddp_back_pass_f64(eng_s.h, C.byref(bs)))
+        eng_s._ck(eng_s.lib.ddp_forward_pass_f64(eng_s.h, C.byref(model), C.byref(fs)))
+        torch.cuda.synchronize()
+        props["slice_bitwise_equal"] = bool(torch.equal(K_s, K[:S]) and torch.equal(k_s, k[:S]) and torch.equal(Vx_s, Vx[:S]) and
+                                            torch.equal(xn_s, xnew[:S]) and torch.equal(c_s, cost[:S]) and torch.equal(dV_s, dV[:S]))
+        eng_s.close()
+        del K_s, k_s, Vx_s, dV_s, xn_s, un_s, c_s, dv_s
+    except Exception as exc:
+        props["error"] = str(exc)
+
     # ---- end-to-end: same step through ddp_ilqg_iter_host_f64 on pinned host buffers
     e2e = None
     try:
@@ -437,7 +472,7 @@ def main_gpu(args):
                                              f"({'inside libddp: ddp_comm_allreduce_stats_f64' if lib_comm else 'torch.distributed'})") if world > 1
                                 else "single GPU", kernel_variant=eng.kernel_variant),
                     clocks=clocks, e2e=e2e, gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu_baseline,
-                    check=dict(diverged=n_div, mean_cost_new=float(stats_h[0] / max(stats_h[5], 1)),
+                    check=dict(diverged=n_div, properties=props, mean_cost_new=float(stats_h[0] / max(stats_h[5], 1)),
                                accepted_frac=float(stats_h[3] / max(stats_h[5], 1))))
         print(json.dumps(line))
     if world > 1:
