@@ -23,15 +23,17 @@ class BoxQPOpts(C.Structure):       # ddp_boxqp_opts
 class BackPassArgs(C.Structure):    # ddp_back_pass_args
     _fields_ = [("cx", Tensor), ("cu", Tensor), ("cxx", Tensor), ("cxu", Tensor), ("cuu", Tensor),
                 ("fx", Tensor), ("fu", Tensor), ("lam", C.c_void_p), ("reg_type", C.c_int32),
-                ("lims", C.c_void_p), ("u", Tensor), ("active", C.c_void_p),
+                ("lims", C.c_void_p), ("lims_stride_t", C.c_int64), ("u", Tensor), ("active", C.c_void_p),
+                ("fxx", Tensor), ("fxu", Tensor), ("fuu", Tensor),
                 ("diverge", C.c_void_p), ("K", C.c_void_p), ("k", C.c_void_p), ("Vx", C.c_void_p),
                 ("Vxx", C.c_void_p), ("Vxx1", C.c_void_p), ("Quu", C.c_void_p), ("dV", C.c_void_p),
+                ("Vxx_tri", C.c_void_p), ("Quu_tri", C.c_void_p),
                 ("qp", BoxQPOpts)]
 
 
 class GpsArgs(C.Structure):         # ddp_gps_args
     _fields_ = [("K_prev", Tensor), ("k_prev", Tensor), ("Sigi_prev", Tensor), ("eta", C.c_void_p),
-                ("Quui", C.c_void_p)]
+                ("Quui", C.c_void_p), ("Quui_tri", C.c_void_p)]
 
 
 class Model(C.Structure):           # ddp_model
@@ -42,7 +44,7 @@ class Model(C.Structure):           # ddp_model
 class ForwardPassArgs(C.Structure):  # ddp_forward_pass_args
     _fields_ = [("K", C.c_void_p), ("k", C.c_void_p), ("x0", Tensor), ("x", Tensor), ("u", Tensor),
                 ("alpha", C.c_void_p), ("alpha_scalar", C.c_double), ("u_scale", C.c_double),
-                ("lims", C.c_void_p), ("active", C.c_void_p),
+                ("lims", C.c_void_p), ("lims_stride_t", C.c_int64), ("active", C.c_void_p),
                 ("xnew", C.c_void_p), ("unew", C.c_void_p), ("cost", C.c_void_p), ("cost_t", C.c_void_p),
                 ("cx", C.c_void_p), ("cu", C.c_void_p)]
 
@@ -59,7 +61,14 @@ class IlqgOpts(C.Structure):        # ddp_ilqg_opts
                 ("tol_grad", C.c_double), ("max_iter", C.c_int32), ("lam", C.c_double),
                 ("dlam", C.c_double), ("lam_factor", C.c_double), ("lam_max", C.c_double),
                 ("lam_min", C.c_double), ("reg_type", C.c_int32), ("reduce_ratio_min", C.c_double),
-                ("lims", C.c_void_p)]
+                ("lims", C.c_void_p), ("x_init", C.c_void_p), ("cost_init", C.c_void_p),
+                ("trace", C.c_void_p), ("trace_cap", C.c_int32)]
+
+
+class IlqgTrace(C.Structure):       # ddp_ilqg_trace
+    _fields_ = [("lam", C.c_double), ("dlam", C.c_double), ("cost", C.c_double), ("alpha", C.c_double),
+                ("grad_norm", C.c_double), ("improvement", C.c_double), ("reduce_ratio", C.c_double),
+                ("accepted", C.c_int32), ("bp_retries", C.c_int32)]
 
 
 class IlqgState(C.Structure):       # ddp_ilqg_state
@@ -93,7 +102,18 @@ class IterHostArgs(C.Structure):    # ddp_iter_host_args
                 ("Q", C.c_void_p), ("R", C.c_void_p), ("cxu", C.c_void_p),
                 ("reg_type", C.c_int32), ("q_diagonal", C.c_int32), ("alpha", C.c_double),
                 ("xnew", C.c_void_p), ("unew", C.c_void_p), ("cost", C.c_void_p), ("dV", C.c_void_p),
-                ("diverge", C.c_void_p), ("chunk", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
+                ("diverge", C.c_void_p), ("chunk", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+                ("keep_policy", C.c_int32), ("inputs_resident", C.c_int32), ("commit_accepted", C.c_int32), ("pad_", C.c_int32),
+                ("cost_prev", C.c_void_p)]
+
+
+class IterArgs(C.Structure):        # ddp_iter_args
+    _fields_ = [("x", C.c_void_p), ("u", C.c_void_p), ("lam", C.c_void_p), ("alpha", C.c_void_p),
+                ("alpha_scalar", C.c_double), ("reg_type", C.c_int32), ("pad_", C.c_int32),
+                ("lims", C.c_void_p), ("active", C.c_void_p),
+                ("xnew", C.c_void_p), ("unew", C.c_void_p), ("cost", C.c_void_p), ("dV", C.c_void_p),
+                ("diverge", C.c_void_p), ("K", C.c_void_p), ("k", C.c_void_p), ("Vx", C.c_void_p),
+                ("chunk", C.c_int64), ("n_chunks", C.c_int64)]
 
 
 # every symbol include/ddp.h declares: (name, restype, argtypes)
@@ -133,7 +153,19 @@ SYMBOLS = [
     ("ddp_ilqgkl_solve_f64", C.c_int, [C.c_void_p, C.POINTER(Model), C.POINTER(IlqgklOpts), C.POINTER(IlqgklArgs),
                                        C.POINTER(C.c_int32)]),
     ("ddp_ilqg_iter_host_f64", C.c_int, [C.c_void_p, C.POINTER(IterHostArgs)]),
+    ("ddp_iter_host_policy", C.c_int, [C.c_void_p] + [C.POINTER(C.c_void_p)] * 5),
+    ("ddp_ilqg_iter_f64", C.c_int, [C.c_void_p, C.POINTER(Model), C.POINTER(IterArgs)]),
+    ("ddp_selftest_peak_f64", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 ]
+
+# Python mirror <-> C struct, for the layout tests (sizeof and offsetof of every field, tests/test_cpu_host.py)
+STRUCTS = {"ddp_tensor": Tensor, "ddp_boxqp_opts": BoxQPOpts, "ddp_back_pass_args": BackPassArgs, "ddp_gps_args": GpsArgs,
+           "ddp_model": Model, "ddp_forward_pass_args": ForwardPassArgs, "ddp_kl_args": KlArgs, "ddp_ilqg_opts": IlqgOpts,
+           "ddp_ilqg_trace": IlqgTrace, "ddp_ilqg_state": IlqgState, "ddp_ilqgkl_opts": IlqgklOpts,
+           "ddp_ilqgkl_state": IlqgklState, "ddp_ilqgkl_args": IlqgklArgs, "ddp_iter_host_args": IterHostArgs,
+           "ddp_iter_args": IterArgs}
+# ctypes field name -> C field name where they differ (Python keywords / shorter names)
+FIELD_ALIASES = {"lam": "lambda", "dlam": "dlambda", "lam_factor": "lambda_factor", "lam_max": "lambda_max", "lam_min": "lambda_min"}
 
 _lib = None
 

@@ -99,9 +99,11 @@ __global__ void __launch_bounds__(NT) bp_generic_kernel(BackParams P) {
     carve(smem_raw, n, m, GPS, s);
     const bool use_qp = (P.lims != nullptr) && !(P.lims[0] > P.lims[m]);   // backward_pass.jl:31
     const long long nn = (long long)n * n, mn = (long long)m * n, mm = (long long)m * m;
+    if (P.redo_count && *P.redo_count == 0) return;          // follow-up launch of the tile kernel with nothing handed over
 
     for (long long b = blockIdx.x; b < P.B; b += gridDim.x) {
         if (P.active && !P.active[b]) continue;
+        if (P.redo && !P.redo[b]) continue;
         __syncthreads();
         const double lam = GPS ? 0.0 : P.lambda[b];
         const double eta = GPS ? P.eta[b] : 1.0;
@@ -111,6 +113,10 @@ __global__ void __launch_bounds__(NT) bp_generic_kernel(BackParams P) {
         double* Vxxb = P.Vxx ? P.Vxx + b * (long long)N * nn : nullptr;
         double* Quub = P.Quu ? P.Quu + b * (long long)N * mm : nullptr;
         double* Quuib = (GPS && P.Quui) ? P.Quui + b * (long long)N * mm : nullptr;
+        const long long trn = (long long)n * (n + 1) / 2, trm = (long long)m * (m + 1) / 2;      // packed upper triangles
+        double* Vtb = P.Vxx_tri ? P.Vxx_tri + b * (long long)N * trn : nullptr;
+        double* Qtb = P.Quu_tri ? P.Quu_tri + b * (long long)N * trm : nullptr;
+        double* Qitb = (GPS && P.Quui_tri) ? P.Quui_tri + b * (long long)N * trm : nullptr;
         // ---- terminal step (backward_pass.jl:21-23 / :280-283)
         {
             const double* cxN = tp(P.cx, b, N - 1);
@@ -122,6 +128,7 @@ __global__ void __launch_bounds__(NT) bp_generic_kernel(BackParams P) {
                 double v = cxxN[e];
                 s.V[i + ldn * j] = v;
                 if (Vxxb) Vxxb[(long long)(N - 1) * nn + e] = v;
+                if (Vtb && i <= j) Vtb[(long long)(N - 1) * trn + (long long)j * (j + 1) / 2 + i] = v;
             }
             for (int e = tid; e < m * n; e += NT) Kb[(long long)(N - 1) * mn + e] = 0.0;
             for (int a = tid; a < m; a += NT) { kb[(long long)(N - 1) * m + a] = 0.0; s.kw[a] = 0.0; }
@@ -132,14 +139,20 @@ __global__ void __launch_bounds__(NT) bp_generic_kernel(BackParams P) {
                     s.Quu[e] = v;
                     s.QuuF[e] = v;
                     if (Quub) Quub[(long long)(N - 1) * mm + e] = v;
+                    if (Qtb && (e % m) <= (e / m)) Qtb[(long long)(N - 1) * trm + (long long)(e / m) * (e / m + 1) / 2 + (e % m)] = v;
                 }
                 __syncthreads();
                 if (tid == 0) inv_gj(m, s.QuuF, s.Inv);
                 __syncthreads();
-                if (Quuib)
-                    for (int e = tid; e < m * m; e += NT) Quuib[(long long)(N - 1) * mm + e] = s.Inv[e];
-            } else if (Quub) {
-                for (int e = tid; e < m * m; e += NT) Quub[(long long)(N - 1) * mm + e] = cuuN[e];
+                for (int e = tid; e < m * m; e += NT) {
+                    if (Quuib) Quuib[(long long)(N - 1) * mm + e] = s.Inv[e];
+                    if (Qitb && (e % m) <= (e / m)) Qitb[(long long)(N - 1) * trm + (long long)(e / m) * (e / m + 1) / 2 + (e % m)] = s.Inv[e];
+                }
+            } else if (Quub || Qtb) {
+                for (int e = tid; e < m * m; e += NT) {
+                    if (Quub) Quub[(long long)(N - 1) * mm + e] = cuuN[e];
+                    if (Qtb && (e % m) <= (e / m)) Qtb[(long long)(N - 1) * trm + (long long)(e / m) * (e / m + 1) / 2 + (e % m)] = cuuN[e];
+                }
             }
             if (tid == 0) s.flags[0] = 0;
         }
@@ -196,6 +209,12 @@ __global__ void __launch_bounds__(NT) bp_generic_kernel(BackParams P) {
                     double acc = 0.0;
                     for (int q = 0; q < n; q++) acc = fma(s.Fx[q + ldn * r], s.W[q + ldn * c], acc);
                     double v = cxxi[e] + acc;
+                    if (!GPS && P.fxx.p) {                        // Qxx[p,q] += sum_k Vx_k fxx[k,q,p]  (backward_pass.jl:118)
+                        const double* t3 = tp(P.fxx, b, i) + (long long)n * c + nn * r;
+                        double so = 0.0;
+                        for (int q = 0; q < n; q++) so = fma(s.Vx[q], t3[q], so);
+                        v += so;
+                    }
                     if (GPS) {
                         double kl = 0.0;                          // cxxkl = K' Σi K
                         for (int q = 0; q < m; q++) kl = fma(s.Kp[q + ldm * r], s.S[q + ldm * c], kl);
@@ -217,6 +236,13 @@ __global__ void __launch_bounds__(NT) bp_generic_kernel(BackParams P) {
                         for (int q = 0; q < n; q++) ff = fma(s.Fu[q + ldn * a], s.Fx[q + ldn * j], ff);
                         vr = v + lam * ff;
                     }
+                    if (!GPS && P.fxu.p) {                        // Qux[a,j] += sum_k Vx_k fxu[k,j,a]  (:106-109, :121)
+                        const double* t3 = tp(P.fxu, b, i) + (long long)n * j + nn * a;
+                        double so = 0.0;
+                        for (int q = 0; q < n; q++) so = fma(s.Vx[q], t3[q], so);
+                        v += so;
+                        vr += so;
+                    }
                     s.Qux[a + ldm * j] = v;
                     s.Quxr[a + ldm * j] = vr;
                 }
@@ -235,6 +261,13 @@ __global__ void __launch_bounds__(NT) bp_generic_kernel(BackParams P) {
                         vf = v + lam * ff;
                     } else if (P.reg_type == 1 && a == c) {
                         vf = v + lam;
+                    }
+                    if (!GPS && P.fuu.p) {                        // Quu[a,c] += sum_k Vx_k fuu[k,c,a]  (:112-115, :123)
+                        const double* t3 = tp(P.fuu, b, i) + (long long)n * c + (long long)n * m * a;
+                        double so = 0.0;
+                        for (int q = 0; q < n; q++) so = fma(s.Vx[q], t3[q], so);
+                        v += so;
+                        vf += so;
                     }
                     s.Quu[e] = v;
                     s.QuuF[e] = vf;
@@ -258,8 +291,9 @@ __global__ void __launch_bounds__(NT) bp_generic_kernel(BackParams P) {
                     s.Qu[a] = v;
                     if (use_qp) {                                  // :45-46
                         double ui = tp(P.u, b, i)[a];
-                        s.lo[a] = P.lims[a] - ui;
-                        s.up[a] = P.lims[m + a] - ui;
+                        const double* li = P.lims + (long long)i * P.lims_st;      // time-varying limits: block i
+                        s.lo[a] = li[a] - ui;
+                        s.up[a] = li[m + a] - ui;
                     }
                 }
             }
@@ -367,14 +401,19 @@ __global__ void __launch_bounds__(NT) bp_generic_kernel(BackParams P) {
                 double v = 0.5 * (s.W[r + ldn * c] + s.W[c + ldn * r]);
                 s.V[r + ldn * c] = v;
                 if (Vxxb) Vxxb[(long long)i * nn + e] = v;
+                if (Vtb && r <= c) Vtb[(long long)i * trn + (long long)c * (c + 1) / 2 + r] = v;
             }
             for (int r = tid; r < n; r += NT) { s.Vx[r] = s.VxN[r]; Vxb[(long long)i * n + r] = s.VxN[r]; }
             for (int e = tid; e < m * n; e += NT) Kb[(long long)i * mn + e] = s.K[(e % m) + ldm * (e / m)];
             for (int a = tid; a < m; a += NT) { kb[(long long)i * m + a] = s.k[a]; s.kw[a] = s.k[a]; }
-            if (Quub)
-                for (int e = tid; e < m * m; e += NT) Quub[(long long)i * mm + e] = s.Quu[e];
-            if (Quuib)
-                for (int e = tid; e < m * m; e += NT) Quuib[(long long)i * mm + e] = s.Inv[e];
+            for (int e = tid; e < m * m; e += NT) {
+                const long long te = (long long)(e / m) * (e / m + 1) / 2 + (e % m);
+                const bool up = (e % m) <= (e / m);
+                if (Quub) Quub[(long long)i * mm + e] = s.Quu[e];
+                if (Qtb && up) Qtb[(long long)i * trm + te] = s.Quu[e];
+                if (Quuib) Quuib[(long long)i * mm + e] = s.Inv[e];
+                if (Qitb && up) Qitb[(long long)i * trm + te] = s.Inv[e];
+            }
             __syncthreads();
         }
         // ---- epilogue
@@ -386,6 +425,8 @@ __global__ void __launch_bounds__(NT) bp_generic_kernel(BackParams P) {
             for (long long e = tid; e < (long long)(upto + 1) * n; e += NT) Vxb[e] = 0.0;
             if (Vxxb)
                 for (long long e = tid; e < (long long)(upto + 1) * nn; e += NT) Vxxb[e] = 0.0;
+            if (Vtb)
+                for (long long e = tid; e < (long long)(upto + 1) * trn; e += NT) Vtb[e] = 0.0;
         }
         if (P.Vxx1)
             for (int e = tid; e < n * n; e += NT)

@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(128, MINB) bp_small_kernel(BackParams P) {
     double* sfx_lane = sfx + s_row * FxStage<N>::ROW + 2 * s_ch;
     const bool use_qp = (P.lims != nullptr) && !(P.lims[0] > P.lims[M]);     // backward_pass.jl:31
     const double lam = P.lambda[b];
-    const bool reg2 = (P.reg_type == 2);
+    const bool reg2 = (P.reg_type == 2), reg1 = (P.reg_type == 1);     // any other value: no regularisation, as `regType == 1 ? λ : 0`
     double* Kb = P.K + b * (long long)T * N * M;
     double* kb = P.k + b * (long long)T * M;
     double* Vxb = P.Vx + b * (long long)T * N;
@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(128, MINB) bp_small_kernel(BackParams P) {
                 for (int q = 0; q < N; q++) { acc = fma(cur.fu[q + N * a], Z[q + N * c], acc); ff = fma(cur.fu[q + N * a], cur.fu[q + N * c], ff); }
                 const double v = cuui[a + M * c] + acc;
                 Quu[a + M * c] = v;
-                QuuF[a + M * c] = reg2 ? v + lam * ff : ((a == c) ? v + lam : v);
+                QuuF[a + M * c] = reg2 ? v + lam * ff : ((reg1 && a == c) ? v + lam : v);
             }
 #pragma unroll
         for (int r = 0; r < N; r++) {
@@ -395,6 +395,7 @@ int launch_small(ddp_handle_s* h, const BackParams& P) {
 int launch_back_pass_small(ddp_handle_s* h, const BackParams& P, bool gps, bool* handled) {
     *handled = false;
     if (gps || P.T < 2) return 0;
+    if ((P.lims && P.lims_st != 0) || P.fxx.p || P.fxu.p || P.fuu.p || P.Vxx_tri || P.Quu_tri) return 0;   // generic kernel
     int rc = 0;
 #define SMALL_CASE(NN, MM) if (P.n == NN && P.m == MM) { rc = launch_small<NN, MM>(h, P); *handled = true; return rc; }
     SMALL_CASE(4, 1)

@@ -27,6 +27,7 @@
 //
 // Restrictions (anything else dispatches to the generic kernel): Cholesky branch only (lims ==
 // NULL), 16-byte aligned fx/fu/cxx with even strides, symmetric cxx (it is a Hessian).
+#include <algorithm>
 #include <cstdlib>
 #include "ddp_common.cuh"
 
@@ -121,7 +122,9 @@ __device__ __forceinline__ bool gj_inverse8(double& I0, double& I1, int lane, in
 
 constexpr int gidx(int at, int bt) { return at * 5 - (at * (at - 1)) / 2 + (bt - at); }   // upper-tile index, 15 tiles
 
-template <bool LTV, bool GPS, bool REG2>
+// HIST: the optional Vxx histories (full and packed) are compiled in only when asked for, so the benchmarked variants
+// carry neither their pointers nor their branches through the step loop
+template <bool LTV, bool GPS, bool REG2, bool HIST>
 __global__ void __launch_bounds__(wpb(LTV) * 32, 2) bp_tile32x8_kernel(BackParams P) {
     constexpr int WPB = wpb(LTV);
     extern __shared__ double smem_raw[];
@@ -178,8 +181,16 @@ __global__ void __launch_bounds__(wpb(LTV) * 32, 2) bp_tile32x8_kernel(BackParam
         double* Kb = P.K + b * (long long)N * 256;
         double* kb = P.k + b * (long long)N * 8;
         double* Vxb = P.Vx + b * (long long)N * 32;
-        double* Vxxb = P.Vxx ? P.Vxx + b * (long long)N * 1024 : nullptr;
+        double* Vxxb = (HIST && P.Vxx) ? P.Vxx + b * (long long)N * 1024 : nullptr;
         double* Quub = P.Quu ? P.Quu + b * (long long)N * 64 : nullptr;
+        // packed upper triangle of Vxx (528 per step), optional: the pointer is re-formed from the parameter block at each use
+        // so that this rarely used output costs the step loop no register
+        auto dump_tri = [&](long long step) {                                          // column c: rows 0..c are contiguous
+            double* o = P.Vxx_tri + (b * (long long)N + step) * 528;
+#pragma unroll 4
+            for (int c = 0; c < 32; c++)
+                if (lane <= c) o[c * (c + 1) / 2 + lane] = sV[swz(lane, c)];
+        };
         const double* cxb = P.cx.p + b * P.cx.sb;
         const double* cub = P.cu.p + b * P.cu.sb;
         __syncwarp();
@@ -197,6 +208,23 @@ __global__ void __launch_bounds__(wpb(LTV) * 32, 2) bp_tile32x8_kernel(BackParam
                 st2(&sV[swz(i, col)], t.x, t.y);
                 if (Vxxb) st2(Vxxb + (long long)(N - 1) * 1024 + col * 32 + i, t.x, t.y);
             }
+            // the products below assume Vxx = Vxx': an inexactly symmetric (or NaN) terminal cxx goes to the generic kernel
+            __syncwarp();
+            {
+                bool asym = false;
+                for (int c = lane; c < 512; c += 32) {
+                    const int col = c >> 4, i = (c & 15) << 1;
+                    const double2 t = ld2(&sV[swz(i, col)]);
+                    if (t.x != sV[swz(col, i)] || t.y != sV[swz(col, i + 1)]) asym = true;
+                }
+                asym = __any_sync(0xffffffffu, asym);
+                if (lane == 0) {
+                    P.redo[b] = asym ? 1 : 0;
+                    if (asym) atomicAdd(P.redo_count, 1);
+                }
+                if (asym) continue;
+            }
+            if (HIST && P.Vxx_tri) dump_tri(N - 1);
             for (int c = lane; c < 128; c += 32) st2(Kb + (long long)(N - 1) * 256 + 2 * c, 0.0, 0.0);
             if (lane < 8) kb[(long long)(N - 1) * 8 + lane] = 0.0;
             if (GPS) {                              // Quu(N) = cuu/eta + Sigma_i_prev(N), Sigma(N) = inv  (backward_pass.jl:282-283)
@@ -268,6 +296,7 @@ __global__ void __launch_bounds__(wpb(LTV) * 32, 2) bp_tile32x8_kernel(BackParam
                     st2(Vxxb + (long long)(i + 1) * 1024 + col * 32 + r, t.x, t.y);
                 }
             }
+            if (HIST && P.Vxx_tri && i < N - 2) dump_tri(i + 1);
             // ---- G starts from the cost terms: their global loads are in flight during the tensor phase
             double G[15][2];
             if (cost_shared) {
@@ -615,6 +644,12 @@ __global__ void __launch_bounds__(wpb(LTV) * 32, 2) bp_tile32x8_kernel(BackParam
                 st2(Vxxb + col * 32 + r, t.x, t.y);
             }
         }
+        if (HIST && P.Vxx_tri) {
+            if (diverge > 0) {
+                for (long long e = lane; e < (long long)diverge * 528; e += 32) P.Vxx_tri[b * (long long)N * 528 + e] = 0.0;
+                if (diverge < N - 1) dump_tri(diverge);
+            } else if (N >= 2) dump_tri(0);
+        }
         if (P.Vxx1) {
             for (int c = lane; c < 512; c += 32) {
                 int col = c >> 4, r = (c & 15) << 1;
@@ -636,9 +671,11 @@ bool aligned16(const TensorD& t) { return ((uintptr_t)t.p % 16 == 0) && (t.sb % 
 
 }  // namespace
 
-int launch_back_pass_tile(ddp_handle_s* h, const BackParams& P, bool gps, bool* handled) {
+int launch_back_pass_tile(ddp_handle_s* h, const BackParams& P_in, bool gps, bool* handled) {
     *handled = false;
+    BackParams P = P_in;
     if (P.n != 32 || P.m != 8 || P.lims != nullptr || P.T < 2) return 0;
+    if (P.fxx.p || P.fxu.p || P.fuu.p || P.Quu_tri || P.Quui_tri) return 0;          // second-order terms / packed Quu: generic kernel
     if (!aligned16(P.fx) || !aligned16(P.fu) || !aligned16(P.cxx)) return 0;
     if (((uintptr_t)P.K % 16) || (P.Vxx && ((uintptr_t)P.Vxx % 16)) || (P.Vxx1 && ((uintptr_t)P.Vxx1 % 16))) return 0;
     if (gps && !aligned16(P.Kp)) return 0;
@@ -650,11 +687,29 @@ int launch_back_pass_tile(ddp_handle_s* h, const BackParams& P, bool gps, bool* 
     long long need = (P.B + WPB - 1) / WPB;
     if (grid > need) grid = need;
     cudaError_t e = cudaSuccess;
-#define LAUNCH_TILE(L, G, R2)                                                                                            \
-    do {                                                                                                                 \
-        e = cudaFuncSetAttribute(bp_tile32x8_kernel<L, G, R2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); \
-        if (e == cudaSuccess) bp_tile32x8_kernel<L, G, R2><<<(unsigned)grid, WPB * 32, bytes, h->stream>>>(P);            \
+    if (h->redo_cap < P.B) {                   // hand-over mask: one int counter (16 bytes reserved) + one byte per trajectory
+        if (h->redo) cudaFree(h->redo);
+        h->redo = nullptr; h->redo_cap = 0;
+        const long long cap = std::max<long long>(P.B, h->B);
+        e = cudaMalloc((void**)&h->redo, (size_t)cap + 16);
+        if (e != cudaSuccess) return (int)e;
+        h->redo_cap = cap;
+    }
+    P.redo_count = reinterpret_cast<int*>(h->redo);
+    P.redo = h->redo + 16;
+    e = cudaMemsetAsync(P.redo_count, 0, sizeof(int), h->stream);
+    if (e != cudaSuccess) return (int)e;
+#define LAUNCH_TILE1(L, G, R2, H)                                                                                           \
+    do {                                                                                                                    \
+        e = cudaFuncSetAttribute(bp_tile32x8_kernel<L, G, R2, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); \
+        if (e == cudaSuccess) bp_tile32x8_kernel<L, G, R2, H><<<(unsigned)grid, WPB * 32, bytes, h->stream>>>(P);            \
     } while (0)
+#define LAUNCH_TILE(L, G, R2)                     \
+    do {                                          \
+        if (hist) LAUNCH_TILE1(L, G, R2, true);   \
+        else LAUNCH_TILE1(L, G, R2, false);       \
+    } while (0)
+    const bool hist = (P.Vxx != nullptr) || (P.Vxx_tri != nullptr);
     const bool r2 = !gps && (P.reg_type == 2);
     if (ltv && gps) LAUNCH_TILE(true, true, false);
     else if (ltv && r2) LAUNCH_TILE(true, false, true);
@@ -663,8 +718,11 @@ int launch_back_pass_tile(ddp_handle_s* h, const BackParams& P, bool gps, bool* 
     else if (r2) LAUNCH_TILE(false, false, true);
     else LAUNCH_TILE(false, false, false);
 #undef LAUNCH_TILE
+#undef LAUNCH_TILE1
     if (e != cudaSuccess) return (int)e;
     h->launches++;
     *handled = true;
-    return (int)cudaGetLastError();
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    return launch_back_pass_generic(h, P, gps);     // processes the handed-over trajectories; exits at once when there are none
 }

@@ -16,7 +16,7 @@
 #define DSUB(a, b) __dsub_rn((a), (b))
 #define DDIV(a, b) __ddiv_rn((a), (b))
 
-__device__ __forceinline__ double clampd(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
+__device__ __forceinline__ double clampd(double v, double lo, double hi) { return clamp_jl(v, lo, hi); }   // NaN-preserving, boxQP.jl:58
 
 // Upper Cholesky factor of A[idx,idx] (reads the upper triangle only; R'R = A), nf x nf, written to
 // R with leading dimension ldr.  Returns false when a pivot is <= 0 or NaN (LAPACK dpotrf's test).

@@ -51,7 +51,10 @@ bool fill_back_params(ddp_handle_s* h, const ddp_back_pass_args* a, BackParams& 
     P.n = h->n; P.m = h->m; P.T = h->T; P.B = h->B;
     P.cx = mk(a->cx); P.cu = mk(a->cu); P.cxx = mk(a->cxx); P.cxu = mk(a->cxu); P.cuu = mk(a->cuu);
     P.fx = mk(a->fx); P.fu = mk(a->fu); P.u = mk(a->u);
-    P.lambda = a->lambda; P.reg_type = a->reg_type; P.lims = a->lims; P.active = a->active;
+    P.lambda = a->lambda; P.reg_type = a->reg_type; P.lims = a->lims; P.lims_st = a->lims_stride_t; P.active = a->active;
+    if (a->lims_stride_t != 0 && a->lims_stride_t != 2 * (int64_t)h->m) { why = "lims_stride_t must be 0 or 2m"; return false; }
+    P.fxx = mk(a->fxx); P.fxu = mk(a->fxu); P.fuu = mk(a->fuu);
+    P.Vxx_tri = a->Vxx_tri; P.Quu_tri = a->Quu_tri; P.Quui_tri = nullptr; P.redo = nullptr; P.redo_count = nullptr;
     P.Kp = TensorD{nullptr, 0, 0}; P.kp = P.Kp; P.Sip = P.Kp; P.eta = nullptr; P.Quui = nullptr;
     P.diverge = a->diverge; P.K = a->K; P.k = a->k; P.Vx = a->Vx; P.Vxx = a->Vxx; P.Vxx1 = a->Vxx1;
     P.Quu = a->Quu; P.dV = a->dV;
@@ -104,6 +107,7 @@ int ddp_destroy(ddp_handle_t h) {
     if (h->cache && h->cache_free) h->cache_free(h->cache);
     if (h->comm) ddp_comm_destroy(h);
     if (h->ws) cudaFree(h->ws);
+    if (h->redo) cudaFree(h->redo);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
     return DDP_OK;
@@ -202,7 +206,8 @@ int ddp_back_pass_gps_f64(ddp_handle_t h, const ddp_back_pass_args* a, const ddp
     if (!fill_back_params(h, a, P, why)) return fail(h, DDP_ERR_INVALID, "ddp_back_pass_gps_f64: " + why);
     if (!g || !g->K_prev.ptr || !g->Sigi_prev.ptr || !g->eta) return fail(h, DDP_ERR_INVALID, "ddp_back_pass_gps_f64: K_prev, Sigi_prev, eta are required");
     if (!a->Quu || !g->Quui) return fail(h, DDP_ERR_INVALID, "ddp_back_pass_gps_f64: Quu and Quui outputs are required");
-    P.Kp = mk(g->K_prev); P.kp = mk(g->k_prev); P.Sip = mk(g->Sigi_prev); P.eta = g->eta; P.Quui = g->Quui;
+    P.Kp = mk(g->K_prev); P.kp = mk(g->k_prev); P.Sip = mk(g->Sigi_prev); P.eta = g->eta; P.Quui = g->Quui; P.Quui_tri = g->Quui_tri;
+    if (P.fxx.p || P.fxu.p || P.fuu.p) return fail(h, DDP_ERR_UNSUPPORTED, "ddp_back_pass_gps_f64: second-order terms are not part of back_pass_gps (backward_pass.jl:259)");
     P.reg_type = 0; P.lambda = nullptr;
     CU(h, cudaSetDevice(h->device));
     bool handled = false;
@@ -256,7 +261,8 @@ int ddp_forward_pass_f64(ddp_handle_t h, const ddp_model* model, const ddp_forwa
     P.n = h->n; P.m = h->m; P.T = h->T; P.B = h->B;
     P.K = a->K; P.k = a->k; P.x0 = mk(a->x0); P.x = mk(a->x); P.u = mk(a->u);
     P.alpha = a->alpha; P.alpha_scalar = a->alpha_scalar; P.u_scale = (a->u_scale == 0.0) ? 1.0 : a->u_scale;
-    P.lims = a->lims; P.active = a->active;
+    P.lims = a->lims; P.lims_st = a->lims_stride_t; P.active = a->active;
+    if (a->lims_stride_t != 0 && a->lims_stride_t != 2 * (int64_t)h->m) return fail(h, DDP_ERR_INVALID, "ddp_forward_pass_f64: lims_stride_t must be 0 or 2m");
     P.xnew = a->xnew; P.unew = a->unew; P.cost = a->cost; P.cost_t = a->cost_t; P.cx = a->cx; P.cu = a->cu;
     CU(h, cudaSetDevice(h->device));
     bool handled = false;
@@ -278,7 +284,7 @@ int ddp_forward_costs_multi_f64(ddp_handle_t h, const ddp_model* model, const dd
     P.n = h->n; P.m = h->m; P.T = h->T; P.B = h->B;
     P.K = a->K; P.k = a->k; P.x0 = mk(a->x0); P.x = mk(a->x); P.u = mk(a->u);
     P.alpha = nullptr; P.alpha_scalar = 1.0; P.u_scale = (a->u_scale == 0.0) ? 1.0 : a->u_scale;
-    P.lims = a->lims; P.active = a->active;
+    P.lims = a->lims; P.lims_st = a->lims_stride_t; P.active = a->active;
     P.xnew = a->xnew; P.unew = a->unew; P.cost = a->cost; P.cost_t = nullptr; P.cx = nullptr; P.cu = nullptr;
     CU(h, cudaSetDevice(h->device));
     bool handled = false;

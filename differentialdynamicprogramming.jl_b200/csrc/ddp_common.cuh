@@ -12,6 +12,10 @@ struct TensorD {                 // device-side mirror of ddp_tensor
 __host__ __device__ inline TensorD mk(const ddp_tensor& t) { return TensorD{t.ptr, (long long)t.stride_b, (long long)t.stride_t}; }
 __device__ __forceinline__ const double* tp(const TensorD& t, long long b, int i) { return t.p + b * t.sb + (long long)i * t.st; }
 
+// Julia's clamp(x, lo, hi) = ifelse(x > hi, hi, ifelse(x < lo, lo, x)): NaN stays NaN (CUDA's fmin/fmax would drop it) and
+// an inverted interval (lo > hi) resolves the way the reference's does (forward_pass.jl:23, boxQP.jl:58).
+__device__ __forceinline__ double clamp_jl(double v, double lo, double hi) { return (v > hi) ? hi : ((v < lo) ? lo : v); }
+
 struct QPOpts {
     int max_iter;
     double min_grad, min_rel_improve, step_dec, min_step, armijo;
@@ -23,8 +27,10 @@ struct BackParams {
     TensorD cx, cu, cxx, cxu, cuu, fx, fu, u;
     const double* lambda;
     int reg_type;
-    const double* lims;          // (m,2) or nullptr (Cholesky branch)
+    const double* lims;          // (m,2[,T]) or nullptr (Cholesky branch)
+    long long lims_st;           // 0 or 2m (time-varying limits)
     const unsigned char* active;
+    TensorD fxx, fxu, fuu;       // optional second-order dynamics terms (generic kernel only)
     // gps
     TensorD Kp, kp, Sip;
     const double* eta;
@@ -32,6 +38,12 @@ struct BackParams {
     // outputs
     int* diverge;
     double *K, *k, *Vx, *Vxx, *Vxx1, *Quu, *dV;
+    double *Vxx_tri, *Quu_tri, *Quui_tri;     // packed upper-triangle histories or nullptr
+    // hand-over from the tile kernel to the generic one: trajectories whose terminal cxx is not exactly symmetric (the tile
+    // kernel's products assume a symmetric Vxx) are flagged in redo[] and counted in *redo_count; the generic launch that
+    // follows processes only those (and returns at once when the count is zero)
+    unsigned char* redo;
+    int* redo_count;
     QPOpts qp;
 };
 
@@ -53,6 +65,7 @@ struct FwdParams {
     const double* alpha;
     double alpha_scalar, u_scale;
     const double* lims;
+    long long lims_st;
     const unsigned char* active;
     double *xnew, *unew, *cost, *cost_t, *cx, *cu;
 };
@@ -81,6 +94,8 @@ struct ddp_handle_s {
     void* comm = nullptr;                // ncclComm_t (comm.cu)
     void* ws = nullptr;                  // workspace arena of the solve drivers, kept between calls (solve.cu)
     size_t ws_cap = 0;
+    unsigned char* redo = nullptr;       // tile -> generic hand-over mask (back_pass_tile.cu), redo_cap bytes + one int counter in front
+    long long redo_cap = 0;
     // scratch for the solve driver / host-iteration pipeline is allocated lazily by those entry points
 };
 

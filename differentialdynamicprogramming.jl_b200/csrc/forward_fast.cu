@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(FW_WPB * 32, 2) fwd_lin32x8_kernel(FwdParams P
                 un0 = __dadd_rn(__dadd_rn(un0, __dmul_rn(kk.x, alpha)), p0);   // forward_pass.jl:18,20: separate roundings, no FMA
                 un1 = __dadd_rn(__dadd_rn(un1, __dmul_rn(kk.y, alpha)), p1);
             }
-            if (has_lims) { un0 = fmin(fmax(un0, lo0), hi0); un1 = fmin(fmax(un1, lo1), hi1); }
+            if (has_lims) { un0 = clamp_jl(un0, lo0, hi0); un1 = clamp_jl(un1, lo1, hi1); }
             if (un0 != un0) un0 = 0.0;
             if (un1 != un1) un1 = 0.0;
             if (g == 0) {
@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(FW_WPB * 32, 2) fwd_lin32x8_multi_kernel(FwdPa
                     }
                     un0 = __dadd_rn(__dadd_rn(un0, __dmul_rn(kk.x, MA.a[a])), p0);
                     un1 = __dadd_rn(__dadd_rn(un1, __dmul_rn(kk.y, MA.a[a])), p1);
-                    if (has_lims) { un0 = fmin(fmax(un0, lo0), hi0); un1 = fmin(fmax(un1, lo1), hi1); }
+                    if (has_lims) { un0 = clamp_jl(un0, lo0, hi0); un1 = clamp_jl(un1, lo1, hi1); }
                     if (un0 != un0) un0 = 0.0;
                     if (un1 != un1) un1 = 0.0;
                     if (g == 0) stg2(&su[a * 8 + 2 * q], un0, un1);
@@ -499,7 +499,7 @@ __global__ void __launch_bounds__(128) fwd_pend_kernel(FwdParams P) {
                 if (t + PEND_PF < N) pend_load<POLICY>(ring[d], P, b, t + PEND_PF);
                 double un = __dmul_rn(c.u, P.u_scale);
                 if (POLICY) un = pend_policy_control(un, c.k, alpha, c.K01, c.K23, c.x01, c.x23, x);
-                if (has_lims) un = fmin(fmax(un, lo), hi);
+                if (has_lims) un = clamp_jl(un, lo, hi);
                 if (un != un) un = 0.0;
                 stg2(xnb + (long long)t * 4, x[0], x[1]);
                 stg2(xnb + (long long)t * 4 + 2, x[2], x[3]);
@@ -624,7 +624,7 @@ __global__ void __launch_bounds__(PS_W * 32) fwd_pend_staged_kernel(FwdParams P)
                     const double2 xo01 = ldg2(rX + 4 * s_), xo23 = ldg2(rX + 4 * s_ + 2);
                     un = pend_policy_control(un, rk[s_], alpha, K01, K23, xo01, xo23, x);
                 }
-                if (has_lims) un = fmin(fmax(un, lo), hi);
+                if (has_lims) un = clamp_jl(un, lo, hi);
                 if (un != un) un = 0.0;
                 stg2(rX + 4 * s_, x[0], x[1]);
                 stg2(rX + 4 * s_ + 2, x[2], x[3]);
@@ -770,7 +770,7 @@ __global__ void __launch_bounds__(PS_W * 32) fwd_pend_multi_kernel(FwdParams P, 
                     if (a < na) {
                         const double alpha = MA.a[a];
                         double un = pend_policy_control(__dmul_rn(uu, P.u_scale), kk, alpha, K01, K23, xo01, xo23, x[a]);
-                        if (has_lims) un = fmin(fmax(un, lo), hi);
+                        if (has_lims) un = clamp_jl(un, lo, hi);
                         if (un != un) un = 0.0;
                         double qd[4];
                         const double cs = pend_state_cost(x[a], goal, Q, qd);
@@ -801,6 +801,7 @@ bool al16(const void* p) { return ((uintptr_t)p % 16) == 0; }
 
 int launch_forward_fast(ddp_handle_s* h, const FwdParams& P, bool* handled) {
     *handled = false;
+    if (P.lims && P.lims_st != 0) return 0;               // time-varying limits: generic kernel
     const bool policy = (P.K != nullptr);
     if (P.model.kind == DDP_MODEL_LINEAR && P.n == 32 && P.m == 8 && P.model.A.st == 0 && P.model.Bm.st == 0) {
         if (!al16(P.u.p) || (P.u.sb % 2) || (P.u.st % 2)) return 0;
@@ -857,6 +858,7 @@ int launch_forward_fast(ddp_handle_s* h, const FwdParams& P, bool* handled) {
 // not the headline one (the caller then loops over ddp_forward_pass launches)
 int launch_forward_multi(ddp_handle_s* h, const FwdParams& P, int na, const double* alpha, double* cost_out, bool* handled) {
     *handled = false;
+    if (P.lims && P.lims_st != 0) return 0;
     if (P.model.kind == DDP_MODEL_PENDCART && P.n == 4 && P.m == 1 && P.K != nullptr && na >= 1) {
         // same view requirements as the staged single-alpha kernel
         if (!((P.T % 2 == 0) && al16(P.u.p) && (P.u.sb % 2 == 0) && P.u.st == 1 && P.x.st == 4 && al16(P.k) && al16(P.K) && al16(P.x.p) &&

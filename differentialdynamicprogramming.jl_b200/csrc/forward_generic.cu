@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(WPB * 32) fwd_generic_kernel(FwdParams P) {
                     double un = ut[a] * P.u_scale;
                     un = un + P.k[(b * N + t) * m + a] * alpha;
                     un = un + acc;
-                    if (P.lims) un = fmin(fmax(un, P.lims[a]), P.lims[m + a]);
+                    if (P.lims) { const double* li = P.lims + (long long)t * P.lims_st; un = clamp_jl(un, li[a], li[m + a]); }   // NaN survives the clamp, as in Julia
                     if (un != un) un = 0.0;                                // u[isnan.(u)] .= 0 in f
                     su[a] = un;
                     unb[(long long)t * m + a] = un;
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(WPB * 32) fwd_generic_kernel(FwdParams P) {
                         for (int j = 0; j < n; j++) acc = fma(Kt[a + m * j], sdx[j], acc);
                         un = un + acc;
                     }
-                    if (P.lims) un = fmin(fmax(un, P.lims[a]), P.lims[m + a]);
+                    if (P.lims) { const double* li = P.lims + (long long)t * P.lims_st; un = clamp_jl(un, li[a], li[m + a]); }   // NaN survives the clamp, as in Julia
                     if (un != un) un = 0.0;
                     su[a] = un;
                     unb[(long long)t * m + a] = un;

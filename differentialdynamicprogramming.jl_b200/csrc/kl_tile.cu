@@ -204,9 +204,10 @@ __global__ void __launch_bounds__(KW * 32, 2) kl_tile32x8_kernel(KlParams P) {
             for (int o = 16; o > 0; o >>= 1) part += shx(part, o);
             {
                 double v = part + 0.5 * (-8.0 + log(pdp / pdn));
-                if (!pos) v = nan("");
-                v = fmax(0.0, v);
-                if (v != v) v = INFINITY;                  // the reference returns Inf when logdet throws
+                // klutils.jl:98 max.(0, kldiv): Julia's max keeps NaN (CUDA's fmax would turn it into 0 = "KL too small");
+                // a non-positive pivot = logdet throws = the reference's catch branch returns Inf (klutils.jl:92-96)
+                v = (v != v) ? v : fmax(0.0, v);
+                if (!pos) v = INFINITY;
                 if (P.kl_t && lane == 0) P.kl_t[b * N + t] = v;
                 klsum += v;
             }

@@ -158,8 +158,10 @@ __global__ void __launch_bounds__(KT) kl_div_kernel(KlParams P) {
             }
             if (tid == 0) {
                 double v = red[0] + 0.5 * (-(double)m + scal[0] - scal[1]);
-                v = fmax(0.0, v);
-                if (v != v) v = INFINITY;                 // the reference returns Inf when logdet throws
+                // klutils.jl:98 max.(0, kldiv): Julia's max keeps NaN (CUDA's fmax would turn it into 0 = "KL too small");
+                // a failed logdet arrives here as +Inf (the reference's catch branch returns Inf, klutils.jl:92-96)
+                v = (v != v) ? v : fmax(0.0, v);
+                if (scal[0] != scal[0] || scal[1] != scal[1]) v = INFINITY;     // logdet_chol failed: not positive definite
                 if (P.kl_t) P.kl_t[b * N + t] = v;
                 klsum += v;
             }
@@ -277,4 +279,78 @@ int launch_batch_stats(ddp_handle_s* h, long long B, const double* cost_old, con
     batch_stats_kernel<<<(unsigned)grid, 256, 0, h->stream>>>(B, cost_old, cost_new, dV, alpha, alpha_scalar, diverge, active, stats8);
     h->launches++;
     return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// ddp_selftest_peak_f64: the FP64 roofline denominators measured on the device the handle lives on
+// (MEASURED_PEAKS.json carries no FP64 figure).  Dependent chains with 8 independent accumulators per
+// thread / warp, every SM filled to 2048 threads; the same kernels as profiles/microbench/ubench.cu.
+namespace {
+
+__global__ void __launch_bounds__(256) peak_dfma_kernel(double* out, int iters, double a, double b) {
+    double acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] = threadIdx.x * 1e-3 + i;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc[i] = fma(acc[i], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += acc[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(256) peak_dmma_kernel(double* out, int iters) {
+    double a = threadIdx.x * 1e-3, b = 1.0 + threadIdx.x * 1e-4;
+    double c[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { c[i][0] = i; c[i][1] = -i; }
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += c[i][0] + c[i][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+}  // namespace
+
+extern "C" int ddp_selftest_peak_f64(ddp_handle_t h, int32_t kind, int32_t reps, double* tflops, double* ms_out) {
+    if (!h) return DDP_ERR_INVALID;
+    if ((kind != 0 && kind != 1) || !tflops) { h->err = "ddp_selftest_peak_f64: kind must be 0 (DFMA) or 1 (DMMA), tflops is required"; return DDP_ERR_INVALID; }
+    if (reps < 1) reps = 3;
+    const int threads = 256, blocks = h->sm_count * 8;
+    const int iters = kind == 0 ? 40000 : 8000;          // ~6 ms per launch either way
+    double* out = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaError_t e = cudaSetDevice(h->device);
+    if (e == cudaSuccess) e = cudaMalloc(&out, sizeof(double) * (size_t)blocks * threads);
+    if (e == cudaSuccess) e = cudaEventCreate(&e0);
+    if (e == cudaSuccess) e = cudaEventCreate(&e1);
+    double best_ms = 1e30;
+    for (int r = 0; r <= reps && e == cudaSuccess; r++) {       // r == 0 is the warm-up
+        cudaEventRecord(e0, h->stream);
+        if (kind == 0) peak_dfma_kernel<<<blocks, threads, 0, h->stream>>>(out, iters, 1.0000001, 1e-9);
+        else peak_dmma_kernel<<<blocks, threads, 0, h->stream>>>(out, iters);
+        h->launches++;
+        cudaEventRecord(e1, h->stream);
+        e = cudaEventSynchronize(e1);
+        float ms = 0.f;
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+        if (r > 0 && ms < best_ms) best_ms = ms;
+    }
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (out) cudaFree(out);
+    if (e != cudaSuccess) { h->err = std::string("ddp_selftest_peak_f64: ") + cudaGetErrorString(e); return DDP_ERR_CUDA; }
+    const double flops = kind == 0 ? 2.0 * 8 * (double)iters * (double)blocks * threads          // 8 FMAs per thread-iteration
+                                   : 2.0 * 256 * 8 * (double)iters * (double)blocks * (threads / 32);   // 8 m8n8k4 tiles (512 flop) per warp-iteration
+    *tflops = flops / (best_ms * 1e-3) * 1e-12;
+    if (ms_out) *ms_out = best_ms;
+    return DDP_OK;
 }

@@ -220,8 +220,11 @@ __global__ void __launch_bounds__(128) df_pendcart_kernel(int T, long long B, co
 // state-machine kernels
 
 struct SolveState {
-    double *lambda, *dlambda, *cost, *costnew, *alpha, *gnorm, *dV, *last_dcost;
-    int *aidx, *status, *iter, *acc, *diverge;
+    double *lambda, *dlambda, *cost, *costnew, *alpha, *gnorm, *dV, *last_dcost, *ratio;
+    int *aidx, *status, *iter, *acc, *diverge, *bpr;
+    ddp_ilqg_trace* trace;     // (trace_cap, B) or nullptr
+    int trace_cap;
+    long long B;
     unsigned char *active, *need_bp, *bp_ok, *need_fwd, *accepted;
     int* counters;    // [0] bp retries, [1] still searching, [2] still active, [3] init pending
 };
@@ -239,6 +242,7 @@ __global__ void bp_retry_kernel(long long B, SolveState s, SolveOpts o) {
     if (b >= B || !s.need_bp[b]) return;
     if (s.diverge[b] > 0) {
         const double lam = s.lambda[b], dl = s.dlambda[b];
+        s.bpr[b] += 1;
         s.dlambda[b] = fmax(dl * o.lam_factor, o.lam_factor);     // tuple assignment: λ uses the OLD dλ (Q1)
         const double ln = fmax(lam * dl, o.lam_min);
         s.lambda[b] = ln;
@@ -271,6 +275,8 @@ __global__ void __launch_bounds__(128) gnorm_kernel(int m, int T, long long B, c
     if (lane == 0) {
         const double gn = acc / (double)T;
         s.gnorm[b] = gn;
+        s.ratio[b] = 0.0;                                      // reduce_ratio = 0. at the top of every iteration (iLQG.jl:223)
+        if (s.trace && s.iter[b] - 1 < s.trace_cap) s.trace[(long long)(s.iter[b] - 1) * s.B + b].grad_norm = gn;   // :257
         if (gn < o.tol_grad && s.lambda[b] < 1e-5) {          // SUCCESS: gradient norm < tol_grad
             s.status[b] = 0;
             s.active[b] = 0;
@@ -296,6 +302,7 @@ __global__ void linesearch_kernel(long long B, SolveState s, SolveOpts o) {
     if (expected > 0) ratio = dcost / expected;
     else ratio = (dcost > 0) ? 1.0 : ((dcost < 0) ? -1.0 : dcost);     // sign(Δcost)
     s.last_dcost[b] = dcost;
+    s.ratio[b] = ratio;
     if (ratio > o.reduce_ratio_min) {
         s.accepted[b] = 1;
         s.need_fwd[b] = 0;
@@ -325,6 +332,7 @@ __global__ void linesearch_multi_kernel(long long B, SolveState s, SolveOpts o, 
         if (expected > 0) ratio = dcost / expected;
         else ratio = (dcost > 0) ? 1.0 : ((dcost < 0) ? -1.0 : dcost);
         s.last_dcost[b] = dcost;
+        s.ratio[b] = ratio;
         s.aidx[b] = ai;
         s.alpha[b] = a;
         if (ratio > o.reduce_ratio_min) { found = true; break; }
@@ -366,6 +374,14 @@ __global__ void accept_kernel(long long B, SolveState s, SolveOpts o) {
             return;
         }
     }
+    if (s.trace && s.iter[b] - 1 < s.trace_cap) {               // "update trace" (iLQG.jl:324-330): not reached by the two breaks above
+        ddp_ilqg_trace& r = s.trace[(long long)(s.iter[b] - 1) * s.B + b];
+        r.lambda = s.lambda[b]; r.dlambda = s.dlambda[b]; r.cost = s.cost[b];
+        r.alpha = was_accepted ? s.alpha[b] : nan("");          // αi = NaN on a rejected iteration (:312)
+        r.improvement = s.last_dcost[b]; r.reduce_ratio = s.ratio[b];
+        r.accepted = was_accepted ? 1 : 0; r.bp_retries = s.bpr[b];
+    }
+    s.bpr[b] = 0;
     s.iter[b] += 1;
     if (s.acc[b] > o.max_iter) {                                // while accepted_iter <= max_iter
         s.status[b] = 3;
@@ -423,9 +439,24 @@ __global__ void init_state_kernel(long long B, SolveState s, double lam, double 
     long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     s.lambda[b] = lam; s.dlambda[b] = dlam; s.cost[b] = 0.0; s.costnew[b] = 0.0; s.alpha[b] = alpha0; s.gnorm[b] = nan("");
-    s.dV[2 * b] = s.dV[2 * b + 1] = 0.0; s.last_dcost[b] = 0.0;
-    s.aidx[b] = 0; s.status[b] = -1; s.iter[b] = 1; s.acc[b] = 1; s.diverge[b] = 0;
+    s.dV[2 * b] = s.dV[2 * b + 1] = 0.0; s.last_dcost[b] = 0.0; s.ratio[b] = 0.0;
+    s.aidx[b] = 0; s.status[b] = -1; s.iter[b] = 1; s.acc[b] = 1; s.diverge[b] = 0; s.bpr[b] = 0;
     s.active[b] = 1; s.need_bp[b] = 0; s.bp_ok[b] = 0; s.need_fwd[b] = 1; s.accepted[b] = 0;
+}
+
+// pre-rolled start (iLQG.jl:193-197): x = x0 (n,N), cost given, no initial rollout
+__global__ void init_prerolled_kernel(long long B, SolveState s, const double* __restrict__ cost_init) {
+    long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    s.cost[b] = cost_init[b];
+    s.need_fwd[b] = 0;
+    s.need_bp[b] = 1;
+}
+
+// the outer loop's safety cap was reached: whoever is still running is reported as such
+__global__ void mark_incomplete_kernel(long long B, SolveState s) {
+    long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B && s.active[b]) s.status[b] = 6;
 }
 
 __global__ void export_state_kernel(long long B, SolveState s, ddp_ilqg_state* out) {
@@ -547,13 +578,18 @@ int ddp_ilqg_solve_f64(ddp_handle_t h, const ddp_model* model, const ddp_ilqg_op
                        double* x, double* u, double* K, double* k, double* Vx, double* Vxx1, ddp_ilqg_state* state,
                        int32_t* n_outer) {
     if (!h) return DDP_ERR_INVALID;
-    if (!model || !opts || !x0 || !u0 || !x || !u || !K || !k || !Vx || !state) { h->err = "ddp_ilqg_solve_f64: missing argument"; return DDP_ERR_INVALID; }
+    if (!model || !opts || (!x0 && !opts->x_init) || !u0 || !x || !u || !K || !k || !Vx || !state) { h->err = "ddp_ilqg_solve_f64: missing argument"; return DDP_ERR_INVALID; }
     if (model->kind != DDP_MODEL_LINEAR && model->kind != DDP_MODEL_PENDCART) {
         h->err = "ddp_ilqg_solve_f64: unknown model kind (arbitrary host callbacks cannot run on the device; no CPU fallback)";
         return DDP_ERR_UNSUPPORTED;
     }
     if (model->kind == DDP_MODEL_PENDCART && (h->n != 4 || h->m != 1)) { h->err = "pendcart model needs n == 4, m == 1"; return DDP_ERR_INVALID; }
     if (opts->n_alpha < 1 || opts->n_alpha > 16) { h->err = "ddp_ilqg_solve_f64: need 1 <= n_alpha <= 16"; return DDP_ERR_INVALID; }
+    if (opts->reg_type != 1 && opts->reg_type != 2) { h->err = "ddp_ilqg_solve_f64: reg_type must be 1 or 2"; return DDP_ERR_INVALID; }
+    if ((opts->x_init == nullptr) != (opts->cost_init == nullptr)) {
+        h->err = "ddp_ilqg_solve_f64: Initial trajectory supplied, initial cost must also be supplied (x_init and cost_init go together)";
+        return DDP_ERR_INVALID;
+    }
     const int n = h->n, m = h->m, T = h->T;
     const long long B = h->B;
     cudaError_t err = cudaSuccess;
@@ -566,8 +602,9 @@ int ddp_ilqg_solve_f64(ddp_handle_t h, const ddp_model* model, const ddp_ilqg_op
     const bool use_multi = ((model->kind == DDP_MODEL_LINEAR && h->n == 32 && h->m == 8 && model->A.stride_t == 0 && model->Bm.stride_t == 0) ||
                             (model->kind == DDP_MODEL_PENDCART && h->T % 2 == 0)) &&
                            !(h->flags & 1u) && !getenv("DDP_NO_MULTI_ALPHA");
-    int hc[4];
+    int hc[4] = {0, 0, 0, 0};
     int outer = 0;
+    bool incomplete = false;
     const unsigned gB = (unsigned)((B + 255) / 256), gW = (unsigned)((B * 32 + 127) / 128);
     cudaStream_t st = h->stream;
     ModelD M;
@@ -584,7 +621,8 @@ int ddp_ilqg_solve_f64(ddp_handle_t h, const ddp_model* model, const ddp_ilqg_op
     CUS(mem.alloc(&s.lambda, B)); CUS(mem.alloc(&s.dlambda, B)); CUS(mem.alloc(&s.cost, B)); CUS(mem.alloc(&s.costnew, B));
     CUS(mem.alloc(&s.alpha, B)); CUS(mem.alloc(&s.gnorm, B)); CUS(mem.alloc(&s.dV, 2 * B)); CUS(mem.alloc(&s.last_dcost, B));
     CUS(mem.alloc(&s.aidx, B)); CUS(mem.alloc(&s.status, B)); CUS(mem.alloc(&s.iter, B)); CUS(mem.alloc(&s.acc, B));
-    CUS(mem.alloc(&s.diverge, B));
+    CUS(mem.alloc(&s.diverge, B)); CUS(mem.alloc(&s.bpr, B)); CUS(mem.alloc(&s.ratio, B));
+    s.trace = (opts->trace && opts->trace_cap > 0) ? opts->trace : nullptr; s.trace_cap = s.trace ? opts->trace_cap : 0; s.B = B;
     CUS(mem.alloc(&s.active, B)); CUS(mem.alloc(&s.need_bp, B)); CUS(mem.alloc(&s.bp_ok, B)); CUS(mem.alloc(&s.need_fwd, B));
     CUS(mem.alloc(&s.accepted, B)); CUS(mem.alloc(&s.counters, 4));
     CUS(mem.alloc(&cx, (size_t)B * T * n)); CUS(mem.alloc(&cu, (size_t)B * T * m));
@@ -609,8 +647,16 @@ int ddp_ilqg_solve_f64(ddp_handle_t h, const ddp_model* model, const ddp_ilqg_op
     FP.xnew = xnew; FP.unew = unew; FP.cost = s.costnew; FP.cost_t = nullptr; FP.cx = nullptr; FP.cu = nullptr;
     FP.alpha_scalar = 1.0;
 
+    if (opts->x_init) {
+        // ---- pre-rolled initial trajectory and its cost (iLQG.jl:193-197)
+        CUS(cudaMemcpyAsync(x, opts->x_init, sizeof(double) * (size_t)B * T * n, cudaMemcpyDeviceToDevice, st));
+        CUS(cudaMemcpyAsync(u, u0, sizeof(double) * (size_t)B * T * m, cudaMemcpyDeviceToDevice, st));
+        init_prerolled_kernel<<<gB, 256, 0, st>>>(B, s, opts->cost_init);
+        h->launches++;
+        FP.x0 = TensorD{opts->x_init, (long long)T * n, 0};                // x0[:,1] of the pre-rolled trajectory (:268)
+    }
     // ---- initial rollout over α with the open-loop controls αi*u0 (iLQG.jl:181-192)
-    for (int ai = 0; ai < o.n_alpha; ai++) {
+    for (int ai = 0; ai < o.n_alpha && !opts->x_init; ai++) {
         FP.K = nullptr; FP.k = nullptr; FP.x = TensorD{nullptr, 0, 0};
         FP.u = TensorD{u0, (long long)T * m, m};
         FP.alpha = nullptr; FP.u_scale = o.alpha[ai];
@@ -636,7 +682,10 @@ int ddp_ilqg_solve_f64(ddp_handle_t h, const ddp_model* model, const ddp_ilqg_op
     BP.qp = QPOpts{100, 1e-8, 1e-8, 0.6, 1e-22, 0.1};
 
     {
-        const int outer_cap = opts->max_iter * 8 + 256;
+        // Every outer iteration either accepts a step (at most max_iter + 1 of those per trajectory) or raises λ, and λ
+        // passes λmax after at most ~13 consecutive increases from λmin (λ grows by 1.6^k at the k-th): 16 (max_iter + 1)
+        // + 256 outer iterations cannot be exceeded by the reference's own rules; the cap only guards the loop.
+        const int outer_cap = (opts->max_iter + 1) * 16 + 256;
         for (outer = 0; outer < outer_cap; outer++) {
             // STEP 1: derivatives along the trajectories whose x,u changed (need_bp marks exactly those here)
             {
@@ -701,11 +750,13 @@ int ddp_ilqg_solve_f64(ddp_handle_t h, const ddp_model* model, const ddp_ilqg_op
             CUS(cudaStreamSynchronize(st));
             if (hc[2] == 0) { outer++; break; }
         }
+        if (hc[2] != 0) { mark_incomplete_kernel<<<gB, 256, 0, st>>>(B, s); h->launches++; incomplete = true; }
     }
     export_state_kernel<<<gB, 256, 0, st>>>(B, s, state);
     h->launches++;
     CUS(cudaStreamSynchronize(st));
     if (n_outer) *n_outer = outer;
+    if (incomplete) { h->err = "ddp_ilqg_solve_f64: outer-loop safety cap reached; trajectories with status 6 did not finish"; return DDP_ERR_INCOMPLETE; }
     return DDP_OK;
 fail:
     h->err = std::string("ddp_ilqg_solve_f64: ") + cudaGetErrorString(err);
@@ -716,60 +767,190 @@ fail:
 }  // extern "C"
 
 namespace {
-constexpr int NS = 4;     // chunk slots in flight
-struct Slot { double *fx, *fu, *cx, *cu, *x, *u, *lam, *K, *k, *Vx, *xnew, *unew, *cost, *dV; int* div; };
+
+// ---------------------------------------------------------------------------------------------
+// One chunk of one iteration: derivative step + backward sweep + forward rollout of `nb` trajectories, back to back on
+// stream `st`.  Shared by the device-resident chunked iteration (ddp_ilqg_iter_f64) and the host-buffer pipeline.
+struct ChunkIO {
+    const double *x, *u, *lambda, *alpha;           // inputs of the chunk
+    const unsigned char* active;
+    double *cx, *cu;                                 // derivative scratch (nb trajectories) -- or uploaded by the host path
+    double *fx, *fu;                                 // pendcart Jacobian scratch (nb) or nullptr
+    double *K, *k, *Vx;                              // policy of the chunk
+    double *xnew, *unew, *cost, *dV;
+    int* diverge;
+};
+
+int run_chunk(ddp_handle_s* h, cudaStream_t st, const ModelD& M, const ChunkIO& c, long long nb, int reg_type, double alpha_scalar,
+              const double* lims, const double* cxu_zero, bool form_derivs) {
+    const int n = h->n, m = h->m, T = h->T;
+    const long long Tn = (long long)T * n, Tm = (long long)T * m;
+    cudaStream_t saved = h->stream;
+    h->stream = st;
+    int rc = 0;
+    if (form_derivs) {                               // STEP 1 (iLQG.jl:225-229)
+        launch_df_cost(h, st, n, m, T, nb, c.x, c.u, M.Q, M.R, M.goal, c.active, c.cx, c.cu, (M.flags & DDP_MODEL_Q_DIAGONAL) != 0);
+        if (M.kind == DDP_MODEL_PENDCART) {
+            df_pendcart_kernel<<<(unsigned)((nb * T + 127) / 128), 128, 0, st>>>(T, nb, c.x, c.u, M.p[0], M.p[1], M.p[2], M.p[3], c.active, c.fx, c.fu);
+            h->launches++;
+        }
+    }
+    BackParams BP{};
+    BP.n = n; BP.m = m; BP.T = T; BP.B = nb;
+    BP.cx = TensorD{c.cx, Tn, n}; BP.cu = TensorD{c.cu, Tm, m};
+    BP.cxx = M.Q; BP.cuu = M.R; BP.cxu = TensorD{cxu_zero, 0, 0};
+    if (M.kind == DDP_MODEL_PENDCART) { BP.fx = TensorD{c.fx, (long long)T * 16, 16}; BP.fu = TensorD{c.fu, (long long)T * 4, 4}; }
+    else { BP.fx = M.A; BP.fu = M.Bm; }
+    BP.u = TensorD{c.u, Tm, m};
+    BP.lambda = c.lambda; BP.reg_type = reg_type; BP.lims = lims; BP.active = c.active;
+    BP.diverge = c.diverge; BP.K = c.K; BP.k = c.k; BP.Vx = c.Vx; BP.dV = c.dV;
+    BP.qp = QPOpts{100, 1e-8, 1e-8, 0.6, 1e-22, 0.1};
+    rc = run_back(h, BP);
+    if (rc == 0) {
+        FwdParams FP{};
+        FP.n = n; FP.m = m; FP.T = T; FP.B = nb; FP.model = M;
+        FP.K = c.K; FP.k = c.k; FP.x0 = TensorD{c.x, Tn, 0}; FP.x = TensorD{c.x, Tn, n}; FP.u = TensorD{c.u, Tm, m};
+        FP.alpha = c.alpha; FP.alpha_scalar = alpha_scalar; FP.u_scale = 1.0;
+        FP.lims = lims; FP.active = c.active; FP.xnew = c.xnew; FP.unew = c.unew; FP.cost = c.cost;
+        rc = run_fwd(h, FP);
+    }
+    h->stream = saved;
+    return rc;
+}
+
+// model descriptor of a chunk: per-trajectory tensors advance by b0 trajectories, shared ones stay
+ModelD model_at(const ModelD& M, long long b0) {
+    ModelD r = M;
+    r.A.p = M.A.p ? M.A.p + b0 * M.A.sb : nullptr;
+    r.Bm.p = M.Bm.p ? M.Bm.p + b0 * M.Bm.sb : nullptr;
+    r.Q.p = M.Q.p + b0 * M.Q.sb;
+    r.R.p = M.R.p + b0 * M.R.sb;
+    return r;
+}
+
+bool fill_model_d(const ddp_model* model, ModelD& M) {
+    M.kind = model->kind; M.A = mk(model->A); M.Bm = mk(model->Bm); M.Q = mk(model->Q); M.R = mk(model->R); M.goal = model->goal;
+    for (int i = 0; i < 8; i++) M.p[i] = model->p[i];
+    M.terminal_cost = model->terminal_cost ? 1 : 0;
+    M.flags = model->flags;
+    return true;
+}
+
+// chunk-sized scratch of the device-resident chunked iteration, kept on the handle between calls
+struct ChunkScratch {
+    std::vector<void*> ptrs;
+    long long cap = 0;
+    bool policy = false, pend = false;
+    double *cx = nullptr, *cu = nullptr, *fx = nullptr, *fu = nullptr, *K = nullptr, *k = nullptr, *Vx = nullptr, *zeros = nullptr;
+    ~ChunkScratch() { for (void* p : ptrs) cudaFree(p); }
+    template <typename T_>
+    cudaError_t get(T_** p, size_t count) {
+        void* q = nullptr;
+        cudaError_t e = cudaMalloc(&q, std::max<size_t>(count * sizeof(T_), 256));
+        if (e == cudaSuccess) { ptrs.push_back(q); *p = (T_*)q; }
+        return e;
+    }
+};
+void free_chunk_scratch(void* p) { delete static_cast<ChunkScratch*>(p); }
+
+cudaError_t make_chunk_scratch(ddp_handle_s* h, long long cap, bool policy, bool pend, ChunkScratch** out) {
+    ChunkScratch* c = new ChunkScratch();
+    cudaError_t err = cudaSuccess;
+    const size_t Tn = (size_t)h->T * h->n, Tm = (size_t)h->T * h->m;
+    CUS(c->get(&c->cx, cap * Tn)); CUS(c->get(&c->cu, cap * Tm));
+    if (policy) { CUS(c->get(&c->K, cap * Tm * h->n)); CUS(c->get(&c->k, cap * Tm)); CUS(c->get(&c->Vx, cap * Tn)); }
+    if (pend) { CUS(c->get(&c->fx, cap * h->T * 16)); CUS(c->get(&c->fu, cap * h->T * 4)); }
+    CUS(c->get(&c->zeros, (size_t)h->n * h->m));
+    CUS(cudaMemset(c->zeros, 0, sizeof(double) * h->n * h->m));
+    c->cap = cap; c->policy = policy; c->pend = pend;
+    *out = c;
+    return cudaSuccess;
+fail:
+    delete c;
+    return err;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-buffer pipeline state: full-batch device mirrors of every host array (a chunk is a slice of them, so nothing is
+// recycled and the policy of the whole batch can stay), three streams, a ring of events
+constexpr int NEV = 64;
 struct IterCache {
-    DevBuf mem;
+    std::vector<void*> ptrs;
     cudaStream_t s_in = nullptr, s_cp = nullptr, s_out = nullptr;
-    cudaEvent_t ev_in[NS] = {}, ev_cp[NS] = {}, ev_out[NS] = {}, ev_start = nullptr, ev_end = nullptr;
-    Slot sl[NS] = {};
+    cudaEvent_t ev_in[NEV] = {}, ev_cp[NEV] = {}, ev_start = nullptr, ev_end = nullptr;
+    double *fx = nullptr, *fu = nullptr, *x = nullptr, *u = nullptr, *lam = nullptr, *xnew = nullptr, *unew = nullptr, *cost = nullptr, *dV = nullptr, *cprev = nullptr;
+    double *cx = nullptr, *cu = nullptr;          // full batch when the host supplies them, else one chunk
+    double *K = nullptr, *k = nullptr, *Vx = nullptr;   // full batch (keep_policy) or one chunk
+    int* div = nullptr;
     double *dQ = nullptr, *dR = nullptr, *dcxu = nullptr;
     long long chunk = 0;
+    bool keep_policy = false, host_derivs = false, inputs_valid = false;
+    template <typename T_>
+    cudaError_t get(T_** p, size_t count) {
+        void* q = nullptr;
+        cudaError_t e = cudaMalloc(&q, std::max<size_t>(count * sizeof(T_), 256));
+        if (e == cudaSuccess) { ptrs.push_back(q); *p = (T_*)q; }
+        return e;
+    }
     ~IterCache() {
-        for (int i = 0; i < NS; i++) {
+        for (int i = 0; i < NEV; i++) {
             if (ev_in[i]) cudaEventDestroy(ev_in[i]);
             if (ev_cp[i]) cudaEventDestroy(ev_cp[i]);
-            if (ev_out[i]) cudaEventDestroy(ev_out[i]);
         }
         if (ev_start) cudaEventDestroy(ev_start);
         if (ev_end) cudaEventDestroy(ev_end);
         if (s_in) cudaStreamDestroy(s_in);
         if (s_cp) cudaStreamDestroy(s_cp);
         if (s_out) cudaStreamDestroy(s_out);
+        for (void* p : ptrs) cudaFree(p);
     }
 };
 void free_iter_cache(void* p) { delete static_cast<IterCache*>(p); }
 
-cudaError_t make_iter_cache(ddp_handle_s* h, long long chunk, IterCache** out) {
+cudaError_t make_iter_cache(ddp_handle_s* h, long long chunk, bool keep_policy, bool host_derivs, IterCache** out) {
     IterCache* c = new IterCache();
     cudaError_t err = cudaSuccess;
     const int n = h->n, m = h->m, T = h->T;
+    const size_t B = (size_t)h->B;
     const size_t nn = (size_t)n * n, nm = (size_t)n * m, Tn = (size_t)T * n, Tm = (size_t)T * m;
+    const size_t pol = keep_policy ? B : (size_t)chunk, der = host_derivs ? B : (size_t)chunk;
     CUS(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
     CUS(cudaStreamCreateWithFlags(&c->s_cp, cudaStreamNonBlocking));
     CUS(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
-    for (int i = 0; i < NS; i++) {
+    for (int i = 0; i < NEV; i++) {
         CUS(cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
         CUS(cudaEventCreateWithFlags(&c->ev_cp[i], cudaEventDisableTiming));
-        CUS(cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming));
     }
     CUS(cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming));
     CUS(cudaEventCreateWithFlags(&c->ev_end, cudaEventDisableTiming));
-    for (int i = 0; i < NS; i++) {
-        Slot& s = c->sl[i];
-        CUS(c->mem.alloc(&s.fx, chunk * nn)); CUS(c->mem.alloc(&s.fu, chunk * nm)); CUS(c->mem.alloc(&s.cx, chunk * Tn)); CUS(c->mem.alloc(&s.cu, chunk * Tm));
-        CUS(c->mem.alloc(&s.x, chunk * Tn)); CUS(c->mem.alloc(&s.u, chunk * Tm)); CUS(c->mem.alloc(&s.lam, chunk));
-        CUS(c->mem.alloc(&s.K, chunk * Tm * n)); CUS(c->mem.alloc(&s.k, chunk * Tm)); CUS(c->mem.alloc(&s.Vx, chunk * Tn));
-        CUS(c->mem.alloc(&s.xnew, chunk * Tn)); CUS(c->mem.alloc(&s.unew, chunk * Tm)); CUS(c->mem.alloc(&s.cost, chunk)); CUS(c->mem.alloc(&s.dV, 2 * chunk));
-        CUS(c->mem.alloc(&s.div, chunk));
-    }
-    CUS(c->mem.alloc(&c->dQ, nn)); CUS(c->mem.alloc(&c->dR, (size_t)m * m)); CUS(c->mem.alloc(&c->dcxu, nm));
-    c->chunk = chunk;
+    CUS(c->get(&c->fx, B * nn)); CUS(c->get(&c->fu, B * nm)); CUS(c->get(&c->x, B * Tn)); CUS(c->get(&c->u, B * Tm)); CUS(c->get(&c->lam, B));
+    CUS(c->get(&c->xnew, B * Tn)); CUS(c->get(&c->unew, B * Tm)); CUS(c->get(&c->cost, B)); CUS(c->get(&c->dV, 2 * B)); CUS(c->get(&c->div, B));
+    CUS(c->get(&c->cx, der * Tn)); CUS(c->get(&c->cu, der * Tm));
+    CUS(c->get(&c->K, pol * Tm * n)); CUS(c->get(&c->k, pol * Tm)); CUS(c->get(&c->Vx, pol * Tn));
+    CUS(c->get(&c->dQ, nn)); CUS(c->get(&c->dR, (size_t)m * m)); CUS(c->get(&c->dcxu, nm)); CUS(c->get(&c->cprev, B));
+    c->chunk = chunk; c->keep_policy = keep_policy; c->host_derivs = host_derivs;
     *out = c;
     return cudaSuccess;
 fail:
     delete c;
     return err;
+}
+
+// x,u <- xnew,unew where the step was accepted: ratio = Δcost / expected > 0, expected = -α(dV1 + α dV2) (iLQG.jl:269-280, 302)
+__global__ void __launch_bounds__(256) commit_accepted_kernel(int n, int m, int T, long long B, double alpha, const double* __restrict__ cost_old,
+                                                              const double* __restrict__ cost_new, const double* __restrict__ dV,
+                                                              const int* __restrict__ diverge, const double* __restrict__ xnew,
+                                                              const double* __restrict__ unew, double* __restrict__ x, double* __restrict__ u) {
+    for (long long b = blockIdx.x; b < B; b += gridDim.x) {
+        if (diverge[b] > 0) continue;
+        const double dcost = cost_old[b] - cost_new[b];
+        const double expected = -alpha * (dV[2 * b] + alpha * dV[2 * b + 1]);
+        const double ratio = (expected > 0) ? dcost / expected : ((dcost > 0) ? 1.0 : ((dcost < 0) ? -1.0 : dcost));
+        if (!(ratio > 0.0)) continue;
+        const long long ox = b * T * n, ou = b * T * m;
+        for (int e = threadIdx.x; e < T * n; e += blockDim.x) x[ox + e] = xnew[ox + e];
+        for (int e = threadIdx.x; e < T * m; e += blockDim.x) u[ou + e] = unew[ou + e];
+    }
 }
 }  // namespace
 
@@ -777,11 +958,14 @@ extern "C" {
 
 int ddp_ilqg_iter_host_f64(ddp_handle_t h, ddp_iter_host_args* a) {
     if (!h) return DDP_ERR_INVALID;
-    if (!a || !a->fx || !a->fu || ((a->cx == nullptr) != (a->cu == nullptr)) || !a->x || !a->u || !a->lambda || !a->Q || !a->R || !a->cxu || !a->xnew ||
-        !a->unew || !a->cost || !a->dV || !a->diverge) {
+    const bool resident = a && a->inputs_resident != 0;
+    if (!a || (!resident && (!a->fx || !a->fu || !a->x || !a->u || !a->lambda)) || ((a->cx == nullptr) != (a->cu == nullptr)) || !a->Q || !a->R ||
+        !a->cxu || !a->xnew || !a->unew || !a->cost || !a->dV || !a->diverge) {
         h->err = "ddp_ilqg_iter_host_f64: missing argument";
         return DDP_ERR_INVALID;
     }
+    if (a->reg_type != 1 && a->reg_type != 2) { h->err = "ddp_ilqg_iter_host_f64: reg_type must be 1 or 2"; return DDP_ERR_INVALID; }
+    if (a->commit_accepted && !a->cost_prev) { h->err = "ddp_ilqg_iter_host_f64: commit_accepted needs cost_prev (the cost of the current x,u)"; return DDP_ERR_INVALID; }
     const int n = h->n, m = h->m, T = h->T;
     const long long B = h->B;
     // Chunk schedule.  Default: chunks are whole "rounds" of the resident warp set of the sweep kernels
@@ -804,110 +988,178 @@ int ddp_ilqg_iter_host_f64(ddp_handle_t h, ddp_iter_host_args* a) {
         take(1);
     }
     cudaError_t err = cudaSuccess;
-    cudaStream_t saved = h->stream;
     const size_t nn = (size_t)n * n, nm = (size_t)n * m, Tn = (size_t)T * n, Tm = (size_t)T * m;
     long long h2d = 0, d2h = 0;
     ModelD M{};
     IterCache* C = nullptr;
     const bool host_derivs = (a->cx != nullptr);   // NULL: cx = Qx, cu = Ru are formed on the device (the reference's df step)
+    const bool keep = a->keep_policy != 0;
 
     CUS(cudaSetDevice(h->device));
-    if (h->cache && static_cast<IterCache*>(h->cache)->chunk != chunk) { h->cache_free(h->cache); h->cache = nullptr; }
+    if (h->cache && h->cache_free != free_iter_cache) { h->cache_free(h->cache); h->cache = nullptr; }     // another entry point's scratch
+    if (h->cache) {
+        IterCache* c0 = static_cast<IterCache*>(h->cache);
+        if (c0->chunk != chunk || c0->keep_policy != keep || c0->host_derivs != host_derivs) {
+            if (resident) { h->err = "ddp_ilqg_iter_host_f64: inputs_resident needs the same chunk / keep_policy / cx,cu configuration as the call that uploaded them"; return DDP_ERR_INVALID; }
+            h->cache_free(h->cache); h->cache = nullptr;
+        }
+    }
     if (!h->cache) {
-        CUS(make_iter_cache(h, chunk, &C));
+        if (resident) { h->err = "ddp_ilqg_iter_host_f64: inputs_resident without a previous call on this handle"; return DDP_ERR_INVALID; }
+        err = make_iter_cache(h, chunk, keep, host_derivs, &C);
+        if (err == cudaErrorMemoryAllocation) { cudaGetLastError(); h->err = "ddp_ilqg_iter_host_f64: out of device memory (try keep_policy = 0)"; return DDP_ERR_NOMEM; }
+        CUS(err);
         h->cache = C;
         h->cache_free = free_iter_cache;
     }
     C = static_cast<IterCache*>(h->cache);
+    if (resident && !C->inputs_valid) { h->err = "ddp_ilqg_iter_host_f64: inputs_resident without a completed previous call"; return DDP_ERR_INVALID; }
     {
+    cudaStream_t saved = h->stream;
     cudaStream_t s_in = C->s_in, s_cp = C->s_cp, s_out = C->s_out;
-    cudaEvent_t *ev_in = C->ev_in, *ev_cp = C->ev_cp, *ev_out = C->ev_out;
-    Slot* sl = C->sl;
-    double *dQ = C->dQ, *dR = C->dR, *dcxu = C->dcxu;
     // everything below is ordered after work already queued on the handle's stream
     CUS(cudaEventRecord(C->ev_start, saved));
     CUS(cudaStreamWaitEvent(s_in, C->ev_start, 0));
     CUS(cudaStreamWaitEvent(s_cp, C->ev_start, 0));
     CUS(cudaStreamWaitEvent(s_out, C->ev_start, 0));
-    CUS(cudaMemcpyAsync(dQ, a->Q, nn * 8, cudaMemcpyHostToDevice, s_in));
-    CUS(cudaMemcpyAsync(dR, a->R, (size_t)m * m * 8, cudaMemcpyHostToDevice, s_in));
-    CUS(cudaMemcpyAsync(dcxu, a->cxu, nm * 8, cudaMemcpyHostToDevice, s_in));
+    CUS(cudaMemcpyAsync(C->dQ, a->Q, nn * 8, cudaMemcpyHostToDevice, s_in));
+    CUS(cudaMemcpyAsync(C->dR, a->R, (size_t)m * m * 8, cudaMemcpyHostToDevice, s_in));
+    CUS(cudaMemcpyAsync(C->dcxu, a->cxu, nm * 8, cudaMemcpyHostToDevice, s_in));
     h2d += (long long)(nn + (size_t)m * m + nm) * 8;
     M.kind = DDP_MODEL_LINEAR; M.goal = nullptr; M.terminal_cost = 0; M.flags = a->q_diagonal ? DDP_MODEL_Q_DIAGONAL : 0;
-    M.Q = TensorD{dQ, 0, 0}; M.R = TensorD{dR, 0, 0};
-
+    M.Q = TensorD{C->dQ, 0, 0}; M.R = TensorD{C->dR, 0, 0};
     {
         long long b0 = 0;
         for (int c = 0; c < (int)sizes.size(); b0 += sizes[c], c++) {
             const long long nb = sizes[c];
-            const int si = c % NS;
-            Slot& s = sl[si];
-            // inputs may be overwritten once the kernels of the chunk that used this slot are done
-            if (c >= NS) CUS(cudaStreamWaitEvent(s_in, ev_cp[si], 0));
-            CUS(cudaMemcpyAsync(s.fx, a->fx + b0 * nn, nb * nn * 8, cudaMemcpyHostToDevice, s_in));
-            CUS(cudaMemcpyAsync(s.fu, a->fu + b0 * nm, nb * nm * 8, cudaMemcpyHostToDevice, s_in));
+            const int ei = c % NEV;
+            const long long pb = keep ? b0 : 0, db = host_derivs ? b0 : 0;     // slice of the policy / derivative arrays
+            if (!resident) {
+                CUS(cudaMemcpyAsync(C->fx + b0 * nn, a->fx + b0 * nn, nb * nn * 8, cudaMemcpyHostToDevice, s_in));
+                CUS(cudaMemcpyAsync(C->fu + b0 * nm, a->fu + b0 * nm, nb * nm * 8, cudaMemcpyHostToDevice, s_in));
+                CUS(cudaMemcpyAsync(C->x + b0 * Tn, a->x + b0 * Tn, nb * Tn * 8, cudaMemcpyHostToDevice, s_in));
+                CUS(cudaMemcpyAsync(C->u + b0 * Tm, a->u + b0 * Tm, nb * Tm * 8, cudaMemcpyHostToDevice, s_in));
+                CUS(cudaMemcpyAsync(C->lam + b0, a->lambda + b0, nb * 8, cudaMemcpyHostToDevice, s_in));
+                h2d += (long long)nb * (long long)(nn + nm + Tn + Tm + 1) * 8;
+            }
             if (host_derivs) {
-                CUS(cudaMemcpyAsync(s.cx, a->cx + b0 * Tn, nb * Tn * 8, cudaMemcpyHostToDevice, s_in));
-                CUS(cudaMemcpyAsync(s.cu, a->cu + b0 * Tm, nb * Tm * 8, cudaMemcpyHostToDevice, s_in));
+                CUS(cudaMemcpyAsync(C->cx + b0 * Tn, a->cx + b0 * Tn, nb * Tn * 8, cudaMemcpyHostToDevice, s_in));
+                CUS(cudaMemcpyAsync(C->cu + b0 * Tm, a->cu + b0 * Tm, nb * Tm * 8, cudaMemcpyHostToDevice, s_in));
                 h2d += (long long)nb * (long long)(Tn + Tm) * 8;
             }
-            CUS(cudaMemcpyAsync(s.x, a->x + b0 * Tn, nb * Tn * 8, cudaMemcpyHostToDevice, s_in));
-            CUS(cudaMemcpyAsync(s.u, a->u + b0 * Tm, nb * Tm * 8, cudaMemcpyHostToDevice, s_in));
-            CUS(cudaMemcpyAsync(s.lam, a->lambda + b0, nb * 8, cudaMemcpyHostToDevice, s_in));
-            h2d += (long long)nb * (long long)(nn + nm + Tn + Tm + 1) * 8;
-            CUS(cudaEventRecord(ev_in[si], s_in));
-            // kernels: outputs of this slot must have been copied out by the previous user
-            CUS(cudaStreamWaitEvent(s_cp, ev_in[si], 0));
-            if (c >= NS) CUS(cudaStreamWaitEvent(s_cp, ev_out[si], 0));
-            if (!host_derivs) {        // STEP 1 on the device: cx = Q x, cu = R u  (iLQG.jl:225-229, demo_linear.jl:38-39)
-                launch_df_cost(h, s_cp, n, m, T, nb, s.x, s.u, M.Q, M.R, nullptr, nullptr, s.cx, s.cu, a->q_diagonal != 0);
-            }
-            BackParams BP{};
-            BP.n = n; BP.m = m; BP.T = T; BP.B = nb;
-            BP.cx = TensorD{s.cx, (long long)Tn, n}; BP.cu = TensorD{s.cu, (long long)Tm, m};
-            BP.cxx = M.Q; BP.cuu = M.R; BP.cxu = TensorD{dcxu, 0, 0};
-            BP.fx = TensorD{s.fx, (long long)nn, 0}; BP.fu = TensorD{s.fu, (long long)nm, 0};
-            BP.u = TensorD{s.u, (long long)Tm, m};
-            BP.lambda = s.lam; BP.reg_type = a->reg_type; BP.lims = nullptr; BP.active = nullptr;
-            BP.Kp = TensorD{nullptr, 0, 0}; BP.kp = BP.Kp; BP.Sip = BP.Kp; BP.eta = nullptr; BP.Quui = nullptr;
-            BP.diverge = s.div; BP.K = s.K; BP.k = s.k; BP.Vx = s.Vx; BP.Vxx = nullptr; BP.Vxx1 = nullptr; BP.Quu = nullptr; BP.dV = s.dV;
-            BP.qp = QPOpts{100, 1e-8, 1e-8, 0.6, 1e-22, 0.1};
-            FwdParams FP{};
-            FP.n = n; FP.m = m; FP.T = T; FP.B = nb; FP.model = M;
-            FP.model.A = TensorD{s.fx, (long long)nn, 0}; FP.model.Bm = TensorD{s.fu, (long long)nm, 0};
-            FP.K = s.K; FP.k = s.k; FP.x0 = TensorD{s.x, (long long)Tn, 0}; FP.x = TensorD{s.x, (long long)Tn, n};
-            FP.u = TensorD{s.u, (long long)Tm, m}; FP.alpha = nullptr; FP.alpha_scalar = a->alpha; FP.u_scale = 1.0;
-            FP.lims = nullptr; FP.active = nullptr; FP.xnew = s.xnew; FP.unew = s.unew; FP.cost = s.cost;
-            h->stream = s_cp;
-            int rc = run_back(h, BP);
-            if (rc == 0) rc = run_fwd(h, FP);
-            h->stream = saved;
+            CUS(cudaEventRecord(C->ev_in[ei], s_in));
+            CUS(cudaStreamWaitEvent(s_cp, C->ev_in[ei], 0));
+            ChunkIO io{};
+            io.x = C->x + b0 * Tn; io.u = C->u + b0 * Tm; io.lambda = C->lam + b0; io.alpha = nullptr; io.active = nullptr;
+            io.cx = C->cx + db * Tn; io.cu = C->cu + db * Tm; io.fx = nullptr; io.fu = nullptr;
+            io.K = C->K + pb * Tm * n; io.k = C->k + pb * Tm; io.Vx = C->Vx + pb * Tn;
+            io.xnew = C->xnew + b0 * Tn; io.unew = C->unew + b0 * Tm; io.cost = C->cost + b0; io.dV = C->dV + 2 * b0; io.diverge = C->div + b0;
+            ModelD Mc = M;
+            Mc.A = TensorD{C->fx + b0 * nn, (long long)nn, 0}; Mc.Bm = TensorD{C->fu + b0 * nm, (long long)nm, 0};
+            const int rc = run_chunk(h, s_cp, Mc, io, nb, a->reg_type, a->alpha, nullptr, C->dcxu, !host_derivs);
             CUS((cudaError_t)rc);
-            CUS(cudaEventRecord(ev_cp[si], s_cp));
+            CUS(cudaEventRecord(C->ev_cp[ei], s_cp));
             // results back to the host
-            CUS(cudaStreamWaitEvent(s_out, ev_cp[si], 0));
-            CUS(cudaMemcpyAsync(a->xnew + b0 * Tn, s.xnew, nb * Tn * 8, cudaMemcpyDeviceToHost, s_out));
-            CUS(cudaMemcpyAsync(a->unew + b0 * Tm, s.unew, nb * Tm * 8, cudaMemcpyDeviceToHost, s_out));
-            CUS(cudaMemcpyAsync(a->cost + b0, s.cost, nb * 8, cudaMemcpyDeviceToHost, s_out));
-            CUS(cudaMemcpyAsync(a->dV + 2 * b0, s.dV, nb * 16, cudaMemcpyDeviceToHost, s_out));
-            CUS(cudaMemcpyAsync(a->diverge + b0, s.div, nb * 4, cudaMemcpyDeviceToHost, s_out));
+            CUS(cudaStreamWaitEvent(s_out, C->ev_cp[ei], 0));
+            CUS(cudaMemcpyAsync(a->xnew + b0 * Tn, io.xnew, nb * Tn * 8, cudaMemcpyDeviceToHost, s_out));
+            CUS(cudaMemcpyAsync(a->unew + b0 * Tm, io.unew, nb * Tm * 8, cudaMemcpyDeviceToHost, s_out));
+            CUS(cudaMemcpyAsync(a->cost + b0, io.cost, nb * 8, cudaMemcpyDeviceToHost, s_out));
+            CUS(cudaMemcpyAsync(a->dV + 2 * b0, io.dV, nb * 16, cudaMemcpyDeviceToHost, s_out));
+            CUS(cudaMemcpyAsync(a->diverge + b0, io.diverge, nb * 4, cudaMemcpyDeviceToHost, s_out));
             d2h += (long long)nb * (long long)((Tn + Tm + 3) * 8 + 4);
-            CUS(cudaEventRecord(ev_out[si], s_out));
         }
+    }
+    if (a->commit_accepted) {          // x,u <- xnew,unew on the device where the step is accepted (iLQG.jl:275-303)
+        CUS(cudaMemcpyAsync(C->cprev, a->cost_prev, (size_t)B * 8, cudaMemcpyHostToDevice, s_cp));
+        h2d += B * 8;
+        commit_accepted_kernel<<<(unsigned)std::min<long long>(B, (long long)h->sm_count * 8), 256, 0, s_cp>>>(n, m, T, B, a->alpha, C->cprev, C->cost, C->dV,
+                                                                                                              C->div, C->xnew, C->unew, C->x, C->u);
+        h->launches++;
     }
     CUS(cudaEventRecord(C->ev_end, s_out));
     CUS(cudaStreamWaitEvent(saved, C->ev_end, 0));       // later work on the handle's stream sees the results
     CUS(cudaStreamSynchronize(s_out));
     CUS(cudaStreamSynchronize(s_cp));
     CUS(cudaStreamSynchronize(s_in));
+    C->inputs_valid = true;
     }
     a->h2d_bytes = h2d;
     a->d2h_bytes = d2h;
     return DDP_OK;
 fail:
-    h->stream = saved;
-    cudaDeviceSynchronize();
     h->err = std::string("ddp_ilqg_iter_host_f64: ") + cudaGetErrorString(err);
+    cudaDeviceSynchronize();
+    return DDP_ERR_CUDA;
+}
+
+int ddp_iter_host_policy(ddp_handle_t h, double** K, double** k, double** Vx, double** xnew, double** unew) {
+    if (!h) return DDP_ERR_INVALID;
+    IterCache* C = (h->cache && h->cache_free == free_iter_cache) ? static_cast<IterCache*>(h->cache) : nullptr;
+    if (!C || !C->inputs_valid) { h->err = "ddp_iter_host_policy: no completed ddp_ilqg_iter_host_f64 call on this handle"; return DDP_ERR_INVALID; }
+    if (K) *K = C->keep_policy ? C->K : nullptr;
+    if (k) *k = C->keep_policy ? C->k : nullptr;
+    if (Vx) *Vx = C->keep_policy ? C->Vx : nullptr;
+    if (xnew) *xnew = C->xnew;
+    if (unew) *unew = C->unew;
+    return DDP_OK;
+}
+
+int ddp_ilqg_iter_f64(ddp_handle_t h, const ddp_model* model, ddp_iter_args* a) {
+    if (!h) return DDP_ERR_INVALID;
+    if (!model || !a || !a->x || !a->u || !a->lambda || !a->xnew || !a->unew || !a->cost || !a->dV || !a->diverge) {
+        h->err = "ddp_ilqg_iter_f64: missing argument";
+        return DDP_ERR_INVALID;
+    }
+    if (a->reg_type != 1 && a->reg_type != 2) { h->err = "ddp_ilqg_iter_f64: reg_type must be 1 or 2"; return DDP_ERR_INVALID; }
+    const bool keep = (a->K != nullptr);
+    if ((a->k != nullptr) != keep || (a->Vx != nullptr) != keep) { h->err = "ddp_ilqg_iter_f64: K, k, Vx must be all given or all NULL"; return DDP_ERR_INVALID; }
+    if (model->kind != DDP_MODEL_LINEAR && model->kind != DDP_MODEL_PENDCART) { h->err = "ddp_ilqg_iter_f64: unknown model kind (no CPU fallback for host callbacks)"; return DDP_ERR_UNSUPPORTED; }
+    if (model->kind == DDP_MODEL_PENDCART && (h->n != 4 || h->m != 1)) { h->err = "pendcart model needs n == 4, m == 1"; return DDP_ERR_INVALID; }
+    if (model->kind == DDP_MODEL_LINEAR && (!model->A.ptr || !model->Bm.ptr)) { h->err = "linear model needs A and B"; return DDP_ERR_INVALID; }
+    if (!model->Q.ptr || !model->R.ptr) { h->err = "model needs Q and R"; return DDP_ERR_INVALID; }
+    const int n = h->n, m = h->m, T = h->T;
+    const long long B = h->B;
+    const size_t Tn = (size_t)T * n, Tm = (size_t)T * m;
+    const bool pend = model->kind == DDP_MODEL_PENDCART;
+    // default chunk: 55 rounds of the resident warp set (sm_count x 8 trajectories) ~ 65 120 trajectories on a B200
+    long long chunk = a->chunk > 0 ? a->chunk : (long long)h->sm_count * 8 * 55;
+    if (chunk > B) chunk = B;
+    cudaError_t err = cudaSuccess;
+    ModelD M{};
+    fill_model_d(model, M);
+    ChunkScratch* S = nullptr;
+    CUS(cudaSetDevice(h->device));
+    if (h->cache && h->cache_free != free_chunk_scratch) { h->cache_free(h->cache); h->cache = nullptr; }
+    if (h->cache) {
+        ChunkScratch* s0 = static_cast<ChunkScratch*>(h->cache);
+        if (s0->cap < chunk || s0->policy != !keep || s0->pend != pend) { h->cache_free(h->cache); h->cache = nullptr; }
+    }
+    if (!h->cache) {
+        err = make_chunk_scratch(h, chunk, !keep, pend, &S);
+        if (err == cudaErrorMemoryAllocation) { cudaGetLastError(); h->err = "ddp_ilqg_iter_f64: out of device memory for the chunk scratch (use a smaller chunk)"; return DDP_ERR_NOMEM; }
+        CUS(err);
+        h->cache = S;
+        h->cache_free = free_chunk_scratch;
+    }
+    S = static_cast<ChunkScratch*>(h->cache);
+    {
+        long long nchunks = 0;
+        for (long long b0 = 0; b0 < B; b0 += chunk, nchunks++) {
+            const long long nb = std::min<long long>(chunk, B - b0);
+            ChunkIO io{};
+            io.x = a->x + b0 * Tn; io.u = a->u + b0 * Tm; io.lambda = a->lambda + b0; io.alpha = a->alpha ? a->alpha + b0 : nullptr;
+            io.active = a->active ? a->active + b0 : nullptr;
+            io.cx = S->cx; io.cu = S->cu; io.fx = S->fx; io.fu = S->fu;
+            io.K = keep ? a->K + b0 * Tm * n : S->K; io.k = keep ? a->k + b0 * Tm : S->k; io.Vx = keep ? a->Vx + b0 * Tn : S->Vx;
+            io.xnew = a->xnew + b0 * Tn; io.unew = a->unew + b0 * Tm; io.cost = a->cost + b0; io.dV = a->dV + 2 * b0; io.diverge = a->diverge + b0;
+            const int rc = run_chunk(h, h->stream, model_at(M, b0), io, nb, a->reg_type, a->alpha_scalar, a->lims, S->zeros, true);
+            CUS((cudaError_t)rc);
+        }
+        a->n_chunks = nchunks;
+    }
+    return DDP_OK;
+fail:
+    h->err = std::string("ddp_ilqg_iter_f64: ") + cudaGetErrorString(err);
     return DDP_ERR_CUDA;
 }
 

@@ -50,7 +50,7 @@ extern "C" {
 #define DDP_API
 #endif
 
-#define DDP_VERSION 100          /* 0.1.0 */
+#define DDP_VERSION 200          /* 0.2.0 */
 #define DDP_MAX_N 64
 #define DDP_MAX_M 16
 
@@ -59,7 +59,8 @@ enum {
     DDP_ERR_INVALID = -1,        /* bad argument / shape */
     DDP_ERR_CUDA = -2,           /* CUDA runtime error */
     DDP_ERR_UNSUPPORTED = -3,    /* size or option outside the built kernels */
-    DDP_ERR_NOMEM = -4
+    DDP_ERR_NOMEM = -4,
+    DDP_ERR_INCOMPLETE = -5      /* a driver loop hit its safety cap; per-trajectory status says which ones */
 };
 
 typedef struct ddp_handle_s* ddp_handle_t;
@@ -118,8 +119,16 @@ typedef struct ddp_back_pass_args {
     int32_t reg_type;            /* 1: Quu + λI, 2: Vxx + λI  (iLQG.jl regType)                   */
     const double* lims;          /* (m,2) column-major [lower(m); upper(m)], NULL or lower[0] >  */
                                  /* upper[0]  => Cholesky branch (backward_pass.jl:31)           */
+    int64_t lims_stride_t;       /* 0: one (m,2) block for all steps (the reference); 2m: lims is (m,2,T), time-varying  */
+                                 /* limits (the branch test of :31 then reads step 1's block)               */
     ddp_tensor u;                /* (m,T,B), read only when lims is active                       */
     const uint8_t* active;       /* [B] or NULL; trajectories with active[b]==0 are skipped      */
+    /* optional second-order dynamics terms of the 15-argument back_pass (backward_pass.jl:81-160, quirk Q12), any of them
+     * absent (ptr == NULL) = `isempty`: fxx (n,n,n[,T][,B]), fxu (n,n,m[,T][,B]), fuu (n,m,m[,T][,B]), column-major with
+     * the OUTPUT index k of f first:  Qxx[p,q] += sum_k Vx_k fxx[k,q,p],  Qux[a,j] += sum_k Vx_k fxu[k,j,a],
+     * Quu[a,c] += sum_k Vx_k fuu[k,c,a]  (the contraction `vectens` of backward_pass.jl:1 intends; the regularised copies
+     * Qux_reg / QuuF receive the same terms, :120-123). */
+    ddp_tensor fxx, fxu, fuu;
     /* outputs (device) */
     int32_t* diverge;            /* [B] 1-based failed timestep, 0 = ok                          */
     double* K;                   /* (m,n,T,B)                                                    */
@@ -129,6 +138,11 @@ typedef struct ddp_back_pass_args {
     double* Vxx1;                /* (n,n,B) or NULL: Vxx at the first timestep only              */
     double* Quu;                 /* (m,m,T,B) or NULL: unregularised Quu (the policy's Σi)       */
     double* dV;                  /* (2,B) expected cost reduction terms                          */
+    /* packed upper-triangle histories: entry (r,c), r <= c, of step t at [c(c+1)/2 + r + tri*(t + T b)];
+     * half the bytes of Vxx / Quu (Vxx is exactly symmetric, backward_pass.jl:71-72; of Quu the upper triangle is what
+     * cholesky(Hermitian(.)) reads).  Independent of Vxx / Quu above; either, both or neither may be given. */
+    double* Vxx_tri;             /* (n(n+1)/2,T,B) or NULL */
+    double* Quu_tri;             /* (m(m+1)/2,T,B) or NULL */
     ddp_boxqp_opts qp;           /* used when lims is active; max_iter == 0 => defaults          */
 } ddp_back_pass_args;
 
@@ -142,6 +156,7 @@ typedef struct ddp_gps_args {
     ddp_tensor Sigi_prev;        /* (m,m,T,B)  traj_prev.Σi           */
     const double* eta;           /* [B] dual variable η per trajectory */
     double* Quui;                /* (m,m,T,B) out: Σ = inv(Quu), required */
+    double* Quui_tri;            /* (m(m+1)/2,T,B) or NULL: packed upper triangle of Σ (exactly symmetric) */
 } ddp_gps_args;
 
 /* a->Quu is required here (it is the new policy's Σi); a->lambda / a->reg_type are ignored. */
@@ -187,6 +202,7 @@ typedef struct ddp_forward_pass_args {
     double alpha_scalar;
     double u_scale;              /* multiplies u before use (the initial rollout's αi*u); 0 => 1  */
     const double* lims;          /* (m,2) or NULL; clamp is applied whenever non-NULL (Q6)        */
+    int64_t lims_stride_t;       /* 0, or 2m for time-varying limits (m,2,T)                      */
     const uint8_t* active;       /* [B] or NULL                                                   */
     /* outputs */
     double* xnew;                /* (n,T,B) */
@@ -264,7 +280,27 @@ typedef struct ddp_ilqg_opts {          /* defaults: iLQG.jl:143-163 */
     int32_t reg_type;                   /* 1 */
     double reduce_ratio_min;            /* 0 */
     const double* lims;                 /* DEVICE (m,2) or NULL */
+    /* pre-rolled start (iLQG.jl:193-197: size(x0) == (n,N) "and cost set accordingly"): DEVICE x_init (n,T,B) and
+     * cost_init [B] (total cost of each trajectory); both NULL = roll out from x0 over the step sizes (:181-192).
+     * With a pre-rolled start the x0 argument of ddp_ilqg_solve_f64 is ignored (x0 = x_init[:,1]). */
+    const double* x_init;
+    const double* cost_init;
+    /* per-iteration trace (the reference's MVHistory keys, iLQG.jl:176-177, 257, 325-330): DEVICE buffer of
+     * trace_cap x B records or NULL.  Record (it, b) holds what trajectory b's trace would hold at ITS iteration
+     * `it` (1-based `iter` of the reference).  Entries never written stay as the caller initialised them. */
+    struct ddp_ilqg_trace* trace;
+    int32_t trace_cap;
 } ddp_ilqg_opts;
+
+typedef struct ddp_ilqg_trace {         /* one iteration of one trajectory */
+    double lambda, dlambda;             /* :λ, :dλ   (values used by this iteration's backward pass)         */
+    double cost;                        /* :cost     (total cost after the iteration; unchanged on a reject)  */
+    double alpha;                       /* :α        (accepted step size; NaN on a rejected iteration, :313)  */
+    double grad_norm;                   /* :grad_norm (:256-257)                                              */
+    double improvement;                 /* :improvement = Δcost of the last tried step size (:326)            */
+    double reduce_ratio;                /* :reduce_ratio (:327)                                               */
+    int32_t accepted, bp_retries;       /* 1 = accepted; number of λ increases inside STEP 2 (:244-249)      */
+} ddp_ilqg_trace;
 
 /* per-trajectory solver state, one struct per trajectory (device array of B) */
 typedef struct ddp_ilqg_state {
@@ -272,7 +308,8 @@ typedef struct ddp_ilqg_state {
     int32_t iter;                       /* the reference's `iter` counter (1-based, at exit)       */
     int32_t accepted_iter;
     int32_t status;                     /* -1 running, 0 tol_grad, 1 tol_fun, 2 λ>λmax, 3 max_iter,
-                                           4 initial rollout diverged (reference returns nothing) */
+                                           4 initial rollout diverged (reference returns nothing),
+                                           6 safety cap of the outer loop hit (call returns DDP_ERR_INCOMPLETE) */
     int32_t pad;
 } ddp_ilqg_state;
 
@@ -347,9 +384,53 @@ typedef struct ddp_iter_host_args {
     int32_t* diverge;
     int64_t chunk;               /* trajectories per chunk, 0 = library default */
     int64_t h2d_bytes, d2h_bytes; /* out: bytes moved */
+    int32_t keep_policy;         /* 1: the whole batch's K,k,Vx stay on the device after the call (ddp_iter_host_policy);
+                                    0: they live in one chunk-sized scratch and are gone when the call returns */
+    int32_t inputs_resident;     /* 1: fx,fu,x,u,lambda are NOT uploaded: the device copies of the previous call on this
+                                    handle are used (a real iLQG loop keeps them there); host pointers may be NULL */
+    int32_t commit_accepted;     /* 1: after the call the device copies x,u are replaced by xnew,unew for trajectories whose
+                                    step was accepted (ratio > 0, iLQG.jl:269-303), ready for inputs_resident = 1        */
+    int32_t pad_;
+    const double* cost_prev;     /* [B] HOST: total cost of the current (x,u); required with commit_accepted           */
 } ddp_iter_host_args;
 
 DDP_API int ddp_ilqg_iter_host_f64(ddp_handle_t h, ddp_iter_host_args* a);
+/* Device pointers of what the last ddp_ilqg_iter_host_f64 call on this handle left on the device: the policy K (m,n,T,B),
+ * k (m,T,B), Vx (n,T,B) (NULL unless keep_policy was set) and the rollout xnew (n,T,B), unew (m,T,B).  Owned by the handle,
+ * valid until the next host iteration with another configuration or ddp_destroy.  Any out pointer may be NULL. */
+DDP_API int ddp_iter_host_policy(ddp_handle_t h, double** K, double** k, double** Vx, double** xnew, double** unew);
+
+/* ---- one iteration, device resident, chunked over a batch larger than the policy's HBM residency ------------------------ */
+/* One backward sweep + one forward rollout over the handle's B trajectories for a built-in model, all arrays on the DEVICE.
+ * The batch is processed in chunks of `chunk` trajectories so that the policy (K,k,Vx: 592 KiB per trajectory at n=32, m=8,
+ * T=256 -- 137 GB+ at BASELINE config 5's 262144 trajectories per GPU) only ever exists for one chunk: the derivative step
+ * (cx = Q(x-goal), cu = R u; pendcart also fx,fu), the backward sweep and the rollout of a chunk run back to back on the
+ * handle's stream re-using one chunk-sized scratch (SURVEY section 7 "HBM capacity").  Pass K,k,Vx (full size) to keep the
+ * policy instead.  Asynchronous on the handle's stream. */
+typedef struct ddp_iter_args {
+    const double *x, *u;         /* (n,T,B), (m,T,B) current trajectory                                   */
+    const double* lambda;        /* [B]                                                                    */
+    const double* alpha;         /* [B] or NULL => alpha_scalar                                            */
+    double alpha_scalar;
+    int32_t reg_type;            /* 1 or 2                                                                 */
+    int32_t pad_;
+    const double* lims;          /* (m,2) or NULL                                                          */
+    const uint8_t* active;       /* [B] or NULL                                                            */
+    double *xnew, *unew;         /* (n,T,B), (m,T,B)                                                       */
+    double *cost, *dV;           /* [B], (2,B)                                                             */
+    int32_t* diverge;            /* [B]                                                                    */
+    double *K, *k, *Vx;          /* all three full size (.,T,B) to keep the policy, or all NULL (chunk scratch) */
+    int64_t chunk;               /* trajectories per chunk; 0 = library default (sm_count * 8 * 55 rounds)  */
+    int64_t n_chunks;            /* out */
+} ddp_iter_args;
+
+DDP_API int ddp_ilqg_iter_f64(ddp_handle_t h, const ddp_model* model, ddp_iter_args* a);
+
+/* ---- self test: the FP64 denominators of the roofline, measured on this device ------------------------------------------ */
+/* kind 0: DFMA (fma.rn.f64, 8 independent chains per thread); kind 1: DMMA (mma.sync.m8n8k4.f64, the instruction of the
+ * n=32, m=8 sweep kernels).  Runs `reps` timed launches on the handle's stream (after one warm-up) and returns the best
+ * TFLOP/s and its launch time.  Synchronous.  bench.py calls this before its timed region ("measure it"). */
+DDP_API int ddp_selftest_peak_f64(ddp_handle_t h, int32_t kind, int32_t reps, double* tflops, double* ms);
 
 #ifdef __cplusplus
 }

@@ -72,7 +72,7 @@ NOFMA void chol_solve(int m, const double* R, int nf, double* v) {
     }
 }
 
-inline double clampd(double v, double lo, double hi) { return std::fmin(std::fmax(v, lo), hi); }
+inline double clampd(double v, double lo, double hi) { return (v > hi) ? hi : ((v < lo) ? lo : v); }   // Julia's clamp: NaN stays NaN
 
 // boxQP.jl:29-188; returns result (or -1 where cholesky throws)
 NOFMA QPOut boxqp(int m, const double* H, const double* g, const double* lower, const double* upper, const double* x0,

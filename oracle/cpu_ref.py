@@ -11,19 +11,48 @@ LIB = os.path.join(HERE, "_build", "libcpu_ref.so")
 _lib = None
 
 
-def build():
-    subprocess.check_call(["make", "-s", "-C", HERE])
+def _host_stamp():
+    """Identifies the host CPU the library was compiled for (-march=native): model name + ISA flags."""
+    import hashlib
+    try:
+        with open("/proc/cpuinfo") as f:
+            txt = f.read()
+        keep = [ln for ln in txt.splitlines() if ln.startswith(("model name", "flags"))][:2]
+    except OSError:
+        keep = ["unknown"]
+    return hashlib.sha256("\n".join(keep).encode()).hexdigest()
+
+
+def build(force=False):
+    stamp = os.path.join(HERE, "_build", "host.stamp")
+    cur = _host_stamp()
+    stale = force or not os.path.exists(LIB) or not os.path.exists(stamp) or open(stamp).read() != cur
+    if stale and os.path.exists(LIB):
+        os.remove(LIB)                     # another host's -march=native binary: rebuild for this one
+    try:
+        subprocess.check_call(["make", "-s", "-C", HERE])
+    except subprocess.CalledProcessError:  # a compiler without -march=native support for this CPU
+        subprocess.check_call(["make", "-s", "-C", HERE, "MARCH=x86-64-v3"])
+    with open(stamp, "w") as f:
+        f.write(cur)
     return LIB
 
 
 def load():
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB):
-            build()
+        build()
         _lib = C.CDLL(LIB)
         _lib.cpu_ref_num_threads.restype = C.c_int
     return _lib
+
+
+def host_cores():
+    """CPUs this process may run on (what OpenMP should use; torchrun exports OMP_NUM_THREADS=1, which is not it)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
 def _p(a):

@@ -162,6 +162,13 @@ class PosDefException(Exception):
     pass
 
 
+def _clamp_jl(x, lo, hi):
+    """Julia's ``clamp(x, lo, hi) = ifelse(x > hi, hi, ifelse(x < lo, lo, x))`` (Base), elementwise: NaN stays NaN and an
+    inverted interval resolves hi-first -- what ``clamp.(…)`` does at boxQP.jl:58,139,144 and forward_pass.jl:23."""
+    x = np.asarray(x, dtype=np.float64)
+    return np.where(x > hi, hi, np.where(x < lo, lo, x))
+
+
 def boxQP(H, g, lower, upper, x0, *, maxIter=100, minGrad=1e-8, minRelImprove=1e-8, stepDec=0.6,
           minStep=1e-22, Armijo=0.1, hermitian_check=True):
     """Projected-Newton box-constrained QP, boxQP.jl:29-188.
@@ -185,7 +192,7 @@ def boxQP(H, g, lower, upper, x0, *, maxIter=100, minGrad=1e-8, minRelImprove=1e
     nfactor = 0
     Hfree = np.zeros((n, n))                       # :53
 
-    x = np.minimum(np.maximum(np.asarray(x0, dtype=np.float64).reshape(-1), lower), upper)  # :58 clamp
+    x = _clamp_jl(np.asarray(x0, dtype=np.float64).reshape(-1), lower, upper)  # :58 clamp
     value = _qp_value(H, g, x)                     # :63
 
     it = 1
@@ -231,11 +238,11 @@ def boxQP(H, g, lower, upper, x0, *, maxIter=100, minGrad=1e-8, minRelImprove=1e
         if sdotg >= 0:                             # :133 (should not happen) -> leaves result == 0
             break
         step = 1.0                                 # :138
-        xc = np.minimum(np.maximum(x + step * search, lower), upper)
+        xc = _clamp_jl(x + step * search, lower, upper)
         vc = _qp_value(H, g, xc)
         while (vc - oldvalue) / (step * sdotg) < Armijo:   # :142
             step = step * stepDec
-            xc = np.minimum(np.maximum(x + step * search, lower), upper)
+            xc = _clamp_jl(x + step * search, lower, upper)
             vc = _qp_value(H, g, xc)
             if step < minStep:
                 result = 2
@@ -461,7 +468,7 @@ def forward_pass(traj_new: GaussianPolicy, x0, u, x, alpha, f: Callable, costfun
             dx = diff(xnew[i], x[i])
             unew[i] = unew[i] + traj_new.K[i] @ dx                           # :20
         if has_lims:
-            unew[i] = np.minimum(np.maximum(unew[i], lims[:, 0]), lims[:, 1])
+            unew[i] = _clamp_jl(unew[i], lims[:, 0], lims[:, 1])            # :23 (NaN survives; f zeroes it)
         xnewi = f(xnew[i], unew[i], i + 1)                                   # :25 (called at i=N too)
         if i < N - 1:
             xnew[i + 1] = xnewi
@@ -516,7 +523,10 @@ def kl_div_wiki(xnew, xold, sigma_new, traj_new: GaussianPolicy, traj_prev: Gaus
         Sip = traj_prev.Sigmai[t]
         kd = kp - kn
         Kd = Kp - Kn
-        v = 0.5 * (np.trace(Sip @ Sn) + kd @ Sip @ kd - m + _logdet(Sp) - _logdet(Sn))
+        try:
+            v = 0.5 * (np.trace(Sip @ Sn) + kd @ Sip @ kd - m + _logdet(Sp) - _logdet(Sn))
+        except ValueError:                     # klutils.jl:92-96: `catch e ... return Inf` (a scalar, for the whole call)
+            return np.full(T, np.inf)
         v += 0.5 * (mut @ Kd.T @ Sip @ Kd @ mut + np.trace(Kd.T @ Sip @ Kd @ St))
         v += kd @ Sip @ Kd @ mut
         kld[t] = v

@@ -26,29 +26,70 @@ def test_library_exports_every_declared_symbol(ddp):
         assert hasattr(lib, name), name
     bound = {s[0] for s in ddp._lib.SYMBOLS}
     assert declared == bound                       # the ctypes mirror binds exactly the header's surface
-    assert ddp.load().ddp_version() == 100
+    assert ddp.load().ddp_version() == 200
 
 
-def test_struct_sizes_match_the_header(ddp):
-    """sizeof of every ABI struct, compiled from include/ddp.h with gcc, equals the ctypes mirror."""
-    src = r'''
-#include <stdio.h>
-#include "ddp.h"
-int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(ddp_tensor), sizeof(ddp_boxqp_opts),
-  sizeof(ddp_back_pass_args), sizeof(ddp_gps_args), sizeof(ddp_model), sizeof(ddp_forward_pass_args), sizeof(ddp_kl_args),
-  sizeof(ddp_ilqg_opts), sizeof(ddp_ilqg_state), sizeof(ddp_iter_host_args), sizeof(ddp_ilqgkl_opts), sizeof(ddp_ilqgkl_state),
-  sizeof(ddp_ilqgkl_args)); return 0; }
-'''
+def struct_layout_from_header(ddp):
+    """{struct: (sizeof, {field: offsetof})} compiled from include/ddp.h with gcc -- the C side of the layout tests."""
+    L = ddp._lib
+    lines = []
+    for cname, cls in L.STRUCTS.items():
+        lines.append(f'printf("S {cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            cf = L.FIELD_ALIASES.get(fname, fname)
+            lines.append(f'printf("F {cname} {fname} %zu\\n", offsetof({cname}, {cf}));')
+    src = "#include <stdio.h>\n#include <stddef.h>\n#include \"ddp.h\"\nint main(void) {\n" + "\n".join(lines) + "\nreturn 0; }\n"
     import tempfile
     with tempfile.TemporaryDirectory() as td:
         c = os.path.join(td, "s.c"); exe = os.path.join(td, "s")
         open(c, "w").write(src)
         subprocess.check_call(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
-        sizes = list(map(int, subprocess.check_output([exe]).split()))
+        out = subprocess.check_output([exe], text=True)
+    layout = {}
+    for ln in out.splitlines():
+        f = ln.split()
+        if f[0] == "S":
+            layout[f[1]] = (int(f[2]), {})
+        else:
+            layout[f[1]][1][f[2]] = int(f[3])
+    return layout
+
+
+def test_struct_layouts_match_the_header(ddp):
+    """sizeof of every ABI struct AND offsetof of every field, compiled from include/ddp.h with gcc, equal the ctypes
+    mirror: a field-order slip with an unchanged size cannot pass."""
     L = ddp._lib
-    mirror = [L.Tensor, L.BoxQPOpts, L.BackPassArgs, L.GpsArgs, L.Model, L.ForwardPassArgs, L.KlArgs, L.IlqgOpts, L.IlqgState, L.IterHostArgs,
-              L.IlqgklOpts, L.IlqgklState, L.IlqgklArgs]
-    assert sizes == [ctypes.sizeof(t) for t in mirror]
+    hdr = open(os.path.join(ROOT, "include", "ddp.h")).read()
+    declared = set(re.findall(r"typedef struct (ddp_\w+) \{", hdr))
+    assert declared == set(L.STRUCTS)                      # every struct of the header has a mirror
+    layout = struct_layout_from_header(ddp)
+    for cname, cls in L.STRUCTS.items():
+        size, offs = layout[cname]
+        assert ctypes.sizeof(cls) == size, cname
+        for fname, _ in cls._fields_:
+            assert getattr(cls, fname).offset == offs[fname], (cname, fname)
+
+
+def test_julia_structs_match_the_header(ddp):
+    """julia/DifferentialDynamicProgramming.jl cannot be executed here (no Julia in the container); its ccall structs are
+    generated from the same table as the ctypes mirror (scripts/gen_julia_structs.py) and must be up to date, and every
+    generated struct lists the C fields in the C order with the Julia type of the C type's size."""
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import gen_julia_structs as G
+    generated = G.generate()
+    committed = open(os.path.join(ROOT, "julia", "ddp_structs.jl")).read()
+    assert generated == committed, "run python scripts/gen_julia_structs.py"
+    layout = struct_layout_from_header(ddp)
+    for cname, (jname, fields) in G.parse(committed).items():
+        size, offs = layout[cname]
+        off = 0
+        for fname, jtype in fields:
+            sz, al = G.JULIA_SIZES[jtype] if jtype in G.JULIA_SIZES else G.struct_size_align(jtype, committed, layout)
+            off = (off + al - 1) // al * al
+            cf = fname
+            assert offs[G.c_field(cname, fname)] == off, (cname, fname, off)
+            off += sz
+        assert (off + 7) // 8 * 8 == size, cname
 
 
 def test_no_cpu_fallback(ddp):
