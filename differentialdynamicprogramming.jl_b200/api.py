@@ -125,6 +125,13 @@ class Engine:
     def allreduce_stats(self, stats_ptr: int):
         self._ck(self.lib.ddp_comm_allreduce_stats_f64(self.h, C.c_void_p(stats_ptr)))
 
+    def selftest_peak(self, kind: str = "dmma", reps: int = 3):
+        """FP64 peak of this device in TFLOP/s measured by the library's own microkernels (ddp_selftest_peak_f64):
+        ``"dfma"`` (FMA pipe) or ``"dmma"`` (mma.sync.m8n8k4.f64, the instruction of the n=32, m=8 sweeps).  Returns (TFLOP/s, ms)."""
+        tf, ms = C.c_double(0.0), C.c_double(0.0)
+        self._ck(self.lib.ddp_selftest_peak_f64(self.h, {"dfma": 0, "dmma": 1}[kind], reps, C.byref(tf), C.byref(ms)))
+        return tf.value, ms.value
+
     def empty(self, shape, dtype=np.float64) -> DevArray:
         return DevArray(self, shape, dtype)
 
@@ -165,10 +172,14 @@ def _pack_mat(eng: Engine, a, B: int, N: int, r: int, c: int, name: str):
 
 
 def _lims_dev(eng: Engine, lims, m: int):
+    """(m,2) -> device [lower(m); upper(m)]; (N,m,2) time-varying -> device (N,2,m) blocks.  Returns (DevArray|None, stride_t)."""
     if lims is None or np.asarray(lims).size == 0:
-        return None
-    lims = np.asarray(lims, dtype=np.float64).reshape(m, 2)
-    return eng.upload(np.ascontiguousarray(lims.T))      # [lower(m); upper(m)]
+        return None, 0
+    lims = np.asarray(lims, dtype=np.float64)
+    if lims.ndim == 3:
+        return eng.upload(np.ascontiguousarray(np.swapaxes(lims.reshape(-1, m, 2), -1, -2))), 2 * m
+    lims = lims.reshape(m, 2)
+    return eng.upload(np.ascontiguousarray(lims.T)), 0
 
 
 # ---------------------------------------------------------------------------------------------
@@ -227,20 +238,50 @@ def _back_common(cx, cu, cxx, cxu, cuu, fx, fu, lims, u, force_generic, engine):
         dev, t = _pack_mat(eng, arr, B, N, r, c, name)
         keep.append(dev)
         setattr(a, name, t)
-    ld = _lims_dev(eng, lims, m)
+    ld, lst = _lims_dev(eng, lims, m)
     if ld is not None:
         keep.append(ld)
         a.lims = ld.ptr
+        a.lims_stride_t = lst
         dev, t = _pack_vec(eng, u, B, N, m, "u")
         keep.append(dev)
         a.u = t
     return eng, a, keep, batched, B, N, n, m
 
 
+def _pack_tens3(eng: Engine, a, B: int, N: int, d1: int, d2: int, d3: int, name: str):
+    """Second-order dynamics tensor, math layout (d1,d2,d3) | (N,d1,d2,d3) | (B|1,N|1,d1,d2,d3) with the reference's index
+    order (size(fxu) == (n,n,m[,N]), iLQG.jl:80) -> device column-major (first index fastest) + strides."""
+    a = np.asarray(a, dtype=np.float64)
+    if a.ndim == 3:
+        a = a[None, None]
+    elif a.ndim == 4:
+        a = a[None]
+    if a.ndim != 5 or a.shape[2:] != (d1, d2, d3) or a.shape[0] not in (1, B) or a.shape[1] not in (1, N):
+        raise ValueError(f"size({name}) should be ({d1}, {d2}, {d3}[, {N}]), got {a.shape}")
+    dev = eng.upload(np.ascontiguousarray(np.transpose(a, (0, 1, 4, 3, 2))))
+    Nx = a.shape[1]
+    blk = d1 * d2 * d3
+    return dev, _tensor(dev.ptr, Nx * blk if (a.shape[0] == B and B > 1) else 0, blk if (Nx == N and N > 1) else 0)
+
+
+def _unpack_tri(tri: np.ndarray, d: int) -> np.ndarray:
+    """(..., d(d+1)/2) packed upper triangle (column by column) -> (..., d, d) symmetric."""
+    r, c = np.triu_indices(d)
+    order = np.argsort(c * (c + 1) // 2 + r, kind="stable")
+    r, c = r[order], c[order]
+    full = np.zeros(tri.shape[:-1] + (d, d))
+    full[..., r, c] = tri
+    full[..., c, r] = tri
+    return full
+
+
 def _back_outputs(eng, a, B, N, n, m, want_Vxx, want_Quu):
     out = dict(diverge=eng.empty((B,), np.int32), K=eng.empty((B, N, n, m)), k=eng.empty((B, N, m)),
                Vx=eng.empty((B, N, n)), dV=eng.empty((B, 2)), Vxx1=eng.empty((B, n, n)))
-    if want_Vxx:
+    if want_Vxx == "upper":                      # packed upper-triangle history: half the bytes (SURVEY 8f-3)
+        out["Vxx_tri"] = eng.empty((B, N, n * (n + 1) // 2))
+    elif want_Vxx:
         out["Vxx"] = eng.empty((B, N, n, n))
     if want_Quu:
         out["Quu"] = eng.empty((B, N, m, m))
@@ -249,14 +290,29 @@ def _back_outputs(eng, a, B, N, n, m, want_Vxx, want_Quu):
     return out
 
 
-def back_pass(cx, cu, cxx, cxu, cuu, fx, fu, lam, regType, lims, x, u, *, want_Vxx=True, force_generic=False,
-              engine: Engine = None):
-    """``back_pass(cx,cu,cxx,cxu,cuu,fx,fu,λ,regType,lims,x,u)`` -- backward_pass.jl:162-252.
+def back_pass(cx, cu, cxx, cxu, cuu, fx, fu, *rest, want_Vxx=True, force_generic=False, engine: Engine = None):
+    """``back_pass(cx,cu,cxx,cxu,cuu,fx,fu,λ,regType,lims,x,u)`` -- backward_pass.jl:162-252, or the 15-argument form
+    ``back_pass(cx,cu,cxx,cxu,cuu,fx,fu,fxx,fxu,fuu,λ,regType,lims,x,u)`` (backward_pass.jl:81-160) whose second-order
+    tensors ``fxx (n,n,n[,N])``, ``fxu (n,n,m[,N])``, ``fuu (n,m,m[,N])`` may each be ``None``/empty.
 
     Returns ``(diverge, GaussianPolicy, Vx, Vxx, dV)``; with a leading batch axis on the inputs the
     outputs carry it too (``diverge`` becomes an int array, the policy holds batched arrays).
+    ``want_Vxx="upper"`` stores the history as packed upper triangles on the device (half the bytes) and expands it here;
+    ``lims`` may be ``(m,2)`` or time-varying ``(N,m,2)``.
     """
+    if len(rest) == 8:
+        fxx, fxu, fuu, lam, regType, lims, x, u = rest
+    elif len(rest) == 5:
+        fxx = fxu = fuu = None
+        lam, regType, lims, x, u = rest
+    else:
+        raise TypeError("back_pass takes 12 or 15 positional arguments")
     eng, a, keep, batched, B, N, n, m = _back_common(cx, cu, cxx, cxu, cuu, fx, fu, lims, u, force_generic, engine)
+    for name, arr, dims in (("fxx", fxx, (n, n, n)), ("fxu", fxu, (n, n, m)), ("fuu", fuu, (n, m, m))):
+        if arr is not None and np.asarray(arr).size > 0:
+            dev, t = _pack_tens3(eng, arr, B, N, *dims, name)
+            keep.append(dev)
+            setattr(a, name, t)
     lam_dev = eng.upload(np.broadcast_to(np.asarray(lam, dtype=np.float64), (B,)))
     a.lam = lam_dev.ptr
     a.reg_type = int(regType)
@@ -273,7 +329,10 @@ def _collect_back(out, batched, B, N, n, m, Quui):
     K = np.swapaxes(out["K"].numpy(), -1, -2)                # (B,N,n,m) col-major -> (B,N,m,n)
     k = out["k"].numpy()
     Vx = out["Vx"].numpy()
-    Vxx = np.swapaxes(out["Vxx"].numpy(), -1, -2) if "Vxx" in out else np.swapaxes(out["Vxx1"].numpy(), -1, -2)
+    if "Vxx_tri" in out:
+        Vxx = _unpack_tri(out["Vxx_tri"].numpy(), n)
+    else:
+        Vxx = np.swapaxes(out["Vxx"].numpy(), -1, -2) if "Vxx" in out else np.swapaxes(out["Vxx1"].numpy(), -1, -2)
     Quu = np.swapaxes(out["Quu"].numpy(), -1, -2) if "Quu" in out else None
     dV = out["dV"].numpy()
     Sig = np.swapaxes(Quui.numpy(), -1, -2) if Quui is not None else None
@@ -463,10 +522,11 @@ def forward_pass(traj_new: GaussianPolicy, x0, u, x, alpha, f, costfun, lims, di
         dal = eng.upload(np.broadcast_to(alpha, (B,))); keep.append(dal)
         a.alpha = dal.ptr
     a.u_scale = float(u_scale)
-    ld = _lims_dev(eng, lims, m)
+    ld, lst = _lims_dev(eng, lims, m)
     if ld is not None:
         keep.append(ld)
         a.lims = ld.ptr
+        a.lims_stride_t = lst
     xnew, unew, cost = eng.empty((B, N, n)), eng.empty((B, N, m)), eng.empty((B,))
     a.xnew, a.unew, a.cost = xnew.ptr, unew.ptr, cost.ptr
     Tc = N + model.terminal_cost
@@ -512,10 +572,11 @@ def forward_costs(traj_new: GaussianPolicy, x0, u, x, alphas, f, costfun, lims, 
     a.K, a.k = dK.ptr, dk.ptr
     dx, a.x = _pack_vec(eng, x, B, N, n, "x"); keep.append(dx)
     a.u_scale = 1.0
-    ld = _lims_dev(eng, lims, m)
+    ld, lst = _lims_dev(eng, lims, m)
     if ld is not None:
         keep.append(ld)
         a.lims = ld.ptr
+        a.lims_stride_t = lst
     xnew, unew, cost = eng.empty((B, N, n)), eng.empty((B, N, m)), eng.empty((B,))
     a.xnew, a.unew, a.cost = xnew.ptr, unew.ptr, cost.ptr
     al = np.ascontiguousarray(np.asarray(alphas, dtype=np.float64).reshape(-1))
@@ -575,21 +636,27 @@ def kl_div_wiki(xnew, xold, fx, R1, traj_new: GaussianPolicy, traj_prev: Gaussia
 DEFAULT_ALPHA = 10.0 ** np.linspace(0, -3, 11)        # iLQG.jl:145
 STATUS = {-1: "running", 0: "SUCCESS: gradient norm < tol_grad", 1: "SUCCESS: cost change < tol_fun",
           2: "EXIT: lambda > lambda_max", 3: "EXIT: Maximum iterations reached",
-          4: "EXIT: Initial control sequence caused divergence"}
+          4: "EXIT: Initial control sequence caused divergence", 6: "outer-loop safety cap reached"}
+TRACE_DTYPE = np.dtype([("lam", "f8"), ("dlam", "f8"), ("cost", "f8"), ("alpha", "f8"), ("grad_norm", "f8"), ("improvement", "f8"),
+                        ("reduce_ratio", "f8"), ("accepted", "i4"), ("bp_retries", "i4")])
 
 
 def iLQG(f, costfun, df, x0, u0, *, lims=None, alpha=None, tol_fun=1e-7, tol_grad=1e-4, max_iter=500, lam=1.0, dlam=1.0,
-         lamfactor=1.6, lammax=1e10, lammin=1e-6, regType=1, reduce_ratio_min=0.0, diff_fun=None, force_generic=False,
-         engine: Engine = None):
+         lamfactor=1.6, lammax=1e10, lammin=1e-6, regType=1, reduce_ratio_min=0.0, diff_fun=None, cost=None, trace_iters=0,
+         force_generic=False, engine: Engine = None):
     """``iLQG(f,costfun,df,x0,u0;kw...)`` -- iLQG.jl:143-341, for one trajectory or a batch.
 
     ``f, costfun, df`` must be the callbacks of one device model descriptor.  ``x0`` is ``(n,)`` /
-    ``(B,n)``, ``u0`` is ``(N,m)`` / ``(B,N,m)``.  Returns ``(x, u, traj_new, Vx, Vxx, cost, trace)`` like the
+    ``(B,n)``, ``u0`` is ``(N,m)`` / ``(B,N,m)``; a pre-rolled initial trajectory ``x0`` of shape ``(N,n)`` / ``(B,N,n)``
+    together with its ``cost`` (total, or per step: it is summed) starts from that trajectory instead of rolling out
+    (iLQG.jl:193-197).  Returns ``(x, u, traj_new, Vx, Vxx, cost, trace)`` like the
     reference; ``Vxx`` is the value Hessian at the first timestep only (the history is optional on
     the device), ``cost`` the total cost, ``trace`` a dict with the per-trajectory final
-    ``status, iter, accepted_iter, lam, dlam, g_norm`` and ``n_outer``.  Unbatched calls return ``None``
-    when the initial controls diverge (iLQG.jl:209) and raise ``RuntimeError`` when no iteration
-    completed (iLQG.jl:335), as the reference does.
+    ``status, iter, accepted_iter, lam, dlam, g_norm`` and ``n_outer``; with ``trace_iters = k > 0`` also
+    ``trace["iterations"]``: a structured array ``(k,)`` / ``(k,B)`` with the reference's per-iteration trace keys
+    (``lam, dlam, cost, alpha, grad_norm, improvement, reduce_ratio`` -- iLQG.jl:257, 325-330; NaN where the reference
+    records nothing).  Unbatched calls return ``None`` when the initial controls diverge (iLQG.jl:209) and raise
+    ``RuntimeError`` when no iteration completed (iLQG.jl:335), as the reference does.
     """
     if diff_fun is not None:
         raise NotImplementedError("only the default diff_fun (-) is supported on the device")
@@ -601,8 +668,12 @@ def iLQG(f, costfun, df, x0, u0, *, lims=None, alpha=None, tol_fun=1e-7, tol_gra
     B = u0.shape[0] if batched else 1
     N, m = u0.shape[-2:]
     x0 = np.asarray(x0, dtype=np.float64)
-    if x0.ndim == 2 and not batched and x0.shape[0] == N:
-        raise NotImplementedError("pre-rolled initial trajectories are not supported by the device driver")
+    prerolled = x0.ndim == u0.ndim and x0.ndim >= 2          # size(x0,2) == N branch (iLQG.jl:193)
+    if prerolled:
+        if x0.shape[-2] != N:
+            raise RuntimeError("pre-rolled initial trajectory must be of correct length (size(x0,2) == N)")      # iLQG.jl:199
+        if cost is None:
+            raise RuntimeError("Initial trajectory supplied, initial cost must also be supplied")
     n = x0.shape[-1]
     alpha = DEFAULT_ALPHA if alpha is None else np.asarray(alpha, dtype=np.float64)
     eng = engine or Engine(n, m, N, B, force_generic=force_generic)
@@ -614,23 +685,46 @@ def iLQG(f, costfun, df, x0, u0, *, lims=None, alpha=None, tol_fun=1e-7, tol_gra
     o.tol_fun, o.tol_grad, o.max_iter = tol_fun, tol_grad, max_iter
     o.lam, o.dlam, o.lam_factor, o.lam_max, o.lam_min = lam, dlam, lamfactor, lammax, lammin
     o.reg_type, o.reduce_ratio_min = int(regType), float(reduce_ratio_min)
-    ld = _lims_dev(eng, lims, m)
+    ld, lst = _lims_dev(eng, lims, m)
+    if lst:
+        raise NotImplementedError("time-varying lims are supported by back_pass / forward_pass, not by the iLQG driver")
     if ld is not None:
         keep.append(ld)
         o.lims = ld.ptr
-    dx0 = eng.upload(np.broadcast_to(x0.reshape(-1, n), (B, n)))
+    if prerolled:
+        xi = eng.upload(x0.reshape(B, N, n)); keep.append(xi)
+        c0 = np.asarray(cost, dtype=np.float64)
+        c0 = c0.reshape(B, -1).sum(axis=1) if c0.size != B else c0.reshape(B)
+        ci = eng.upload(c0); keep.append(ci)
+        o.x_init, o.cost_init = xi.ptr, ci.ptr
+        dx0 = eng.upload(np.ascontiguousarray(x0.reshape(B, N, n)[:, 0]))
+    else:
+        dx0 = eng.upload(np.broadcast_to(x0.reshape(-1, n), (B, n)))
+    tr = None
+    if trace_iters > 0:
+        init = np.zeros((trace_iters, B), dtype=TRACE_DTYPE)
+        for key in ("lam", "dlam", "cost", "alpha", "grad_norm", "improvement", "reduce_ratio"):
+            init[key] = np.nan
+        init["accepted"] = -1
+        tr = eng.upload(init.view(np.uint8).reshape(trace_iters, B, TRACE_DTYPE.itemsize), np.uint8)
+        o.trace, o.trace_cap = tr.ptr, trace_iters
     du0 = eng.upload(u0.reshape(B, N, m))
-    x, u = eng.empty((B, N, n)), eng.empty((B, N, m))
+    # zero-initialised: a trajectory whose initial rollout diverges (status 4) never gets an x, u
+    x, u = eng.empty((B, N, n)).zero(), eng.empty((B, N, m)).zero()
     K, k, Vx, Vxx1 = eng.empty((B, N, n, m)).zero(), eng.empty((B, N, m)).zero(), eng.empty((B, N, n)).zero(), eng.empty((B, n, n)).zero()
     st = eng.empty((B, C.sizeof(L.IlqgState)), np.uint8)
     n_outer = C.c_int32(0)
-    eng._ck(eng.lib.ddp_ilqg_solve_f64(eng.h, C.byref(M), C.byref(o), dx0.ptr, du0.ptr, x.ptr, u.ptr, K.ptr, k.ptr, Vx.ptr,
-                                       Vxx1.ptr, st.ptr, C.byref(n_outer)))
+    rc = eng.lib.ddp_ilqg_solve_f64(eng.h, C.byref(M), C.byref(o), dx0.ptr, du0.ptr, x.ptr, u.ptr, K.ptr, k.ptr, Vx.ptr,
+                                    Vxx1.ptr, st.ptr, C.byref(n_outer))
+    if rc != -5:                                           # DDP_ERR_INCOMPLETE still delivers every output (status 6 marks the stragglers)
+        eng._ck(rc)
     states = np.frombuffer(st.numpy().tobytes(), dtype=np.dtype(
         [("lam", "f8"), ("dlam", "f8"), ("cost", "f8"), ("g_norm", "f8"), ("last_dcost", "f8"), ("last_alpha", "f8"),
          ("iter", "i4"), ("accepted_iter", "i4"), ("status", "i4"), ("pad", "i4")]))
     trace = {key: states[key].copy() for key in ("status", "iter", "accepted_iter", "lam", "dlam", "g_norm", "last_dcost", "last_alpha")}
     trace["n_outer"] = int(n_outer.value)
+    if tr is not None:
+        trace["iterations"] = np.frombuffer(tr.numpy().tobytes(), dtype=TRACE_DTYPE).reshape(trace_iters, B).copy()
     xs, us = x.numpy(), u.numpy()
     Ks, ks = np.swapaxes(K.numpy(), -1, -2), k.numpy()
     Vxs, Vxxs = Vx.numpy(), np.swapaxes(Vxx1.numpy(), -1, -2)
@@ -641,7 +735,7 @@ def iLQG(f, costfun, df, x0, u0, *, lims=None, alpha=None, tol_fun=1e-7, tol_gra
         return None
     if trace["iter"][0] == 1:
         raise RuntimeError("Failure: no iterations completed, something is wrong.")
-    trace = {key: (v[0] if isinstance(v, np.ndarray) else v) for key, v in trace.items()}
+    trace = {key: ((v[:, 0] if key == "iterations" else v[0]) if isinstance(v, np.ndarray) else v) for key, v in trace.items()}
     return xs[0], us[0], GaussianPolicy(N, n, m, Ks[0], ks[0]), Vxs[0], Vxxs[0], float(cost[0]), trace
 
 
@@ -650,17 +744,34 @@ def iLQG(f, costfun, df, x0, u0, *, lims=None, alpha=None, tol_fun=1e-7, tol_gra
 # ---------------------------------------------------------------------------------------------
 
 
-def iLQGkl(dynamics, costfun, derivs, x0, traj_prev: GaussianPolicy, fx_model, R1, *, kl_step=1.0, lims=None, max_iter=50,
+@dataclass
+class SimpleLTVModel:
+    """What ``iLQGkl`` needs of the reference's ``model`` argument (LinearTimeVaryingModelsBase.SimpleLTVModel,
+    demo_linear.jl:118 -- third party, not vendored): ``fx`` = what ``df(model,x,u)`` returns as the state Jacobian and
+    ``R1`` = what ``covariance(model,x,u)`` returns (forward_pass.jl:38,42)."""
+    fx: np.ndarray
+    R1: np.ndarray
+
+
+def _split_model(model, R1):
+    if R1 is not None:                      # (…, traj_prev, fx_model, R1) spelling
+        return model, R1
+    return model.fx, model.R1
+
+
+def iLQGkl(dynamics, costfun, derivs, x0, traj_prev: GaussianPolicy, model, R1=None, *, kl_step=1.0, lims=None, max_iter=50,
            etabracket=(1e-8, 1.0, 1e16), del0=1e-4, cost=None, max_eta_retries=200, force_generic=False):
     """``iLQGkl(dynamics,costfun,derivs,x0,traj_prev,model;kw...)`` -- iLQGkl.jl:25-183 + 238-252.
 
     Every sweep runs on the device (``ddp_back_pass_gps_f64``, ``ddp_forward_pass_f64``, ``ddp_kl_div_f64``,
     ``ddp_model_derivs_f64``); only the scalar η-bracket update of ``calc_η`` (klutils.jl:110-130) and the
-    loop control are host code.  ``fx_model``/``R1`` stand for the un-vendored ``model`` argument
-    (what ``df(model,x,u)`` and ``covariance(model,x,u)`` return, forward_pass.jl:38,42).  ``x0`` is the
+    loop control are host code.  ``model`` is a :class:`SimpleLTVModel` (``fx``, ``R1``:
+    what ``df(model,x,u)`` and ``covariance(model,x,u)`` return, forward_pass.jl:38,42, of the un-vendored third-party type);
+    the older spelling ``(…, traj_prev, fx_model, R1)`` works too.  ``x0`` is the
     pre-rolled trajectory (N,n) and ``cost`` its cost, as the reference requires (iLQGkl.jl:63-70).
     Unbatched only (one trajectory), like the reference.
     """
+    fx_model, R1 = _split_model(model, R1)
     model = _model_of(dynamics, costfun)
     u = np.array(traj_prev.k, dtype=np.float64)                     # :47
     x = np.asarray(x0, dtype=np.float64)
@@ -737,7 +848,7 @@ KL_STATUS = {-1: "running", 0: "KL constraint satisfied", 1: "eta > 0.999 eta_ma
              5: "eta-retry limit reached"}
 
 
-def iLQGkl_device(dynamics, costfun, derivs, x0, traj_prev: GaussianPolicy, fx_model, R1, *, kl_step=1.0, lims=None, max_iter=50,
+def iLQGkl_device(dynamics, costfun, derivs, x0, traj_prev: GaussianPolicy, model, R1=None, *, kl_step=1.0, lims=None, max_iter=50,
                   etabracket=(1e-8, 1.0, 1e16), del0=1e-4, cost=None, max_eta_retries=200, force_generic=False,
                   engine: Engine = None):
     """Whole ``iLQGkl`` outer loop on the device for one trajectory or a batch (``ddp_ilqgkl_solve_f64``):
@@ -749,6 +860,7 @@ def iLQGkl_device(dynamics, costfun, derivs, x0, traj_prev: GaussianPolicy, fx_m
     ``status, iter, eta bracket, divergence, dcost, expected, retries`` (no per-iteration history: nothing is
     read back inside the loop except two counters).
     """
+    fx_model, R1 = _split_model(model, R1)
     model = _model_of(dynamics, costfun)
     x = np.asarray(x0, dtype=np.float64)
     batched = x.ndim == 3
@@ -767,7 +879,7 @@ def iLQGkl_device(dynamics, costfun, derivs, x0, traj_prev: GaussianPolicy, fx_m
     o.kl_step, o.max_iter, o.del0, o.max_eta_retries = float(kl_step), int(max_iter), float(del0), int(max_eta_retries)
     for i in range(3):
         o.eta_bracket[i] = float(etabracket[i])
-    ld = _lims_dev(eng, lims, m)
+    ld, _ = _lims_dev(eng, lims, m)
     if ld is not None:
         keep.append(ld)
         o.lims = ld.ptr
@@ -817,7 +929,7 @@ class HostIteration:
     FIELDS_IN = ("fx", "fu", "cx", "cu", "x", "u", "lam")
     FIELDS_OUT = ("xnew", "unew", "cost", "dV")
 
-    def __init__(self, eng: Engine, Q, R, cxu=None, reg_type=1, alpha=1.0, chunk=0, device_derivs=False):
+    def __init__(self, eng: Engine, Q, R, cxu=None, reg_type=1, alpha=1.0, chunk=0, device_derivs=False, keep_policy=True):
         self.eng = eng
         n, m, T, B = eng.n, eng.m, eng.T, eng.B
         shapes = dict(fx=(B, n, n), fu=(B, m, n), cx=(B, T, n), cu=(B, T, m), x=(B, T, n), u=(B, T, m), lam=(B,),
@@ -837,6 +949,7 @@ class HostIteration:
             self.args.cx = self.args.cu = None
         self.args.Q, self.args.R, self.args.cxu = self.Q.ctypes.data, self.R.ctypes.data, self.cxu.ctypes.data
         self.args.reg_type, self.args.alpha, self.args.chunk = reg_type, alpha, chunk
+        self.args.keep_policy = 1 if keep_policy else 0
         self.args.q_diagonal = 1 if np.count_nonzero(self.Q - np.diag(np.diagonal(self.Q))) == 0 else 0
 
     def _pinned(self, shape, dtype):
@@ -849,11 +962,88 @@ class HostIteration:
         buf = (C.c_char * max(nbytes, 8)).from_address(p.value)
         return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape, dtype=np.int64))).reshape(shape)
 
-    def run(self):
+    def run(self, inputs_resident=False, commit_accepted=False, cost_prev=None):
+        """One iteration.  ``inputs_resident``: use the device copies of ``fx,fu,x,u,lam`` left by the previous call instead of
+        uploading them; ``commit_accepted`` (+ ``cost_prev``, the cost of the current trajectories): afterwards the device copies
+        of ``x,u`` hold ``xnew,unew`` where the step was accepted, so the next call can run with ``inputs_resident``."""
+        self.args.inputs_resident = 1 if inputs_resident else 0
+        self.args.commit_accepted = 1 if commit_accepted else 0
+        if commit_accepted:
+            self._cprev = np.ascontiguousarray(cost_prev, dtype=np.float64)
+            self.args.cost_prev = self._cprev.ctypes.data
         self.eng._ck(self.eng.lib.ddp_ilqg_iter_host_f64(self.eng.h, C.byref(self.args)))
         return int(self.args.h2d_bytes), int(self.args.d2h_bytes)
+
+    def policy_ptrs(self):
+        """Device pointers ``(K, k, Vx, xnew, unew)`` of what the last ``run`` left on the device (ddp_iter_host_policy);
+        ``K, k, Vx`` are ``None`` unless the iteration was created with ``keep_policy``."""
+        ps = [C.c_void_p() for _ in range(5)]
+        self.eng._ck(self.eng.lib.ddp_iter_host_policy(self.eng.h, *[C.byref(p) for p in ps]))
+        return tuple(p.value for p in ps)
+
+    def policy(self, b0=0, b1=None):
+        """Download the policy of trajectories ``b0:b1`` kept on the device: ``(K (nb,T,m,n), k (nb,T,m), Vx (nb,T,n))``."""
+        n, m, T, B = self.eng.n, self.eng.m, self.eng.T, self.eng.B
+        b1 = B if b1 is None else b1
+        Kp, kp, Vxp, _, _ = self.policy_ptrs()
+        if Kp is None:
+            raise RuntimeError("the policy was not kept on the device (keep_policy=False)")
+        nb = b1 - b0
+        K, k, Vx = np.empty((nb, T, n, m)), np.empty((nb, T, m)), np.empty((nb, T, n))
+        for arr, p, per in ((K, Kp, T * n * m), (k, kp, T * m), (Vx, Vxp, T * n)):
+            self.eng._ck(self.eng.lib.ddp_download(self.eng.h, arr.ctypes.data, p + 8 * per * b0, arr.nbytes))
+        return np.swapaxes(K, -1, -2), k, Vx
 
     def close(self):
         for p in self._ptrs:
             self.eng.lib.ddp_host_free(p)
         self._ptrs = []
+
+
+# ---------------------------------------------------------------------------------------------
+# one device-resident iteration, chunked (ddp_ilqg_iter_f64): batches larger than the policy's HBM residency
+# ---------------------------------------------------------------------------------------------
+
+
+def iterate_chunked(model, x, u, lam, alpha=1.0, *, regType=1, lims=None, chunk=0, keep_policy=False, engine: Engine = None):
+    """One ``back_pass`` + ``forward_pass(α)`` over a batch ``x (B,N,n)``, ``u (B,N,m)`` of a device model with the policy
+    living in a chunk-sized scratch (``ddp_ilqg_iter_f64``; BASELINE config 5).  The derivative step of the model
+    (``cx = Q(x-goal)``, ``cu = R u``; pendcart also ``fx, fu``) runs on the device per chunk.
+    Returns ``dict(xnew, unew, cost, dV, diverge, n_chunks[, K, k, Vx])``."""
+    x = np.asarray(x, dtype=np.float64)
+    u = np.asarray(u, dtype=np.float64)
+    B, N, n = x.shape
+    m = u.shape[-1]
+    eng = engine or Engine(n, m, N, B)
+    M, keep = _pack_model(eng, model, B, N, n, m)
+    a = L.IterArgs()
+    dx, du = eng.upload(x), eng.upload(u)
+    dl = eng.upload(np.broadcast_to(np.asarray(lam, dtype=np.float64), (B,)))
+    a.x, a.u, a.lam = dx.ptr, du.ptr, dl.ptr
+    alpha = np.asarray(alpha, dtype=np.float64)
+    if alpha.ndim == 0:
+        a.alpha_scalar = float(alpha)
+    else:
+        dal = eng.upload(np.broadcast_to(alpha, (B,))); keep.append(dal)
+        a.alpha = dal.ptr
+    a.reg_type = int(regType)
+    ld, lst = _lims_dev(eng, lims, m)
+    if lst:
+        raise NotImplementedError("time-varying lims: use back_pass / forward_pass")
+    if ld is not None:
+        keep.append(ld)
+        a.lims = ld.ptr
+    xnew, unew, cost, dV, dv = eng.empty((B, N, n)), eng.empty((B, N, m)), eng.empty((B,)), eng.empty((B, 2)), eng.empty((B,), np.int32)
+    a.xnew, a.unew, a.cost, a.dV, a.diverge = xnew.ptr, unew.ptr, cost.ptr, dV.ptr, dv.ptr
+    pol = None
+    if keep_policy:
+        pol = (eng.empty((B, N, n, m)), eng.empty((B, N, m)), eng.empty((B, N, n)))
+        a.K, a.k, a.Vx = (p.ptr for p in pol)
+    a.chunk = int(chunk)
+    eng._ck(eng.lib.ddp_ilqg_iter_f64(eng.h, C.byref(M), C.byref(a)))
+    eng.synchronize()
+    out = dict(xnew=xnew.numpy(), unew=unew.numpy(), cost=cost.numpy(), dV=dV.numpy(), diverge=dv.numpy(), n_chunks=int(a.n_chunks))
+    if pol is not None:
+        out.update(K=np.swapaxes(pol[0].numpy(), -1, -2), k=pol[1].numpy(), Vx=pol[2].numpy())
+    del keep
+    return out

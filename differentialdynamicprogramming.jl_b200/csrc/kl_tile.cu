@@ -126,14 +126,12 @@ __global__ void __launch_bounds__(KW * 32, 2) kl_tile32x8_kernel(KlParams P) {
             // ---- pivots of Sp' and Sn' (determinant of the transpose = determinant): accumulator layout, shuffles; one pivot
             //      of both matrices per call, interleaved with the DMMAs below
             double pdp = 1.0, pdn = 1.0;
-            bool pos = true;
             double A0 = Sp2.x, A1 = Sp2.y, B0 = Sn2.x, B1 = Sn2.y;
             auto piv_step = [&](const int p) {
                 const double ownA = (p & 1) ? A1 : A0, ownB = (p & 1) ? B1 : B0;
                 const double dA = shf(ownA, 4 * p + (p >> 1)), dB = shf(ownB, 4 * p + (p >> 1));
                 const double cA = shf(ownA, (lane & ~3) | (p >> 1)), cB = shf(ownB, (lane & ~3) | (p >> 1));
                 const double rA0 = shf(A0, 4 * p + q), rA1 = shf(A1, 4 * p + q), rB0 = shf(B0, 4 * p + q), rB1 = shf(B1, 4 * p + q);
-                if (!(dA > 0.0) || !(dB > 0.0)) pos = false;
                 pdp *= dA;
                 pdn *= dB;
                 const double fA = (g != p) ? cA * rcp_nr(dA) : 0.0, fB = (g != p) ? cB * rcp_nr(dB) : 0.0;   // the pivot row stays
@@ -207,7 +205,8 @@ __global__ void __launch_bounds__(KW * 32, 2) kl_tile32x8_kernel(KlParams P) {
                 // klutils.jl:98 max.(0, kldiv): Julia's max keeps NaN (CUDA's fmax would turn it into 0 = "KL too small");
                 // a non-positive pivot = logdet throws = the reference's catch branch returns Inf (klutils.jl:92-96)
                 v = (v != v) ? v : fmax(0.0, v);
-                if (!pos) v = INFINITY;
+                // Julia's logdet throws for a negative (or zero) determinant -- not for any non-positive pivot: det = product of pivots
+                if (!(pdp > 0.0) || !(pdn > 0.0)) v = INFINITY;
                 if (P.kl_t && lane == 0) P.kl_t[b * N + t] = v;
                 klsum += v;
             }

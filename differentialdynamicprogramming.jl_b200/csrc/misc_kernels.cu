@@ -53,21 +53,25 @@ __global__ void __launch_bounds__(128) boxqp_kernel(long long B, int m, const do
 //                 + ½(μ'ΔK'ΣipΔKμ + tr(ΔK'ΣipΔK Σt)) + Δk'ΣipΔKμ)
 constexpr int KT = 128;
 
-__device__ double logdet_chol(int m, const double* A, double* R) {   // A sym PD (m x m, ld m)
+// logdet(A) of a symmetric m x m matrix (ld m) by elimination without pivoting (LDL'): det = product of the pivots.  Like Julia's
+// logdet (klutils.jl:89) it fails -- NaN here, "throws" there -- for a determinant <= 0, not for any non-positive pivot.
+__device__ double logdet_chol(int m, const double* A, double* R) {
     double ld = 0.0;
+    bool neg = false;
     for (int j = 0; j < m; j++) {
-        for (int i = 0; i < j; i++) {
+        for (int i = 0; i < j; i++) {                 // R[i,j] = L[j,i] D[i]
             double s = A[i + m * j];
-            for (int p = 0; p < i; p++) s -= R[p + m * i] * R[p + m * j];
-            R[i + m * j] = s / R[i + m * i];
+            for (int p = 0; p < i; p++) s -= R[p + m * i] * R[p + m * j] / R[p + m * p];
+            R[i + m * j] = s;
         }
         double d = A[j + m * j];
-        for (int p = 0; p < j; p++) d -= R[p + m * j] * R[p + m * j];
-        if (!(d > 0.0)) return nan("");
-        R[j + m * j] = sqrt(d);
-        ld += log(d);
+        for (int p = 0; p < j; p++) d -= R[p + m * j] * R[p + m * j] / R[p + m * p];
+        if (!(d != 0.0)) return nan("");              // zero or NaN pivot
+        R[j + m * j] = d;
+        if (d < 0.0) neg = !neg;
+        ld += log(fabs(d));
     }
-    return ld;   // = 2 Σ log R_jj
+    return neg ? nan("") : ld;
 }
 
 __global__ void __launch_bounds__(KT) kl_div_kernel(KlParams P) {

@@ -272,11 +272,24 @@ def _lims_active(lims) -> bool:
     lims = np.asarray(lims)
     if lims.size == 0:
         return False
+    if lims.ndim == 3:                         # time-varying extension: the test reads the first step's block
+        lims = lims[0]
     return not (lims[0, 0] > lims[0, 1])
 
 
-def back_pass(cx, cu, cxx, cxu, cuu, fx, fu, lam, regType, lims, x, u, *, boxqp_hermitian_check=False):
-    """One backward sweep; covers the three live dispatch variants backward_pass.jl:162-252.
+def vectens(a, b):
+    """The contraction the 15-argument ``back_pass`` methods call (backward_pass.jl:107,113,118) but the reference never
+    defines (quirk Q12; only the broken ``choleskyvectens`` at backward_pass.jl:1 exists, whose shape says what was meant):
+    ``vectens(a, b)[p, q] = sum_k a[k] * b[k, q, p]`` for ``b`` of shape (n, d2, d3) -> result (d3, d2)."""
+    return np.einsum("k,kqp->pq", a, b)
+
+
+def back_pass(cx, cu, cxx, cxu, cuu, fx, fu, lam, regType, lims, x, u, *, boxqp_hermitian_check=False,
+              fxx=None, fxu=None, fuu=None):
+    """One backward sweep; covers the three live dispatch variants backward_pass.jl:162-252 and, with ``fxx``/``fxu``/``fuu``
+    (each ``(n,·,·)`` or ``(N,n,·,·)``, ``None`` = ``isempty``), the second-order terms of the 15-argument methods
+    (backward_pass.jl:81-160) with ``vectens`` as defined above.  ``lims`` may be ``(m,2)`` or, as an extension,
+    ``(N,m,2)`` time-varying.
 
     Returns ``(diverge, GaussianPolicy, Vx, Vxx, dV)`` as backward_pass.jl:251.  The policy's
     ``Sigmai`` holds the unregularised ``Quu`` (slice N-1 = cuu) and ``Sigma`` is ``None`` (the
@@ -307,11 +320,23 @@ def back_pass(cx, cu, cxx, cxu, cuu, fx, fu, lam, regType, lims, x, u, *, boxqp_
         Qu = cu[i] + fui.T @ Vxn                                 # :240
         Qx = cx[i] + fxi.T @ Vxn                                 # :241
         Qux = cxui.T + (fui.T @ Vxxn) @ fxi                      # :242
+        if fxu is not None:                                      # :106-109
+            fxuVx = vectens(Vxn, _t(np.asarray(fxu), i, 3))
+            Qux = Qux + fxuVx
         Quu[i] = cuui + (fui.T @ Vxxn) @ fui                     # :243
+        if fuu is not None:                                      # :112-115
+            fuuVx = vectens(Vxn, _t(np.asarray(fuu), i, 3))
+            Quu[i] = Quu[i] + fuuVx
         Qxx = cxxi + (fxi.T @ Vxxn) @ fxi                        # :244
+        if fxx is not None:                                      # :118
+            Qxx = Qxx + vectens(Vxn, _t(np.asarray(fxx), i, 3))
         Vxx_reg = Vxxn + (lam * np.eye(n) if regType == 2 else 0.0)                 # :245
         Qux_reg = cxui.T + (fui.T @ Vxx_reg) @ fxi                                  # :246
+        if fxu is not None:                                      # :121
+            Qux_reg = Qux_reg + fxuVx
         QuuF = cuui + (fui.T @ Vxx_reg) @ fui + (lam * np.eye(m) if regType == 1 else 0.0)  # :247
+        if fuu is not None:                                      # :123
+            QuuF = QuuF + fuuVx
         # ---- @end_backward_pass  :28-79
         if not use_qp:
             R, ok = seq_chol_upper(QuuF)                         # :35 upper triangle only
@@ -323,8 +348,9 @@ def back_pass(cx, cu, cxx, cxu, cuu, fx, fu, lam, regType, lims, x, u, *, boxqp_
             for j in range(n):                                                       # :42
                 K_i[:, j] = -seq_solve_upper(R, seq_solve_upper_t(R, Qux_reg[:, j]))
         else:
-            lower = lims[:, 0] - u[i]                            # :45
-            upper = lims[:, 1] - u[i]
+            li = lims if np.ndim(lims) == 2 else lims[i]         # time-varying limits: block i
+            lower = li[:, 0] - u[i]                              # :45
+            upper = li[:, 1] - u[i]
             try:
                 k_i, result, R, free, _ = boxQP(QuuF, Qu, lower, upper, k[min(i + 1, N - 2)],
                                                 hermitian_check=boxqp_hermitian_check)   # :49
@@ -468,7 +494,8 @@ def forward_pass(traj_new: GaussianPolicy, x0, u, x, alpha, f: Callable, costfun
             dx = diff(xnew[i], x[i])
             unew[i] = unew[i] + traj_new.K[i] @ dx                           # :20
         if has_lims:
-            unew[i] = _clamp_jl(unew[i], lims[:, 0], lims[:, 1])            # :23 (NaN survives; f zeroes it)
+            li = lims if np.ndim(lims) == 2 else lims[i]
+            unew[i] = _clamp_jl(unew[i], li[:, 0], li[:, 1])                # :23 (NaN survives; f zeroes it)
         xnewi = f(xnew[i], unew[i], i + 1)                                   # :25 (called at i=N too)
         if i < N - 1:
             xnew[i + 1] = xnewi

@@ -36,3 +36,15 @@ def relerr(a, b):
     a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
     den = np.max(np.abs(b))
     return float(np.max(np.abs(a - b)) / (den if den > 0 else 1.0))
+
+
+def relerr_elem(a, b, floor=1e-4):
+    """Largest ELEMENT-WISE relative error |a-b| / max(|b|, floor * max|b|): every entry is measured against its own
+    magnitude; entries smaller than ``floor`` times the tensor's largest (where FP64 cancellation makes a relative
+    figure meaningless) are measured against that floor instead."""
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    if b.size == 0:
+        return 0.0
+    scale = np.max(np.abs(b))
+    den = np.maximum(np.abs(b), floor * (scale if scale > 0 else 1.0))
+    return float(np.max(np.abs(a - b) / den))

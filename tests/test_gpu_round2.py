@@ -1,0 +1,456 @@
+"""GPU parity, round 2: the paths added to close VERDICT r01 -- second-order terms (quirk Q12), time-varying limits,
+packed upper-triangle Vxx history, asymmetric terminal cxx, borderline-PD `diverge` parity of the tile kernel, the
+pendulum's ZoH Jacobians against scipy's expm, pre-rolled start + per-iteration trace of the iLQG driver, the
+policy kept by the host-buffer pipeline, the chunked device iteration, NaN handling of the clamps and of the KL
+evaluation.  Everything goes through the C ABI (ctypes) and is compared with the CPU oracle on the same inputs.
+
+Tolerances: integer outcomes exact; floating point 1e-8 relative, ELEMENT-WISE where stated (helpers.relerr_elem)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from helpers import make_batch_lq, relerr, relerr_elem
+from oracle import ddp_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-8
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# back_pass extensions
+# ---------------------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("regType", [1, 2])
+@pytest.mark.parametrize("tv", [False, True])
+def test_second_order_terms(ddp, regType, tv):
+    """15-argument back_pass (backward_pass.jl:81-160) with vectens(a,b)[p,q] = sum_k a_k b[k,q,p] (quirk Q12)."""
+    B, n, m, N = 3, 6, 2, 14
+    A, Bm, Q, R, x, u = make_batch_lq(40, B, n, m, N)
+    rng = np.random.default_rng(41)
+    cx, cu = x @ Q.T, u @ R.T
+    fx = A[:, None] + 1e-3 * rng.standard_normal((B, N, n, n))
+    fu = Bm[:, None] + 1e-3 * rng.standard_normal((B, N, n, m))
+    shp = (B, N) if tv else (B, 1)
+    sym = lambda t: 0.5 * (t + np.swapaxes(t, -1, -2))
+    fxx = 0.02 * sym(rng.standard_normal(shp + (n, n, n)))                      # fxx[k,q,p] symmetric in (q,p)
+    fxu = 0.02 * rng.standard_normal(shp + (n, n, m))
+    fuu = 0.002 * sym(rng.standard_normal(shp + (n, m, m)))
+    cxu = 0.01 * rng.standard_normal((n, m))
+    dv, pol, Vx, Vxx, dV = ddp.back_pass(cx, cu, Q, cxu, R, fx, fu, fxx, fxu, fuu, 0.7, regType, None, x, u)
+    for b in range(B):
+        sl = (lambda t: t[b]) if tv else (lambda t: t[b, 0])
+        d0, p0, Vx0, Vxx0, dV0 = O.back_pass(cx[b], cu[b], Q, cxu, R, fx[b], fu[b], 0.7, regType, None, x[b], u[b],
+                                             fxx=sl(fxx), fxu=sl(fxu), fuu=sl(fuu))
+        assert dv[b] == d0 == 0
+        for got, ref in ((pol.K[b], p0.K), (pol.k[b], p0.k), (Vx[b], Vx0), (Vxx[b], Vxx0), (dV[b], dV0), (pol.Sigmai[b], p0.Sigmai)):
+            assert relerr_elem(got, ref) < TOL
+    # the terms matter: without them the gains differ
+    dv2, pol2, *_ = ddp.back_pass(cx, cu, Q, cxu, R, fx, fu, 0.7, regType, None, x, u)
+    assert relerr(pol2.K, pol.K) > 1e-4
+    # only some of the tensors given (`isempty` for the others)
+    dv3, pol3, Vx3, *_ = ddp.back_pass(cx, cu, Q, cxu, R, fx, fu, None, fxu, None, 0.7, regType, None, x, u)
+    d0, p0, Vx0, _, _ = O.back_pass(cx[0], cu[0], Q, cxu, R, fx[0], fu[0], 0.7, regType, None, x[0], u[0],
+                                    fxu=(fxu[0] if tv else fxu[0, 0]))
+    assert relerr_elem(pol3.K[0], p0.K) < TOL and relerr_elem(Vx3[0], Vx0) < TOL
+
+
+def test_time_varying_lims(ddp):
+    """lims (N,m,2): back_pass boxQP branch and forward_pass clamp read block i (SURVEY 8f-4 extension)."""
+    B, n, m, N = 4, 5, 2, 20
+    A, Bm, Q, R, x, u = make_batch_lq(42, B, n, m, N)
+    cx, cu = x @ Q.T, u @ R.T
+    Rs = 0.5 * (R + R.T)
+    half = 0.05 + 0.3 * np.abs(np.sin(np.arange(N)))[:, None] * np.ones((N, m))
+    lims = np.stack([-half, half * 1.2], axis=-1)                                # (N,m,2)
+    dv, pol, Vx, Vxx, dV = ddp.back_pass(cx, cu, Q, np.zeros((n, m)), Rs, A[:, None], Bm[:, None], 1.0, 1, lims, x, u)
+    for b in range(B):
+        d0, p0, Vx0, Vxx0, dV0 = O.back_pass(cx[b], cu[b], Q, np.zeros((n, m)), Rs, A[b], Bm[b], 1.0, 1, lims, x[b], u[b])
+        assert dv[b] == d0
+        assert np.array_equal(pol.K[b] == 0, p0.K == 0)                          # identical clamped sets at every step
+        for got, ref in ((pol.K[b], p0.K), (pol.k[b], p0.k), (Vx[b], Vx0), (Vxx[b], Vxx0)):
+            assert relerr_elem(got, ref) < TOL
+        model = ddp.LinearModel(A[b], Bm[b], Q, R)
+        om = O.LinearModel(A[b], Bm[b], Q, R)
+        polb = ddp.GaussianPolicy(N, n, m, pol.K[b], pol.k[b])
+        xn, un, cn = ddp.forward_pass(polb, x[b, 0], u[b], x[b], 1.0, model.f, model.costfun, lims)
+        x0_, u0_, c0_ = O.forward_pass(O.GaussianPolicy(N, n, m, pol.K[b], pol.k[b], None, None), x[b, 0], u[b], x[b], 1.0, om.f, om.costfun, lims)
+        assert relerr_elem(xn, x0_) < TOL and relerr_elem(un, u0_) < TOL and abs(cn - c0_) <= TOL * abs(c0_)
+        assert np.array_equal(un == lims[:, :, 0], u0_ == lims[:, :, 0]) and np.array_equal(un == lims[:, :, 1], u0_ == lims[:, :, 1])
+
+
+@pytest.mark.parametrize("n,m,N,generic", [(32, 8, 12, False), (32, 8, 12, True), (4, 1, 25, False), (7, 3, 10, False)])
+def test_vxx_packed_history(ddp, n, m, N, generic):
+    """want_Vxx="upper": the packed upper-triangle history (half the bytes) expands to exactly the full one."""
+    A, Bm, Q, R, x, u = make_batch_lq(43, 5, n, m, N)
+    cx, cu = x @ Q.T, u @ R.T
+    args = (cx, cu, Q, np.zeros((n, m)), R, A[:, None], Bm[:, None], 0.8, 1, None, x, u)
+    full = ddp.back_pass(*args, force_generic=generic)
+    tri = ddp.back_pass(*args, want_Vxx="upper", force_generic=generic)
+    assert np.array_equal(full[0], tri[0])
+    assert np.array_equal(full[3], tri[3])                                        # Vxx history, bit for bit
+    assert np.array_equal(full[1].K, tri[1].K) and np.array_equal(full[2], tri[2])
+
+
+def test_vxx_packed_history_diverged(ddp):
+    B, n, m, N = 3, 32, 8, 10
+    A, Bm, Q, R, x, u = make_batch_lq(5, B, n, m, N)
+    cx, cu = x @ Q.T, u @ R.T
+    Rneg = -0.5 * np.eye(m)
+    lam = np.array([1.0, 0.1, 1.0])
+    args = (cx, cu, Q, np.zeros((n, m)), Rneg, A[:, None], Bm[:, None], lam, 1, None, x, u)
+    full, tri = ddp.back_pass(*args), ddp.back_pass(*args, want_Vxx="upper")
+    assert np.array_equal(full[0], tri[0]) and full[0][1] == N - 1
+    assert np.array_equal(full[3], tri[3])
+
+
+@pytest.mark.parametrize("gps", [False, True])
+def test_asymmetric_terminal_cxx_is_handed_to_the_generic_kernel(ddp, gps):
+    """The tile kernel assumes Vxx = Vxx'.  A terminal cxx that is not exactly symmetric (the reference takes it as it is,
+    backward_pass.jl:22) is detected in the kernel and that trajectory is processed by the generic kernel instead."""
+    B, n, m, N = 5, 32, 8, 9
+    A, Bm, Q, R, x, u = make_batch_lq(44, B, n, m, N)
+    rng = np.random.default_rng(45)
+    cx, cu = x @ Q.T, u @ R.T
+    cxx = np.tile(Q, (B, N, 1, 1))
+    cxx[1, N - 1] += 1e-3 * rng.standard_normal((n, n))                           # trajectory 1: asymmetric terminal Hessian
+    cxx[3, 2] += 1e-3 * rng.standard_normal((n, n))                               # trajectory 3: asymmetric at an inner step only
+    if not gps:
+        dv, pol, Vx, Vxx, dV = ddp.back_pass(cx, cu, cxx, np.zeros((n, m)), R, A[:, None], Bm[:, None], 1.0, 1, None, x, u)
+    else:
+        prev = ddp.back_pass(cx, cu, Q, np.zeros((n, m)), R, A[:, None], Bm[:, None], 1.0, 1, None, x, u)[1]
+        prev = ddp.GaussianPolicy(N, n, m, prev.K, np.zeros_like(prev.k), None, prev.Sigmai)
+        dv, pol, Vx, Vxx, dV = ddp.back_pass_gps(cx, cu, cxx, np.zeros((B, N, n, m)), np.tile(R, (B, N, 1, 1)), np.tile(A[:, None], (1, N, 1, 1)),
+                                                 np.tile(Bm[:, None], (1, N, 1, 1)), None, x, u, (prev, np.array([1e-8, 2.0, 1e16])))
+    for b in range(B):
+        if not gps:
+            d0, p0, Vx0, Vxx0, dV0 = O.back_pass(cx[b], cu[b], cxx[b], np.zeros((n, m)), R, A[b], Bm[b], 1.0, 1, None, x[b], u[b])
+        else:
+            pb = O.GaussianPolicy(N, n, m, prev.K[b], prev.k[b], None, prev.Sigmai[b])
+            d0, p0, Vx0, Vxx0, dV0 = O.back_pass_gps(cx[b], cu[b], cxx[b], np.zeros((N, n, m)), np.tile(R, (N, 1, 1)), np.tile(A[b], (N, 1, 1)),
+                                                     np.tile(Bm[b], (N, 1, 1)), None, x[b], u[b], (O.grad_kl(pb), np.array([1e-8, 2.0, 1e16])))
+        assert dv[b] == d0 == 0
+        for got, ref in ((pol.K[b], p0.K), (pol.k[b], p0.k), (Vx[b], Vx0), (Vxx[b], Vxx0), (dV[b], dV0)):
+            assert relerr_elem(got, ref) < TOL, b
+
+
+def test_tile_diverge_parity_at_the_pd_boundary(ddp):
+    """`diverge` of the tile kernel (Gauss-Jordan pivots of the full 8 x 8) against the oracle's cholesky(Hermitian(QuuF)) on both
+    sides of the positive-definiteness boundary: with cuu = -c I the smallest eigenvalue of QuuF = Quu + lambda I crosses zero at
+    a lambda* that is bisected to 1e-12; at lambda* (1 +- 1e-9), (1 +- 1e-6) and (1 +- 1e-3) both must agree on failure/success and
+    on the failing step."""
+    B, n, m, N = 8, 32, 8, 12
+    A, Bm, Q, R, x, u = make_batch_lq(46, 1, n, m, N)
+    cx, cu = x @ Q.T, u @ R.T
+    Rneg = -0.3 * np.eye(m)
+    odiv = lambda lam: O.back_pass(cx[0], cu[0], Q, np.zeros((n, m)), Rneg, A[0], Bm[0], lam, 1, None, x[0], u[0])[0]
+    lo, hi = 0.0, 1.0
+    assert odiv(lo) > 0 and odiv(hi) == 0
+    while hi - lo > 1e-12 * hi:
+        mid = 0.5 * (lo + hi)
+        if odiv(mid) > 0:
+            lo = mid
+        else:
+            hi = mid
+    lams = np.array([lo * (1 - 1e-3), lo * (1 - 1e-6), lo * (1 - 1e-9), lo, hi, hi * (1 + 1e-9), hi * (1 + 1e-6), hi * (1 + 1e-3)])
+    rep = lambda a: np.repeat(a, B, axis=0)
+    dv, pol, Vx, Vxx, dV = ddp.back_pass(rep(cx), rep(cu), Q, np.zeros((n, m)), Rneg, rep(A)[:, None], rep(Bm)[:, None], lams, 1, None, rep(x), rep(u))
+    want = np.array([odiv(l) for l in lams])
+    assert (want[:4] > 0).all() and (want[4:] == 0).all()
+    # within 1e-9 of the boundary the two factorisations may round a pivot of size ~1e-10 * lambda either way; outside they must agree
+    far = np.array([0, 1, 6, 7])
+    assert np.array_equal(dv[far], want[far]), (dv, want)
+    near = np.array([2, 3, 4, 5])
+    agree = int(np.sum(dv[near] == want[near]))
+    assert agree >= 2, (dv, want)       # at most the two points closest to the boundary (lo, hi themselves: 1e-12 apart) may flip
+    for b in np.nonzero((dv == 0) & (want == 0))[0]:
+        p0 = O.back_pass(cx[0], cu[0], Q, np.zeros((n, m)), Rneg, A[0], Bm[0], lams[b], 1, None, x[0], u[0])[1]
+        assert relerr(pol.K[b], p0.K) < (1e-3 if b in near else TOL)            # near-singular QuuF: conditioning, not parity
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# model derivatives (row f1)
+# ---------------------------------------------------------------------------------------------------------------
+
+def test_pendcart_zoh_jacobians_vs_expm(ddp):
+    """ddp_model_derivs_f64 (3 x 3 exponential + exact nilpotent block) vs scipy.linalg.expm of the reference's 5 x 5 generator
+    (system_pendcart.jl:137-154), element-wise to 1e-12."""
+    import ddp_b200
+    from ddp_b200 import _lib as L
+    rng = np.random.default_rng(47)
+    B, N = 6, 50
+    x = np.stack([rng.uniform(-4, 4, (B, N)), rng.uniform(-8, 8, (B, N)), rng.uniform(-2, 2, (B, N)), rng.uniform(-3, 3, (B, N))], axis=-1)
+    u = rng.uniform(-5, 5, (B, N, 1))
+    eng = ddp.Engine(4, 1, N, B)
+    pm = ddp.PendcartModel()
+    M, keep = ddp_b200.api._pack_model(eng, pm, B, N, 4, 1)
+    dx, du = eng.upload(x), eng.upload(u)
+    fx, fu, cx, cu = eng.empty((B, N, 4, 4)), eng.empty((B, N, 1, 4)), eng.empty((B, N, 4)), eng.empty((B, N, 1))
+    eng._ck(eng.lib.ddp_model_derivs_f64(eng.h, C.byref(M), dx.ptr, du.ptr, fx.ptr, fu.ptr, cx.ptr, cu.ptr))
+    eng.synchronize()
+    fxd, fud = np.swapaxes(fx.numpy(), -1, -2), np.swapaxes(fu.numpy(), -1, -2)
+    om = O.PendcartModel()
+    for b in range(B):
+        fx0, fu0, _, _, _, cx0, cu0, *_ = om.df(x[b].copy(), u[b].copy())
+        assert relerr_elem(fxd[b], fx0, floor=1e-12) < 1e-12
+        assert relerr_elem(fud[b], fu0, floor=1e-12) < 1e-12
+        assert relerr_elem(cx.numpy()[b], cx0) < 1e-14 and relerr_elem(cu.numpy()[b], cu0) < 1e-14
+    # structural zeros / ones of the exponential are exact
+    assert np.all(fxd[..., 0, 2:] == 0) and np.all(fxd[..., 2, 2] == 1) and np.all(fxd[..., 3, 3] == 1) and np.all(fxd[..., 2, 3] == pm.p[2])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# iLQG driver: pre-rolled start, per-iteration trace
+# ---------------------------------------------------------------------------------------------------------------
+
+def _trace_arrays(tr, key):
+    return {it: v for it, v in tr[key]}
+
+
+@pytest.mark.parametrize("lims", [None, 0.25])
+def test_ilqg_prerolled_and_trace(ddp, lims):
+    """x0 of size (n,N) + cost (iLQG.jl:193-197) and the reference's per-iteration trace keys (iLQG.jl:257, 325-330)."""
+    B, n, m, N = 4, 8, 2, 40
+    A, Bm, Q, R, x, u = make_batch_lq(48, B, n, m, N)
+    lm = None if lims is None else np.array([[-lims, lims]] * m)
+    costs = np.array([O.LinearModel(A[b], Bm[b], Q, R).costfun(x[b], u[b]) for b in range(B)])
+    model = ddp.LinearModel(A[:, None], Bm[:, None], Q, R)
+    xs, us, pol, Vx, Vxx, cost, tr = ddp.iLQG(model.f, model.costfun, model.df, x, u, lims=lm, cost=costs, max_iter=30, trace_iters=64)
+    it_tr = tr["iterations"]
+    for b in range(B):
+        om = O.LinearModel(A[b], Bm[b], Q, R)
+        x0_, u0_, p0, Vx0, Vxx0, c0, t0 = O.iLQG(om.f, om.costfun, om.df, x[b].copy(), u[b].copy(), lims=lm, cost=costs[b], max_iter=30)
+        assert tr["status"][b] == t0["status"] and tr["iter"][b] == t0["iters"]
+        assert relerr(xs[b], x0_) < 1e-7 and relerr(us[b], u0_) < 1e-7 and abs(cost[b] - np.sum(c0)) <= 1e-9 * abs(np.sum(c0))
+        for key, okey in (("lam", "lam"), ("dlam", "dlam"), ("cost", "cost"), ("alpha", "alpha"), ("improvement", "improvement"),
+                          ("reduce_ratio", "reduce_ratio"), ("grad_norm", "grad_norm")):
+            ref = _trace_arrays(t0, okey)
+            for it in range(1, t0["iters"] + 1):
+                got = it_tr[key][it - 1, b]
+                if it in ref:
+                    want = ref[it]
+                    if np.isnan(want):
+                        assert np.isnan(got), (key, it)
+                    elif key in ("lam", "dlam", "alpha"):
+                        assert got == want, (key, it, got, want)                  # schedules are exact
+                    else:
+                        assert abs(got - want) <= 1e-6 * max(abs(want), 1e-12) + 1e-13, (key, it, got, want)
+                else:
+                    assert np.isnan(got), (key, it)                               # the reference records nothing here (break before trace)
+        n_rec = len(_trace_arrays(t0, "lam")) - 1
+        assert np.all(it_tr["accepted"][:n_rec, b] >= 0) and np.all(it_tr["accepted"][n_rec:, b] == -1)
+    # a pre-rolled start equals the plain start when the rollout is the one the driver would make itself (alpha = 1, no lims)
+    if lims is None:
+        r2 = ddp.iLQG(model.f, model.costfun, model.df, x[:, 0], u, max_iter=30)
+        assert np.array_equal(r2[6]["status"], tr["status"]) and np.array_equal(r2[6]["iter"], tr["iter"])
+        assert relerr(r2[0], xs) < 1e-9
+    with pytest.raises(RuntimeError, match="initial cost must also be supplied"):
+        ddp.iLQG(model.f, model.costfun, model.df, x, u)
+    with pytest.raises(RuntimeError, match="correct length"):
+        ddp.iLQG(model.f, model.costfun, model.df, x[:, :-1], u, cost=costs)
+
+
+def test_ilqg_status4_rows_are_zero(ddp):
+    """A trajectory whose initial rollout diverges for every step size returns zeros, not uninitialised memory."""
+    B, n, m, N = 3, 6, 2, 200
+    A, Bm, Q, R, x, u = make_batch_lq(49, B, n, m, N)
+    A = A.copy()
+    A[1] = 3.0 * np.eye(n)                                                        # |x| passes 1e8 for any alpha
+    model = ddp.LinearModel(A[:, None], Bm[:, None], Q, R)
+    xs, us, pol, Vx, Vxx, cost, tr = ddp.iLQG(model.f, model.costfun, model.df, x[:, 0], u, max_iter=5)
+    assert tr["status"][1] == 4 and tr["status"][0] != 4
+    assert np.all(xs[1] == 0) and np.all(us[1] == 0) and np.all(pol.K[1] == 0)
+    with pytest.raises(ddp.DDPError, match="reg_type"):
+        ddp.iLQG(model.f, model.costfun, model.df, x[:, 0], u, regType=0)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# host pipeline keeps the policy; chunked device iteration
+# ---------------------------------------------------------------------------------------------------------------
+
+def _fill_host_iteration(it, A, Bm, x, u, lam):
+    it.bufs["fx"][...] = np.swapaxes(A, -1, -2)
+    it.bufs["fu"][...] = np.swapaxes(Bm, -1, -2)
+    it.bufs["x"][...] = x
+    it.bufs["u"][...] = u
+    it.bufs["lam"][...] = lam
+
+
+@pytest.mark.parametrize("chunk", [16, 0])
+def test_host_iteration_keeps_the_whole_policy(ddp, chunk):
+    """After ddp_ilqg_iter_host_f64 the gains of EVERY trajectory are on the device (first and last chunk alike), bit-identical to
+    ddp_back_pass_f64's, and the rollout equals forward_pass's."""
+    B, n, m, N = 70, 32, 8, 24
+    A, Bm, Q, R, x, u = make_batch_lq(50, B, n, m, N)
+    lam = 1.0 + 0.01 * np.arange(B)
+    eng = ddp.Engine(n, m, N, B)
+    it = ddp.HostIteration(eng, Q, R, reg_type=1, alpha=1.0, chunk=chunk, device_derivs=True, keep_policy=True)
+    _fill_host_iteration(it, A, Bm, x, u, lam)
+    it.run()
+    K, k, Vx = it.policy()
+    dv, pol, Vx0, _, dV0 = ddp.back_pass(x @ Q.T, u @ R.T, Q, np.zeros((n, m)), R, A[:, None], Bm[:, None], lam, 1, None, x, u)
+    assert np.array_equal(it.bufs["diverge"], dv)
+    for b in (0, 1, B // 2, B - 2, B - 1):
+        assert np.array_equal(K[b], pol.K[b]) and np.array_equal(k[b], pol.k[b]) and np.array_equal(Vx[b], Vx0[b]), b
+    assert np.array_equal(K, pol.K) and np.array_equal(it.bufs["dV"], dV0)
+    Kl, kl, _ = it.policy(B - 3, B)
+    assert np.array_equal(Kl, pol.K[B - 3:])
+    # the policy is not kept unless asked for
+    it2 = ddp.HostIteration(eng, Q, R, reg_type=1, alpha=1.0, chunk=16, device_derivs=True, keep_policy=False)
+    _fill_host_iteration(it2, A, Bm, x, u, lam)
+    it2.run()
+    assert it2.policy_ptrs()[0] is None
+    assert np.array_equal(it2.bufs["xnew"], it.bufs["xnew"]) and np.array_equal(it2.bufs["cost"], it.bufs["cost"])
+    it.close(); it2.close()
+
+
+def test_host_iteration_resident_inputs_and_commit(ddp):
+    """Second iteration with the inputs left on the device and x,u replaced by the accepted rollout == a fresh call on xnew,unew."""
+    B, n, m, N = 40, 32, 8, 20
+    A, Bm, Q, R, x, u = make_batch_lq(51, B, n, m, N)
+    lam = np.ones(B)
+    cost0 = np.array([O.LinearModel(A[b], Bm[b], Q, R).costfun(x[b], u[b]) for b in range(B)])
+    eng = ddp.Engine(n, m, N, B)
+    it = ddp.HostIteration(eng, Q, R, reg_type=1, alpha=1.0, chunk=16, device_derivs=True)
+    _fill_host_iteration(it, A, Bm, x, u, lam)
+    h2d1, _ = it.run(commit_accepted=True, cost_prev=cost0)
+    x1, u1, c1 = it.bufs["xnew"].copy(), it.bufs["unew"].copy(), it.bufs["cost"].copy()
+    assert np.all(c1 < cost0)                                                    # every step accepted on this LQ batch
+    h2d2, _ = it.run(inputs_resident=True)
+    assert h2d2 < 0.01 * h2d1                                                    # nothing but the three shared cost matrices went up
+    x2, c2, K2 = it.bufs["xnew"].copy(), it.bufs["cost"].copy(), it.policy()[0]
+    eng_b = ddp.Engine(n, m, N, B)
+    itb = ddp.HostIteration(eng_b, Q, R, reg_type=1, alpha=1.0, chunk=16, device_derivs=True)
+    _fill_host_iteration(itb, A, Bm, x1, u1, lam)
+    itb.run()
+    assert np.array_equal(itb.bufs["xnew"], x2) and np.array_equal(itb.bufs["cost"], c2) and np.array_equal(itb.policy()[0], K2)
+    it.close(); itb.close()
+    with pytest.raises(ddp.DDPError, match="inputs_resident"):
+        e3 = ddp.Engine(n, m, N, B)
+        it3 = ddp.HostIteration(e3, Q, R, device_derivs=True)
+        it3.run(inputs_resident=True)
+
+
+@pytest.mark.parametrize("model_kind", ["linear", "pendcart"])
+def test_chunked_device_iteration(ddp, model_kind):
+    """ddp_ilqg_iter_f64 with the policy in a chunk-sized scratch == the unchunked sweeps (bitwise), ragged last chunk."""
+    if model_kind == "linear":
+        B, n, m, N = 45, 32, 8, 16
+        A, Bm, Q, R, x, u = make_batch_lq(52, B, n, m, N)
+        model = ddp.LinearModel(A[:, None], Bm[:, None], Q, R)
+        lims = None
+        reg = 1
+    else:
+        B, n, m, N = 300, 4, 1, 60
+        rng = np.random.default_rng(53)
+        model = ddp.PendcartModel()
+        x0 = np.stack([np.pi - 0.6 + 0.2 * rng.uniform(-1, 1, B), np.zeros(B), np.zeros(B), np.zeros(B)], axis=-1)
+        u = 0.5 * rng.standard_normal((B, N, 1))
+        x, _, _ = ddp.forward_pass(ddp.GaussianPolicy.empty(), x0, u, None, 1.0, model.f, model.costfun, None)
+        lims = np.array([[-5.0, 5.0]])
+        reg = 2
+    lam = 1.0 + 0.001 * np.arange(B)
+    one = ddp.iterate_chunked(model, x, u, lam, 0.7, regType=reg, lims=lims, chunk=B, keep_policy=True)
+    many = ddp.iterate_chunked(model, x, u, lam, 0.7, regType=reg, lims=lims, chunk=16 if model_kind == "linear" else 128)
+    assert one["n_chunks"] == 1 and many["n_chunks"] == (3 if model_kind == "linear" else 3)
+    for key in ("xnew", "unew", "cost", "dV", "diverge"):
+        assert np.array_equal(one[key], many[key]), key
+    # against the oracle on a few trajectories
+    for b in (0, B // 2, B - 1):
+        if model_kind == "linear":
+            om = O.LinearModel(A[b], Bm[b], Q, R)
+        else:
+            om = O.PendcartModel()
+        fx, fu, _, _, _, cx, cu, cxx, cxu, cuu = om.df(x[b].copy(), u[b].copy())
+        d0, p0, Vx0, _, dV0 = O.back_pass(cx, cu, cxx, cxu, cuu, fx, fu, lam[b], reg, lims, x[b], u[b])
+        xn, un, cn = O.forward_pass(p0, x[b, 0], u[b], x[b], 0.7, om.f, om.costfun, lims)
+        assert one["diverge"][b] == d0
+        assert relerr_elem(one["K"][b], p0.K) < 1e-7 and relerr_elem(one["xnew"][b], xn) < TOL and relerr(one["dV"][b], dV0) < TOL
+        assert abs(one["cost"][b] - np.sum(cn)) <= TOL * abs(np.sum(cn))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# NaN handling: clamps keep NaN like Julia's clamp, the KL evaluation never turns NaN into "KL too small"
+# ---------------------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("n,m,generic", [(32, 8, False), (6, 2, True)])
+def test_forward_pass_nan_control_is_zeroed_not_clamped(ddp, n, m, generic):
+    """clamp.(NaN, lo, hi) is NaN in Julia and the model's f then sets it to 0 (demo_linear.jl:42): a NaN control becomes 0 even when
+    0 lies outside [lo, hi]."""
+    B, N = 3, 12
+    A, Bm, Q, R, x, u = make_batch_lq(54, B, n, m, N)
+    u = u.copy()
+    u[1, 4, 0] = np.nan
+    lims = np.array([[0.05, 0.3]] * m)                                            # 0 is outside
+    model = ddp.LinearModel(A[:, None], Bm[:, None], Q, R)
+    xn, un, cn = ddp.forward_pass(ddp.GaussianPolicy.empty(), x[:, 0], u, None, 1.0, model.f, model.costfun, lims, force_generic=generic)
+    assert un[1, 4, 0] == 0.0
+    for b in range(B):
+        om = O.LinearModel(A[b], Bm[b], Q, R)
+        x0_, u0_, c0_ = O.forward_pass(O.GaussianPolicy.empty(), x[b, 0], u[b].copy(), None, 1.0, om.f, om.costfun, lims)
+        assert relerr_elem(xn[b], x0_) < TOL and np.array_equal(un[b], u0_)
+
+
+def test_boxqp_nan_start_propagates(ddp):
+    """clamp.(x0, lower, upper) keeps a NaN x0 (boxQP.jl:58): the QP then fails exactly as the oracle's does instead of starting from `lower`."""
+    m = 3
+    rng = np.random.default_rng(55)
+    G = rng.standard_normal((4, m, m))
+    H = G @ np.swapaxes(G, -1, -2) + 0.5 * np.eye(m)
+    g = rng.standard_normal((4, m))
+    lo, up = -np.ones((4, m)), np.ones((4, m))
+    x0 = np.zeros((4, m))
+    x0[2, 1] = np.nan
+    xs, res, Hf, free, nf = ddp.boxQP(H, g, lo, up, x0)
+    for b in range(4):
+        xo, ro, Ho, fo, no = O.boxQP(H[b], g[b], lo[b], up[b], x0[b])
+        assert res[b] == ro and np.array_equal(free[b], fo)
+        assert np.array_equal(xs[b], xo, equal_nan=True)
+    assert np.isnan(xs[2]).any()
+
+
+@pytest.mark.parametrize("n,m", [(32, 8), (6, 2)])
+def test_kl_nan_and_not_pd_are_not_small(ddp, n, m):
+    """NaN rollout -> NaN divergence (Julia's max(0, NaN)); non-PD Sigma_prev -> Inf (the catch branch of klutils.jl:92-96).
+    Either way calc_eta takes the 'eta too small' branch and raises eta, never the 'KL too small' one."""
+    N, B = 10, 3
+    A, Bm, Q, R, x, u = make_batch_lq(56, B, n, m, N)
+    cx, cu = x @ Q.T, u @ R.T
+    dv, pol, _, _, _ = ddp.back_pass(cx, cu, Q, np.zeros((n, m)), R, A[:, None], Bm[:, None], 1.0, 1, None, x, u)
+    Si = pol.Sigmai.copy()
+    Si[:, N - 1] = R
+    S = np.linalg.inv(Si)
+    prev = ddp.GaussianPolicy(N, n, m, pol.K, np.zeros_like(pol.k), S, Si)
+    new = ddp.GaussianPolicy(N, n, m, 0.9 * pol.K, 0.1 * pol.k, 1.1 * S, Si / 1.1)
+    xnew = x + 0.01
+    xnew_nan = xnew.copy()
+    xnew_nan[1, 3, 0] = np.nan
+    R1 = 1e-4 * np.eye(n)
+    kt, km = ddp.kl_div_wiki(xnew_nan, x, A[:, None], R1, new, prev)
+    assert np.isfinite(km[0]) and np.isfinite(km[2]) and np.isnan(km[1]) and np.isnan(kt[1, 3])
+    Sbad = S.copy()
+    Sbad[2, 5] = np.diag([-1.0] + [1.0] * (m - 1))                                # negative determinant: Julia's logdet throws
+    prev_bad = ddp.GaussianPolicy(N, n, m, pol.K, np.zeros_like(pol.k), Sbad, Si)
+    kt2, km2 = ddp.kl_div_wiki(xnew, x, A[:, None], R1, new, prev_bad)
+    assert np.isposinf(km2[2]) and np.isfinite(km2[0])
+    # the oracle agrees on both
+    for b, (xn, pv) in ((1, (xnew_nan, prev)), (2, (xnew, prev_bad))):
+        pn = O.GaussianPolicy(N, n, m, new.K[b], new.k[b], new.Sigma[b], new.Sigmai[b])
+        pp = O.GaussianPolicy(N, n, m, pv.K[b], pv.k[b], pv.Sigma[b], pv.Sigmai[b])
+        sig = O.forward_covariance(np.tile(A[b], (N, 1, 1)), R1, pn)
+        ko = O.kl_div_wiki(xn[b], x[b], sig, pn, pp)
+        assert (np.isnan(np.mean(ko)) and b == 1) or (np.isposinf(np.mean(ko)) and b == 2)
+    # calc_eta on such a divergence raises eta (klutils.jl:123-126), in the oracle and in the device state machine alike
+    eb = np.array([1e-8, 1.0, 1e16])
+    out, sat, _ = O.calc_eta(xnew_nan[1], x[1], O.forward_covariance(np.tile(A[1], (N, 1, 1)), R1, O.GaussianPolicy(N, n, m, new.K[1], new.k[1], new.Sigma[1], new.Sigmai[1])),
+                             eb.copy(), O.GaussianPolicy(N, n, m, new.K[1], new.k[1], new.Sigma[1], new.Sigmai[1]),
+                             O.GaussianPolicy(N, n, m, prev.K[1], prev.k[1], prev.Sigma[1], prev.Sigmai[1]), 1.0)
+    assert not sat and out[1] > 1.0 and out[0] == 1.0
+
+
+def test_selftest_peak(ddp):
+    eng = ddp.Engine(32, 8, 16, 8)
+    dfma, ms1 = eng.selftest_peak("dfma")
+    dmma, ms2 = eng.selftest_peak("dmma")
+    assert 20.0 < dfma < 60.0 and 20.0 < dmma < 60.0, (dfma, dmma)              # B200: ~34 and ~37 TFLOP/s
+    assert ms1 > 0.5 and ms2 > 0.5
