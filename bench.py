@@ -836,7 +836,8 @@ def run_solve_e2e(g):
     Q, R = H_STEP * np.eye(n), 0.1 * H_STEP * np.eye(m)
     eng = ddp.Engine(n, m, T, Bs, device=local_rank)
     model = ddp.LinearModel(A[:, None], Bm[:, None], Q, R)
-    ddp.iLQG(model.f, model.costfun, model.df, x0[:256], u0[:256], max_iter=3)            # warm the allocator / module
+    warm = ddp.LinearModel(A[:256, None], Bm[:256, None], Q, R)
+    ddp.iLQG(warm.f, warm.costfun, warm.df, x0[:256], u0[:256], max_iter=3)               # warm the allocator / module
     t0 = time.perf_counter()
     xs, us, pol, Vx, Vxx, cost, tr = ddp.iLQG(model.f, model.costfun, model.df, x0, u0, engine=eng)
     dt = time.perf_counter() - t0

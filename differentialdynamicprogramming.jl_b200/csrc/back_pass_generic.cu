@@ -441,6 +441,24 @@ __global__ void __launch_bounds__(NT) bp_generic_kernel(BackParams P) {
 
 }  // namespace
 
+// Hand-over buffers of the specialised kernels (see BackParams::redo): one int counter (16 bytes reserved) + one byte per
+// trajectory, kept on the handle; the counter is reset on the handle's stream before the specialised kernel runs.
+int prepare_redo(ddp_handle_s* h, BackParams& P) {
+    cudaError_t e = cudaSuccess;
+    if (h->redo_cap < P.B) {
+        if (h->redo) cudaFree(h->redo);
+        h->redo = nullptr; h->redo_cap = 0;
+        const long long cap = P.B > h->B ? P.B : h->B;
+        e = cudaMalloc((void**)&h->redo, (size_t)cap + 16);
+        if (e != cudaSuccess) return (int)e;
+        h->redo_cap = cap;
+    }
+    P.redo_count = reinterpret_cast<int*>(h->redo);
+    P.redo = h->redo + 16;
+    e = cudaMemsetAsync(P.redo_count, 0, sizeof(int), h->stream);
+    return (int)e;
+}
+
 int launch_back_pass_generic(ddp_handle_s* h, const BackParams& P, bool gps) {
     size_t bytes = smem_doubles(P.n, P.m, gps) * sizeof(double);
     if ((long long)bytes > h->max_smem_optin) return (int)cudaErrorInvalidValue;

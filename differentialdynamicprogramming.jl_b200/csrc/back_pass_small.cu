@@ -18,98 +18,74 @@
 
 namespace {
 
-template <int N, int M>
-struct StepIn {
-    double fu[N * M], cx[N], cu[M], u[M];
-};
-
 __device__ __forceinline__ void cp_async16s(double* dst_smem, const double* src) {
     unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src));
 }
-
-template <int N>
-__device__ __forceinline__ void load_fx_direct(double* f, const BackParams& P, long long b, int i) {
-    const double* fx = tp(P.fx, b, i);
-#pragma unroll
-    for (int e = 0; e < N * N; e++) f[e] = fx[e];
+__device__ __forceinline__ void cp_async8s(double* dst_smem, const double* src) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src));
 }
 
-// rows of the staging ring: N*N doubles + one 16-byte pad => a thread's 16-byte reads of its own row are
-// conflict-free (row stride 144 B at N = 4)
-template <int N>
-struct FxStage {
-    static constexpr int ROW = N * N + 2;
-    static constexpr int CH = (N * N) / 2;            // 16-byte chunks per row
+// One staged row = every per-step input of one trajectory: [fx N*N | fu N*M | cx N | cu M | u M], padded so that the row stride is
+// 2 (mod 4) doubles: a thread's 16-byte reads of its own row are then bank-conflict free (quarter-warp strides cover all 8 bank groups).
+template <int N, int M>
+struct Row {
+    static constexpr int FX = 0, FU = N * N, CX = FU + N * M, CU = CX + N, UU = CU + M, LEN = UU + M;
+    static constexpr int ROW = LEN + ((2 - (LEN & 3)) & 3);
+    static constexpr bool OK = (N % 2 == 0) && (32 % ((N * N) / 2) == 0) && (32 % ((N * M + 1) / 2) == 0) && ((N * M) % 2 == 0);
 };
 
-// Coalesced copy of the warp's 32 fx blocks of step i into the ring: lane -> (row = lane / CH + (32 / CH) k, chunk = lane % CH).
-// The per-lane source pointer (row, chunk) and the row validity mask are formed once per trajectory set; per step the
-// address work is one 64-bit multiply-add plus one add per instruction.
-template <int N>
-__device__ __forceinline__ void stage_fx(double* sdst_lane, const double* src_lane, long long rowstep, unsigned rowmask) {
-    constexpr int CH = FxStage<N>::CH, ROW = FxStage<N>::ROW, RPI = 32 / CH;    // rows per instruction
+// symmetric n x n matrix kept as its upper triangle, column by column: (r,c), r <= c, at c(c+1)/2 + r
+__host__ __device__ constexpr int tri(int r, int c) { return (r <= c) ? c * (c + 1) / 2 + r : r * (r + 1) / 2 + c; }
+
+// Coalesced copy of one field of the warp's 32 trajectories at step i into the ring: CH 16-byte chunks per row, lane ->
+// (row = lane / CH + (32 / CH) k, chunk = lane % CH): CH lanes read one contiguous run of one trajectory.
+template <int CH>
+__device__ __forceinline__ void stage_field(double* sdst_row0, int ROWLEN, const TensorD& t, long long b0, long long B, int i, int lane, bool full) {
+    constexpr int RPI = 32 / CH;
+    const int row = lane / CH, ch = lane % CH;
+    const double* src = t.p + (b0 + row) * t.sb + (long long)i * t.st + 2 * ch;
+    double* dst = sdst_row0 + row * ROWLEN + 2 * ch;
 #pragma unroll
     for (int k = 0; k < CH; k++) {
-        if ((rowmask >> k) & 1u) cp_async16s(sdst_lane + k * RPI * ROW, src_lane);
-        src_lane += rowstep;
+        if (full || b0 + row + RPI * k < B) cp_async16s(dst + k * RPI * ROWLEN, src);
+        src += RPI * t.sb;
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
-template <int N, int M>
-__device__ __forceinline__ void load_step(StepIn<N, M>& s, const BackParams& P, long long b, int i, bool use_qp) {
-    const double* fu = tp(P.fu, b, i);
-    const double* cx = tp(P.cx, b, i);
-    const double* cu = tp(P.cu, b, i);
-    if ((N * M) % 2 == 0 && ((uintptr_t)fu % 16) == 0) {
-#pragma unroll
-        for (int e = 0; e < N * M; e += 2) { double2 t = *reinterpret_cast<const double2*>(fu + e); s.fu[e] = t.x; s.fu[e + 1] = t.y; }
-    } else {
-#pragma unroll
-        for (int e = 0; e < N * M; e++) s.fu[e] = fu[e];
-    }
-    if (N % 2 == 0 && ((uintptr_t)cx % 16) == 0) {
-#pragma unroll
-        for (int e = 0; e < N; e += 2) { double2 t = *reinterpret_cast<const double2*>(cx + e); s.cx[e] = t.x; s.cx[e + 1] = t.y; }
-        goto cx_done;
-    }
-#pragma unroll
-    for (int e = 0; e < N; e++) s.cx[e] = cx[e];
-cx_done:
-#pragma unroll
-    for (int e = 0; e < M; e++) { s.cu[e] = cu[e]; s.u[e] = use_qp ? tp(P.u, b, i)[e] : 0.0; }
-}
-
+// One thread per trajectory.  STAGE: every per-step input arrives through the warp's double-buffered cp.async ring (see Row);
+// !STAGE (odd sizes, unaligned views, DDP_SMALL_NOSTAGE): direct loads with a one-step register prefetch.  Same arithmetic either way.
 template <int N, int M, int MINB, bool STAGE>
 __global__ void __launch_bounds__(128, MINB) bp_small_kernel(BackParams P) {
-    __shared__ __align__(16) double s_fx[STAGE ? 4 * 2 * 32 * FxStage<N>::ROW : 2];
-    // cost Hessians shared by the batch and constant in time (the usual case): one copy per CTA, read by broadcast
-    __shared__ double s_cost[N * N + N * M + M * M];
+    using RW = Row<N, M>;
+    constexpr int NT = N * (N + 1) / 2;
+    extern __shared__ __align__(16) double s_ring[];         // STAGE: 4 warps x 2 buffers x 32 rows (dynamic: above the 48 KB static limit)
+    // cost Hessians shared by the batch and constant in time (the usual case): one copy per CTA, read by broadcast; cxx symmetrised
+    __shared__ double s_cost[NT + N * M + M * M];
     const bool cost_shared = (P.cxx.sb == 0 && P.cxx.st == 0 && P.cxu.sb == 0 && P.cxu.st == 0 && P.cuu.sb == 0 && P.cuu.st == 0);
     if (cost_shared) {
-        for (int e = threadIdx.x; e < N * N + N * M + M * M; e += blockDim.x)
-            s_cost[e] = (e < N * N) ? P.cxx.p[e] : (e < N * N + N * M) ? P.cxu.p[e - N * N] : P.cuu.p[e - N * N - N * M];
+        for (int e = threadIdx.x; e < NT + N * M + M * M; e += blockDim.x) {
+            double v;
+            if (e < NT) {
+                int c = 0;
+                while ((c + 1) * (c + 2) / 2 <= e) c++;
+                const int r = e - c * (c + 1) / 2;
+                v = 0.5 * (P.cxx.p[r + N * c] + P.cxx.p[c + N * r]);
+            } else v = (e < NT + N * M) ? P.cxu.p[e - NT] : P.cuu.p[e - NT - N * M];
+            s_cost[e] = v;
+        }
         __syncthreads();
     }
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const long long b_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long b0 = b_raw - lane;                       // first trajectory of this warp
     if (b0 >= P.B) return;                                   // warp-uniform
-    const bool valid = (b_raw < P.B) && !(P.active && !P.active[b_raw]);
+    bool valid = (b_raw < P.B) && !(P.active && !P.active[b_raw]);
     const long long b = (b_raw < P.B) ? b_raw : P.B - 1;     // out-of-range lanes shadow the last trajectory, store nothing
-    double* sfx = s_fx + (STAGE ? wid * 2 * 32 * FxStage<N>::ROW : 0);
+    const bool full = (b0 + 32 <= P.B);                      // warp-uniform: no row predicates in the staging copies
+    double* ring = s_ring + (STAGE ? wid * 2 * 32 * RW::ROW : 0);
     const int T = P.T;
-    // staging maps (see stage_fx)
-    constexpr int S_CH = FxStage<N>::CH, S_RPI = 32 / (S_CH > 0 ? S_CH : 1);
-    const int s_row = lane / S_CH, s_ch = lane % S_CH;
-    const double* fx_lane = P.fx.p + (b0 + s_row) * P.fx.sb + 2 * s_ch;
-    const long long fx_rowstep = (long long)S_RPI * P.fx.sb;
-    unsigned fx_rowmask = 0;
-#pragma unroll
-    for (int k = 0; k < S_CH; k++)
-        if (b0 + s_row + (long long)S_RPI * k < P.B) fx_rowmask |= 1u << k;
-    double* sfx_lane = sfx + s_row * FxStage<N>::ROW + 2 * s_ch;
     const bool use_qp = (P.lims != nullptr) && !(P.lims[0] > P.lims[M]);     // backward_pass.jl:31
     const double lam = P.lambda[b];
     const bool reg2 = (P.reg_type == 2), reg1 = (P.reg_type == 1);     // any other value: no regularisation, as `regType == 1 ? λ : 0`
@@ -123,15 +99,62 @@ __global__ void __launch_bounds__(128, MINB) bp_small_kernel(BackParams P) {
 #pragma unroll
     for (int a = 0; a < M; a++) { lims_lo[a] = use_qp ? P.lims[a] : 0.0; lims_hi[a] = use_qp ? P.lims[M + a] : 0.0; }
 
-    double V[N * N], Vx[N];            // V column-major: V[r + N c]
+    auto stage = [&](int i) {                                // all inputs of step i -> ring buffer (i & 1)
+        double* r0 = ring + (i & 1) * 32 * RW::ROW;
+        stage_field<(N * N) / 2>(r0 + RW::FX, RW::ROW, P.fx, b0, P.B, i, lane, full);
+        stage_field<(N * M) / 2>(r0 + RW::FU, RW::ROW, P.fu, b0, P.B, i, lane, full);
+        stage_field<N / 2>(r0 + RW::CX, RW::ROW, P.cx, b0, P.B, i, lane, full);
+        if (full || b_raw < P.B) {
+            double* rr = r0 + lane * RW::ROW;
+            const double* cus = tp(P.cu, b_raw, i);
+            if (M % 2 == 0) {
+#pragma unroll
+                for (int a = 0; a < M; a += 2) cp_async16s(rr + RW::CU + a, cus + a);
+            } else {
+#pragma unroll
+                for (int a = 0; a < M; a++) cp_async8s(rr + RW::CU + a, cus + a);
+            }
+            if (use_qp) {
+                const double* us = tp(P.u, b_raw, i);
+                if (M % 2 == 0) {
+#pragma unroll
+                    for (int a = 0; a < M; a += 2) cp_async16s(rr + RW::UU + a, us + a);
+                } else {
+#pragma unroll
+                    for (int a = 0; a < M; a++) cp_async8s(rr + RW::UU + a, us + a);
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    double Vs[NT], Vx[N];              // Vxx(i+1): upper triangle (exactly symmetric, backward_pass.jl:71-72)
     {
         const double* cxN = tp(P.cx, b, T - 1);
         const double* cxxN = tp(P.cxx, b, T - 1);
         const double* cuuN = tp(P.cuu, b, T - 1);
+        // The products below assume Vxx = Vxx'.  A terminal cxx that is not exactly symmetric (the reference takes it as it is,
+        // backward_pass.jl:22) is handed to the generic kernel (see BackParams::redo).
+        bool asym = false;
+#pragma unroll
+        for (int c = 0; c < N; c++)
+#pragma unroll
+            for (int r = 0; r <= c; r++) {
+                const double v = cxxN[r + N * c];
+                Vs[tri(r, c)] = v;
+                if (r < c && v != cxxN[c + N * r]) asym = true;
+                if (v != v) asym = true;
+            }
+        if (valid) {
+            P.redo[b] = asym ? 1 : 0;
+            if (asym) atomicAdd(P.redo_count, 1);
+        }
+        if (asym) valid = false;
 #pragma unroll
         for (int e = 0; e < N; e++) { Vx[e] = cxN[e]; if (valid) Vxb[(long long)(T - 1) * N + e] = Vx[e]; }
+        if (valid && Vxxb)
 #pragma unroll
-        for (int e = 0; e < N * N; e++) { V[e] = cxxN[e]; if (valid && Vxxb) Vxxb[(long long)(T - 1) * N * N + e] = V[e]; }
+            for (int e = 0; e < N * N; e++) Vxxb[(long long)(T - 1) * N * N + e] = Vs[tri(e % N, e / N)];
         if (valid) {
 #pragma unroll
             for (int e = 0; e < N * M; e++) Kb[(long long)(T - 1) * N * M + e] = 0.0;
@@ -147,31 +170,47 @@ __global__ void __launch_bounds__(128, MINB) bp_small_kernel(BackParams P) {
     for (int a = 0; a < M; a++) kw[a] = 0.0;
     double dV0 = 0.0, dV1 = 0.0;
     int diverge = 0;
-    StepIn<N, M> cur, nxt;
-    double cfx[N * N];
     bool alive = valid;
+    // !STAGE: one-step register prefetch of the inputs
+    double pf[STAGE ? 1 : RW::LEN];
+    auto load_direct = [&](int i) {
+        const double* fx = tp(P.fx, b, i);
+        const double* fu = tp(P.fu, b, i);
+        const double* cx = tp(P.cx, b, i);
+        const double* cu = tp(P.cu, b, i);
+#pragma unroll
+        for (int e = 0; e < N * N; e++) pf[(STAGE ? 0 : RW::FX + e)] = fx[e];
+#pragma unroll
+        for (int e = 0; e < N * M; e++) pf[(STAGE ? 0 : RW::FU + e)] = fu[e];
+#pragma unroll
+        for (int e = 0; e < N; e++) pf[(STAGE ? 0 : RW::CX + e)] = cx[e];
+#pragma unroll
+        for (int e = 0; e < M; e++) { pf[(STAGE ? 0 : RW::CU + e)] = cu[e]; pf[(STAGE ? 0 : RW::UU + e)] = use_qp ? tp(P.u, b, i)[e] : 0.0; }
+    };
     if (T >= 2) {
-        load_step<N, M>(cur, P, b, T - 2, use_qp);
-        if (STAGE) stage_fx<N>(sfx_lane + ((T - 2) & 1) * 32 * FxStage<N>::ROW, fx_lane + (long long)(T - 2) * P.fx.st, fx_rowstep, fx_rowmask);
+        if (STAGE) stage(T - 2);
+        else load_direct(T - 2);
     }
     for (int i = T - 2; i >= 0; i--) {
+        double in[RW::LEN];                                          // this step's [fx | fu | cx | cu | u]
         if (STAGE) {
             asm volatile("cp.async.wait_group 0;" ::: "memory");
             __syncwarp();                                            // the warp's copies of step i have landed
-            const double* row = sfx + (i & 1) * 32 * FxStage<N>::ROW + lane * FxStage<N>::ROW;
+            const double* row = ring + (i & 1) * 32 * RW::ROW + lane * RW::ROW;
 #pragma unroll
-            for (int e = 0; e < N * N; e += 2) { double2 t = *reinterpret_cast<const double2*>(row + e); cfx[e] = t.x; cfx[e + 1] = t.y; }
+            for (int e = 0; e + 1 < RW::LEN; e += 2) { const double2 t = *reinterpret_cast<const double2*>(row + e); in[e] = t.x; in[e + 1] = t.y; }
+            if (RW::LEN & 1) in[RW::LEN - 1] = row[RW::LEN - 1];
             // the other buffer was read in step i+1, before the __syncwarp above: refill it with step i-1
-            if (i > 0) stage_fx<N>(sfx_lane + ((i - 1) & 1) * 32 * FxStage<N>::ROW, fx_lane + (long long)(i - 1) * P.fx.st, fx_rowstep, fx_rowmask);
+            if (i > 0) stage(i - 1);
         } else {
-            load_fx_direct<N>(cfx, P, b, i);
+#pragma unroll
+            for (int e = 0; e < RW::LEN; e++) in[e] = pf[STAGE ? 0 : e];
+            if (i > 0) load_direct(i - 1);                           // in flight during this step's arithmetic
         }
-        if (i > 0) load_step<N, M>(nxt, P, b, i - 1, use_qp);        // in flight during this step's arithmetic
         if (alive) {
-        const double* cxxi = cost_shared ? s_cost : tp(P.cxx, b, i);
-        const double* cxui = cost_shared ? s_cost + N * N : tp(P.cxu, b, i);
-        const double* cuui = cost_shared ? s_cost + N * N + N * M : tp(P.cuu, b, i);
-        // ---- W = V fx, Z = V fu
+        const double* cfx = in + RW::FX;
+        const double* cfu = in + RW::FU;
+        // ---- W = V fx, Z = V fu   (V symmetric: VS(r,q))
         double W[N * N], Z[N * M];
 #pragma unroll
         for (int c = 0; c < N; c++)
@@ -179,7 +218,7 @@ __global__ void __launch_bounds__(128, MINB) bp_small_kernel(BackParams P) {
             for (int r = 0; r < N; r++) {
                 double acc = 0.0;
 #pragma unroll
-                for (int q = 0; q < N; q++) acc = fma(V[r + N * q], cfx[q + N * c], acc);
+                for (int q = 0; q < N; q++) acc = fma(Vs[tri(r, q)], cfx[q + N * c], acc);
                 W[r + N * c] = acc;
             }
 #pragma unroll
@@ -188,27 +227,33 @@ __global__ void __launch_bounds__(128, MINB) bp_small_kernel(BackParams P) {
             for (int r = 0; r < N; r++) {
                 double acc = 0.0;
 #pragma unroll
-                for (int q = 0; q < N; q++) acc = fma(V[r + N * q], cur.fu[q + N * c], acc);
+                for (int q = 0; q < N; q++) acc = fma(Vs[tri(r, q)], cfu[q + N * c], acc);
                 Z[r + N * c] = acc;
             }
-        // ---- Q expansion (backward_pass.jl:240-247)
-        double Qxx[N * N], Qux[M * N], Quxr[M * N], Quu[M * M], QuuF[M * M], Qx[N], Qu[M];
+        // ---- Q expansion (backward_pass.jl:240-247); Qxx = cxx + fx'V fx is symmetric: upper triangle only
+        double Qxx[NT], Qux[M * N], Quxr[M * N], Quu[M * M], QuuF[M * M], Qx[N], Qu[M];
+        {
+            const double* cxxi = cost_shared ? nullptr : tp(P.cxx, b, i);
 #pragma unroll
-        for (int c = 0; c < N; c++)
+            for (int c = 0; c < N; c++)
 #pragma unroll
-            for (int r = 0; r < N; r++) {
-                double acc = 0.0;
+                for (int r = 0; r <= c; r++) {
+                    double acc = 0.0;
 #pragma unroll
-                for (int q = 0; q < N; q++) acc = fma(cfx[q + N * r], W[q + N * c], acc);
-                Qxx[r + N * c] = cxxi[r + N * c] + acc;
-            }
+                    for (int q = 0; q < N; q++) acc = fma(cfx[q + N * r], W[q + N * c], acc);
+                    const double cs = cost_shared ? s_cost[tri(r, c)] : 0.5 * (cxxi[r + N * c] + cxxi[c + N * r]);
+                    Qxx[tri(r, c)] = cs + acc;
+                }
+        }
+        const double* cxui = cost_shared ? s_cost + NT : tp(P.cxu, b, i);
+        const double* cuui = cost_shared ? s_cost + NT + N * M : tp(P.cuu, b, i);
 #pragma unroll
         for (int j = 0; j < N; j++)
 #pragma unroll
             for (int a = 0; a < M; a++) {
                 double acc = 0.0, ff = 0.0;
 #pragma unroll
-                for (int q = 0; q < N; q++) { acc = fma(cur.fu[q + N * a], W[q + N * j], acc); ff = fma(cur.fu[q + N * a], cfx[q + N * j], ff); }
+                for (int q = 0; q < N; q++) { acc = fma(cfu[q + N * a], W[q + N * j], acc); ff = fma(cfu[q + N * a], cfx[q + N * j], ff); }
                 const double v = cxui[j + N * a] + acc;
                 Qux[a + M * j] = v;
                 Quxr[a + M * j] = reg2 ? v + lam * ff : v;
@@ -219,7 +264,7 @@ __global__ void __launch_bounds__(128, MINB) bp_small_kernel(BackParams P) {
             for (int a = 0; a < M; a++) {
                 double acc = 0.0, ff = 0.0;
 #pragma unroll
-                for (int q = 0; q < N; q++) { acc = fma(cur.fu[q + N * a], Z[q + N * c], acc); ff = fma(cur.fu[q + N * a], cur.fu[q + N * c], ff); }
+                for (int q = 0; q < N; q++) { acc = fma(cfu[q + N * a], Z[q + N * c], acc); ff = fma(cfu[q + N * a], cfu[q + N * c], ff); }
                 const double v = cuui[a + M * c] + acc;
                 Quu[a + M * c] = v;
                 QuuF[a + M * c] = reg2 ? v + lam * ff : ((reg1 && a == c) ? v + lam : v);
@@ -229,14 +274,14 @@ __global__ void __launch_bounds__(128, MINB) bp_small_kernel(BackParams P) {
             double acc = 0.0;
 #pragma unroll
             for (int q = 0; q < N; q++) acc = fma(cfx[q + N * r], Vx[q], acc);
-            Qx[r] = cur.cx[r] + acc;
+            Qx[r] = in[RW::CX + r] + acc;
         }
 #pragma unroll
         for (int a = 0; a < M; a++) {
             double acc = 0.0;
 #pragma unroll
-            for (int q = 0; q < N; q++) acc = fma(cur.fu[q + N * a], Vx[q], acc);
-            Qu[a] = cur.cu[a] + acc;
+            for (int q = 0; q < N; q++) acc = fma(cfu[q + N * a], Vx[q], acc);
+            Qu[a] = in[RW::CU + a] + acc;
         }
         // ---- gains: Cholesky or box QP, in the oracle's arithmetic order
         double ki[M], R[M * M], Ki[M * N];
@@ -258,7 +303,7 @@ __global__ void __launch_bounds__(128, MINB) bp_small_kernel(BackParams P) {
         } else {
             double lo[M], up[M];
 #pragma unroll
-            for (int a = 0; a < M; a++) { lo[a] = lims_lo[a] - cur.u[a]; up[a] = lims_hi[a] - cur.u[a]; }      // :45-46
+            for (int a = 0; a < M; a++) { lo[a] = lims_lo[a] - in[RW::UU + a]; up[a] = lims_hi[a] - in[RW::UU + a]; }      // :45-46
             int nfac = 0;
             const int res = boxqp_seq<M>(M, QuuF, M, Qu, lo, up, kw, P.qp, ki, R, M, &fm, &nfac);
             if (res < 1) failed = true;                                                                  // :50-56
@@ -321,23 +366,24 @@ __global__ void __launch_bounds__(128, MINB) bp_small_kernel(BackParams P) {
             }
             Vx[r] = ((Qx[r] + t1) + t2) + t3;
         }
+        // Vxx = Qxx + K'Quu K + K'Qux + Qux'K, symmetrised (:70-72): the upper triangle of the symmetric part, written
+        // straight into Vs (V was last read by W and Z).  K'Qux + Qux'K is symmetric as it stands; K'Quu K is symmetrised
+        // explicitly when Quu may be unsymmetric (M > 1).
 #pragma unroll
         for (int c = 0; c < N; c++)
 #pragma unroll
-            for (int r = 0; r < N; r++) {
-                double t1 = 0.0, t2 = 0.0, t3 = 0.0;
+            for (int r = 0; r <= c; r++) {
+                double t1 = 0.0, t1t = 0.0, t2 = 0.0, t3 = 0.0;
 #pragma unroll
                 for (int a = 0; a < M; a++) {
                     t1 = fma(Ki[a + M * r], QK[a + M * c], t1);
+                    if (M > 1) t1t = fma(Ki[a + M * c], QK[a + M * r], t1t);
                     t2 = fma(Ki[a + M * r], Qux[a + M * c], t2);
                     t3 = fma(Qux[a + M * r], Ki[a + M * c], t3);
                 }
-                W[r + N * c] = ((Qxx[r + N * c] + t1) + t2) + t3;
+                if (M > 1) t1 = 0.5 * (t1 + t1t);
+                Vs[tri(r, c)] = ((Qxx[tri(r, c)] + t1) + t2) + t3;
             }
-#pragma unroll
-        for (int c = 0; c < N; c++)
-#pragma unroll
-            for (int r = 0; r < N; r++) V[r + N * c] = 0.5 * (W[r + N * c] + W[c + N * r]);
         // ---- store
         if (vec_out && (N * M) % 2 == 0 && N % 2 == 0) {
 #pragma unroll
@@ -354,14 +400,14 @@ __global__ void __launch_bounds__(128, MINB) bp_small_kernel(BackParams P) {
         for (int a = 0; a < M; a++) { kb[(long long)i * M + a] = ki[a]; kw[a] = ki[a]; }
         if (Vxxb)
 #pragma unroll
-            for (int e = 0; e < N * N; e++) Vxxb[(long long)i * N * N + e] = V[e];
+            for (int e = 0; e < N * N; e++) Vxxb[(long long)i * N * N + e] = Vs[tri(e % N, e / N)];
         if (Quub)
 #pragma unroll
             for (int e = 0; e < M * M; e++) Quub[(long long)i * M * M + e] = Quu[e];
         }
         }
-        cur = nxt;
     }
+    if (STAGE) asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (!valid) return;
     if (diverge > 0) {                               // outputs below the failed step stay zero (quirk Q10)
         for (long long e = 0; e < (long long)diverge * N * M; e++) Kb[e] = 0.0;
@@ -372,22 +418,48 @@ __global__ void __launch_bounds__(128, MINB) bp_small_kernel(BackParams P) {
     }
     if (P.Vxx1)
 #pragma unroll
-        for (int e = 0; e < N * N; e++) P.Vxx1[b * N * N + e] = (diverge > 0) ? 0.0 : V[e];
+        for (int e = 0; e < N * N; e++) P.Vxx1[b * N * N + e] = (diverge > 0) ? 0.0 : Vs[tri(e % N, e / N)];
     P.diverge[b] = diverge;
     P.dV[2 * b] = dV0;
     P.dV[2 * b + 1] = dV1;
 }
 
+#ifndef SMALL_MINB
+#define SMALL_MINB 2
+#endif
+bool al16v(const TensorD& t) { return ((uintptr_t)t.p % 16 == 0) && (t.sb % 2 == 0) && (t.st % 2 == 0); }
+
 template <int N, int M>
-int launch_small(ddp_handle_s* h, const BackParams& P) {
+int launch_small(ddp_handle_s* h, const BackParams& P_in) {
+    BackParams P = P_in;
+    int rc = prepare_redo(h, P);                     // hand-over of trajectories with an unsymmetric terminal cxx to the generic kernel
+    if (rc != 0) return rc;
     const unsigned grid = (unsigned)((P.B + 127) / 128);
-    const bool stage = ((N * N) % 2 == 0) && (32 % ((N * N) / 2) == 0) && ((uintptr_t)P.fx.p % 16 == 0) && (P.fx.sb % 2 == 0) && (P.fx.st % 2 == 0) &&
-                       !(getenv("DDP_SMALL_NOSTAGE"));
-    // 2 CTAs (8 warps) per SM: 168- and 128-register builds (3 / 4 CTAs) spill and measured 24-41 ms against 12 ms
-    if (stage) bp_small_kernel<N, M, 2, true><<<grid, 128, 0, h->stream>>>(P);
-    else bp_small_kernel<N, M, 2, false><<<grid, 128, 0, h->stream>>>(P);
+    const bool u_ok = (P.lims == nullptr) || ((M % 2 == 0) ? al16v(P.u) : ((uintptr_t)P.u.p % 8 == 0));
+    const bool cu_ok = (M % 2 == 0) ? al16v(P.cu) : true;
+    const bool stage = Row<N, M>::OK && al16v(P.fx) && al16v(P.fu) && al16v(P.cx) && cu_ok && u_ok && !(getenv("DDP_SMALL_NOSTAGE"));
+    // 2 CTAs (8 warps) per SM: 168- and 128-register builds (3 / 4 CTAs) spill
+    if (stage && Row<N, M>::OK) {
+        const size_t bytes = sizeof(double) * 4 * 2 * 32 * Row<N, M>::ROW;
+        // residency: 2 CTAs (8 warps, <= 255 registers) or 3 CTAs (12 warps, 168 registers, a few spilled doubles) per SM;
+        // DDP_SMALL_MINB selects for the A/B measurement, the default is the faster one on B200 (profiles/README_r02.md)
+        const char* mb = getenv("DDP_SMALL_MINB");
+        const int minb = mb ? atoi(mb) : SMALL_MINB;
+        cudaError_t ea;
+        if (minb == 3) {
+            ea = cudaFuncSetAttribute(bp_small_kernel<N, M, 3, Row<N, M>::OK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+            if (ea != cudaSuccess) return (int)ea;
+            bp_small_kernel<N, M, 3, Row<N, M>::OK><<<grid, 128, bytes, h->stream>>>(P);
+        } else {
+            ea = cudaFuncSetAttribute(bp_small_kernel<N, M, 2, Row<N, M>::OK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+            if (ea != cudaSuccess) return (int)ea;
+            bp_small_kernel<N, M, 2, Row<N, M>::OK><<<grid, 128, bytes, h->stream>>>(P);
+        }
+    } else bp_small_kernel<N, M, 2, false><<<grid, 128, 16, h->stream>>>(P);
     h->launches++;
-    return (int)cudaGetLastError();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    return launch_back_pass_generic(h, P, false);    // processes the handed-over trajectories; exits at once when there are none
 }
 
 }  // namespace

@@ -687,18 +687,10 @@ int launch_back_pass_tile(ddp_handle_s* h, const BackParams& P_in, bool gps, boo
     long long need = (P.B + WPB - 1) / WPB;
     if (grid > need) grid = need;
     cudaError_t e = cudaSuccess;
-    if (h->redo_cap < P.B) {                   // hand-over mask: one int counter (16 bytes reserved) + one byte per trajectory
-        if (h->redo) cudaFree(h->redo);
-        h->redo = nullptr; h->redo_cap = 0;
-        const long long cap = std::max<long long>(P.B, h->B);
-        e = cudaMalloc((void**)&h->redo, (size_t)cap + 16);
-        if (e != cudaSuccess) return (int)e;
-        h->redo_cap = cap;
+    {
+        const int rc0 = prepare_redo(h, P);    // hand-over mask for trajectories with an unsymmetric terminal cxx
+        if (rc0 != 0) return rc0;
     }
-    P.redo_count = reinterpret_cast<int*>(h->redo);
-    P.redo = h->redo + 16;
-    e = cudaMemsetAsync(P.redo_count, 0, sizeof(int), h->stream);
-    if (e != cudaSuccess) return (int)e;
 #define LAUNCH_TILE1(L, G, R2, H)                                                                                           \
     do {                                                                                                                    \
         e = cudaFuncSetAttribute(bp_tile32x8_kernel<L, G, R2, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); \

@@ -102,6 +102,7 @@ struct ddp_handle_s {
 // launchers implemented in the .cu files; each returns a cudaError_t-compatible int (0 = ok) and
 // sets *launched to the number of kernels it enqueued.
 int launch_back_pass_generic(ddp_handle_s* h, const BackParams& P, bool gps);
+int prepare_redo(ddp_handle_s* h, BackParams& P);
 int launch_back_pass_tile(ddp_handle_s* h, const BackParams& P, bool gps, bool* handled);
 int launch_back_pass_small(ddp_handle_s* h, const BackParams& P, bool gps, bool* handled);
 int launch_forward_generic(ddp_handle_s* h, const FwdParams& P);

@@ -42,8 +42,8 @@ def test_second_order_terms(ddp, regType, tv):
         sl = (lambda t: t[b]) if tv else (lambda t: t[b, 0])
         d0, p0, Vx0, Vxx0, dV0 = O.back_pass(cx[b], cu[b], Q, cxu, R, fx[b], fu[b], 0.7, regType, None, x[b], u[b],
                                              fxx=sl(fxx), fxu=sl(fxu), fuu=sl(fuu))
-        assert dv[b] == d0 == 0
-        for got, ref in ((pol.K[b], p0.K), (pol.k[b], p0.k), (Vx[b], Vx0), (Vxx[b], Vxx0), (dV[b], dV0), (pol.Sigmai[b], p0.Sigmai)):
+        assert dv[b] == d0               # some of these problems lose positive definiteness through fuu: same failing step then
+        for got, ref in ((pol.K[b], p0.K), (pol.k[b], p0.k), (Vx[b], Vx0), (Vxx[b], Vxx0), (dV[b], dV0), (pol.Sigmai[b][d0:], p0.Sigmai[d0:])):
             assert relerr_elem(got, ref) < TOL
     # the terms matter: without them the gains differ
     dv2, pol2, *_ = ddp.back_pass(cx, cu, Q, cxu, R, fx, fu, 0.7, regType, None, x, u)
@@ -52,7 +52,7 @@ def test_second_order_terms(ddp, regType, tv):
     dv3, pol3, Vx3, *_ = ddp.back_pass(cx, cu, Q, cxu, R, fx, fu, None, fxu, None, 0.7, regType, None, x, u)
     d0, p0, Vx0, _, _ = O.back_pass(cx[0], cu[0], Q, cxu, R, fx[0], fu[0], 0.7, regType, None, x[0], u[0],
                                     fxu=(fxu[0] if tv else fxu[0, 0]))
-    assert relerr_elem(pol3.K[0], p0.K) < TOL and relerr_elem(Vx3[0], Vx0) < TOL
+    assert dv3[0] == d0 and relerr_elem(pol3.K[0], p0.K) < TOL and relerr_elem(Vx3[0], Vx0) < TOL
 
 
 def test_time_varying_lims(ddp):
@@ -454,3 +454,32 @@ def test_selftest_peak(ddp):
     dmma, ms2 = eng.selftest_peak("dmma")
     assert 20.0 < dfma < 60.0 and 20.0 < dmma < 60.0, (dfma, dmma)              # B200: ~34 and ~37 TFLOP/s
     assert ms1 > 0.5 and ms2 > 0.5
+
+
+def test_small_kernel_asymmetric_terminal_cxx_and_residency_variants(ddp, monkeypatch):
+    """bp_small_kernel keeps Vxx as its upper triangle: an inexactly symmetric terminal cxx goes to the generic kernel (same
+    hand-over as the tile kernel), and the 3-CTA/SM build (168 registers) gives the same bits as the 2-CTA/SM one."""
+    rng = np.random.default_rng(60)
+    B, n, m, N = 40, 4, 1, 30
+    fx = np.eye(n) + 0.05 * rng.standard_normal((B, N, n, n)); fu = 0.1 * rng.standard_normal((B, N, n, m))
+    x = rng.standard_normal((B, N, n)); u = 0.3 * rng.standard_normal((B, N, m))
+    Q, R = np.diag([10.0, 1, 2, 1]), np.eye(m)
+    cx, cu = x @ Q.T, u @ R.T
+    cxx = np.tile(Q, (B, N, 1, 1))
+    cxx[7, N - 1] += 0.05 * rng.standard_normal((n, n))
+    cxx[33, 4] += 0.05 * rng.standard_normal((n, n))                              # inner step: symmetrised in the kernel
+    lims = np.array([[-0.4, 0.4]])
+    args = (cx, cu, cxx, np.zeros((n, m)), R, fx, fu, 0.7, 2, lims, x, u)
+    monkeypatch.setenv("DDP_SMALL_MINB", "2")
+    r2 = ddp.back_pass(*args)
+    monkeypatch.setenv("DDP_SMALL_MINB", "3")
+    r3 = ddp.back_pass(*args)
+    monkeypatch.delenv("DDP_SMALL_MINB", raising=False)
+    for a, b in ((r2[0], r3[0]), (r2[1].K, r3[1].K), (r2[1].k, r3[1].k), (r2[2], r3[2]), (r2[3], r3[3]), (r2[4], r3[4])):
+        assert np.array_equal(a, b)
+    for b in (0, 7, 33, B - 1):
+        d0, p0, Vx0, Vxx0, dV0 = O.back_pass(cx[b], cu[b], cxx[b], np.zeros((n, m)), R, fx[b], fu[b], 0.7, 2, lims, x[b], u[b])
+        assert r2[0][b] == d0
+        assert np.array_equal(r2[1].K[b] == 0, p0.K == 0)
+        for got, ref in ((r2[1].K[b], p0.K), (r2[1].k[b], p0.k), (r2[2][b], Vx0), (r2[3][b], Vxx0), (r2[4][b], dV0)):
+            assert relerr_elem(got, ref) < TOL, b
