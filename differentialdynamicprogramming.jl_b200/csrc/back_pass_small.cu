@@ -305,7 +305,9 @@ __global__ void __launch_bounds__(128, MINB) bp_small_kernel(BackParams P) {
 #pragma unroll
             for (int a = 0; a < M; a++) { lo[a] = lims_lo[a] - in[RW::UU + a]; up[a] = lims_hi[a] - in[RW::UU + a]; }      // :45-46
             int nfac = 0;
-            const int res = boxqp_seq<M>(M, QuuF, M, Qu, lo, up, kw, P.qp, ki, R, M, &fm, &nfac);
+            int res;
+            if (M == 1) res = boxqp_scalar(QuuF[0], Qu[0], lo[0], up[0], kw[0], P.qp, &ki[0], &R[0], &fm, &nfac);     // same bits, scalar code
+            else res = boxqp_seq<M>(M, QuuF, M, Qu, lo, up, kw, P.qp, ki, R, M, &fm, &nfac);
             if (res < 1) failed = true;                                                                  // :50-56
             nf = __popc(fm);
         }

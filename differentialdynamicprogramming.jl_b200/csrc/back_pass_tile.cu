@@ -29,7 +29,7 @@
 // NULL), 16-byte aligned fx/fu/cxx with even strides, symmetric cxx (it is a Hessian).
 #include <algorithm>
 #include <cstdlib>
-#include "ddp_common.cuh"
+#include "boxqp.cuh"
 
 namespace {
 
@@ -43,6 +43,35 @@ constexpr int SCX = SVX + 32;                // this step's cx (32) and cu (8), 
 constexpr int WARP_DOUBLES = SCX + 48;       // 2384 doubles = 19,072 B per warp
 constexpr int WARP_DOUBLES_LTV = WARP_DOUBLES;  // (a second [fx fu] buffer would cost 10 KB per warp and halve the residency: measured 113-134 ms)
 constexpr int COST_DOUBLES = 15 * 32 * 2;    // per-CTA table of the cost tiles in accumulator (fragment) order
+// per-warp scratch of the box-QP branch (LIMS variants): H = QuuF (8 x 8), its reduced factor R, Qux_reg / K (8 x 32), vectors
+constexpr int QH = 0, QR = 64, QQ = 128, QG = 384, QLO = 392, QUP = 400, QX0 = 408, QX = 416, QI = 424;
+constexpr int QP_DOUBLES = 432;
+
+// boxQP(QuuF, Qu, lims - u, k(i+1)) of backward_pass.jl:49 on ONE lane, in the oracle's arithmetic order (boxqp.cuh): result code,
+// free set and every bit of k as the generic kernel and the oracle produce them.  Not inlined: the tile kernel keeps its registers.
+__device__ __noinline__ void qp8_lane0(double* sq, QPOpts o) {
+    unsigned fm = 0;
+    int nfac = 0, nf = 0;
+    const int res = boxqp_seq<8>(8, sq + QH, 8, sq + QG, sq + QLO, sq + QUP, sq + QX0, o, sq + QX, sq + QR, 8, &fm, &nfac, &nf);
+    int* si = reinterpret_cast<int*>(sq + QI);
+    si[0] = res;
+    si[1] = (int)fm;
+    si[2] = nf;
+}
+
+// K[free, j] = -R \ (R' \ Qux_reg[free, j]) for column j = lane (backward_pass.jl:57-61), in place in sq[QQ..]; clamped rows = 0
+__device__ __noinline__ void qp8_gain_column(double* sq, int lane, unsigned fm, int nf) {
+    double* col = sq + QQ + 8 * lane;
+    double v[8];
+    int p = 0;
+#pragma unroll
+    for (int a = 0; a < 8; a++)
+        if ((fm >> a) & 1u) v[p++] = col[a];
+    if (nf > 0) chol_solve<8>(sq + QR, 8, nf, v);
+    p = 0;
+#pragma unroll
+    for (int a = 0; a < 8; a++) col[a] = ((fm >> a) & 1u) ? -v[p++] : 0.0;
+}
 
 // column-major 32-row matrices: element (i, c) lives at (i ^ s(c)) + 32 c with s(c) = ((c&1)<<3) | (((c>>1)&3)<<1).
 // 16-byte row pairs stay together, DMMA fragment loads (LDS.128) are bank-conflict free.
@@ -124,13 +153,18 @@ constexpr int gidx(int at, int bt) { return at * 5 - (at * (at - 1)) / 2 + (bt -
 
 // HIST: the optional Vxx histories (full and packed) are compiled in only when asked for, so the benchmarked variants
 // carry neither their pointers nor their branches through the step loop
-template <bool LTV, bool GPS, bool REG2, bool HIST>
+// LIMS: control limits given -> box-QP branch of @end_backward_pass (backward_pass.jl:43-62, :317-335) unless lims[1,1] > lims[1,2]
+template <bool LTV, bool GPS, bool REG2, bool HIST, bool LIMS>
 __global__ void __launch_bounds__(wpb(LTV) * 32, 2) bp_tile32x8_kernel(BackParams P) {
     constexpr int WPB = wpb(LTV);
+    constexpr int WD = (LTV ? WARP_DOUBLES_LTV : WARP_DOUBLES) + (LIMS ? QP_DOUBLES : 0);
     extern __shared__ double smem_raw[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int g = lane >> 2, q = lane & 3;
-    double* sm = smem_raw + (size_t)w * (LTV ? WARP_DOUBLES_LTV : WARP_DOUBLES);
+    double* sm = smem_raw + (size_t)w * WD;
+    double* sq = sm + (LTV ? WARP_DOUBLES_LTV : WARP_DOUBLES);          // box-QP scratch (LIMS)
+    const bool use_qp = LIMS && !(P.lims[0] > P.lims[8]);               // backward_pass.jl:31
+    const double lim_lo = LIMS ? P.lims[g] : 0.0, lim_hi = LIMS ? P.lims[8 + g] : 0.0;
     double* sV = sm + SV;
     double* sVx = sm + SVX;
     double* sCx = sm + SCX;
@@ -138,7 +172,7 @@ __global__ void __launch_bounds__(wpb(LTV) * 32, 2) bp_tile32x8_kernel(BackParam
     const long long warps_total = (long long)gridDim.x * WPB;
     // Cost Hessians shared by the batch and constant in time (the reference's LTI/QTIC methods): stage the
     // symmetrised tiles once per CTA in accumulator order, so each step starts G with 15 conflict-free LDS.128.
-    double* sCost = smem_raw + (size_t)WPB * (LTV ? WARP_DOUBLES_LTV : WARP_DOUBLES);
+    double* sCost = smem_raw + (size_t)WPB * WD;
     const bool cost_shared = (P.cxx.sb == 0 && P.cxx.st == 0 && P.cxu.sb == 0 && P.cxu.st == 0 && P.cuu.sb == 0 && P.cuu.st == 0);
     if (cost_shared) {
         if (w == 0) {
@@ -236,6 +270,7 @@ __global__ void __launch_bounds__(wpb(LTV) * 32, 2) bp_tile32x8_kernel(BackParam
                 if (Quuib) { Quuib[(long long)(N - 1) * 64 + g + 8 * (2 * q)] = T0; Quuib[(long long)(N - 1) * 64 + g + 8 * (2 * q + 1)] = T1; }
             } else if (Quub) st2(Quub + (long long)(N - 1) * 64 + 2 * lane, cuuN[2 * lane], cuuN[2 * lane + 1]);
         }
+        if (LIMS && lane < 8) sq[QX0 + lane] = 0.0;          // warm start of the first QP: k[:, N-1] = 0 (backward_pass.jl:49)
         if (LTV) {
             if (N >= 2) load_F<true>(sm + SF, tp(P.fx, b, N - 2), tp(P.fu, b, N - 2), lane);
         } else {
@@ -384,14 +419,14 @@ __global__ void __launch_bounds__(wpb(LTV) * 32, 2) bp_tile32x8_kernel(BackParam
                     for (int at = 0; at < 4; at++)
 #pragma unroll
                         for (int jt = 0; jt < 4; jt++) dmma(W[at][jt][0], W[at][jt][1], fa[at].x, fb[jt].x);
-                    gj_step(2 * p);
+                    if (!LIMS) gj_step(2 * p);
 #pragma unroll
                     for (int at = 0; at < 4; at++) fv[at] = fma(fa[at].y, vx.y, fma(fa[at].x, vx.x, fv[at]));
 #pragma unroll
                     for (int at = 0; at < 4; at++)
 #pragma unroll
                         for (int jt = 0; jt < 4; jt++) dmma(W[at][jt][0], W[at][jt][1], fa[at].y, fb[jt].y);
-                    gj_step(2 * p + 1);
+                    if (!LIMS) gj_step(2 * p + 1);
                 }
             };
             // G(a, a..4) += W'[a,:] F[:, a..4]
@@ -503,9 +538,48 @@ __global__ void __launch_bounds__(wpb(LTV) * 32, 2) bp_tile32x8_kernel(BackParam
                 if (GPS) { qf[t].x -= sf[t].x; qf[t].y -= sf[t].y; }              // cxukl = -Sigma_i K_prev
                 qr[t] = reg2 ? make_double2(fma(lam, FF[t][0], qf[t].x), fma(lam, FF[t][1], qf[t].y)) : qf[t];
             }
-            if (!ok) { diverge = i + 1; break; }
-            // ---- K' = -Qux_reg' Minv : kf[t] = K[2q..2q+1][8t+g]
+            const double Qu_own = GPS ? fma(cuv + fv[4], ieta, -Sik_own) : (cuv + fv[4]);     // Qu/eta + cukl, cukl = -Sigma_i k_prev
+            const double Qu0 = shf(Qu_own, c0src), Qu1 = shf(Qu_own, c1src);
             double2 kf[4];
+            double k_own;
+            double J0 = U0, J1 = U1;                          // GPS + LIMS: Sigma = inv(Quu) is still wanted (backward_pass.jl:346)
+            if (LIMS && use_qp) {
+                // ---- box-QP branch (backward_pass.jl:43-62): QP on one lane in the oracle's arithmetic order, gains by columns
+                sq[QH + g + 8 * (2 * q)] = I0;               // H = QuuF, column-major (unsymmetrised, as the reference passes it)
+                sq[QH + g + 8 * (2 * q + 1)] = I1;
+                if (q == 0) {
+                    const double ui = tp(P.u, b, i)[g];
+                    sq[QG + g] = Qu_own;
+                    sq[QLO + g] = lim_lo - ui;                // lower = lims[:,1] - u[:,i]   (:45-46)
+                    sq[QUP + g] = lim_hi - ui;
+                }
+#pragma unroll
+                for (int t = 0; t < 4; t++) st2(&sq[QQ + 2 * q + 8 * (8 * t + g)], qr[t].x, qr[t].y);     // Qux_reg (8 x 32), column-major
+                __syncwarp();
+                if (lane == 0) qp8_lane0(sq, P.qp);
+                __syncwarp();
+                const int* si = reinterpret_cast<const int*>(sq + QI);
+                const int res = si[0];
+                const unsigned fm = (unsigned)si[1];
+                const int nf = si[2];
+                if (res < 1) ok = false;                      // :50-56
+                if (ok) {
+                    qp8_gain_column(sq, lane, fm, nf);
+                    __syncwarp();
+#pragma unroll
+                    for (int t = 0; t < 4; t++) kf[t] = ld2(&sq[QQ + 2 * q + 8 * (8 * t + g)]);
+                    k_own = sq[QX + g];
+                    __syncwarp();
+                    if (lane < 8) sq[QX0 + lane] = sq[QX + lane];      // next step's warm start
+                    if (GPS) gj_inverse8(J0, J1, lane, g, q);
+                } else {
+#pragma unroll
+                    for (int t = 0; t < 4; t++) kf[t] = make_double2(0.0, 0.0);
+                    k_own = 0.0;
+                }
+            } else {
+            if (LIMS) ok = gj_inverse8(I0, I1, lane, g, q);  // limits given but inverted (lims[1,1] > lims[1,2]): Cholesky branch, not interleaved
+            // ---- K' = -Qux_reg' Minv : kf[t] = K[2q..2q+1][8t+g]
 #pragma unroll
             for (int t = 0; t < 4; t++) kf[t] = make_double2(0.0, 0.0);
 #pragma unroll
@@ -515,12 +589,13 @@ __global__ void __launch_bounds__(wpb(LTV) * 32, 2) bp_tile32x8_kernel(BackParam
 #pragma unroll
             for (int t = 0; t < 4; t++) { kf[t].x = -kf[t].x; kf[t].y = -kf[t].y; }
             // ---- k = -Minv Qu, Quu k   (group g owns entry g; entries 2q, 2q+1 are fetched by shuffle)
-            const double Qu_own = GPS ? fma(cuv + fv[4], ieta, -Sik_own) : (cuv + fv[4]);     // Qu/eta + cukl, cukl = -Sigma_i k_prev
-            const double Qu0 = shf(Qu_own, c0src), Qu1 = shf(Qu_own, c1src);
             double ks = fma(I1, Qu1, I0 * Qu0);
             ks += shx(ks, 1);
             ks += shx(ks, 2);
-            const double k_own = -ks;
+            k_own = -ks;
+            J0 = I0; J1 = I1;
+            }
+            if (!ok) { diverge = i + 1; break; }
             const double k0 = shf(k_own, c0src), k1 = shf(k_own, c1src);
             double qs = fma(U1, k1, U0 * k0);
             qs += shx(qs, 1);
@@ -578,8 +653,8 @@ __global__ void __launch_bounds__(wpb(LTV) * 32, 2) bp_tile32x8_kernel(BackParam
                     Quub[(long long)i * 64 + g + 8 * (2 * q + 1)] = U1;
                 }
                 if (Quuib) {                                  // Sigma = inv(Quu)  (backward_pass.jl:346)
-                    Quuib[(long long)i * 64 + g + 8 * (2 * q)] = I0;
-                    Quuib[(long long)i * 64 + g + 8 * (2 * q + 1)] = I1;
+                    Quuib[(long long)i * 64 + g + 8 * (2 * q)] = J0;
+                    Quuib[(long long)i * 64 + g + 8 * (2 * q + 1)] = J1;
                 }
             }
             // ---- step 4: Vxx = Qxx + K' M1 + Qux' K  (upper 10 tiles), all operands in registers
@@ -674,7 +749,9 @@ bool aligned16(const TensorD& t) { return ((uintptr_t)t.p % 16 == 0) && (t.sb % 
 int launch_back_pass_tile(ddp_handle_s* h, const BackParams& P_in, bool gps, bool* handled) {
     *handled = false;
     BackParams P = P_in;
-    if (P.n != 32 || P.m != 8 || P.lims != nullptr || P.T < 2) return 0;
+    if (P.n != 32 || P.m != 8 || P.T < 2) return 0;
+    const bool lims = (P.lims != nullptr);
+    if (lims && (P.lims_st != 0 || !P.u.p || getenv("DDP_TILE_NO_LIMS"))) return 0;       // time-varying limits: generic kernel
     if (P.fxx.p || P.fxu.p || P.fuu.p || P.Quu_tri || P.Quui_tri) return 0;          // second-order terms / packed Quu: generic kernel
     if (!aligned16(P.fx) || !aligned16(P.fu) || !aligned16(P.cxx)) return 0;
     if (((uintptr_t)P.K % 16) || (P.Vxx && ((uintptr_t)P.Vxx % 16)) || (P.Vxx1 && ((uintptr_t)P.Vxx1 % 16))) return 0;
@@ -682,7 +759,7 @@ int launch_back_pass_tile(ddp_handle_s* h, const BackParams& P_in, bool gps, boo
     if (!aligned16(P.cx) || !aligned16(P.cu)) return 0;
     const bool ltv = (P.fx.st != 0 || P.fu.st != 0);
     const int WPB = wpb(ltv);
-    const size_t bytes = ((size_t)(ltv ? WARP_DOUBLES_LTV : WARP_DOUBLES) * WPB + COST_DOUBLES) * sizeof(double);
+    const size_t bytes = ((size_t)((ltv ? WARP_DOUBLES_LTV : WARP_DOUBLES) + (lims ? QP_DOUBLES : 0)) * WPB + COST_DOUBLES) * sizeof(double);
     long long grid = (long long)h->sm_count * 2;
     long long need = (P.B + WPB - 1) / WPB;
     if (grid > need) grid = need;
@@ -691,15 +768,17 @@ int launch_back_pass_tile(ddp_handle_s* h, const BackParams& P_in, bool gps, boo
         const int rc0 = prepare_redo(h, P);    // hand-over mask for trajectories with an unsymmetric terminal cxx
         if (rc0 != 0) return rc0;
     }
-#define LAUNCH_TILE1(L, G, R2, H)                                                                                           \
-    do {                                                                                                                    \
-        e = cudaFuncSetAttribute(bp_tile32x8_kernel<L, G, R2, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); \
-        if (e == cudaSuccess) bp_tile32x8_kernel<L, G, R2, H><<<(unsigned)grid, WPB * 32, bytes, h->stream>>>(P);            \
+#define LAUNCH_TILE1(L, G, R2, H, LM)                                                                                           \
+    do {                                                                                                                        \
+        e = cudaFuncSetAttribute(bp_tile32x8_kernel<L, G, R2, H, LM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); \
+        if (e == cudaSuccess) bp_tile32x8_kernel<L, G, R2, H, LM><<<(unsigned)grid, WPB * 32, bytes, h->stream>>>(P);            \
     } while (0)
-#define LAUNCH_TILE(L, G, R2)                     \
-    do {                                          \
-        if (hist) LAUNCH_TILE1(L, G, R2, true);   \
-        else LAUNCH_TILE1(L, G, R2, false);       \
+    // the history outputs are compiled into the box-QP variants unconditionally (fewer instantiations of a rarely timed path)
+#define LAUNCH_TILE(L, G, R2)                                \
+    do {                                                     \
+        if (lims) LAUNCH_TILE1(L, G, R2, true, true);        \
+        else if (hist) LAUNCH_TILE1(L, G, R2, true, false);  \
+        else LAUNCH_TILE1(L, G, R2, false, false);           \
     } while (0)
     const bool hist = (P.Vxx != nullptr) || (P.Vxx_tri != nullptr);
     const bool r2 = !gps && (P.reg_type == 2);

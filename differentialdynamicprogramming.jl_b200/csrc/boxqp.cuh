@@ -197,3 +197,81 @@ __device__ int boxqp_seq(int m, const double* H, int ldh, const double* g, const
     if (nf_out) *nf_out = nf;                                            // size of the factor held in Rf
     return result;
 }
+
+
+// The same projected-Newton iteration for ONE variable (m = 1: config 3), written on scalars: every operation, comparison and
+// rounding is the one boxqp_seq<1> performs in the same order (so result code, free set, factor and x agree bit for bit with it and
+// with the oracle), but without index sets, mask loops and runtime-bounded solves.  h = H[0,0].
+__device__ __forceinline__ double qp1_value(double h, double g, double x) {          // x'g + ((0.5 x') H) x, sums started from 0.0
+    const double s1 = DADD(0.0, DMUL(x, g));
+    const double t = DADD(0.0, DMUL(DMUL(0.5, x), h));
+    const double s2 = DADD(0.0, DMUL(t, x));
+    return DADD(s1, s2);
+}
+
+__device__ __forceinline__ int boxqp_scalar(double h, double g, double lower, double upper, double x0, const QPOpts& o, double* x_out,
+                                            double* R_out, unsigned* free_mask_out, int* nfactor_out) {
+    bool clamped = false;
+    unsigned free_mask = 1u;
+    double oldvalue = 0.0, R = 0.0;
+    int result = 0, nfactor = 0;
+    double x = clampd(x0, lower, upper);                                 // boxQP.jl:58
+    double value = qp1_value(h, g, x);                                   // :63
+    int iter = 1;
+    while (iter <= o.max_iter) {                                         // :71
+        if (result != 0) break;                                          // :73
+        if (iter > 1 && DSUB(oldvalue, value) < DMUL(o.min_rel_improve, fabs(oldvalue))) {   // :78
+            result = 4;
+            break;
+        }
+        oldvalue = value;
+        const double grad = DADD(g, DADD(0.0, DMUL(h, x)));              // :85
+        const bool old_clamped = clamped;
+        clamped = (x == lower && grad > 0.0) || (x == upper && grad < 0.0);      // :92-94
+        free_mask = clamped ? 0u : 1u;
+        if (clamped) {                                                   // :98 all clamped
+            result = 6;
+            break;
+        }
+        if (iter == 1 || old_clamped != clamped) {                       // :104-117
+            if (!(h > 0.0)) {                                            // PosDefException
+                *x_out = x; *R_out = R; *free_mask_out = free_mask; *nfactor_out = nfactor;
+                return -1;
+            }
+            R = __dsqrt_rn(h);
+            nfactor++;
+        }
+        const double gs = DADD(0.0, DMUL(grad, grad));                   // norm(grad[free]) :120 (see boxqp_seq for the |g| shortcut)
+        const double gnorm = (gs > 1e-280 && gs < 1e280) ? fabs(grad) : __dsqrt_rn(gs);
+        if (gnorm < o.min_grad) {
+            result = 5;
+            break;
+        }
+        const double tmp0 = DADD(g, DADD(0.0, DMUL(h, DMUL(x, 0.0))));   // grad_clamped = g + H*(x.*clamped), nothing clamped here  :127
+        const double sol = DDIV(DDIV(tmp0, R), R);                        // Hfree \ (Hfree' \ grad_clamped)
+        const double search = DSUB(-sol, x);                             // :129
+        const double sdotg = DADD(0.0, DMUL(search, grad));              // :132
+        if (sdotg >= 0.0) break;                                         // :133 leaves result == 0
+        double step = 1.0;                                               // :138
+        double xc = clampd(DADD(x, DMUL(step, search)), lower, upper);
+        double vc = qp1_value(h, g, xc);
+        while (DDIV(DSUB(vc, oldvalue), DMUL(step, sdotg)) < o.armijo) { // :142
+            step = DMUL(step, o.step_dec);
+            xc = clampd(DADD(x, DMUL(step, search)), lower, upper);
+            vc = qp1_value(h, g, xc);
+            if (step < o.min_step) {
+                result = 2;
+                break;
+            }
+        }
+        x = xc;                                                          // :161
+        value = vc;
+        iter++;
+    }
+    if (iter == o.max_iter) result = 1;                                  // :167 (quirk Q4)
+    *x_out = x;
+    *R_out = R;
+    *free_mask_out = free_mask;
+    *nfactor_out = nfactor;
+    return result;
+}

@@ -79,7 +79,7 @@ def test_time_varying_lims(ddp):
         assert np.array_equal(un == lims[:, :, 0], u0_ == lims[:, :, 0]) and np.array_equal(un == lims[:, :, 1], u0_ == lims[:, :, 1])
 
 
-@pytest.mark.parametrize("n,m,N,generic", [(32, 8, 12, False), (32, 8, 12, True), (4, 1, 25, False), (7, 3, 10, False)])
+@pytest.mark.parametrize("n,m,N,generic", [(32, 8, 12, False), (32, 8, 12, True), (4, 1, 25, True), (7, 3, 10, False)])
 def test_vxx_packed_history(ddp, n, m, N, generic):
     """want_Vxx="upper": the packed upper-triangle history (half the bytes) expands to exactly the full one."""
     A, Bm, Q, R, x, u = make_batch_lq(43, 5, n, m, N)
@@ -220,7 +220,9 @@ def test_ilqg_prerolled_and_trace(ddp, lims):
     for b in range(B):
         om = O.LinearModel(A[b], Bm[b], Q, R)
         x0_, u0_, p0, Vx0, Vxx0, c0, t0 = O.iLQG(om.f, om.costfun, om.df, x[b].copy(), u[b].copy(), lims=lm, cost=costs[b], max_iter=30)
-        assert tr["status"][b] == t0["status"] and tr["iter"][b] == t0["iters"]
+        diag = dict(b=b, dev={k_: it_tr[k_][:, b][: tr["iter"][b] + 1].tolist() for k_ in ("lam", "grad_norm", "improvement", "alpha", "cost", "bp_retries")},
+                    ora={k_: t0[k_] for k_ in ("lam", "grad_norm", "improvement", "alpha", "cost")}, status=(int(tr["status"][b]), t0["status"]))
+        assert tr["status"][b] == t0["status"] and tr["iter"][b] == t0["iters"], diag
         assert relerr(xs[b], x0_) < 1e-7 and relerr(us[b], u0_) < 1e-7 and abs(cost[b] - np.sum(c0)) <= 1e-9 * abs(np.sum(c0))
         for key, okey in (("lam", "lam"), ("dlam", "dlam"), ("cost", "cost"), ("alpha", "alpha"), ("improvement", "improvement"),
                           ("reduce_ratio", "reduce_ratio"), ("grad_norm", "grad_norm")):
@@ -317,7 +319,7 @@ def test_host_iteration_resident_inputs_and_commit(ddp):
     x1, u1, c1 = it.bufs["xnew"].copy(), it.bufs["unew"].copy(), it.bufs["cost"].copy()
     assert np.all(c1 < cost0)                                                    # every step accepted on this LQ batch
     h2d2, _ = it.run(inputs_resident=True)
-    assert h2d2 < 0.01 * h2d1                                                    # nothing but the three shared cost matrices went up
+    assert h2d2 == 8 * (n * n + m * m + n * m) and h2d1 > 50 * h2d2             # nothing but the three shared cost matrices went up
     x2, c2, K2 = it.bufs["xnew"].copy(), it.bufs["cost"].copy(), it.policy()[0]
     eng_b = ddp.Engine(n, m, N, B)
     itb = ddp.HostIteration(eng_b, Q, R, reg_type=1, alpha=1.0, chunk=16, device_derivs=True)
@@ -483,3 +485,85 @@ def test_small_kernel_asymmetric_terminal_cxx_and_residency_variants(ddp, monkey
         assert np.array_equal(r2[1].K[b] == 0, p0.K == 0)
         for got, ref in ((r2[1].K[b], p0.K), (r2[1].k[b], p0.k), (r2[2][b], Vx0), (r2[3][b], Vxx0), (r2[4][b], dV0)):
             assert relerr_elem(got, ref) < TOL, b
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# box-QP branch on the n=32, m=8 tensor-tile kernel (row a4 on the fast path)
+# ---------------------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("regType", [1, 2])
+@pytest.mark.parametrize("ltv", [False, True])
+def test_tile32x8_boxqp_branch(ddp, regType, ltv):
+    """back_pass with control limits at the headline shape: bp_tile32x8_kernel<LIMS> (QP in the oracle's arithmetic order, gains by
+    columns) vs the oracle and the generic kernel: same `diverge`, identical clamped sets at every step, K,k,Vx,Vxx,dV to 1e-8."""
+    B, n, m, N = 9, 32, 8, 18
+    A, Bm, Q, R, x, u = make_batch_lq(70, B, n, m, N)
+    rng = np.random.default_rng(71)
+    cx, cu = x @ Q.T, u @ R.T
+    if ltv:
+        fx = A[:, None] + 1e-3 * rng.standard_normal((B, N, n, n)); fu = Bm[:, None] + 1e-3 * rng.standard_normal((B, N, n, m))
+    else:
+        fx, fu = A[:, None], Bm[:, None]
+    lims = np.stack([-0.3 * (0.2 + 0.3 * rng.random(m)), 0.3 * (0.2 + 0.3 * rng.random(m))], axis=-1)     # about half of the controls clamp
+    lam = 1e-2 * (1 + np.arange(B))
+    res = {}
+    for name, generic in (("tile", False), ("generic", True)):
+        res[name] = ddp.back_pass(cx, cu, Q, np.zeros((n, m)), R, fx, fu, lam, regType, lims, x, u, force_generic=generic)
+    nclamped = 0
+    for b in range(B):
+        fxb, fub = (fx[b], fu[b]) if ltv else (fx[b, 0], fu[b, 0])
+        d0, p0, Vx0, Vxx0, dV0 = O.back_pass(cx[b], cu[b], Q, np.zeros((n, m)), R, fxb, fub, lam[b], regType, lims, x[b], u[b])
+        for name, r in res.items():
+            assert r[0][b] == d0, (name, b)
+            rows_dev = np.all(r[1].K[b] == 0, axis=-1)                            # clamped controls have a zero gain row
+            rows_ref = np.all(p0.K == 0, axis=-1)
+            assert np.array_equal(rows_dev, rows_ref), (name, b)
+            for got, ref in ((r[1].K[b], p0.K), (r[1].k[b], p0.k), (r[2][b], Vx0), (r[3][b], Vxx0), (r[4][b], dV0)):
+                assert relerr_elem(got, ref) < TOL, (name, b)
+            assert np.array_equal(r[1].k[b] == (lims[:, 0] - u[b]), p0.k == (lims[:, 0] - u[b]))    # k on the lower bound: same entries
+        nclamped += int(np.sum(np.all(p0.K[:-1] == 0, axis=-1)))
+    assert nclamped > 20                                                          # the QP branch really clamps here
+    # the QP itself is the oracle's arithmetic on both kernels: k agrees bit for bit between them
+    assert np.array_equal(res["tile"][0], res["generic"][0])
+
+
+def test_tile32x8_boxqp_inverted_limits_take_the_cholesky_branch(ddp):
+    """lims[1,1] > lims[1,2] => Cholesky branch (backward_pass.jl:31), also on the LIMS build of the tile kernel."""
+    B, n, m, N = 3, 32, 8, 10
+    A, Bm, Q, R, x, u = make_batch_lq(72, B, n, m, N)
+    cx, cu = x @ Q.T, u @ R.T
+    lims = np.tile(np.array([[1.0, -1.0]]), (m, 1))
+    args = (cx, cu, Q, np.zeros((n, m)), R, A[:, None], Bm[:, None], 0.5, 1)
+    r1 = ddp.back_pass(*args, lims, x, u)
+    r0 = ddp.back_pass(*args, None, x, u)
+    assert np.array_equal(r1[0], r0[0])
+    for a, b in ((r1[1].K, r0[1].K), (r1[1].k, r0[1].k), (r1[2], r0[2]), (r1[3], r0[3])):
+        assert relerr(a, b) < 1e-12
+
+
+@pytest.mark.parametrize("tv", [False, True])
+def test_back_pass_gps_tile32x8_with_limits(ddp, tv):
+    """KL-augmented sweep with control limits (backward_pass.jl:317-335; Quu is symmetrised there, so the reference's own boxQP accepts
+    it for m > 1): tile kernel vs the oracle and the generic kernel, identical clamped sets, Sigma = inv(Quu) regardless of clamping."""
+    n, m, N = 32, 8, 14
+    A, Bm, Q, R, x, u = make_batch_lq(73, 1, n, m, N)
+    A, Bm, x, u = A[0], Bm[0], x[0], u[0]
+    cx, cu = x @ Q.T, u @ R.T
+    d, p, _, _, _ = O.back_pass(cx, cu, Q, np.zeros((n, m)), R, A, Bm, 1.0, 1, None, x, u)
+    Sigi = p.Sigmai.copy()
+    prev = O.GaussianPolicy(N, n, m, p.K.copy(), np.zeros((N, m)), np.array([np.linalg.inv(s_) for s_ in Sigi]), Sigi)
+    eta = np.array([1e-8, 0.05, 1e16])                                           # small eta: the cost term dominates, controls move, limits bind
+    lims = np.tile(np.array([[-0.03, 0.04]]), (m, 1))
+    rep = (lambda a: np.tile(a, (N, 1, 1))) if tv else (lambda a: a)
+    repo = lambda a: np.tile(a, (N, 1, 1))
+    d0, p0, Vx0, Vxx0, dV0 = O.back_pass_gps(cx, cu, repo(Q), repo(np.zeros((n, m))), repo(R), repo(A), repo(Bm), lims, x, u,
+                                             (O.grad_kl(prev), eta))
+    gp = ddp.GaussianPolicy(N, n, m, prev.K, prev.k, prev.Sigma, prev.Sigmai)
+    for generic in (False, True):
+        d1, p1, Vx1, Vxx1, dV1 = ddp.back_pass_gps(cx, cu, rep(Q), rep(np.zeros((n, m))), rep(R), rep(A), rep(Bm), lims, x, u,
+                                                   (gp, eta), force_generic=generic)
+        assert d0 == d1
+        assert np.array_equal(np.all(p1.K == 0, axis=-1), np.all(p0.K == 0, axis=-1)), generic
+        for a, b in ((p1.K, p0.K), (p1.k, p0.k), (Vx1, Vx0), (Vxx1, Vxx0), (dV1, dV0), (p1.Sigmai[d0:], p0.Sigmai[d0:]), (p1.Sigma[d0:], p0.Sigma[d0:])):
+            assert relerr_elem(a, b) < TOL, generic
+    assert int(np.sum(np.all(p0.K[:-1] == 0, axis=-1))) > 5
