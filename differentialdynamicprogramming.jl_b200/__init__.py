@@ -7,4 +7,4 @@ at the repository root) -- ``import ddp_b200 as ddp``.
 from ._lib import DDPError, DDPLibraryMissing, LIB_PATH, load  # noqa: F401
 from .api import (DEFAULT_ALPHA, STATUS, DevArray, Engine, GaussianPolicy, HostIteration, LinearModel,  # noqa: F401
                   PendcartModel, PosDefException, SimpleLTVModel, TRACE_DTYPE, back_pass, back_pass_gps, boxQP, forward_pass, forward_costs, iLQG, iLQGkl, iLQGkl_device, KL_STATUS,
-                  kl_div_wiki, iterate_chunked)
+                  kl_div_wiki, iterate_chunked, demoQP)

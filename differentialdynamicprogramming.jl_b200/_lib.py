@@ -137,6 +137,7 @@ SYMBOLS = [
     ("ddp_back_pass_f64", C.c_int, [C.c_void_p, C.POINTER(BackPassArgs)]),
     ("ddp_back_pass_gps_f64", C.c_int, [C.c_void_p, C.POINTER(BackPassArgs), C.POINTER(GpsArgs)]),
     ("ddp_boxqp_f64", C.c_int, [C.c_void_p, C.c_int64] + [C.c_void_p] * 5 + [C.POINTER(BoxQPOpts)] + [C.c_void_p] * 5),
+    ("ddp_boxqp_large_f64", C.c_int, [C.c_void_p, C.c_int32, C.c_int64] + [C.c_void_p] * 5 + [C.POINTER(BoxQPOpts)] + [C.c_void_p] * 5),
     ("ddp_forward_pass_f64", C.c_int, [C.c_void_p, C.POINTER(Model), C.POINTER(ForwardPassArgs)]),
     ("ddp_batch_stats_f64", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                       C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -389,6 +389,8 @@ def boxQP(H, g, lower, upper, x0, *, maxIter=100, minGrad=1e-8, minRelImprove=1e
     batched = H.ndim == 3
     Hb = H if batched else H[None]
     B, m, _ = Hb.shape
+    if m > 16:                                            # demoQP-sized problems: one CTA per QP (ddp_boxqp_large_f64)
+        return _boxQP_large(Hb, g, lower, upper, x0, batched, L.BoxQPOpts(maxIter, minGrad, minRelImprove, stepDec, minStep, Armijo), engine)
     eng = engine or Engine(max(m, 1), m, 1, B)
     vec = lambda v: eng.upload(np.broadcast_to(np.asarray(v, dtype=np.float64).reshape(-1, m), (B, m)))
     dH = eng.upload(np.swapaxes(Hb, -1, -2))
@@ -407,6 +409,33 @@ def boxQP(H, g, lower, upper, x0, *, maxIter=100, minGrad=1e-8, minRelImprove=1e
         raise PosDefException("matrix is not positive definite; Cholesky factorization failed")
     nfree = int(np.count_nonzero(np.diag(Hfs[0])))
     return xs[0], int(rs[0]), Hfs[0][:nfree, :nfree], free[0], int(nfs[0])
+
+
+def _boxQP_large(Hb, g, lower, upper, x0, batched, o, engine):
+    B, n, _ = Hb.shape
+    eng = engine or Engine(1, 1, 1, 1)
+    vec = lambda v: eng.upload(np.broadcast_to(np.asarray(v, dtype=np.float64).reshape(-1, n), (B, n)))
+    dH = eng.upload(np.swapaxes(Hb, -1, -2))
+    dg, dl, du, dx0 = vec(g), vec(lower), vec(upper), vec(x0)
+    x, res, Hf = eng.empty((B, n)), eng.empty((B,), np.int32), eng.empty((B, n, n))
+    fr, nf = eng.empty((B, n), np.uint8), eng.empty((B,), np.int32)
+    eng._ck(eng.lib.ddp_boxqp_large_f64(eng.h, n, B, dH.ptr, dg.ptr, dl.ptr, du.ptr, dx0.ptr, C.byref(o), x.ptr, res.ptr, Hf.ptr, fr.ptr, nf.ptr))
+    eng.synchronize()
+    xs, rs, Hfs, free, nfs = x.numpy(), res.numpy(), np.swapaxes(Hf.numpy(), -1, -2), fr.numpy().astype(bool), nf.numpy()
+    if batched:
+        return xs, rs, Hfs, free, nfs
+    if rs[0] < 0:
+        raise PosDefException("matrix is not positive definite; Cholesky factorization failed")
+    nfree = int(np.count_nonzero(np.diag(Hfs[0])))
+    return xs[0], int(rs[0]), Hfs[0][:nfree, :nfree], free[0], int(nfs[0])
+
+
+def demoQP(n=500, seed=None, **kw):
+    """``demoQP`` of boxQP.jl:190-199: a random n = 500 box QP (``H = A*A'``, bounds +-1) solved on the device."""
+    rng = np.random.default_rng(seed)
+    g = rng.standard_normal(n)
+    A = rng.standard_normal((n, n))
+    return boxQP(A @ A.T, g, -np.ones(n), np.ones(n), rng.standard_normal(n), **kw)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -41,29 +41,28 @@ __host__ __device__ constexpr int tri(int r, int c) { return (r <= c) ? c * (c +
 
 // Coalesced copy of one field of the warp's 32 trajectories at step i into the ring: CH 16-byte chunks per row, lane ->
 // (row = lane / CH + (32 / CH) k, chunk = lane % CH): CH lanes read one contiguous run of one trajectory.
+// `src` is the lane's source pointer for (row, chunk) AT THE STEP BEING STAGED (the caller walks it back by the time stride every
+// step), `rowstep` the byte distance of RPI trajectories: per copy one 64-bit add, no multiplies.
 template <int CH>
-__device__ __forceinline__ void stage_field(double* sdst_row0, int ROWLEN, const TensorD& t, long long b0, long long B, int i, int lane, bool full) {
+__device__ __forceinline__ void stage_field(double* dst, int ROWLEN, const char* src, long long rowstep, long long row_abs, long long B, bool full) {
     constexpr int RPI = 32 / CH;
-    const int row = lane / CH, ch = lane % CH;
-    const double* src = t.p + (b0 + row) * t.sb + (long long)i * t.st + 2 * ch;
-    double* dst = sdst_row0 + row * ROWLEN + 2 * ch;
 #pragma unroll
     for (int k = 0; k < CH; k++) {
-        if (full || b0 + row + RPI * k < B) cp_async16s(dst + k * RPI * ROWLEN, src);
-        src += RPI * t.sb;
+        if (full || row_abs + RPI * k < B) cp_async16s(dst + k * RPI * ROWLEN, reinterpret_cast<const double*>(src));
+        src += rowstep;
     }
 }
 
 // One thread per trajectory.  STAGE: every per-step input arrives through the warp's double-buffered cp.async ring (see Row);
 // !STAGE (odd sizes, unaligned views, DDP_SMALL_NOSTAGE): direct loads with a one-step register prefetch.  Same arithmetic either way.
-template <int N, int M, int MINB, bool STAGE>
+template <int N, int M, int MINB, bool STAGE, bool CSH>
 __global__ void __launch_bounds__(128, MINB) bp_small_kernel(BackParams P) {
     using RW = Row<N, M>;
     constexpr int NT = N * (N + 1) / 2;
     extern __shared__ __align__(16) double s_ring[];         // STAGE: 4 warps x 2 buffers x 32 rows (dynamic: above the 48 KB static limit)
     // cost Hessians shared by the batch and constant in time (the usual case): one copy per CTA, read by broadcast; cxx symmetrised
     __shared__ double s_cost[NT + N * M + M * M];
-    const bool cost_shared = (P.cxx.sb == 0 && P.cxx.st == 0 && P.cxu.sb == 0 && P.cxu.st == 0 && P.cuu.sb == 0 && P.cuu.st == 0);
+    constexpr bool cost_shared = CSH;      // cxx, cxu, cuu shared by the batch and constant in time (decided by the launcher)
     if (cost_shared) {
         for (int e = threadIdx.x; e < NT + N * M + M * M; e += blockDim.x) {
             double v;
@@ -99,14 +98,26 @@ __global__ void __launch_bounds__(128, MINB) bp_small_kernel(BackParams P) {
 #pragma unroll
     for (int a = 0; a < M; a++) { lims_lo[a] = use_qp ? P.lims[a] : 0.0; lims_hi[a] = use_qp ? P.lims[M + a] : 0.0; }
 
-    auto stage = [&](int i) {                                // all inputs of step i -> ring buffer (i & 1)
+    // staging: per field one lane pointer (row = lane / CH, chunk = lane % CH) positioned at step T-2 and walked back one time
+    // stride per staged step; the shared-memory destinations are compile-time offsets from two lane bases
+    constexpr int CHX = STAGE ? (N * N) / 2 : 1, CHU = STAGE ? (N * M) / 2 : 1, CHC = STAGE ? N / 2 : 1;
+    const char *sp_fx = nullptr, *sp_fu = nullptr, *sp_cx = nullptr, *sp_cu = nullptr, *sp_u = nullptr;
+    if (STAGE) {
+        const long long t0 = T - 2;
+        sp_fx = reinterpret_cast<const char*>(P.fx.p + (b0 + lane / CHX) * P.fx.sb + t0 * P.fx.st + 2 * (lane % CHX));
+        sp_fu = reinterpret_cast<const char*>(P.fu.p + (b0 + lane / CHU) * P.fu.sb + t0 * P.fu.st + 2 * (lane % CHU));
+        sp_cx = reinterpret_cast<const char*>(P.cx.p + (b0 + lane / CHC) * P.cx.sb + t0 * P.cx.st + 2 * (lane % CHC));
+        sp_cu = reinterpret_cast<const char*>(P.cu.p + b * P.cu.sb + t0 * P.cu.st);
+        sp_u = use_qp ? reinterpret_cast<const char*>(P.u.p + b * P.u.sb + t0 * P.u.st) : nullptr;
+    }
+    auto stage = [&](int i) {                                // all inputs of step i -> ring buffer (i & 1); steps are staged in order T-2, T-3, ...
         double* r0 = ring + (i & 1) * 32 * RW::ROW;
-        stage_field<(N * N) / 2>(r0 + RW::FX, RW::ROW, P.fx, b0, P.B, i, lane, full);
-        stage_field<(N * M) / 2>(r0 + RW::FU, RW::ROW, P.fu, b0, P.B, i, lane, full);
-        stage_field<N / 2>(r0 + RW::CX, RW::ROW, P.cx, b0, P.B, i, lane, full);
-        if (full || b_raw < P.B) {
-            double* rr = r0 + lane * RW::ROW;
-            const double* cus = tp(P.cu, b_raw, i);
+        stage_field<CHX>(r0 + RW::FX + (lane / CHX) * RW::ROW + 2 * (lane % CHX), RW::ROW, sp_fx, (32 / CHX) * 8 * P.fx.sb, b0 + lane / CHX, P.B, full);
+        stage_field<CHU>(r0 + RW::FU + (lane / CHU) * RW::ROW + 2 * (lane % CHU), RW::ROW, sp_fu, (32 / CHU) * 8 * P.fu.sb, b0 + lane / CHU, P.B, full);
+        stage_field<CHC>(r0 + RW::CX + (lane / CHC) * RW::ROW + 2 * (lane % CHC), RW::ROW, sp_cx, (32 / CHC) * 8 * P.cx.sb, b0 + lane / CHC, P.B, full);
+        {
+            double* rr = r0 + lane * RW::ROW;                // out-of-range lanes shadow the last trajectory (b): a valid address
+            const double* cus = reinterpret_cast<const double*>(sp_cu);
             if (M % 2 == 0) {
 #pragma unroll
                 for (int a = 0; a < M; a += 2) cp_async16s(rr + RW::CU + a, cus + a);
@@ -115,7 +126,7 @@ __global__ void __launch_bounds__(128, MINB) bp_small_kernel(BackParams P) {
                 for (int a = 0; a < M; a++) cp_async8s(rr + RW::CU + a, cus + a);
             }
             if (use_qp) {
-                const double* us = tp(P.u, b_raw, i);
+                const double* us = reinterpret_cast<const double*>(sp_u);
                 if (M % 2 == 0) {
 #pragma unroll
                     for (int a = 0; a < M; a += 2) cp_async16s(rr + RW::UU + a, us + a);
@@ -126,6 +137,8 @@ __global__ void __launch_bounds__(128, MINB) bp_small_kernel(BackParams P) {
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
+        sp_fx -= 8 * P.fx.st; sp_fu -= 8 * P.fu.st; sp_cx -= 8 * P.cx.st; sp_cu -= 8 * P.cu.st;
+        if (use_qp) sp_u -= 8 * P.u.st;
     };
 
     double Vs[NT], Vx[N];              // Vxx(i+1): upper triangle (exactly symmetric, backward_pass.jl:71-72)
@@ -314,10 +327,10 @@ __global__ void __launch_bounds__(128, MINB) bp_small_kernel(BackParams P) {
         if (failed) { diverge = i + 1; alive = false; }
         else {
         if (M == 1) {
-            // scalar control: K = -Qux_reg / (R'R); one reciprocal of the factor instead of 2 divisions per column
-            const double rinv = (nf > 0) ? 1.0 / R[0] : 0.0;
+            // scalar control: K = -Qux_reg / QuuF (= R'R); one reciprocal that does not wait for the QP's sqrt/divide chain
+            const double hinv = (nf > 0) ? -1.0 / QuuF[0] : 0.0;
 #pragma unroll
-            for (int j = 0; j < N; j++) Ki[j] = -((Quxr[j] * rinv) * rinv);
+            for (int j = 0; j < N; j++) Ki[j] = Quxr[j] * hinv;
         } else {
 #pragma unroll
         for (int j = 0; j < N; j++) {
@@ -441,23 +454,25 @@ int launch_small(ddp_handle_s* h, const BackParams& P_in) {
     const bool cu_ok = (M % 2 == 0) ? al16v(P.cu) : true;
     const bool stage = Row<N, M>::OK && al16v(P.fx) && al16v(P.fu) && al16v(P.cx) && cu_ok && u_ok && !(getenv("DDP_SMALL_NOSTAGE"));
     // 2 CTAs (8 warps) per SM: 168- and 128-register builds (3 / 4 CTAs) spill
+    const bool csh = (P.cxx.sb == 0 && P.cxx.st == 0 && P.cxu.sb == 0 && P.cxu.st == 0 && P.cuu.sb == 0 && P.cuu.st == 0);
+#define LAUNCH_SMALL(MB, ST, CS, BYTES)                                                                                                   \
+    do {                                                                                                                                  \
+        cudaError_t ea = cudaFuncSetAttribute(bp_small_kernel<N, M, MB, ST, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BYTES)); \
+        if (ea != cudaSuccess) return (int)ea;                                                                                            \
+        bp_small_kernel<N, M, MB, ST, CS><<<grid, 128, (BYTES), h->stream>>>(P);                                                          \
+    } while (0)
     if (stage && Row<N, M>::OK) {
         const size_t bytes = sizeof(double) * 4 * 2 * 32 * Row<N, M>::ROW;
         // residency: 2 CTAs (8 warps, <= 255 registers) or 3 CTAs (12 warps, 168 registers, a few spilled doubles) per SM;
-        // DDP_SMALL_MINB selects for the A/B measurement, the default is the faster one on B200 (profiles/README_r02.md)
+        // DDP_SMALL_MINB selects for the A/B measurement; 2 is the faster one on B200 (12.8 vs 16.4 ms, profiles/README_r02.md)
         const char* mb = getenv("DDP_SMALL_MINB");
         const int minb = mb ? atoi(mb) : SMALL_MINB;
-        cudaError_t ea;
-        if (minb == 3) {
-            ea = cudaFuncSetAttribute(bp_small_kernel<N, M, 3, Row<N, M>::OK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-            if (ea != cudaSuccess) return (int)ea;
-            bp_small_kernel<N, M, 3, Row<N, M>::OK><<<grid, 128, bytes, h->stream>>>(P);
-        } else {
-            ea = cudaFuncSetAttribute(bp_small_kernel<N, M, 2, Row<N, M>::OK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-            if (ea != cudaSuccess) return (int)ea;
-            bp_small_kernel<N, M, 2, Row<N, M>::OK><<<grid, 128, bytes, h->stream>>>(P);
-        }
-    } else bp_small_kernel<N, M, 2, false><<<grid, 128, 16, h->stream>>>(P);
+        if (minb == 3) { if (csh) LAUNCH_SMALL(3, (Row<N, M>::OK), true, bytes); else LAUNCH_SMALL(3, (Row<N, M>::OK), false, bytes); }
+        else { if (csh) LAUNCH_SMALL(2, (Row<N, M>::OK), true, bytes); else LAUNCH_SMALL(2, (Row<N, M>::OK), false, bytes); }
+    } else {
+        if (csh) LAUNCH_SMALL(2, false, true, 16); else LAUNCH_SMALL(2, false, false, 16);
+    }
+#undef LAUNCH_SMALL
     h->launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;

@@ -171,6 +171,15 @@ DDP_API int ddp_boxqp_f64(ddp_handle_t h, int64_t B, const double* H, const doub
                   const double* upper, const double* x0, const ddp_boxqp_opts* opts, double* x,
                   int32_t* result, double* Hfree, uint32_t* free_mask, int32_t* nfactor);
 
+/* Large problems (the reference's demoQP: n = 500, boxQP.jl:190-199): the same iteration with ONE CTA per problem, 1 <= n <= 1024
+ * (n is an argument, not the handle's m).  H (n,n,B), g/lower/upper/x0 (n,B) -> x (n,B), result[B], Hfree (n,n,B; REQUIRED: it is the
+ * work matrix of the factorisation and returns the nfree x nfree upper factor in its leading block, zeros elsewhere), free (n,B) bytes
+ * (1 = free) or NULL, nfactor[B] or NULL.  The Cholesky factor reproduces the oracle's bit for bit (same subtraction order); sums over n
+ * are tree reductions, so result codes / free sets agree with the m <= 16 path except on exact ties (see csrc/boxqp_large.cu). */
+DDP_API int ddp_boxqp_large_f64(ddp_handle_t h, int32_t n, int64_t B, const double* H, const double* g, const double* lower,
+                                const double* upper, const double* x0, const ddp_boxqp_opts* opts, double* x, int32_t* result,
+                                double* Hfree, uint8_t* free_out, int32_t* nfactor);
+
 /* ---- models: the reference's user callbacks f / costfun / df as device descriptors ------- */
 enum { DDP_MODEL_LINEAR = 1, DDP_MODEL_PENDCART = 2 };
 enum { DDP_MODEL_Q_DIAGONAL = 1 };   /* ddp_model.flags: Q is diagonal (e.g. Q = h*I of demo_linear.jl:18): only its diagonal is read */

@@ -222,6 +222,11 @@ def test_ilqg_prerolled_and_trace(ddp, lims):
         x0_, u0_, p0, Vx0, Vxx0, c0, t0 = O.iLQG(om.f, om.costfun, om.df, x[b].copy(), u[b].copy(), lims=lm, cost=costs[b], max_iter=30)
         diag = dict(b=b, dev={k_: it_tr[k_][:, b][: tr["iter"][b] + 1].tolist() for k_ in ("lam", "grad_norm", "improvement", "alpha", "cost", "bp_retries")},
                     ora={k_: t0[k_] for k_ in ("lam", "grad_norm", "improvement", "alpha", "cost")}, status=(int(tr["status"][b]), t0["status"]))
+        if not (tr["status"][b] == t0["status"] and tr["iter"][b] == t0["iters"]):
+            import json, os
+            os.makedirs("gpurun_out", exist_ok=True)
+            diag["dev_iter"] = int(tr["iter"][b]); diag["ora_iter"] = int(t0["iters"]); diag["dev_gnorm_final"] = float(tr["g_norm"][b])
+            json.dump(diag, open("gpurun_out/diag_prerolled.json", "w"), default=str)
         assert tr["status"][b] == t0["status"] and tr["iter"][b] == t0["iters"], diag
         assert relerr(xs[b], x0_) < 1e-7 and relerr(us[b], u0_) < 1e-7 and abs(cost[b] - np.sum(c0)) <= 1e-9 * abs(np.sum(c0))
         for key, okey in (("lam", "lam"), ("dlam", "dlam"), ("cost", "cost"), ("alpha", "alpha"), ("improvement", "improvement"),
@@ -567,3 +572,37 @@ def test_back_pass_gps_tile32x8_with_limits(ddp, tv):
         for a, b in ((p1.K, p0.K), (p1.k, p0.k), (Vx1, Vx0), (Vxx1, Vxx0), (dV1, dV0), (p1.Sigmai[d0:], p0.Sigmai[d0:]), (p1.Sigma[d0:], p0.Sigma[d0:])):
             assert relerr_elem(a, b) < TOL, generic
     assert int(np.sum(np.all(p0.K[:-1] == 0, axis=-1))) > 5
+
+
+@pytest.mark.parametrize("n", [24, 120, 500])
+def test_boxqp_large(ddp, n):
+    """boxQP for problems beyond the m <= 16 kernels (the reference's demoQP is n = 500, boxQP.jl:190-199): one CTA per problem.
+    Against the oracle (n = 24, 120; its Python loops need minutes at 500): result code, free set and number of factorisations
+    exact, the Cholesky factor to 1e-12 (same subtraction order), x to 1e-9.  At every size: the KKT conditions of the solution."""
+    rng = np.random.default_rng(80 + n)
+    A = rng.standard_normal((n, n))
+    H = A @ A.T                                                                   # exactly symmetric, as demoQP builds it (:193-194)
+    g = rng.standard_normal(n)
+    lower, upper = -np.ones(n), np.ones(n)
+    x0 = rng.standard_normal(n)
+    x, res, Hf, free, nfac = ddp.boxQP(H, g, lower, upper, x0)
+    assert res >= 1 and nfac >= 1
+    if n <= 120:
+        xo, ro, Ho, fo, no = O.boxQP(H, g, lower, upper, x0)
+        assert res == ro and nfac == no
+        assert np.array_equal(free, fo)
+        assert relerr(x, xo) < 1e-9
+        assert Hf.shape == Ho.shape and relerr(Hf, Ho) < 1e-12
+    grad = g + H @ x                                                              # KKT: zero gradient on the free set, correct sign on the bounds
+    assert np.all((x >= lower) & (x <= upper))
+    assert np.max(np.abs(grad[free])) < 1e-6 * max(1.0, np.max(np.abs(g)))
+    assert np.all(grad[(x == lower) & ~free] >= 0) and np.all(grad[(x == upper) & ~free] <= 0)
+    assert np.allclose(np.triu(Hf).T @ np.triu(Hf), H[np.ix_(free, free)], rtol=1e-9, atol=1e-9 * np.max(np.abs(H)))     # R'R = H[free,free]
+    if n <= 120:                                                                  # a small batch through the same entry point
+        Hb = np.stack([H, H + np.eye(n)]); gb = np.stack([g, -g])
+        xb, rb, _, fb, _ = ddp.boxQP(Hb, gb, lower, upper, np.zeros(n))
+        for b in range(2):
+            xo, ro, _, fo, _ = O.boxQP(Hb[b], gb[b], lower, upper, np.zeros(n))
+            assert rb[b] == ro and np.array_equal(fb[b], fo) and relerr(xb[b], xo) < 1e-9
+    with pytest.raises(ddp.PosDefException):
+        ddp.boxQP(-H, g, lower, upper, np.zeros(n))
