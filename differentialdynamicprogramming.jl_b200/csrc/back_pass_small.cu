@@ -33,6 +33,7 @@ template <int N, int M>
 struct Row {
     static constexpr int FX = 0, FU = N * N, CX = FU + N * M, CU = CX + N, UU = CU + M, LEN = UU + M;
     static constexpr int ROW = LEN + ((2 - (LEN & 3)) & 3);
+    static constexpr int DEPTH = 3;      // ring buffers per warp: the inputs of step i are requested two steps ahead
     static constexpr bool OK = (N % 2 == 0) && (32 % ((N * N) / 2) == 0) && (32 % ((N * M + 1) / 2) == 0) && ((N * M) % 2 == 0);
 };
 
@@ -46,11 +47,31 @@ __host__ __device__ constexpr int tri(int r, int c) { return (r <= c) ? c * (c +
 template <int CH>
 __device__ __forceinline__ void stage_field(double* dst, int ROWLEN, const char* src, long long rowstep, long long row_abs, long long B, bool full) {
     constexpr int RPI = 32 / CH;
+    if (full) {                                            // warp-uniform: every row of the warp exists, no predicates
 #pragma unroll
-    for (int k = 0; k < CH; k++) {
-        if (full || row_abs + RPI * k < B) cp_async16s(dst + k * RPI * ROWLEN, reinterpret_cast<const double*>(src));
-        src += rowstep;
+        for (int k = 0; k < CH; k++) {
+            cp_async16s(dst + k * RPI * ROWLEN, reinterpret_cast<const double*>(src));
+            src += rowstep;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < CH; k++) {
+            if (row_abs + RPI * k < B) cp_async16s(dst + k * RPI * ROWLEN, reinterpret_cast<const double*>(src));
+            src += rowstep;
+        }
     }
+}
+
+// 1/d for d > 0 in the normal range, to the last bit or two: hardware seed + two Newton steps (the gains K are a 1e-8 quantity,
+// not part of the bit-exact box-QP arithmetic)
+__device__ __forceinline__ double rcp_fast(double d) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    double e = fma(-d, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-d, y, 1.0);
+    y = fma(y, e, y);
+    return y;
 }
 
 // One thread per trajectory.  STAGE: every per-step input arrives through the warp's double-buffered cp.async ring (see Row);
@@ -59,7 +80,7 @@ template <int N, int M, int MINB, bool STAGE, bool CSH>
 __global__ void __launch_bounds__(128, MINB) bp_small_kernel(BackParams P) {
     using RW = Row<N, M>;
     constexpr int NT = N * (N + 1) / 2;
-    extern __shared__ __align__(16) double s_ring[];         // STAGE: 4 warps x 2 buffers x 32 rows (dynamic: above the 48 KB static limit)
+    extern __shared__ __align__(16) double s_ring[];         // STAGE: 4 warps x DEPTH buffers x 32 rows (dynamic: above the 48 KB static limit)
     // cost Hessians shared by the batch and constant in time (the usual case): one copy per CTA, read by broadcast; cxx symmetrised
     __shared__ double s_cost[NT + N * M + M * M];
     constexpr bool cost_shared = CSH;      // cxx, cxu, cuu shared by the batch and constant in time (decided by the launcher)
@@ -83,7 +104,7 @@ __global__ void __launch_bounds__(128, MINB) bp_small_kernel(BackParams P) {
     bool valid = (b_raw < P.B) && !(P.active && !P.active[b_raw]);
     const long long b = (b_raw < P.B) ? b_raw : P.B - 1;     // out-of-range lanes shadow the last trajectory, store nothing
     const bool full = (b0 + 32 <= P.B);                      // warp-uniform: no row predicates in the staging copies
-    double* ring = s_ring + (STAGE ? wid * 2 * 32 * RW::ROW : 0);
+    double* ring = s_ring + (STAGE ? wid * RW::DEPTH * 32 * RW::ROW : 0);
     const int T = P.T;
     const bool use_qp = (P.lims != nullptr) && !(P.lims[0] > P.lims[M]);     // backward_pass.jl:31
     const double lam = P.lambda[b];
@@ -110,8 +131,9 @@ __global__ void __launch_bounds__(128, MINB) bp_small_kernel(BackParams P) {
         sp_cu = reinterpret_cast<const char*>(P.cu.p + b * P.cu.sb + t0 * P.cu.st);
         sp_u = use_qp ? reinterpret_cast<const char*>(P.u.p + b * P.u.sb + t0 * P.u.st) : nullptr;
     }
-    auto stage = [&](int i) {                                // all inputs of step i -> ring buffer (i & 1); steps are staged in order T-2, T-3, ...
-        double* r0 = ring + (i & 1) * 32 * RW::ROW;
+    auto stage = [&](int i) {                                // all inputs of step i -> ring buffer (i % DEPTH); steps are staged in order T-2, T-3, ...
+        if (i < 0) { asm volatile("cp.async.commit_group;" ::: "memory"); return; }      // past the first step: an empty group keeps the wait count uniform
+        double* r0 = ring + (i % RW::DEPTH) * 32 * RW::ROW;
         stage_field<CHX>(r0 + RW::FX + (lane / CHX) * RW::ROW + 2 * (lane % CHX), RW::ROW, sp_fx, (32 / CHX) * 8 * P.fx.sb, b0 + lane / CHX, P.B, full);
         stage_field<CHU>(r0 + RW::FU + (lane / CHU) * RW::ROW + 2 * (lane % CHU), RW::ROW, sp_fu, (32 / CHU) * 8 * P.fu.sb, b0 + lane / CHU, P.B, full);
         stage_field<CHC>(r0 + RW::CX + (lane / CHC) * RW::ROW + 2 * (lane % CHC), RW::ROW, sp_cx, (32 / CHC) * 8 * P.cx.sb, b0 + lane / CHC, P.B, full);
@@ -201,20 +223,20 @@ __global__ void __launch_bounds__(128, MINB) bp_small_kernel(BackParams P) {
         for (int e = 0; e < M; e++) { pf[(STAGE ? 0 : RW::CU + e)] = cu[e]; pf[(STAGE ? 0 : RW::UU + e)] = use_qp ? tp(P.u, b, i)[e] : 0.0; }
     };
     if (T >= 2) {
-        if (STAGE) stage(T - 2);
+        if (STAGE) { stage(T - 2); stage(T - 3); }
         else load_direct(T - 2);
     }
     for (int i = T - 2; i >= 0; i--) {
         double in[RW::LEN];                                          // this step's [fx | fu | cx | cu | u]
         if (STAGE) {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            __syncwarp();                                            // the warp's copies of step i have landed
-            const double* row = ring + (i & 1) * 32 * RW::ROW + lane * RW::ROW;
+            asm volatile("cp.async.wait_group 1;" ::: "memory");      // all but the newest group (step i-1): step i has landed
+            __syncwarp();                                            // ... for every lane of the warp
+            const double* row = ring + (i % RW::DEPTH) * 32 * RW::ROW + lane * RW::ROW;
 #pragma unroll
             for (int e = 0; e + 1 < RW::LEN; e += 2) { const double2 t = *reinterpret_cast<const double2*>(row + e); in[e] = t.x; in[e + 1] = t.y; }
             if (RW::LEN & 1) in[RW::LEN - 1] = row[RW::LEN - 1];
-            // the other buffer was read in step i+1, before the __syncwarp above: refill it with step i-1
-            if (i > 0) stage(i - 1);
+            // the buffer of step i+1 was read before the __syncwarp above: refill it with step i-2
+            stage(i - 2);
         } else {
 #pragma unroll
             for (int e = 0; e < RW::LEN; e++) in[e] = pf[STAGE ? 0 : e];
@@ -328,7 +350,7 @@ __global__ void __launch_bounds__(128, MINB) bp_small_kernel(BackParams P) {
         else {
         if (M == 1) {
             // scalar control: K = -Qux_reg / QuuF (= R'R); one reciprocal that does not wait for the QP's sqrt/divide chain
-            const double hinv = (nf > 0) ? -1.0 / QuuF[0] : 0.0;
+            const double hinv = (nf > 0) ? -rcp_fast(QuuF[0]) : 0.0;       // QuuF > 0 here: its Cholesky factor exists
 #pragma unroll
             for (int j = 0; j < N; j++) Ki[j] = Quxr[j] * hinv;
         } else {
@@ -462,7 +484,7 @@ int launch_small(ddp_handle_s* h, const BackParams& P_in) {
         bp_small_kernel<N, M, MB, ST, CS><<<grid, 128, (BYTES), h->stream>>>(P);                                                          \
     } while (0)
     if (stage && Row<N, M>::OK) {
-        const size_t bytes = sizeof(double) * 4 * 2 * 32 * Row<N, M>::ROW;
+        const size_t bytes = sizeof(double) * 4 * Row<N, M>::DEPTH * 32 * Row<N, M>::ROW;
         // residency: 2 CTAs (8 warps, <= 255 registers) or 3 CTAs (12 warps, 168 registers, a few spilled doubles) per SM;
         // DDP_SMALL_MINB selects for the A/B measurement; 2 is the faster one on B200 (12.8 vs 16.4 ms, profiles/README_r02.md)
         const char* mb = getenv("DDP_SMALL_MINB");

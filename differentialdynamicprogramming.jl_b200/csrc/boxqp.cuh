@@ -199,6 +199,10 @@ __device__ int boxqp_seq(int m, const double* H, int ldh, const double* g, const
 }
 
 
+// sqrt(gs) for the rare |grad| outside the range where sqrt(fl(g*g)) == |g| holds exactly; a real call, so that the compiler cannot
+// turn the range test into a select that evaluates the square root on every iteration
+__device__ __noinline__ double qp_sqrt_slow(double v) { return __dsqrt_rn(v); }
+
 // The same projected-Newton iteration for ONE variable (m = 1: config 3), written on scalars: every operation, comparison and
 // rounding is the one boxqp_seq<1> performs in the same order (so result code, free set, factor and x agree bit for bit with it and
 // with the oracle), but without index sets, mask loops and runtime-bounded solves.  h = H[0,0].
@@ -242,7 +246,8 @@ __device__ __forceinline__ int boxqp_scalar(double h, double g, double lower, do
             nfactor++;
         }
         const double gs = DADD(0.0, DMUL(grad, grad));                   // norm(grad[free]) :120 (see boxqp_seq for the |g| shortcut)
-        const double gnorm = (gs > 1e-280 && gs < 1e280) ? fabs(grad) : __dsqrt_rn(gs);
+        double gnorm = fabs(grad);
+        if (!(gs > 1e-280 && gs < 1e280)) gnorm = qp_sqrt_slow(gs);
         if (gnorm < o.min_grad) {
             result = 5;
             break;

@@ -315,7 +315,7 @@ function iLQG(f, costfun, df, x0, u0;
         αt = ntuple(i -> i <= length(α) ? Float64(α[i]) : 0.0, 16)
         cap = 4 * max_iter + 64
         trace_d = dmalloc(p, cap * B * sizeof(DdpIlqgTrace))
-        init = fill(DdpIlqgTrace(NaN, NaN, NaN, NaN, NaN, NaN, NaN, Int32(-1), Int32(0)), cap, B)       # (it, b): it fastest? no -- record (it,b) at it*B + b
+        init = fill(DdpIlqgTrace(NaN, NaN, NaN, NaN, NaN, NaN, NaN, Int32(-1), Int32(0)), cap, B)       # the device keeps record (it, b) at it*B + b
         init = permutedims(init)                                                                         # Julia (B,cap) column-major == C [cap][B]
         GC.@preserve init check(e, ccall((:ddp_upload, libddp), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Csize_t), e.h, trace_d, pointer(init), sizeof(init)))
         x_init, cost_init = C_NULL, C_NULL
@@ -345,7 +345,7 @@ function iLQG(f, costfun, df, x0, u0;
         download!(e, st, dst)
         tr = Matrix{DdpIlqgTrace}(undef, B, cap)
         download!(e, tr, trace_d)
-        traces = [ilqg_trace(tr[b, :], st[b], λ, dλ, prerolled ? nothing : nothing) for b in 1:B]
+        traces = [ilqg_trace(tr[b, :], st[b], λ, dλ, nothing) for b in 1:B]
         if B == 1
             st[1].status == 4 && return nothing                                                     # iLQG.jl:205-210
             st[1].iter == 1 && error("Failure: no iterations completed, something is wrong.")       # iLQG.jl:335

@@ -213,6 +213,10 @@ def test_ilqg_prerolled_and_trace(ddp, lims):
     B, n, m, N = 4, 8, 2, 40
     A, Bm, Q, R, x, u = make_batch_lq(48, B, n, m, N)
     lm = None if lims is None else np.array([[-lims, lims]] * m)
+    if lims is not None:          # a feasible pre-rolled trajectory (controls inside the limits), as a previous solve would leave it
+        from helpers import rollout
+        u = np.clip(u, -lims, lims)
+        x = np.stack([rollout(A[b], Bm[b], x[b, 0], u[b]) for b in range(B)])
     costs = np.array([O.LinearModel(A[b], Bm[b], Q, R).costfun(x[b], u[b]) for b in range(B)])
     model = ddp.LinearModel(A[:, None], Bm[:, None], Q, R)
     xs, us, pol, Vx, Vxx, cost, tr = ddp.iLQG(model.f, model.costfun, model.df, x, u, lims=lm, cost=costs, max_iter=30, trace_iters=64)
