@@ -201,7 +201,7 @@ __device__ int boxqp_seq(int m, const double* H, int ldh, const double* g, const
 
 // sqrt(gs) for the rare |grad| outside the range where sqrt(fl(g*g)) == |g| holds exactly; a real call, so that the compiler cannot
 // turn the range test into a select that evaluates the square root on every iteration
-__device__ __noinline__ double qp_sqrt_slow(double v) { return __dsqrt_rn(v); }
+static __device__ __noinline__ double qp_sqrt_slow(double v) { return __dsqrt_rn(v); }
 
 // The same projected-Newton iteration for ONE variable (m = 1: config 3), written on scalars: every operation, comparison and
 // rounding is the one boxqp_seq<1> performs in the same order (so result code, free set, factor and x agree bit for bit with it and

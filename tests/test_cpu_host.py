@@ -216,3 +216,43 @@ def test_plain_c_host_runs(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "0 diverged back passes" in r.stdout and "kernel variant: tile32x8" in r.stdout
+
+
+def test_julia_shim_surface_is_consistent_with_the_abi(ddp):
+    """The Julia shim cannot run here; what can be checked statically is: it exports the reference's list
+    (DifferentialDynamicProgramming.jl:6) and defines what it exports, every `ccall` names a symbol of include/ddp.h, and every
+    field it sets through `mk(DdpXxx; field = ...)` exists in the generated struct of that name."""
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import gen_julia_structs as G
+    src = open(os.path.join(ROOT, "julia", "DifferentialDynamicProgramming.jl")).read()
+    exported = set(re.findall(r"\b\w+\b", " ".join(re.findall(r"^export (.*?)(?:#.*)?$", src, re.M))))
+    reference_exports = {"QPTrace", "boxQP", "demoQP", "iLQG", "iLQGkl", "demo_linear", "demo_linear_kl", "demo_pendcart", "GaussianPolicy"}
+    assert reference_exports <= exported
+    for name in exported:
+        assert re.search(rf"(function {name}\b|^{name}\(|struct {name}\b)", src, re.M), f"exported but not defined: {name}"
+    assert re.search(r"function iLQGkl\(dynamics, costfun, derivs, x0, traj_prev::GaussianPolicy, model::SimpleLTVModel;", src)
+    hdr = open(os.path.join(ROOT, "include", "ddp.h")).read()
+    declared = set(re.findall(r"DDP_API\s+[\w\s\*]+?\b(ddp_\w+)\s*\(", hdr))
+    called = set(re.findall(r"ccall\(\(:(ddp_\w+), libddp\)", src))
+    assert called and called <= declared, called - declared
+    structs = {jname: [f for f, _ in fields] for jname, fields in G.parse(G.generate()).values()}
+    for m in re.finditer(r"mk\((Ddp\w+);(.*?)\)\n", src, re.S):
+        jname, body = m.group(1), m.group(2)
+        assert jname in structs, jname
+        # top-level `name = value` pairs of the keyword list
+        depth, tok, keys = 0, "", []
+        for ch in body:
+            if ch in "([{":
+                depth += 1
+            elif ch in ")]}":
+                depth -= 1
+            if ch == "," and depth == 0:
+                keys.append(tok); tok = ""
+            else:
+                tok += ch
+        keys.append(tok)
+        for kv in keys:
+            if "=" in kv:
+                key = kv.split("=", 1)[0].strip().split()[-1]
+                if re.fullmatch(r"\w+", key):
+                    assert key in structs[jname], (jname, key)
