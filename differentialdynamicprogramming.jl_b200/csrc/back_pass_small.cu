@@ -33,7 +33,8 @@ template <int N, int M>
 struct Row {
     static constexpr int FX = 0, FU = N * N, CX = FU + N * M, CU = CX + N, UU = CU + M, LEN = UU + M;
     static constexpr int ROW = LEN + ((2 - (LEN & 3)) & 3);
-    static constexpr int DEPTH = 3;      // ring buffers per warp: the inputs of step i are requested two steps ahead
+    static constexpr int DEPTH = 2;      // ring buffers per warp: the inputs of step i are requested DEPTH-1 steps ahead (3 buffers were
+                                         // measured slower: 11.3 vs 10.8 ms -- the larger ring takes the L1 capacity the row reads live on)
     static constexpr bool OK = (N % 2 == 0) && (32 % ((N * N) / 2) == 0) && (32 % ((N * M + 1) / 2) == 0) && ((N * M) % 2 == 0);
 };
 
@@ -131,12 +132,17 @@ __global__ void __launch_bounds__(128, MINB) bp_small_kernel(BackParams P) {
         sp_cu = reinterpret_cast<const char*>(P.cu.p + b * P.cu.sb + t0 * P.cu.st);
         sp_u = use_qp ? reinterpret_cast<const char*>(P.u.p + b * P.u.sb + t0 * P.u.st) : nullptr;
     }
+    // byte strides of the staging walk, pinned in registers (otherwise re-read from the constant bank every step, with a scoreboard
+    // wait in front of every address update)
+    long long rs_fx = (32 / CHX) * 8 * P.fx.sb, rs_fu = (32 / CHU) * 8 * P.fu.sb, rs_cx = (32 / CHC) * 8 * P.cx.sb;
+    long long ts_fx = 8 * P.fx.st, ts_fu = 8 * P.fu.st, ts_cx = 8 * P.cx.st, ts_cu = 8 * P.cu.st, ts_u = 8 * P.u.st;
+    asm volatile("" : "+l"(rs_fx), "+l"(rs_fu), "+l"(rs_cx), "+l"(ts_fx), "+l"(ts_fu), "+l"(ts_cx), "+l"(ts_cu), "+l"(ts_u));
     auto stage = [&](int i) {                                // all inputs of step i -> ring buffer (i % DEPTH); steps are staged in order T-2, T-3, ...
         if (i < 0) { asm volatile("cp.async.commit_group;" ::: "memory"); return; }      // past the first step: an empty group keeps the wait count uniform
         double* r0 = ring + (i % RW::DEPTH) * 32 * RW::ROW;
-        stage_field<CHX>(r0 + RW::FX + (lane / CHX) * RW::ROW + 2 * (lane % CHX), RW::ROW, sp_fx, (32 / CHX) * 8 * P.fx.sb, b0 + lane / CHX, P.B, full);
-        stage_field<CHU>(r0 + RW::FU + (lane / CHU) * RW::ROW + 2 * (lane % CHU), RW::ROW, sp_fu, (32 / CHU) * 8 * P.fu.sb, b0 + lane / CHU, P.B, full);
-        stage_field<CHC>(r0 + RW::CX + (lane / CHC) * RW::ROW + 2 * (lane % CHC), RW::ROW, sp_cx, (32 / CHC) * 8 * P.cx.sb, b0 + lane / CHC, P.B, full);
+        stage_field<CHX>(r0 + RW::FX + (lane / CHX) * RW::ROW + 2 * (lane % CHX), RW::ROW, sp_fx, rs_fx, b0 + lane / CHX, P.B, full);
+        stage_field<CHU>(r0 + RW::FU + (lane / CHU) * RW::ROW + 2 * (lane % CHU), RW::ROW, sp_fu, rs_fu, b0 + lane / CHU, P.B, full);
+        stage_field<CHC>(r0 + RW::CX + (lane / CHC) * RW::ROW + 2 * (lane % CHC), RW::ROW, sp_cx, rs_cx, b0 + lane / CHC, P.B, full);
         {
             double* rr = r0 + lane * RW::ROW;                // out-of-range lanes shadow the last trajectory (b): a valid address
             const double* cus = reinterpret_cast<const double*>(sp_cu);
@@ -159,8 +165,8 @@ __global__ void __launch_bounds__(128, MINB) bp_small_kernel(BackParams P) {
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
-        sp_fx -= 8 * P.fx.st; sp_fu -= 8 * P.fu.st; sp_cx -= 8 * P.cx.st; sp_cu -= 8 * P.cu.st;
-        if (use_qp) sp_u -= 8 * P.u.st;
+        sp_fx -= ts_fx; sp_fu -= ts_fu; sp_cx -= ts_cx; sp_cu -= ts_cu;
+        if (use_qp) sp_u -= ts_u;
     };
 
     double Vs[NT], Vx[N];              // Vxx(i+1): upper triangle (exactly symmetric, backward_pass.jl:71-72)
@@ -223,20 +229,23 @@ __global__ void __launch_bounds__(128, MINB) bp_small_kernel(BackParams P) {
         for (int e = 0; e < M; e++) { pf[(STAGE ? 0 : RW::CU + e)] = cu[e]; pf[(STAGE ? 0 : RW::UU + e)] = use_qp ? tp(P.u, b, i)[e] : 0.0; }
     };
     if (T >= 2) {
-        if (STAGE) { stage(T - 2); stage(T - 3); }
+        if (STAGE) {
+#pragma unroll
+            for (int d = 0; d < RW::DEPTH - 1; d++) stage(T - 2 - d);
+        }
         else load_direct(T - 2);
     }
     for (int i = T - 2; i >= 0; i--) {
         double in[RW::LEN];                                          // this step's [fx | fu | cx | cu | u]
         if (STAGE) {
-            asm volatile("cp.async.wait_group 1;" ::: "memory");      // all but the newest group (step i-1): step i has landed
+            asm volatile("cp.async.wait_group %0;" ::"n"(RW::DEPTH - 2) : "memory");      // all but the newest DEPTH-2 groups: step i has landed
             __syncwarp();                                            // ... for every lane of the warp
             const double* row = ring + (i % RW::DEPTH) * 32 * RW::ROW + lane * RW::ROW;
 #pragma unroll
             for (int e = 0; e + 1 < RW::LEN; e += 2) { const double2 t = *reinterpret_cast<const double2*>(row + e); in[e] = t.x; in[e + 1] = t.y; }
             if (RW::LEN & 1) in[RW::LEN - 1] = row[RW::LEN - 1];
-            // the buffer of step i+1 was read before the __syncwarp above: refill it with step i-2
-            stage(i - 2);
+            // the buffer of step i+1 was read before the __syncwarp above: refill it with step i-(DEPTH-1)
+            stage(i - (RW::DEPTH - 1));
         } else {
 #pragma unroll
             for (int e = 0; e < RW::LEN; e++) in[e] = pf[STAGE ? 0 : e];

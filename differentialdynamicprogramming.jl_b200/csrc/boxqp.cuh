@@ -246,8 +246,10 @@ __device__ __forceinline__ int boxqp_scalar(double h, double g, double lower, do
             nfactor++;
         }
         const double gs = DADD(0.0, DMUL(grad, grad));                   // norm(grad[free]) :120 (see boxqp_seq for the |g| shortcut)
+        // gnorm only decides `gnorm < min_grad`: outside the exact range both |grad| and sqrt(gs) are below 1e-140 or above 1e140
+        // (or non-finite), so for any min_grad strictly inside (1e-139, 1e139) the decision is the same and no square root is needed
         double gnorm = fabs(grad);
-        if (!(gs > 1e-280 && gs < 1e280)) gnorm = qp_sqrt_slow(gs);
+        if (!(gs > 1e-280 && gs < 1e280) && !(o.min_grad > 1e-139 && o.min_grad < 1e139)) gnorm = qp_sqrt_slow(gs);
         if (gnorm < o.min_grad) {
             result = 5;
             break;
