@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libddp.so")
 SOURCES = ["ddp_api.cu", "back_pass_generic.cu", "back_pass_tile.cu", "back_pass_small.cu",
-           "forward_generic.cu", "forward_fast.cu", "misc_kernels.cu", "solve.cu", "kl_tile.cu", "comm.cu", "boxqp_large.cu"]
+           "forward_generic.cu", "forward_fast.cu", "misc_kernels.cu", "solve.cu", "kl_tile.cu", "comm.cu", "boxqp_large.cu", "forward_multi_tile.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
 

@@ -33,9 +33,15 @@ template <int N, int M>
 struct Row {
     static constexpr int FX = 0, FU = N * N, CX = FU + N * M, CU = CX + N, UU = CU + M, LEN = UU + M;
     static constexpr int ROW = LEN + ((2 - (LEN & 3)) & 3);
+    // output block of one trajectory: OB steps of [K N*M | Vx N | k M], written out as whole lines every OB steps
+    static constexpr int OB = 4;
+    static constexpr int OK_ = 0, OVX = OB * N * M, OKK = OVX + OB * N, OLEN = OKK + OB * M;
+    static constexpr int OROW = OLEN + ((2 - (OLEN & 3)) & 3);
     static constexpr int DEPTH = 2;      // ring buffers per warp: the inputs of step i are requested DEPTH-1 steps ahead (3 buffers were
                                          // measured slower: 11.3 vs 10.8 ms -- the larger ring takes the L1 capacity the row reads live on)
-    static constexpr bool OK = (N % 2 == 0) && (32 % ((N * N) / 2) == 0) && (32 % ((N * M + 1) / 2) == 0) && ((N * M) % 2 == 0);
+    static constexpr bool OK = (N % 2 == 0) && (32 % ((N * N) / 2) == 0) && (32 % ((N * M + 1) / 2) == 0) && ((N * M) % 2 == 0) &&
+                               (32 % (OB * N * M / 2) == 0) && (32 % (OB * N / 2) == 0) && (32 % (OB * M / 2) == 0);
+    static constexpr int WARP_DOUBLES = DEPTH * 32 * ROW + 32 * OROW;     // input ring + output block per warp
 };
 
 // symmetric n x n matrix kept as its upper triangle, column by column: (r,c), r <= c, at c(c+1)/2 + r
@@ -75,6 +81,22 @@ __device__ __forceinline__ double rcp_fast(double d) {
     return y;
 }
 
+// Coalesced write-out of one field of the warp's output block: CH 16-byte chunks per row (= OB steps of the field), lane ->
+// (row = lane / CH + (32 / CH) k, chunk = lane % CH): CH lanes write one contiguous run of one trajectory; `nch` = chunks that exist
+// (the topmost block of a horizon that is not a multiple of OB is partial), `vmask` = trajectories of the warp that store at all.
+template <int CH>
+__device__ __forceinline__ void flush_field(const double* srow0, int OROWLEN, double* g0, long long stride_b, int nch, unsigned vmask, int lane) {
+    constexpr int RPI = 32 / CH;
+    const int row = lane / CH, ch = lane % CH;
+    if (ch >= nch) return;
+#pragma unroll
+    for (int k = 0; k < CH; k++) {
+        const int r = row + RPI * k;
+        if ((vmask >> r) & 1u)
+            *reinterpret_cast<double2*>(g0 + (long long)r * stride_b + 2 * ch) = *reinterpret_cast<const double2*>(srow0 + r * OROWLEN + 2 * ch);
+    }
+}
+
 // One thread per trajectory.  STAGE: every per-step input arrives through the warp's double-buffered cp.async ring (see Row);
 // !STAGE (odd sizes, unaligned views, DDP_SMALL_NOSTAGE): direct loads with a one-step register prefetch.  Same arithmetic either way.
 template <int N, int M, int MINB, bool STAGE, bool CSH>
@@ -105,7 +127,9 @@ __global__ void __launch_bounds__(128, MINB) bp_small_kernel(BackParams P) {
     bool valid = (b_raw < P.B) && !(P.active && !P.active[b_raw]);
     const long long b = (b_raw < P.B) ? b_raw : P.B - 1;     // out-of-range lanes shadow the last trajectory, store nothing
     const bool full = (b0 + 32 <= P.B);                      // warp-uniform: no row predicates in the staging copies
-    double* ring = s_ring + (STAGE ? wid * RW::DEPTH * 32 * RW::ROW : 0);
+    double* ring = s_ring + (STAGE ? wid * RW::WARP_DOUBLES : 0);
+    double* oblk = ring + RW::DEPTH * 32 * RW::ROW;         // STAGE: the warp's output block, row = trajectory
+    double* orow = oblk + lane * RW::OROW;
     const int T = P.T;
     const bool use_qp = (P.lims != nullptr) && !(P.lims[0] > P.lims[M]);     // backward_pass.jl:31
     const double lam = P.lambda[b];
@@ -192,11 +216,20 @@ __global__ void __launch_bounds__(128, MINB) bp_small_kernel(BackParams P) {
         }
         if (asym) valid = false;
 #pragma unroll
-        for (int e = 0; e < N; e++) { Vx[e] = cxN[e]; if (valid) Vxb[(long long)(T - 1) * N + e] = Vx[e]; }
+        for (int e = 0; e < N; e++) {
+            Vx[e] = cxN[e];
+            if (STAGE) orow[RW::OVX + ((T - 1) & (RW::OB - 1)) * N + e] = Vx[e];
+            else if (valid) Vxb[(long long)(T - 1) * N + e] = Vx[e];
+        }
         if (valid && Vxxb)
 #pragma unroll
             for (int e = 0; e < N * N; e++) Vxxb[(long long)(T - 1) * N * N + e] = Vs[tri(e % N, e / N)];
-        if (valid) {
+        if (STAGE) {
+#pragma unroll
+            for (int e = 0; e < N * M; e++) orow[RW::OK_ + ((T - 1) & (RW::OB - 1)) * N * M + e] = 0.0;
+#pragma unroll
+            for (int e = 0; e < M; e++) orow[RW::OKK + ((T - 1) & (RW::OB - 1)) * M + e] = 0.0;
+        } else if (valid) {
 #pragma unroll
             for (int e = 0; e < N * M; e++) Kb[(long long)(T - 1) * N * M + e] = 0.0;
 #pragma unroll
@@ -206,6 +239,24 @@ __global__ void __launch_bounds__(128, MINB) bp_small_kernel(BackParams P) {
 #pragma unroll
             for (int e = 0; e < M * M; e++) Quub[(long long)(T - 1) * M * M + e] = cuuN[e];
     }
+    // write-out of the output block that holds step i (steps OB*j .. OB*j+OB-1, j = i / OB), by the whole warp
+    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+    const bool kvec = (((long long)T * M) % 2 == 0) && ((uintptr_t)P.k % 16 == 0);     // 16-byte stores of k need even trajectory strides
+    auto flush = [&](int i) {
+        if (!STAGE) return;
+        const int j = i / RW::OB;
+        const int steps = (T - RW::OB * j < RW::OB) ? (T - RW::OB * j) : RW::OB;      // the topmost block may be partial
+        __syncwarp();
+        flush_field<RW::OB * N * M / 2>(oblk + RW::OK_, RW::OROW, P.K + b0 * (long long)T * N * M + (long long)RW::OB * j * N * M, (long long)T * N * M,
+                                        steps * N * M / 2, vmask, lane);
+        flush_field<RW::OB * N / 2>(oblk + RW::OVX, RW::OROW, P.Vx + b0 * (long long)T * N + (long long)RW::OB * j * N, (long long)T * N, steps * N / 2, vmask, lane);
+        if ((RW::OB * M) % 2 == 0 && (steps * M) % 2 == 0 && kvec)
+            flush_field<RW::OB * M / 2>(oblk + RW::OKK, RW::OROW, P.k + b0 * (long long)T * M + (long long)RW::OB * j * M, (long long)T * M, steps * M / 2, vmask, lane);
+        else if (valid)                                   // an odd number of k entries in a partial block: the owner stores them
+            for (int e = 0; e < steps * M; e++) kb[(long long)RW::OB * j * M + e] = orow[RW::OKK + e];
+        __syncwarp();
+    };
+    if (STAGE && ((T - 1) & (RW::OB - 1)) == 0) flush(T - 1);       // the terminal step is alone in its block
     double kw[M];
 #pragma unroll
     for (int a = 0; a < M; a++) kw[a] = 0.0;
@@ -431,7 +482,15 @@ __global__ void __launch_bounds__(128, MINB) bp_small_kernel(BackParams P) {
                 Vs[tri(r, c)] = ((Qxx[tri(r, c)] + t1) + t2) + t3;
             }
         // ---- store
-        if (vec_out && (N * M) % 2 == 0 && N % 2 == 0) {
+        if (STAGE) {                                      // into the warp's output block; whole lines leave every OB steps (flush)
+            const int sl = i & (RW::OB - 1);
+#pragma unroll
+            for (int e = 0; e < N * M; e += 2) *reinterpret_cast<double2*>(orow + RW::OK_ + sl * N * M + e) = make_double2(Ki[e], Ki[e + 1]);
+#pragma unroll
+            for (int r = 0; r < N; r += 2) *reinterpret_cast<double2*>(orow + RW::OVX + sl * N + r) = make_double2(Vx[r], Vx[r + 1]);
+#pragma unroll
+            for (int a = 0; a < M; a++) orow[RW::OKK + sl * M + a] = ki[a];
+        } else if (vec_out && (N * M) % 2 == 0 && N % 2 == 0) {
 #pragma unroll
             for (int e = 0; e < N * M; e += 2) *reinterpret_cast<double2*>(Kb + (long long)i * N * M + e) = make_double2(Ki[e], Ki[e + 1]);
 #pragma unroll
@@ -443,7 +502,7 @@ __global__ void __launch_bounds__(128, MINB) bp_small_kernel(BackParams P) {
             for (int r = 0; r < N; r++) Vxb[(long long)i * N + r] = Vx[r];
         }
 #pragma unroll
-        for (int a = 0; a < M; a++) { kb[(long long)i * M + a] = ki[a]; kw[a] = ki[a]; }
+        for (int a = 0; a < M; a++) { if (!STAGE) kb[(long long)i * M + a] = ki[a]; kw[a] = ki[a]; }
         if (Vxxb)
 #pragma unroll
             for (int e = 0; e < N * N; e++) Vxxb[(long long)i * N * N + e] = Vs[tri(e % N, e / N)];
@@ -452,6 +511,7 @@ __global__ void __launch_bounds__(128, MINB) bp_small_kernel(BackParams P) {
             for (int e = 0; e < M * M; e++) Quub[(long long)i * M * M + e] = Quu[e];
         }
         }
+        if (STAGE && (i & (RW::OB - 1)) == 0) flush(i);            // block complete: steps i .. i+OB-1 leave as whole lines
     }
     if (STAGE) asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (!valid) return;
@@ -483,7 +543,8 @@ int launch_small(ddp_handle_s* h, const BackParams& P_in) {
     const unsigned grid = (unsigned)((P.B + 127) / 128);
     const bool u_ok = (P.lims == nullptr) || ((M % 2 == 0) ? al16v(P.u) : ((uintptr_t)P.u.p % 8 == 0));
     const bool cu_ok = (M % 2 == 0) ? al16v(P.cu) : true;
-    const bool stage = Row<N, M>::OK && al16v(P.fx) && al16v(P.fu) && al16v(P.cx) && cu_ok && u_ok && !(getenv("DDP_SMALL_NOSTAGE"));
+    const bool out_ok = ((uintptr_t)P.K % 16 == 0) && ((uintptr_t)P.Vx % 16 == 0);
+    const bool stage = Row<N, M>::OK && al16v(P.fx) && al16v(P.fu) && al16v(P.cx) && cu_ok && u_ok && out_ok && !(getenv("DDP_SMALL_NOSTAGE"));
     // 2 CTAs (8 warps) per SM: 168- and 128-register builds (3 / 4 CTAs) spill
     const bool csh = (P.cxx.sb == 0 && P.cxx.st == 0 && P.cxu.sb == 0 && P.cxu.st == 0 && P.cuu.sb == 0 && P.cuu.st == 0);
 #define LAUNCH_SMALL(MB, ST, CS, BYTES)                                                                                                   \
@@ -493,7 +554,7 @@ int launch_small(ddp_handle_s* h, const BackParams& P_in) {
         bp_small_kernel<N, M, MB, ST, CS><<<grid, 128, (BYTES), h->stream>>>(P);                                                          \
     } while (0)
     if (stage && Row<N, M>::OK) {
-        const size_t bytes = sizeof(double) * 4 * Row<N, M>::DEPTH * 32 * Row<N, M>::ROW;
+        const size_t bytes = sizeof(double) * 4 * Row<N, M>::WARP_DOUBLES;
         // residency: 2 CTAs (8 warps, <= 255 registers) or 3 CTAs (12 warps, 168 registers, a few spilled doubles) per SM;
         // DDP_SMALL_MINB selects for the A/B measurement; 2 is the faster one on B200 (12.8 vs 16.4 ms, profiles/README_r02.md)
         const char* mb = getenv("DDP_SMALL_MINB");

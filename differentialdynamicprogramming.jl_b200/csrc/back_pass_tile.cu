@@ -138,13 +138,13 @@ __device__ __forceinline__ bool gj_inverse8(double& I0, double& I1, int lane, in
         const double colp = shf(own, (lane & ~3) | (p >> 1));     // A[g][p]
         const double rp0 = shf(I0, 4 * p + q), rp1 = shf(I1, 4 * p + q);   // A[p][2q], A[p][2q+1]
         if (!(d > 0.0)) ok = false;
-        // everything that does not need 1/d is formed while the reciprocal is in flight: after it, one FMA (or one product) per entry
-        const double e0 = (2 * q == p) ? 1.0 : rp0, e1 = (2 * q + 1 == p) ? 1.0 : rp1;
-        const double t0 = -colp * e0, t1 = -colp * e1;
-        const double b0 = (2 * q == p) ? 0.0 : I0, b1 = (2 * q + 1 == p) ? 0.0 : I1;
         const double r = rcp_nr(d);
-        I0 = (g == p) ? e0 * r : fma(t0, r, b0);
-        I1 = (g == p) ? e1 * r : fma(t1, r, b1);
+        const double n0 = ((2 * q == p) ? 1.0 : rp0) * r, n1 = ((2 * q + 1 == p) ? 1.0 : rp1) * r;
+        if (g == p) { I0 = n0; I1 = n1; }
+        else {
+            I0 = fma(-colp, n0, (2 * q == p) ? 0.0 : I0);
+            I1 = fma(-colp, n1, (2 * q + 1 == p) ? 0.0 : I1);
+        }
     }
     return ok;
 }
@@ -392,12 +392,13 @@ __global__ void __launch_bounds__(wpb(LTV) * 32, 2) bp_tile32x8_kernel(BackParam
                 const double colp = shf(own, (lane & ~3) | (p >> 1));
                 const double rp0 = shf(I0, 4 * p + q), rp1 = shf(I1, 4 * p + q);
                 if (!(d > 0.0)) ok = false;
-                const double e0 = (2 * q == p) ? 1.0 : rp0, e1 = (2 * q + 1 == p) ? 1.0 : rp1;
-                const double t0 = -colp * e0, t1 = -colp * e1;
-                const double b0 = (2 * q == p) ? 0.0 : I0, b1 = (2 * q + 1 == p) ? 0.0 : I1;
                 const double r = rcp_nr(d);
-                I0 = (g == p) ? e0 * r : fma(t0, r, b0);
-                I1 = (g == p) ? e1 * r : fma(t1, r, b1);
+                const double n0 = ((2 * q == p) ? 1.0 : rp0) * r, n1 = ((2 * q + 1 == p) ? 1.0 : rp1) * r;
+                if (g == p) { I0 = n0; I1 = n1; }              // (forming colp * rp before the reciprocal arrives was measured slower: 94.3 vs 92.9 ms)
+                else {
+                    I0 = fma(-colp, n0, (2 * q == p) ? 0.0 : I0);
+                    I1 = fma(-colp, n1, (2 * q + 1 == p) ? 0.0 : I1);
+                }
             };
             auto w_block0123 = [&](double (&W)[4][4][2]) {      // rows 0..3 of W' (fx'V), the 8 Gauss-Jordan pivots in between
 #pragma unroll

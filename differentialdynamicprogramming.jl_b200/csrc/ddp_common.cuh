@@ -108,6 +108,7 @@ int launch_back_pass_small(ddp_handle_s* h, const BackParams& P, bool gps, bool*
 int launch_forward_generic(ddp_handle_s* h, const FwdParams& P);
 int launch_forward_fast(ddp_handle_s* h, const FwdParams& P, bool* handled);
 int launch_forward_multi(ddp_handle_s* h, const FwdParams& P, int na, const double* alpha, double* cost_out, bool* handled);
+int launch_forward_multi_tile(ddp_handle_s* h, const FwdParams& P, int na, const double* alpha, double* cost_out, bool* handled);
 int launch_boxqp(ddp_handle_s* h, long long B, int m, const double* H, const double* g, const double* lower,
                  const double* upper, const double* x0, QPOpts o, double* x, int* result, double* Hfree,
                  unsigned* free_mask, int* nfactor);

@@ -879,6 +879,17 @@ int launch_forward_multi(ddp_handle_s* h, const FwdParams& P, int na, const doub
     }
     if (!(P.model.kind == DDP_MODEL_LINEAR && P.n == 32 && P.m == 8 && P.model.A.st == 0 && P.model.Bm.st == 0)) return 0;
     if (P.K == nullptr || na < 1) return 0;
+    {   // FP64 tensor-tile rollout of up to 16 step sizes at once (forward_multi_tile.cu); costs to rounding, not bit for bit
+        int done = 0;
+        for (int a0 = 0; a0 < na; a0 += 16) {
+            bool hd = false;
+            const int rc = launch_forward_multi_tile(h, P, (na - a0 < 16) ? (na - a0) : 16, alpha + a0, cost_out + (long long)a0 * P.B, &hd);
+            if (rc != 0) return rc;
+            if (!hd) break;
+            done += 16;
+        }
+        if (done >= na) { *handled = true; return 0; }
+    }
     if (!al16(P.u.p) || (P.u.sb % 2) || (P.u.st % 2) || !al16(P.K) || !al16(P.k)) return 0;
     const bool qdiag = (P.model.flags & 1) != 0;
     if (!qdiag && P.model.Q.sb != 0) return 0;

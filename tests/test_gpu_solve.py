@@ -67,8 +67,11 @@ def test_ilqg_multi_alpha_linesearch(ddp, monkeypatch, lims):
 
 
 @pytest.mark.parametrize("n,m,lims,dense_q", [(32, 8, None, False), (32, 8, 0.2, True), (6, 2, None, False)])
-def test_forward_costs_multi(ddp, n, m, lims, dense_q):
-    """ddp_forward_costs_multi_f64: the cost of every step size from one pass over K equals forward_pass's, bit for bit."""
+def test_forward_costs_multi(ddp, n, m, lims, dense_q, monkeypatch):
+    """ddp_forward_costs_multi_f64: the cost of every step size from one pass over K equals forward_pass's -- bit for bit on the FMA
+    kernels (same per-lane arithmetic), to rounding (1e-13 relative) on the FP64 tensor-tile kernel that takes the headline shape
+    with a diagonal Q (its sums run in tile order)."""
+    monkeypatch.setenv("DDP_MULTI_NO_TILE", "1")
     B, N = 7, 33 if n == 6 else 26
     A, Bm, Q, R, x, u = make_batch_lq(3, B, n, m, N, h=0.05)
     if dense_q:
@@ -85,9 +88,36 @@ def test_forward_costs_multi(ddp, n, m, lims, dense_q):
     alphas = 10.0 ** np.linspace(0.3, -3, 12)                    # 12 > 10: two launches of the multi kernel
     costs = ddp.forward_costs(pol, x[:, 0], u, x, alphas, model.f, model.costfun, lim)
     assert costs.shape == (len(alphas), B)
+    monkeypatch.delenv("DDP_MULTI_NO_TILE", raising=False)
+    costs_tile = ddp.forward_costs(pol, x[:, 0], u, x, alphas, model.f, model.costfun, lim)     # tile kernel where eligible, else the same FMA kernel
     for i, a in enumerate(alphas):
         _, _, c = ddp.forward_pass(pol, x[:, 0], u, x, float(a), model.f, model.costfun, lim)
         assert np.array_equal(costs[i], c), (i, np.max(np.abs(costs[i] - c)))
+        assert np.max(np.abs(costs_tile[i] - c) / np.abs(c)) < 1e-13, (i, np.max(np.abs(costs_tile[i] - c) / np.abs(c)))
+
+
+@pytest.mark.parametrize("lims", [None, 0.15])
+def test_forward_costs_multi_tile_vs_oracle(ddp, lims):
+    """The tensor-tile multi-alpha rollout (fwd_lin32x8_multi_tile_kernel: 16 step sizes as the columns of one state matrix) against
+    the oracle's forward_pass, step size by step size, incl. clamped controls; 3, 8, 11 and 16 step sizes (one and two alpha tiles)."""
+    B, n, m, N = 5, 32, 8, 40
+    A, Bm, Q, R, x, u = make_batch_lq(9, B, n, m, N, h=0.05)
+    Ks, ks = [], []
+    for b in range(B):
+        d, p, _, _, _ = O.back_pass(x[b] @ Q.T, u[b] @ R.T, Q, np.zeros((n, m)), R, A[b], Bm[b], 1.0, 1, None, x[b], u[b])
+        Ks.append(p.K); ks.append(p.k)
+    pol = ddp.GaussianPolicy(N, n, m, np.array(Ks), np.array(ks))
+    model = ddp.LinearModel(A[:, None], Bm[:, None], Q, R)
+    lim = None if lims is None else np.tile(np.array([[-lims, lims]]), (m, 1))
+    for na in (3, 8, 11, 16):
+        alphas = 10.0 ** np.linspace(0.3, -3, na)
+        costs = ddp.forward_costs(pol, x[:, 0], u, x, alphas, model.f, model.costfun, lim)
+        for b in range(B):
+            om = O.LinearModel(A[b], Bm[b], Q, R)
+            pb = O.GaussianPolicy(N, n, m, pol.K[b], pol.k[b], None, None)
+            for i, a in enumerate(alphas):
+                _, _, c0 = O.forward_pass(pb, x[b, 0], u[b], x[b], float(a), om.f, om.costfun, lim)
+                assert abs(costs[i, b] - c0) <= 1e-12 * abs(c0), (na, b, i, costs[i, b], c0)
 
 
 def test_forward_costs_multi_pendcart(ddp):
