@@ -114,6 +114,14 @@ __device__ __forceinline__ void load_F(double* sF, const double* fx, const doubl
     }
 }
 
+// 1/d with ONE Newton step on the hardware seed (relative error ~2^-44: enough for the 1e-8 contract of the gains; experimental)
+__device__ __forceinline__ double rcp_nr1(double d) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    const double e = fma(-d, y, 1.0);
+    return fma(y, e, y);
+}
+
 // 1/d for d > 0 in the normal range: hardware seed + two Newton steps
 __device__ __forceinline__ double rcp_nr(double d) {
     double y;
@@ -154,7 +162,9 @@ constexpr int gidx(int at, int bt) { return at * 5 - (at * (at - 1)) / 2 + (bt -
 // HIST: the optional Vxx histories (full and packed) are compiled in only when asked for, so the benchmarked variants
 // carry neither their pointers nor their branches through the step loop
 // LIMS: control limits given -> box-QP branch of @end_backward_pass (backward_pass.jl:43-62, :317-335) unless lims[1,1] > lims[1,2]
-template <bool LTV, bool GPS, bool REG2, bool HIST, bool LIMS>
+// EXP: experimental schedule of the Gauss-Jordan pivots (0: two per k-step of the fx'V block; 1: one per k-step of the fx'V block and one
+//      per k-step of the W'F block, i.e. spread over 248 instead of 128 DMMAs); selected by DDP_TILE_EXP for A/B measurements
+template <bool LTV, bool GPS, bool REG2, bool HIST, bool LIMS, int EXP = 0>
 __global__ void __launch_bounds__(wpb(LTV) * 32, 2) bp_tile32x8_kernel(BackParams P) {
     constexpr int WPB = wpb(LTV);
     constexpr int WD = (LTV ? WARP_DOUBLES_LTV : WARP_DOUBLES) + (LIMS ? QP_DOUBLES : 0);
@@ -392,7 +402,7 @@ __global__ void __launch_bounds__(wpb(LTV) * 32, 2) bp_tile32x8_kernel(BackParam
                 const double colp = shf(own, (lane & ~3) | (p >> 1));
                 const double rp0 = shf(I0, 4 * p + q), rp1 = shf(I1, 4 * p + q);
                 if (!(d > 0.0)) ok = false;
-                const double r = rcp_nr(d);
+                const double r = (EXP & 2) ? rcp_nr1(d) : rcp_nr(d);
                 const double n0 = ((2 * q == p) ? 1.0 : rp0) * r, n1 = ((2 * q + 1 == p) ? 1.0 : rp1) * r;
                 if (g == p) { I0 = n0; I1 = n1; }              // (forming colp * rp before the reciprocal arrives was measured slower: 94.3 vs 92.9 ms)
                 else {
@@ -419,14 +429,14 @@ __global__ void __launch_bounds__(wpb(LTV) * 32, 2) bp_tile32x8_kernel(BackParam
                     for (int at = 0; at < 4; at++)
 #pragma unroll
                         for (int jt = 0; jt < 4; jt++) dmma(W[at][jt][0], W[at][jt][1], fa[at].x, fb[jt].x);
-                    if (!LIMS) gj_step(2 * p);
+                    if (!LIMS) gj_step((EXP & 1) ? p : 2 * p);
 #pragma unroll
                     for (int at = 0; at < 4; at++) fv[at] = fma(fa[at].y, vx.y, fma(fa[at].x, vx.x, fv[at]));
 #pragma unroll
                     for (int at = 0; at < 4; at++)
 #pragma unroll
                         for (int jt = 0; jt < 4; jt++) dmma(W[at][jt][0], W[at][jt][1], fa[at].y, fb[jt].y);
-                    if (!LIMS) gj_step(2 * p + 1);
+                    if (!LIMS && !(EXP & 1)) gj_step(2 * p + 1);
                 }
             };
             // G(a, a..4) += W'[a,:] F[:, a..4]
@@ -452,6 +462,7 @@ __global__ void __launch_bounds__(wpb(LTV) * 32, 2) bp_tile32x8_kernel(BackParam
                     for (int at = 0; at < 4; at++)
 #pragma unroll
                         for (int bt = at; bt < 5; bt++) dmma(G[gidx(at, bt)][0], G[gidx(at, bt)][1], W[at][p][0], ff[bt].x);
+                    if (!LIMS && (EXP & 1)) gj_step(4 + p);
 #pragma unroll
                     for (int at = 0; at < 4; at++)
 #pragma unroll
@@ -787,7 +798,20 @@ int launch_back_pass_tile(ddp_handle_s* h, const BackParams& P_in, bool gps, boo
     else if (ltv) LAUNCH_TILE(true, false, false);
     else if (gps) LAUNCH_TILE(false, true, false);
     else if (r2) LAUNCH_TILE(false, false, true);
-    else LAUNCH_TILE(false, false, false);
+    else {
+        const char* ex = getenv("DDP_TILE_EXP");
+        const int exv = (ex && !lims && !hist) ? atoi(ex) : 0;
+#define LAUNCH_EXP(V)                                                                                                                          \
+    do {                                                                                                                                       \
+        e = cudaFuncSetAttribute(bp_tile32x8_kernel<false, false, false, false, false, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); \
+        if (e == cudaSuccess) bp_tile32x8_kernel<false, false, false, false, false, V><<<(unsigned)grid, WPB * 32, bytes, h->stream>>>(P);          \
+    } while (0)
+        if (exv == 1) LAUNCH_EXP(1);
+        else if (exv == 2) LAUNCH_EXP(2);
+        else if (exv == 3) LAUNCH_EXP(3);
+        else LAUNCH_TILE(false, false, false);
+#undef LAUNCH_EXP
+    }
 #undef LAUNCH_TILE
 #undef LAUNCH_TILE1
     if (e != cudaSuccess) return (int)e;
