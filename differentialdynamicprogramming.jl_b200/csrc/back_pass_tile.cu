@@ -52,7 +52,7 @@ constexpr int QP_DOUBLES = 432;
 __device__ __noinline__ void qp8_lane0(double* sq, QPOpts o) {
     unsigned fm = 0;
     int nfac = 0, nf = 0;
-    const int res = boxqp_seq<8>(8, sq + QH, 8, sq + QG, sq + QLO, sq + QUP, sq + QX0, o, sq + QX, sq + QR, 8, &fm, &nfac, &nf);
+    const int res = boxqp_seq<8, true>(8, sq + QH, 8, sq + QG, sq + QLO, sq + QUP, sq + QX0, o, sq + QX, sq + QR, 8, &fm, &nfac, &nf);
     int* si = reinterpret_cast<int*>(sq + QI);
     si[0] = res;
     si[1] = (int)fm;
@@ -64,12 +64,12 @@ __device__ __noinline__ void qp8_gain_column(double* sq, int lane, unsigned fm, 
     double* col = sq + QQ + 8 * lane;
     double v[8];
     int p = 0;
-#pragma unroll
+#pragma unroll 1
     for (int a = 0; a < 8; a++)
         if ((fm >> a) & 1u) v[p++] = col[a];
-    if (nf > 0) chol_solve<8>(sq + QR, 8, nf, v);
+    if (nf > 0) chol_solve<8, true>(sq + QR, 8, nf, v);
     p = 0;
-#pragma unroll
+#pragma unroll 1
     for (int a = 0; a < 8; a++) col[a] = ((fm >> a) & 1u) ? -v[p++] : 0.0;
 }
 

@@ -20,12 +20,16 @@ __device__ __forceinline__ double clampd(double v, double lo, double hi) { retur
 
 // Upper Cholesky factor of A[idx,idx] (reads the upper triangle only; R'R = A), nf x nf, written to
 // R with leading dimension ldr.  Returns false when a pivot is <= 0 or NaN (LAPACK dpotrf's test).
-template <int MM>
+// CMP (compact): the loops are kept rolled.  One QP per WARP (the n=32, m=8 tile kernel runs the QP on one lane) makes the fully
+// unrolled m = 8 code an instruction-cache problem (55 % of the stall samples were instruction fetches); the rolled code is the
+// same sequence of operations.
+template <int MM, bool CMP = false>
 __device__ __forceinline__ bool chol_upper_sub(const double* A, int lda, const int* idx, int nf, double* R, int ldr) {
-#pragma unroll
+    constexpr int UF = CMP ? 1 : MM;
+#pragma unroll UF
     for (int j = 0; j < MM; j++) {
         if (j < nf) {
-#pragma unroll
+#pragma unroll UF
             for (int i = 0; i < MM; i++) {
                 if (i < j) {
                     double s = A[idx[i] + lda * idx[j]];
@@ -43,9 +47,10 @@ __device__ __forceinline__ bool chol_upper_sub(const double* A, int lda, const i
 }
 
 // y = R' \ b ; x = R \ y   (in place in v), R upper nf x nf
-template <int MM>
+template <int MM, bool CMP = false>
 __device__ __forceinline__ void chol_solve(const double* R, int ldr, int nf, double* v) {
-#pragma unroll
+    constexpr int UF = CMP ? 1 : MM;
+#pragma unroll UF
     for (int i = 0; i < MM; i++) {
         if (i < nf) {
             double s = v[i];
@@ -53,7 +58,7 @@ __device__ __forceinline__ void chol_solve(const double* R, int ldr, int nf, dou
             v[i] = DDIV(s, R[i + ldr * i]);
         }
     }
-#pragma unroll
+#pragma unroll UF
     for (int ii = 0; ii < MM; ii++) {
         int i = nf - 1 - ii;
         if (i >= 0) {
@@ -65,18 +70,19 @@ __device__ __forceinline__ void chol_solve(const double* R, int ldr, int nf, dou
 }
 
 // x'g + ((0.5 x') H) x   -- the way Julia parses `x'g + 0.5x'H*x` (boxQP.jl:63)
-template <int MM>
+template <int MM, bool CMP = false>
 __device__ __forceinline__ double qp_value(int m, const double* H, int ldh, const double* g, const double* x) {
+    constexpr int UF = CMP ? 1 : MM;
     double s1 = 0.0;
-#pragma unroll
+#pragma unroll UF
     for (int i = 0; i < MM; i++)
         if (i < m) s1 = DADD(s1, DMUL(x[i], g[i]));
     double s2 = 0.0;
-#pragma unroll
+#pragma unroll UF
     for (int j = 0; j < MM; j++) {
         if (j < m) {
             double t = 0.0;
-#pragma unroll
+#pragma unroll UF
             for (int i = 0; i < MM; i++)
                 if (i < m) t = DADD(t, DMUL(DMUL(0.5, x[i]), H[i + ldh * j]));
             s2 = DADD(s2, DMUL(t, x[j]));
@@ -87,20 +93,21 @@ __device__ __forceinline__ double qp_value(int m, const double* H, int ldh, cons
 
 // Returns the reference's result code 0..6, or -1 where the reference's `cholesky` would throw.
 // Outputs: x[m]; Rf (nf x nf upper factor of the last factorisation, leading dim ldr); free_mask; nfactor.
-template <int MM>
+template <int MM, bool CMP = false>
 __device__ int boxqp_seq(int m, const double* H, int ldh, const double* g, const double* lower, const double* upper,
                          const double* x0, const QPOpts& o, double* x, double* Rf, int ldr, unsigned* free_mask_out,
                          int* nfactor_out, int* nf_out = nullptr) {
+    constexpr int UF = CMP ? 1 : MM;
     unsigned clamped = 0u, free_mask = (m >= 32) ? 0xffffffffu : ((1u << m) - 1u);
     const unsigned all_mask = free_mask;
     double oldvalue = 0.0;
     int result = 0, nfactor = 0, nf = 0;
     int idx[MM];
     double grad[MM], search[MM], xc[MM], tmp[MM];
-#pragma unroll
+#pragma unroll UF
     for (int i = 0; i < MM; i++)
         if (i < m) x[i] = clampd(x0[i], lower[i], upper[i]);            // boxQP.jl:58
-    double value = qp_value<MM>(m, H, ldh, g, x);                        // :63
+    double value = qp_value<MM, CMP>(m, H, ldh, g, x);                        // :63
     int iter = 1;
     while (iter <= o.max_iter) {                                         // :71
         if (result != 0) break;                                          // :73
@@ -109,11 +116,11 @@ __device__ int boxqp_seq(int m, const double* H, int ldh, const double* g, const
             break;
         }
         oldvalue = value;
-#pragma unroll
+#pragma unroll UF
         for (int i = 0; i < MM; i++) {                                   // grad = g + H*x  :85
             if (i < m) {
                 double s = 0.0;
-#pragma unroll
+#pragma unroll UF
                 for (int j = 0; j < MM; j++)
                     if (j < m) s = DADD(s, DMUL(H[i + ldh * j], x[j]));
                 grad[i] = DADD(g[i], s);
@@ -121,7 +128,7 @@ __device__ int boxqp_seq(int m, const double* H, int ldh, const double* g, const
         }
         unsigned old_clamped = clamped;
         clamped = 0u;
-#pragma unroll
+#pragma unroll UF
         for (int i = 0; i < MM; i++)                                     // :92-94 exact equality on bounds
             if (i < m && ((x[i] == lower[i] && grad[i] > 0.0) || (x[i] == upper[i] && grad[i] < 0.0))) clamped |= 1u << i;
         free_mask = all_mask & ~clamped;
@@ -131,10 +138,10 @@ __device__ int boxqp_seq(int m, const double* H, int ldh, const double* g, const
         }
         if (iter == 1 || old_clamped != clamped) {                       // :104-117
             nf = 0;
-#pragma unroll
+#pragma unroll UF
             for (int i = 0; i < MM; i++)
                 if (i < m && ((free_mask >> i) & 1u)) idx[nf++] = i;
-            if (!chol_upper_sub<MM>(H, ldh, idx, nf, Rf, ldr)) {
+            if (!chol_upper_sub<MM, CMP>(H, ldh, idx, nf, Rf, ldr)) {
                 *free_mask_out = free_mask;
                 *nfactor_out = nfactor;
                 if (nf_out) *nf_out = 0;
@@ -155,37 +162,37 @@ __device__ int boxqp_seq(int m, const double* H, int ldh, const double* g, const
         for (int p = 0; p < nf; p++) {
             int i = idx[p];
             double s = 0.0;
-#pragma unroll
+#pragma unroll UF
             for (int j = 0; j < MM; j++)
                 if (j < m) s = DADD(s, DMUL(H[i + ldh * j], ((clamped >> j) & 1u) ? x[j] : DMUL(x[j], 0.0)));
             tmp[p] = DADD(g[i], s);
         }
-        chol_solve<MM>(Rf, ldr, nf, tmp);                                // Hfree\(Hfree'\grad_clamped[free])
-#pragma unroll
+        chol_solve<MM, CMP>(Rf, ldr, nf, tmp);                                // Hfree\(Hfree'\grad_clamped[free])
+#pragma unroll UF
         for (int i = 0; i < MM; i++) search[i] = 0.0;
         for (int p = 0; p < nf; p++) search[idx[p]] = DSUB(-tmp[p], x[idx[p]]);          // :129
         double sdotg = 0.0;
-#pragma unroll
+#pragma unroll UF
         for (int i = 0; i < MM; i++)
             if (i < m) sdotg = DADD(sdotg, DMUL(search[i], grad[i]));    // :132
         if (sdotg >= 0.0) break;                                         // :133 leaves result == 0
         double step = 1.0;                                               // :138
-#pragma unroll
+#pragma unroll UF
         for (int i = 0; i < MM; i++)
             if (i < m) xc[i] = clampd(DADD(x[i], DMUL(step, search[i])), lower[i], upper[i]);
-        double vc = qp_value<MM>(m, H, ldh, g, xc);
+        double vc = qp_value<MM, CMP>(m, H, ldh, g, xc);
         while (DDIV(DSUB(vc, oldvalue), DMUL(step, sdotg)) < o.armijo) { // :142
             step = DMUL(step, o.step_dec);
-#pragma unroll
+#pragma unroll UF
             for (int i = 0; i < MM; i++)
                 if (i < m) xc[i] = clampd(DADD(x[i], DMUL(step, search[i])), lower[i], upper[i]);
-            vc = qp_value<MM>(m, H, ldh, g, xc);
+            vc = qp_value<MM, CMP>(m, H, ldh, g, xc);
             if (step < o.min_step) {
                 result = 2;
                 break;
             }
         }
-#pragma unroll
+#pragma unroll UF
         for (int i = 0; i < MM; i++)
             if (i < m) x[i] = xc[i];                                     // :161
         value = vc;

@@ -1,0 +1,7 @@
+#!/bin/bash
+tag=${1:-r02l}
+o=gpurun_out
+mkdir -p $o
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:bp_tile32x8 -s 7 -c 1 -f -o $o/${tag}_bp_tile_lims python scripts/perf_lims.py 2368 3.0 > $o/${tag}_ncu.log 2>&1
+python scripts/ncu_summary.py $o/${tag}_bp_tile_lims.ncu-rep $o/${tag}_bp_tile_lims.txt > /dev/null 2>&1
+head -40 $o/${tag}_bp_tile_lims.txt
