@@ -47,30 +47,182 @@ constexpr int COST_DOUBLES = 15 * 32 * 2;    // per-CTA table of the cost tiles 
 constexpr int QH = 0, QR = 64, QQ = 128, QG = 384, QLO = 392, QUP = 400, QX0 = 408, QX = 416, QI = 424;
 constexpr int QP_DOUBLES = 432;
 
-// boxQP(QuuF, Qu, lims - u, k(i+1)) of backward_pass.jl:49 on ONE lane, in the oracle's arithmetic order (boxqp.cuh): result code,
-// free set and every bit of k as the generic kernel and the oracle produce them.  Not inlined: the tile kernel keeps its registers.
-__device__ __noinline__ void qp8_lane0(double* sq, QPOpts o) {
-    unsigned fm = 0;
-    int nfac = 0, nf = 0;
-    const int res = boxqp_seq<8, true>(8, sq + QH, 8, sq + QG, sq + QLO, sq + QUP, sq + QX0, o, sq + QX, sq + QR, 8, &fm, &nfac, &nf);
-    int* si = reinterpret_cast<int*>(sq + QI);
-    si[0] = res;
-    si[1] = (int)fm;
-    si[2] = nf;
+// boxQP(QuuF, Qu, lims - u, k(i+1)) of backward_pass.jl:49 for m = 8 by the WHOLE WARP, in the oracle's arithmetic: every sum runs
+// in the oracle's index order with separate multiply and add (boxqp.cuh), so result code, free set and every bit of k are what
+// boxqp_seq<8> (generic kernel, oracle) produces -- but the independent rows / columns of each sum live on different lanes:
+//   lane i (= lane & 7; the four groups of eight lanes compute the same thing) owns row i and column i of H, g_i, the bounds and x_i;
+//   H x, x'H, H (x .* clamped)     one sequential 8-term sum per lane, operands by shuffle
+//   x'g, (x'H) x, search'grad      products on the owning lanes, then one sequential chain of adds over shuffled terms
+//   Cholesky of H[free,free]       row by row: lane j owns column j of R; element (i,j) subtracts R[p,i] R[p,j], p ascending
+//   R'y = b                        column sweep (p ascending = the oracle's order);  R z = y: row by row, p ascending inside a row
+// All lanes hold the same scalars, so control flow is warp-uniform.  Not inlined: the tile kernel keeps its registers.
+// Outputs: k -> sq[QX..], the factor (uncompacted: R[p][j] at sq[QR + p + 8 j], valid where p <= j are both free) and 1 / R[j][j] at
+// sq[QG + j] (g is dead by then); returns the result code, *fm_out = free mask.
+__device__ __forceinline__ double shfd(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+__device__ __noinline__ int boxqp_warp8(double* sq, QPOpts o, int lane, unsigned* fm_out) {
+    const int i = lane & 7;
+    double Hrow[8], Hcol[8], Rc[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) { Hrow[j] = sq[QH + i + 8 * j]; Hcol[j] = sq[QH + j + 8 * i]; Rc[j] = 0.0; }
+    const double g = sq[QG + i], lower = sq[QLO + i], upper = sq[QUP + i];
+    double x = clampd(sq[QX0 + i], lower, upper);                        // boxQP.jl:58
+    // x'g + ((0.5 x') H) x with the sums in index order (qp_value)
+    auto value_of = [&](double xv) -> double {
+        double xs[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) xs[j] = shfd(xv, j);
+        const double pg = DMUL(xv, g);
+        double t = 0.0;
+#pragma unroll
+        for (int r = 0; r < 8; r++) t = DADD(t, DMUL(DMUL(0.5, xs[r]), Hcol[r]));      // (0.5 x' H)_i
+        const double q = DMUL(t, xv);
+        double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) { s1 = DADD(s1, shfd(pg, j)); s2 = DADD(s2, shfd(q, j)); }
+        return DADD(s1, s2);
+    };
+    double value = value_of(x);                                          // :63
+    double oldvalue = 0.0;
+    unsigned clamped = 0u, free_mask = 0xffu;
+    int result = 0, iter = 1;
+    while (iter <= o.max_iter) {                                         // :71
+        if (result != 0) break;
+        if (iter > 1 && DSUB(oldvalue, value) < DMUL(o.min_rel_improve, fabs(oldvalue))) { result = 4; break; }     // :78
+        oldvalue = value;
+        double xs[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) xs[j] = shfd(x, j);
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) s = DADD(s, DMUL(Hrow[j], xs[j]));
+        const double grad = DADD(g, s);                                  // :85
+        const unsigned old_clamped = clamped;
+        clamped = __ballot_sync(0xffffffffu, (x == lower && grad > 0.0) || (x == upper && grad < 0.0)) & 0xffu;      // :92-94
+        free_mask = 0xffu & ~clamped;
+        if (clamped == 0xffu) { result = 6; break; }                     // :98
+        const bool me_free = (free_mask >> i) & 1u;
+        if (iter == 1 || old_clamped != clamped) {                       // :104-117: upper factor of H[free,free], row by row
+            bool fail = false;
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                if (!((free_mask >> r) & 1u)) continue;                  // warp-uniform
+                double acc = Hcol[r];                                    // H[r][i] (upper triangle when r <= i)
+#pragma unroll
+                for (int p = 0; p < 8; p++) {
+                    if (p < r && ((free_mask >> p) & 1u)) {
+                        const double rpr = shfd(Rc[p], r);               // R[p][r]
+                        acc = DSUB(acc, DMUL(rpr, Rc[p]));               // - R[p][r] R[p][i]
+                    }
+                }
+                const double d = shfd(acc, r);                           // pivot of row r (lane r's value)
+                if (!(d > 0.0)) { fail = true; break; }
+                const double rrr = __dsqrt_rn(d);
+                if (i == r) Rc[r] = rrr;
+                else if (i > r && me_free) Rc[r] = DDIV(acc, rrr);
+            }
+            if (fail) { *fm_out = free_mask; return -1; }                // PosDefException
+        }
+        double gs = 0.0;                                                 // norm(grad[free]) :120
+        {
+            const double gg = DMUL(grad, grad);
+#pragma unroll
+            for (int p = 0; p < 8; p++)
+                if ((free_mask >> p) & 1u) gs = DADD(gs, shfd(gg, p));
+        }
+        if (__dsqrt_rn(gs) < o.min_grad) { result = 5; break; }
+        double sc = 0.0;                                                 // grad_clamped = g + H (x .* clamped)  :127
+#pragma unroll
+        for (int j = 0; j < 8; j++) sc = DADD(sc, DMUL(Hrow[j], ((clamped >> j) & 1u) ? xs[j] : DMUL(xs[j], 0.0)));
+        double v = DADD(g, sc);                                          // right-hand side, free lanes
+        // R' y = b : column sweep, p ascending over the free indices
+        double ys[8];
+#pragma unroll
+        for (int p = 0; p < 8; p++) {
+            ys[p] = 0.0;
+            if (!((free_mask >> p) & 1u)) continue;
+            const double yp = shfd(DDIV(v, Rc[p]), p);                   // lane p: v / R[p][p]
+            ys[p] = yp;
+            if (i > p && me_free) v = DSUB(v, DMUL(Rc[p], yp));          // - R[p][i] y_p
+        }
+        // R z = y : rows descending, inside a row the terms p ascending (the oracle's loop order)
+        double zs[8];
+#pragma unroll
+        for (int r = 7; r >= 0; r--) {
+            zs[r] = 0.0;
+            if (!((free_mask >> r) & 1u)) continue;
+            double acc = ys[r];
+#pragma unroll
+            for (int p = 0; p < 8; p++) {
+                if (p > r && ((free_mask >> p) & 1u)) acc = DSUB(acc, DMUL(shfd(Rc[r], p), zs[p]));     // R[r][p] lives on lane p
+            }
+            zs[r] = DDIV(acc, shfd(Rc[r], r));
+        }
+        double search = 0.0;
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+            if (i == r && me_free) search = DSUB(-zs[r], x);             // :129
+        double sdotg = 0.0;                                              // :132
+        {
+            const double sg = DMUL(search, grad);
+#pragma unroll
+            for (int j = 0; j < 8; j++) sdotg = DADD(sdotg, shfd(sg, j));
+        }
+        if (sdotg >= 0.0) break;                                         // :133 leaves result == 0
+        double step = 1.0;                                               // :138
+        double xc = clampd(DADD(x, DMUL(step, search)), lower, upper);
+        double vc = value_of(xc);
+        while (DDIV(DSUB(vc, oldvalue), DMUL(step, sdotg)) < o.armijo) { // :142
+            step = DMUL(step, o.step_dec);
+            xc = clampd(DADD(x, DMUL(step, search)), lower, upper);
+            vc = value_of(xc);
+            if (step < o.min_step) { result = 2; break; }
+        }
+        x = xc;                                                          // :161
+        value = vc;
+        iter++;
+    }
+    if (iter == o.max_iter) result = 1;                                  // :167 (quirk Q4)
+    __syncwarp();
+    if (lane < 8) {
+        sq[QX + i] = x;
+        sq[QG + i] = 1.0 / Rc[i];                                        // reciprocal pivots for the gain columns (garbage where clamped: unused)
+#pragma unroll
+        for (int p = 0; p < 8; p++) sq[QR + p + 8 * i] = Rc[p];          // column i of the factor
+    }
+    __syncwarp();
+    *fm_out = free_mask;
+    return result;
 }
 
-// K[free, j] = -R \ (R' \ Qux_reg[free, j]) for column j = lane (backward_pass.jl:57-61), in place in sq[QQ..]; clamped rows = 0
-__device__ __noinline__ void qp8_gain_column(double* sq, int lane, unsigned fm, int nf) {
+// K[free, j] = -R \ (R' \ Qux_reg[free, j]) for column j = lane (backward_pass.jl:57-61), in place in sq[QQ..]; clamped rows = 0.
+// Unrolled on registers; the factor and its reciprocal pivots are read from shared memory by broadcast.  (The gains carry the 1e-8
+// contract, not the bit-exact one of the QP: products with 1/R[j][j] instead of divisions.)
+__device__ __forceinline__ void qp8_gain_column(double* sq, int lane, unsigned fm) {
     double* col = sq + QQ + 8 * lane;
     double v[8];
-    int p = 0;
-#pragma unroll 1
-    for (int a = 0; a < 8; a++)
-        if ((fm >> a) & 1u) v[p++] = col[a];
-    if (nf > 0) chol_solve<8, true>(sq + QR, 8, nf, v);
-    p = 0;
-#pragma unroll 1
-    for (int a = 0; a < 8; a++) col[a] = ((fm >> a) & 1u) ? -v[p++] : 0.0;
+#pragma unroll
+    for (int a = 0; a < 8; a++) v[a] = col[a];
+#pragma unroll
+    for (int a = 0; a < 8; a++) {                                        // R' y = b
+        if (!((fm >> a) & 1u)) continue;
+        double acc = v[a];
+#pragma unroll
+        for (int p = 0; p < 8; p++)
+            if (p < a && ((fm >> p) & 1u)) acc = fma(-sq[QR + p + 8 * a], v[p], acc);
+        v[a] = acc * sq[QG + a];
+    }
+#pragma unroll
+    for (int a = 7; a >= 0; a--) {                                       // R z = y
+        if (!((fm >> a) & 1u)) continue;
+        double acc = v[a];
+#pragma unroll
+        for (int p = 0; p < 8; p++)
+            if (p > a && ((fm >> p) & 1u)) acc = fma(-sq[QR + a + 8 * p], v[p], acc);
+        v[a] = acc * sq[QG + a];
+    }
+#pragma unroll
+    for (int a = 0; a < 8; a++) col[a] = ((fm >> a) & 1u) ? -v[a] : 0.0;
 }
 
 // column-major 32-row matrices: element (i, c) lives at (i ^ s(c)) + 32 c with s(c) = ((c&1)<<3) | (((c>>1)&3)<<1).
@@ -567,15 +719,11 @@ __global__ void __launch_bounds__(wpb(LTV) * 32, 2) bp_tile32x8_kernel(BackParam
 #pragma unroll
                 for (int t = 0; t < 4; t++) st2(&sq[QQ + 2 * q + 8 * (8 * t + g)], qr[t].x, qr[t].y);     // Qux_reg (8 x 32), column-major
                 __syncwarp();
-                if (lane == 0) qp8_lane0(sq, P.qp);
-                __syncwarp();
-                const int* si = reinterpret_cast<const int*>(sq + QI);
-                const int res = si[0];
-                const unsigned fm = (unsigned)si[1];
-                const int nf = si[2];
+                unsigned fm = 0u;
+                const int res = boxqp_warp8(sq, P.qp, lane, &fm);
                 if (res < 1) ok = false;                      // :50-56
                 if (ok) {
-                    qp8_gain_column(sq, lane, fm, nf);
+                    qp8_gain_column(sq, lane, fm);
                     __syncwarp();
 #pragma unroll
                     for (int t = 0; t < 4; t++) kf[t] = ld2(&sq[QQ + 2 * q + 8 * (8 * t + g)]);
