@@ -707,7 +707,7 @@ __global__ void __launch_bounds__(wpb(LTV) * 32, 2) bp_tile32x8_kernel(BackParam
             double k_own;
             double J0 = U0, J1 = U1;                          // GPS + LIMS: Sigma = inv(Quu) is still wanted (backward_pass.jl:346)
             if (LIMS && use_qp) {
-                // ---- box-QP branch (backward_pass.jl:43-62): QP on one lane in the oracle's arithmetic order, gains by columns
+                // ---- box-QP branch (backward_pass.jl:43-62): QP by the warp in the oracle's arithmetic order, gains by columns
                 sq[QH + g + 8 * (2 * q)] = I0;               // H = QuuF, column-major (unsymmetrised, as the reference passes it)
                 sq[QH + g + 8 * (2 * q + 1)] = I1;
                 if (q == 0) {

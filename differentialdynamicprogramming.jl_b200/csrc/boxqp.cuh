@@ -20,7 +20,7 @@ __device__ __forceinline__ double clampd(double v, double lo, double hi) { retur
 
 // Upper Cholesky factor of A[idx,idx] (reads the upper triangle only; R'R = A), nf x nf, written to
 // R with leading dimension ldr.  Returns false when a pivot is <= 0 or NaN (LAPACK dpotrf's test).
-// CMP (compact): the loops are kept rolled.  One QP per WARP (the n=32, m=8 tile kernel runs the QP on one lane) makes the fully
+// CMP (compact): the loops are kept rolled.  One QP per WARP on a single lane (how the n=32, m=8 tile kernel first ran its QP; it now uses boxqp_warp8) makes the fully
 // unrolled m = 8 code an instruction-cache problem (55 % of the stall samples were instruction fetches); the rolled code is the
 // same sequence of operations.
 template <int MM, bool CMP = false>
