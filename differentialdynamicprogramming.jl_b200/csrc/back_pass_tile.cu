@@ -356,6 +356,13 @@ __global__ void __launch_bounds__(wpb(LTV) * 32, 2) bp_tile32x8_kernel(BackParam
         }
         __syncthreads();
     }
+    if (P.stagger > 0) {
+        const bool second = (P.stagger_mode == 1) ? (blockIdx.x & 1) : (blockIdx.x >= (gridDim.x >> 1));
+        if (second) {
+            const long long t0 = clock64();
+            while (clock64() - t0 < P.stagger) {}
+        }
+    }
     // lane constants of the swizzled addressing: swz(8p + 2q, 8t + g) = (p even ? LAe : LAo) + 8p + 256t,
     // swz(8at + g, 8bt + 2q + h) = LM + 8(at ^ h) + 32h + 256bt
     const int gg = (g >> 1) & 3, par = g & 1;
@@ -923,6 +930,12 @@ int launch_back_pass_tile(ddp_handle_s* h, const BackParams& P_in, bool gps, boo
     long long need = (P.B + WPB - 1) / WPB;
     if (grid > need) grid = need;
     cudaError_t e = cudaSuccess;
+    {
+        const char* sg = getenv("DDP_TILE_STAGGER");
+        const char* sgm = getenv("DDP_TILE_STAGGER_MODE");
+        P.stagger = sg ? atoi(sg) : 0;
+        P.stagger_mode = sgm ? atoi(sgm) : 0;
+    }
     {
         const int rc0 = prepare_redo(h, P);    // hand-over mask for trajectories with an unsymmetric terminal cxx
         if (rc0 != 0) return rc0;
