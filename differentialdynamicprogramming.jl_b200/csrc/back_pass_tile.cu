@@ -44,42 +44,62 @@ constexpr int WARP_DOUBLES = SCX + 48;       // 2384 doubles = 19,072 B per warp
 constexpr int WARP_DOUBLES_LTV = WARP_DOUBLES;  // (a second [fx fu] buffer would cost 10 KB per warp and halve the residency: measured 113-134 ms)
 constexpr int COST_DOUBLES = 15 * 32 * 2;    // per-CTA table of the cost tiles in accumulator (fragment) order
 // per-warp scratch of the box-QP branch (LIMS variants): H = QuuF (8 x 8), its reduced factor R, Qux_reg / K (8 x 32), vectors
-constexpr int QH = 0, QR = 64, QQ = 128, QG = 384, QLO = 392, QUP = 400, QX0 = 408, QX = 416, QI = 424;
-constexpr int QP_DOUBLES = 432;
+constexpr int QH = 0, QR = 64, QQ = 128, QG = 384, QLO = 392, QUP = 400, QX0 = 408, QX = 416, QE = 424;     // QE: five exchange slots
+constexpr int QP_DOUBLES = QE + 40;
 
 // boxQP(QuuF, Qu, lims - u, k(i+1)) of backward_pass.jl:49 for m = 8 by the WHOLE WARP, in the oracle's arithmetic: every sum runs
 // in the oracle's index order with separate multiply and add (boxqp.cuh), so result code, free set and every bit of k are what
-// boxqp_seq<8> (generic kernel, oracle) produces -- but the independent rows / columns of each sum live on different lanes:
-//   lane i (= lane & 7; the four groups of eight lanes compute the same thing) owns row i and column i of H, g_i, the bounds and x_i;
-//   H x, x'H, H (x .* clamped)     one sequential 8-term sum per lane, operands by shuffle
-//   x'g, (x'H) x, search'grad      products on the owning lanes, then one sequential chain of adds over shuffled terms
-//   Cholesky of H[free,free]       row by row: lane j owns column j of R; element (i,j) subtracts R[p,i] R[p,j], p ascending
-//   R'y = b                        column sweep (p ascending = the oracle's order);  R z = y: row by row, p ascending inside a row
+// boxqp_seq<8> (generic kernel, oracle) produces -- but the O(m^2) sums are spread over the lanes and the code is kept small
+// (the first versions were 80-140 KB of unrolled code and stalled on instruction fetch):
+//   lane i (= lane & 7; the four groups of eight lanes compute the same thing) owns row i and column i of H, g_i, the bounds, x_i
+//   and column i of the factor; vectors travel through eight-double slots of the per-warp scratch (one store, __syncwarp, four
+//   LDS.128) and are then held by EVERY lane;
+//   H x, x'H, H (x .* clamped)     one sequential 8-term sum per lane (row / column parallel)
+//   x'g, (x'H) x                   products on the owning lanes, exchanged, then one sequential chain of adds on every lane
+//   Cholesky of H[free,free]       row by row: element (r,i) on lane i subtracts R[p,r] R[p,i], p ascending; R[:,r] from the scratch
+//   R'y = b, R z = y, search'grad  replicated: every lane runs the whole sequential solve on the factor in the scratch
 // All lanes hold the same scalars, so control flow is warp-uniform.  Not inlined: the tile kernel keeps its registers.
 // Outputs: k -> sq[QX..], the factor (uncompacted: R[p][j] at sq[QR + p + 8 j], valid where p <= j are both free) and 1 / R[j][j] at
 // sq[QG + j] (g is dead by then); returns the result code, *fm_out = free mask.
-__device__ __forceinline__ double shfd(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
-
 __device__ __noinline__ int boxqp_warp8(double* sq, QPOpts o, int lane, unsigned* fm_out) {
     const int i = lane & 7;
-    double Hrow[8], Hcol[8], Rc[8];
+    double Hrow[8], Hcol[8], Rc[8], xs[8];
 #pragma unroll
-    for (int j = 0; j < 8; j++) { Hrow[j] = sq[QH + i + 8 * j]; Hcol[j] = sq[QH + j + 8 * i]; Rc[j] = 0.0; }
+    for (int j = 0; j < 8; j++) { Hrow[j] = sq[QH + i + 8 * j]; Rc[j] = 0.0; }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const double2 t = *reinterpret_cast<const double2*>(&sq[QH + 2 * j + 8 * i]);
+        Hcol[2 * j] = t.x;
+        Hcol[2 * j + 1] = t.y;
+    }
     const double g = sq[QG + i], lower = sq[QLO + i], upper = sq[QUP + i];
     double x = clampd(sq[QX0 + i], lower, upper);                        // boxQP.jl:58
-    // x'g + ((0.5 x') H) x with the sums in index order (qp_value)
-    auto value_of = [&](double xv) -> double {
-        double xs[8];
+    // all lanes: out[0..7] = the eight lanes' v.  Two uses of one slot are always separated by another __syncwarp.
+    auto share8 = [&](const int slot, const double v, double (&out)[8]) {
+        sq[slot + i] = v;
+        __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 8; j++) xs[j] = shfd(xv, j);
-        const double pg = DMUL(xv, g);
+        for (int j = 0; j < 4; j++) {
+            const double2 t = *reinterpret_cast<const double2*>(&sq[slot + 2 * j]);
+            out[2 * j] = t.x;
+            out[2 * j + 1] = t.y;
+        }
+    };
+    // x'g + ((0.5 x') H) x with the sums in index order (qp_value); leaves xs = the argument on every lane
+    auto value_of = [&](const double xv) -> double {
+        share8(QE + 0, xv, xs);
         double t = 0.0;
 #pragma unroll
         for (int r = 0; r < 8; r++) t = DADD(t, DMUL(DMUL(0.5, xs[r]), Hcol[r]));      // (0.5 x' H)_i
-        const double q = DMUL(t, xv);
-        double s1 = 0.0, s2 = 0.0;
+        double pq[8];
+        share8(QE + 8, DMUL(xv, g), pq);
+        double s1 = 0.0;
 #pragma unroll
-        for (int j = 0; j < 8; j++) { s1 = DADD(s1, shfd(pg, j)); s2 = DADD(s2, shfd(q, j)); }
+        for (int j = 0; j < 8; j++) s1 = DADD(s1, pq[j]);
+        share8(QE + 16, DMUL(t, xv), pq);
+        double s2 = 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) s2 = DADD(s2, pq[j]);
         return DADD(s1, s2);
     };
     double value = value_of(x);                                          // :63
@@ -90,10 +110,7 @@ __device__ __noinline__ int boxqp_warp8(double* sq, QPOpts o, int lane, unsigned
         if (result != 0) break;
         if (iter > 1 && DSUB(oldvalue, value) < DMUL(o.min_rel_improve, fabs(oldvalue))) { result = 4; break; }     // :78
         oldvalue = value;
-        double xs[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) xs[j] = shfd(x, j);
-        double s = 0.0;
+        double s = 0.0;                                                  // xs = x on every lane (left by value_of)
 #pragma unroll
         for (int j = 0; j < 8; j++) s = DADD(s, DMUL(Hrow[j], xs[j]));
         const double grad = DADD(g, s);                                  // :85
@@ -109,64 +126,54 @@ __device__ __noinline__ int boxqp_warp8(double* sq, QPOpts o, int lane, unsigned
                 if (!((free_mask >> r) & 1u)) continue;                  // warp-uniform
                 double acc = Hcol[r];                                    // H[r][i] (upper triangle when r <= i)
 #pragma unroll
-                for (int p = 0; p < 8; p++) {
-                    if (p < r && ((free_mask >> p) & 1u)) {
-                        const double rpr = shfd(Rc[p], r);               // R[p][r]
-                        acc = DSUB(acc, DMUL(rpr, Rc[p]));               // - R[p][r] R[p][i]
-                    }
-                }
-                const double d = shfd(acc, r);                           // pivot of row r (lane r's value)
+                for (int p = 0; p < 8; p++)
+                    if (p < r && ((free_mask >> p) & 1u)) acc = DSUB(acc, DMUL(sq[QR + p + 8 * r], Rc[p]));     // - R[p][r] R[p][i]
+                const double d = __shfl_sync(0xffffffffu, acc, r);       // the pivot: lane r's element
                 if (!(d > 0.0)) { fail = true; break; }
                 const double rrr = __dsqrt_rn(d);
-                if (i == r) Rc[r] = rrr;
-                else if (i > r && me_free) Rc[r] = DDIV(acc, rrr);
+                Rc[r] = (i == r) ? rrr : DDIV(acc, rrr);                 // meaningful on the free lanes i >= r; never read elsewhere
+                sq[QR + r + 8 * i] = Rc[r];
+                __syncwarp();
             }
             if (fail) { *fm_out = free_mask; return -1; }                // PosDefException
         }
+        double gv[8];
+        share8(QE + 24, grad, gv);
         double gs = 0.0;                                                 // norm(grad[free]) :120
-        {
-            const double gg = DMUL(grad, grad);
 #pragma unroll
-            for (int p = 0; p < 8; p++)
-                if ((free_mask >> p) & 1u) gs = DADD(gs, shfd(gg, p));
-        }
+        for (int p = 0; p < 8; p++)
+            if ((free_mask >> p) & 1u) gs = DADD(gs, DMUL(gv[p], gv[p]));
         if (__dsqrt_rn(gs) < o.min_grad) { result = 5; break; }
         double sc = 0.0;                                                 // grad_clamped = g + H (x .* clamped)  :127
 #pragma unroll
         for (int j = 0; j < 8; j++) sc = DADD(sc, DMUL(Hrow[j], ((clamped >> j) & 1u) ? xs[j] : DMUL(xs[j], 0.0)));
-        double v = DADD(g, sc);                                          // right-hand side, free lanes
-        // R' y = b : column sweep, p ascending over the free indices
-        double ys[8];
+        double v[8];
+        share8(QE + 32, DADD(g, sc), v);
+        // R' y = b, then R z = y: the oracle's loops (chol_solve) on the uncompacted factor, by every lane
 #pragma unroll
-        for (int p = 0; p < 8; p++) {
-            ys[p] = 0.0;
-            if (!((free_mask >> p) & 1u)) continue;
-            const double yp = shfd(DDIV(v, Rc[p]), p);                   // lane p: v / R[p][p]
-            ys[p] = yp;
-            if (i > p && me_free) v = DSUB(v, DMUL(Rc[p], yp));          // - R[p][i] y_p
+        for (int a = 0; a < 8; a++) {
+            if (!((free_mask >> a) & 1u)) continue;
+            double acc = v[a];
+#pragma unroll
+            for (int p = 0; p < 8; p++)
+                if (p < a && ((free_mask >> p) & 1u)) acc = DSUB(acc, DMUL(sq[QR + p + 8 * a], v[p]));
+            v[a] = DDIV(acc, sq[QR + a + 8 * a]);
         }
-        // R z = y : rows descending, inside a row the terms p ascending (the oracle's loop order)
-        double zs[8];
 #pragma unroll
-        for (int r = 7; r >= 0; r--) {
-            zs[r] = 0.0;
-            if (!((free_mask >> r) & 1u)) continue;
-            double acc = ys[r];
+        for (int a = 7; a >= 0; a--) {
+            if (!((free_mask >> a) & 1u)) continue;
+            double acc = v[a];
 #pragma unroll
-            for (int p = 0; p < 8; p++) {
-                if (p > r && ((free_mask >> p) & 1u)) acc = DSUB(acc, DMUL(shfd(Rc[r], p), zs[p]));     // R[r][p] lives on lane p
-            }
-            zs[r] = DDIV(acc, shfd(Rc[r], r));
+            for (int p = 0; p < 8; p++)
+                if (p > a && ((free_mask >> p) & 1u)) acc = DSUB(acc, DMUL(sq[QR + a + 8 * p], v[p]));
+            v[a] = DDIV(acc, sq[QR + a + 8 * a]);
         }
-        double search = 0.0;
+        double search = 0.0, sdotg = 0.0;                                // :129, :132
 #pragma unroll
-        for (int r = 0; r < 8; r++)
-            if (i == r && me_free) search = DSUB(-zs[r], x);             // :129
-        double sdotg = 0.0;                                              // :132
-        {
-            const double sg = DMUL(search, grad);
-#pragma unroll
-            for (int j = 0; j < 8; j++) sdotg = DADD(sdotg, shfd(sg, j));
+        for (int j = 0; j < 8; j++) {
+            const double sj = ((free_mask >> j) & 1u) ? DSUB(-v[j], xs[j]) : 0.0;
+            if (i == j) search = sj;
+            sdotg = DADD(sdotg, DMUL(sj, gv[j]));
         }
         if (sdotg >= 0.0) break;                                         // :133 leaves result == 0
         double step = 1.0;                                               // :138
@@ -181,14 +188,13 @@ __device__ __noinline__ int boxqp_warp8(double* sq, QPOpts o, int lane, unsigned
         x = xc;                                                          // :161
         value = vc;
         iter++;
+        (void)me_free;
     }
     if (iter == o.max_iter) result = 1;                                  // :167 (quirk Q4)
     __syncwarp();
     if (lane < 8) {
         sq[QX + i] = x;
         sq[QG + i] = 1.0 / Rc[i];                                        // reciprocal pivots for the gain columns (garbage where clamped: unused)
-#pragma unroll
-        for (int p = 0; p < 8; p++) sq[QR + p + 8 * i] = Rc[p];          // column i of the factor
     }
     __syncwarp();
     *fm_out = free_mask;
@@ -317,7 +323,7 @@ constexpr int gidx(int at, int bt) { return at * 5 - (at * (at - 1)) / 2 + (bt -
 // EXP: experimental schedule of the Gauss-Jordan pivots (0: two per k-step of the fx'V block; 1: one per k-step of the fx'V block and one
 //      per k-step of the W'F block, i.e. spread over 248 instead of 128 DMMAs); selected by DDP_TILE_EXP for A/B measurements
 template <bool LTV, bool GPS, bool REG2, bool HIST, bool LIMS, int EXP = 0>
-__global__ void __launch_bounds__(wpb(LTV) * 32, 2) bp_tile32x8_kernel(BackParams P) {
+__global__ void __launch_bounds__(wpb(LTV) * 32, (EXP & 4) ? 3 : 2) bp_tile32x8_kernel(BackParams P) {
     constexpr int WPB = wpb(LTV);
     constexpr int WD = (LTV ? WARP_DOUBLES_LTV : WARP_DOUBLES) + (LIMS ? QP_DOUBLES : 0);
     extern __shared__ double smem_raw[];
@@ -335,7 +341,7 @@ __global__ void __launch_bounds__(wpb(LTV) * 32, 2) bp_tile32x8_kernel(BackParam
     // Cost Hessians shared by the batch and constant in time (the reference's LTI/QTIC methods): stage the
     // symmetrised tiles once per CTA in accumulator order, so each step starts G with 15 conflict-free LDS.128.
     double* sCost = smem_raw + (size_t)WPB * WD;
-    const bool cost_shared = (P.cxx.sb == 0 && P.cxx.st == 0 && P.cxu.sb == 0 && P.cxu.st == 0 && P.cuu.sb == 0 && P.cuu.st == 0);
+    const bool cost_shared = !(EXP & 4) && (P.cxx.sb == 0 && P.cxx.st == 0 && P.cxu.sb == 0 && P.cxu.st == 0 && P.cuu.sb == 0 && P.cuu.st == 0);
     if (cost_shared) {
         if (w == 0) {
             const double* cxx0 = P.cxx.p;
@@ -535,24 +541,6 @@ __global__ void __launch_bounds__(wpb(LTV) * 32, 2) bp_tile32x8_kernel(BackParam
             //      block 4 (fu'V) first => Quu = G(4,4) is complete after 40 DMMAs and its Gauss-Jordan inverse (a long
             //      latency-bound chain of shuffles and FMAs) is interleaved, pivot by pivot, with the DMMAs of blocks 0,1.
             double fv[5];
-            auto w_block1 = [&](const int a0, double (&Wa)[4][2], double& fva) {
-#pragma unroll
-                for (int jt = 0; jt < 4; jt++) Wa[jt][0] = Wa[jt][1] = 0.0;
-                fva = 0.0;
-#pragma unroll
-                for (int p = 0; p < 4; p++) {
-                    const double2 fa0 = ld2(&sF[FRAG(p, a0)]);
-                    double2 fb[4];
-#pragma unroll
-                    for (int jt = 0; jt < 4; jt++) fb[jt] = ld2(&sV[FRAG(p, jt)]);
-                    const double2 vx = ld2(&sVx[8 * p + 2 * q]);
-#pragma unroll
-                    for (int jt = 0; jt < 4; jt++) dmma(Wa[jt][0], Wa[jt][1], fa0.x, fb[jt].x);
-                    fva = fma(fa0.y, vx.y, fma(fa0.x, vx.x, fva));
-#pragma unroll
-                    for (int jt = 0; jt < 4; jt++) dmma(Wa[jt][0], Wa[jt][1], fa0.y, fb[jt].y);
-                }
-            };
             double I0 = 0.0, I1 = 0.0, U0, U1;
             bool ok = true;
             auto gj_step = [&](const int p) {                 // one pivot of the in-place inverse (see gj_inverse8)
@@ -567,6 +555,25 @@ __global__ void __launch_bounds__(wpb(LTV) * 32, 2) bp_tile32x8_kernel(BackParam
                 else {
                     I0 = fma(-colp, n0, (2 * q == p) ? 0.0 : I0);
                     I1 = fma(-colp, n1, (2 * q + 1 == p) ? 0.0 : I1);
+                }
+            };
+            auto w_block1 = [&](const int a0, double (&Wa)[4][2], double& fva, const int piv = -1) {
+#pragma unroll
+                for (int jt = 0; jt < 4; jt++) Wa[jt][0] = Wa[jt][1] = 0.0;
+                fva = 0.0;
+#pragma unroll
+                for (int p = 0; p < 4; p++) {
+                    const double2 fa0 = ld2(&sF[FRAG(p, a0)]);
+                    double2 fb[4];
+#pragma unroll
+                    for (int jt = 0; jt < 4; jt++) fb[jt] = ld2(&sV[FRAG(p, jt)]);
+                    const double2 vx = ld2(&sVx[8 * p + 2 * q]);
+#pragma unroll
+                    for (int jt = 0; jt < 4; jt++) dmma(Wa[jt][0], Wa[jt][1], fa0.x, fb[jt].x);
+                    if (piv >= 0 && p == 1) gj_step(piv);
+                    fva = fma(fa0.y, vx.y, fma(fa0.x, vx.x, fva));
+#pragma unroll
+                    for (int jt = 0; jt < 4; jt++) dmma(Wa[jt][0], Wa[jt][1], fa0.y, fb[jt].y);
                 }
             };
             auto w_block0123 = [&](double (&W)[4][4][2]) {      // rows 0..3 of W' (fx'V), the 8 Gauss-Jordan pivots in between
@@ -599,7 +606,7 @@ __global__ void __launch_bounds__(wpb(LTV) * 32, 2) bp_tile32x8_kernel(BackParam
                 }
             };
             // G(a, a..4) += W'[a,:] F[:, a..4]
-            auto g_block1 = [&](const int a0, double (&Wa)[4][2]) {
+            auto g_block1 = [&](const int a0, double (&Wa)[4][2], const int piv = -1) {
 #pragma unroll
                 for (int p = 0; p < 4; p++) {
                     double2 ff[5];
@@ -607,6 +614,7 @@ __global__ void __launch_bounds__(wpb(LTV) * 32, 2) bp_tile32x8_kernel(BackParam
                     for (int bt = a0; bt < 5; bt++) ff[bt] = ld2(&sF[FRAG(p, bt)]);
 #pragma unroll
                     for (int bt = a0; bt < 5; bt++) dmma(G[gidx(a0, bt)][0], G[gidx(a0, bt)][1], Wa[p][0], ff[bt].x);
+                    if (piv >= 0 && p == 1) gj_step(piv);
 #pragma unroll
                     for (int bt = a0; bt < 5; bt++) dmma(G[gidx(a0, bt)][0], G[gidx(a0, bt)][1], Wa[p][1], ff[bt].y);
                 }
@@ -647,7 +655,15 @@ __global__ void __launch_bounds__(wpb(LTV) * 32, 2) bp_tile32x8_kernel(BackParam
                 if (reg2) { I0 = fma(lam, FF[4][0], U0); I1 = fma(lam, FF[4][1], U1); }
                 else { I0 = U0 + ((g == 2 * q) ? lam : 0.0); I1 = U1 + ((g == 2 * q + 1) ? lam : 0.0); }
             }
-            {
+            if (EXP & 12) {
+                // one row block of W' at a time (16 instead of 64 registers of W: the three-CTAs-per-SM experiment)
+#pragma unroll
+                for (int at = 0; at < 4; at++) {
+                    double Wa[4][2];
+                    w_block1(at, Wa, fv[at], LIMS ? -1 : 2 * at);
+                    g_block1(at, Wa, LIMS ? -1 : 2 * at + 1);
+                }
+            } else {
                 // blocks 0..3 with the Gauss-Jordan pivots in between; pivot p <= 0  <=>  Cholesky fails
                 double W[4][4][2];
                 w_block0123(W);
@@ -970,6 +986,20 @@ int launch_back_pass_tile(ddp_handle_s* h, const BackParams& P_in, bool gps, boo
         if (exv == 1) LAUNCH_EXP(1);
         else if (exv == 2) LAUNCH_EXP(2);
         else if (exv == 3) LAUNCH_EXP(3);
+        else if (exv == 4) {
+            const size_t bytes3 = bytes - COST_DOUBLES * sizeof(double);
+            long long grid3 = (long long)h->sm_count * 3;
+            if (grid3 > need) grid3 = need;
+            e = cudaFuncSetAttribute(bp_tile32x8_kernel<false, false, false, false, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes3);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(bp_tile32x8_kernel<false, false, false, false, false, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            if (getenv("DDP_TILE_DEBUG")) {
+                int nb = -1;
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, bp_tile32x8_kernel<false, false, false, false, false, 4>, WPB * 32, bytes3);
+                fprintf(stderr, "[ddp] tile EXP=4: %d CTAs/SM, %zu B smem per CTA, grid %lld\n", nb, bytes3, grid3);
+            }
+            if (e == cudaSuccess) bp_tile32x8_kernel<false, false, false, false, false, 4><<<(unsigned)grid3, WPB * 32, bytes3, h->stream>>>(P);
+        }
+        else if (exv == 8) LAUNCH_EXP(8);
         else LAUNCH_TILE(false, false, false);
 #undef LAUNCH_EXP
     }

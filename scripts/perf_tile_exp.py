@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Backward tile kernel at the headline shape (n=32, m=8, T=256) against the start-up stagger of the second CTA per SM
-(DDP_TILE_STAGGER cycles, DDP_TILE_STAGGER_MODE).  usage: python scripts/perf_stagger.py [B] [variant: plain|gps|ltv]"""
+"""Backward tile kernel at the headline shape (n=32, m=8, T=256) for the experimental schedules selected by
+DDP_TILE_EXP.  usage: python scripts/perf_tile_exp.py [B] [exp,exp,...]"""
 import ctypes as C
 import json
 import os
@@ -51,15 +51,16 @@ def run(reps=4):
 
 out = []
 os.environ.pop("DDP_TILE_STAGGER", None)
+os.environ.pop("DDP_TILE_EXP", None)
 base = run()
-Kref = K.clone()
-out.append(dict(stagger=0, mode=0, ms=base))
-for mode in (0, 1):
-    for st in (800, 1600, 2400, 3200, 4000, 4800, 6400):
-        os.environ["DDP_TILE_STAGGER"] = str(st); os.environ["DDP_TILE_STAGGER_MODE"] = str(mode)
-        ms = run()
-        out.append(dict(stagger=st, mode=mode, ms=ms, same=bool(torch.equal(K, Kref))))
-        print(out[-1], file=sys.stderr)
-os.environ.pop("DDP_TILE_STAGGER", None)
-out.append(dict(stagger=0, mode=0, ms=run()))
+Kref, kref, Vxref = K.clone(), k.clone(), Vx.clone()
+out.append(dict(exp=0, ms=base))
+for ex in [int(a) for a in (sys.argv[2].split(",") if len(sys.argv) > 2 else ["4"])]:
+    os.environ["DDP_TILE_EXP"] = str(ex)
+    ms = run()
+    err = max(((K - Kref).abs().max() / Kref.abs().max()).item(), ((Vx - Vxref).abs().max() / Vxref.abs().max()).item())
+    out.append(dict(exp=ex, ms=ms, max_rel_diff_vs_base=err, diverged=int((dv > 0).sum().item())))
+    print(out[-1], file=sys.stderr)
+os.environ.pop("DDP_TILE_EXP", None)
+out.append(dict(exp=0, ms=run()))
 print(json.dumps(dict(B=B, runs=out)))
