@@ -321,7 +321,10 @@ constexpr int gidx(int at, int bt) { return at * 5 - (at * (at - 1)) / 2 + (bt -
 // carry neither their pointers nor their branches through the step loop
 // LIMS: control limits given -> box-QP branch of @end_backward_pass (backward_pass.jl:43-62, :317-335) unless lims[1,1] > lims[1,2]
 // EXP: experimental schedule of the Gauss-Jordan pivots (0: two per k-step of the fx'V block; 1: one per k-step of the fx'V block and one
-//      per k-step of the W'F block, i.e. spread over 248 instead of 128 DMMAs); selected by DDP_TILE_EXP for A/B measurements
+//      per k-step of the W'F block, i.e. spread over 248 instead of 128 DMMAs; bit 1: one Newton step in the pivot reciprocal;
+//      bit 3 (8): W' = F'V one row block at a time (16 instead of 64 registers of W); 4: the same with three CTAs per SM (168
+//      registers, cost tiles read from global memory, no shared cost table)); selected by DDP_TILE_EXP for A/B measurements --
+//      none beats the shipped schedule (profiles/tile_exp_r02.txt)
 template <bool LTV, bool GPS, bool REG2, bool HIST, bool LIMS, int EXP = 0>
 __global__ void __launch_bounds__(wpb(LTV) * 32, (EXP & 4) ? 3 : 2) bp_tile32x8_kernel(BackParams P) {
     constexpr int WPB = wpb(LTV);
@@ -361,13 +364,6 @@ __global__ void __launch_bounds__(wpb(LTV) * 32, (EXP & 4) ? 3 : 2) bp_tile32x8_
             st2(&sCost[(gidx(4, 4) * 32 + lane) * 2], cuu0[g + 8 * (2 * q)], cuu0[g + 8 * (2 * q + 1)]);
         }
         __syncthreads();
-    }
-    if (P.stagger > 0) {
-        const bool second = (P.stagger_mode == 1) ? (blockIdx.x & 1) : (blockIdx.x >= (gridDim.x >> 1));
-        if (second) {
-            const long long t0 = clock64();
-            while (clock64() - t0 < P.stagger) {}
-        }
     }
     // lane constants of the swizzled addressing: swz(8p + 2q, 8t + g) = (p even ? LAe : LAo) + 8p + 256t,
     // swz(8at + g, 8bt + 2q + h) = LM + 8(at ^ h) + 32h + 256bt
@@ -946,12 +942,6 @@ int launch_back_pass_tile(ddp_handle_s* h, const BackParams& P_in, bool gps, boo
     long long need = (P.B + WPB - 1) / WPB;
     if (grid > need) grid = need;
     cudaError_t e = cudaSuccess;
-    {
-        const char* sg = getenv("DDP_TILE_STAGGER");
-        const char* sgm = getenv("DDP_TILE_STAGGER_MODE");
-        P.stagger = sg ? atoi(sg) : 0;
-        P.stagger_mode = sgm ? atoi(sgm) : 0;
-    }
     {
         const int rc0 = prepare_redo(h, P);    // hand-over mask for trajectories with an unsymmetric terminal cxx
         if (rc0 != 0) return rc0;

@@ -45,9 +45,6 @@ struct BackParams {
     unsigned char* redo;
     int* redo_count;
     QPOpts qp;
-    // tile kernel: start-up delay (clock cycles) of the second CTA of every SM, so that the two warps that share a scheduler run
-    // half a step out of phase (one warp's Gauss-Jordan / vector tail under the other's DMMA block) -- see back_pass_tile.cu
-    int stagger = 0, stagger_mode = 0;
 };
 
 struct ModelD {
