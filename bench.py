@@ -524,6 +524,27 @@ def main_gpu(args):
     Qh, Rh = _h(Q), _h(R)
     K_probe = {b: _h(K[b]) for b in (0, B // 2, B - 1)}
     cost0_h = _h(cost0)
+    # =============================================================================================================
+    # C2 with control limits (row a4 at the headline shape: the box-QP branch of the tile kernel) and the line search over
+    # 10 step sizes (row f3: multi-alpha tensor-tile rollout vs serial rollouts), B = 65 536, N = 1 only
+    # =============================================================================================================
+    if world == 1:
+        ctx2 = dict(L=L, eng=eng, dev=dev, tn=tn, empty=empty, ev=ev, n=n, m=m, T=T, B=B, fx=fx, fu=fu, x=x, u=u, cx=cx, cu=cu,
+                    Q=Q, R=R, cxu=cxu, lam=lam, K=K, k=k, model=model, xnew=xnew, unew=unew, cost=cost, args=args, rank=rank, dmma_peak=dmma_peak,
+                    bk_plain=bk)
+        if "linesearch" in want:
+            try:
+                results["line_search"] = run_line_search(ctx2)
+            except Exception as exc:
+                results["line_search"] = dict(error=f"{type(exc).__name__}: {exc}")
+        if "c2lims" in want:
+            try:
+                results["c2_lims"] = run_c2_lims(ctx2)
+            except Exception as exc:
+                results["c2_lims"] = dict(error=f"{type(exc).__name__}: {exc}")
+        del ctx2
+        torch.cuda.empty_cache()
+
     # free the device-resident working set: the e2e path holds its own (full-batch mirrors + the resident policy)
     del K, k, Vx, Vxx1, xnew, unew, cx, cu, x, u, fx, fu, x0, dV, cost, cost0, diverge, ba, fa, fa0, model
     eng.close()
@@ -817,6 +838,142 @@ def run_c4(g):
     return res
 
 
+def run_line_search(g):
+    """Row f3: the cost of 10 step sizes (iLQG.jl:145's alpha list) on the headline policy -- ddp_forward_costs_multi_f64 (one launch,
+    gains read once, FP64 tensor tiles) vs 10 serial rollouts; costs compared with each other and, on samples, with the oracle."""
+    import torch
+    from oracle import ddp_oracle as O
+    L, eng, dev, tn, empty = g["L"], g["eng"], g["dev"], g["tn"], g["empty"]
+    n, m, T, B = g["n"], g["m"], g["T"], g["B"]
+    fx, fu, x, u, Q, R, K, k = g["fx"], g["fu"], g["x"], g["u"], g["Q"], g["R"], g["K"], g["k"]
+    args, rank = g["args"], g["rank"]
+    alphas = np.ascontiguousarray(10.0 ** np.linspace(0, -3, 10))
+    NA = len(alphas)
+    costs, cs = empty(NA, B), empty(NA, B)
+    fa = L.ForwardPassArgs()
+    fa.K, fa.k = K.data_ptr(), k.data_ptr()
+    fa.x0, fa.x, fa.u = tn(x, T * n, 0), tn(x, T * n, n), tn(u, T * m, m)
+    fa.alpha_scalar, fa.u_scale = 1.0, 1.0
+    xs_, us_ = empty(B, T, n), empty(B, T, m)
+    fa.xnew, fa.unew = xs_.data_ptr(), us_.data_ptr()
+    model = g["model"]
+    l0 = eng.launch_count
+
+    def multi(parts):
+        eng._ck(eng.lib.ddp_forward_costs_multi_f64(eng.h, C.byref(model), C.byref(fa), NA, alphas.ctypes.data_as(C.POINTER(C.c_double)), costs.data_ptr()))
+
+    def serial(parts):
+        for j, al in enumerate(alphas):
+            fa.alpha_scalar = float(al)
+            fa.cost = cs[j].data_ptr()
+            eng._ck(eng.lib.ddp_forward_pass_f64(eng.h, C.byref(model), C.byref(fa)))
+        fa.alpha_scalar = 1.0
+
+    steps, warm = max(2, min(args.steps, 5)), 3
+    ms_multi, _ = _timed(multi, steps, warm, torch.cuda.synchronize)
+    launches_multi = (eng.launch_count - l0) / (steps + warm)
+    ms_serial, _ = _timed(serial, steps, warm, torch.cuda.synchronize)
+    rel = ((costs - cs).abs() / cs.abs().clamp_min(1e-300)).max().item()
+    res = dict(workload="line search: cost of 10 step sizes 10^linspace(0,-3,10) on the headline policy, n=32 m=8 T=256, 65536 trajectories",
+               batch=B, n_alpha=NA, steps=steps, warmup=warm, multi_alpha_ms=ms_multi, serial_rollouts_ms=ms_serial, speedup=ms_serial / ms_multi,
+               launches_per_search=launches_multi, max_rel_diff_multi_vs_serial=rel,
+               fp64_frac=100.0 * 512.0 * (T - 1) * B / (ms_multi * 1e-3) * 1e-12 / g["dmma_peak"],
+               note="fp64_frac: 100 m8n8k4 tiles per step and trajectory (16 step sizes fit the same tiles) over the measured DMMA peak")
+    if rank == 0 and args.oracle_samples > 0:
+        ns = max(4, args.oracle_samples // 4)
+        idx = np.sort(np.random.default_rng(9).choice(B, size=ns, replace=False))
+        ii = torch.as_tensor(idx, device=dev)
+        gg = lambda t: _h(t[ii])
+        A_s, B_s = np.swapaxes(gg(fx), -1, -2), np.swapaxes(gg(fu), -1, -2)
+        K_s, k_s, x_s, u_s = np.swapaxes(gg(K), -1, -2), gg(k), gg(x), gg(u)
+        c_s = _h(costs[:, ii])
+        Qh, Rh = _h(Q), _h(R)
+        E = ErrTable()
+        t0 = time.perf_counter()
+        for j in range(ns):
+            pol = O.GaussianPolicy(T, n, m, K_s[j], k_s[j], None, None)
+            om = O.LinearModel(A_s[j], B_s[j], Qh, Rh)
+            for a_i, al in enumerate(alphas):
+                _, _, c0 = O.forward_pass(pol, x_s[j, 0], u_s[j], x_s[j], float(al), om.f, om.costfun, None)
+                E.rel("cost", np.array([c_s[a_i, j]]), np.array([float(np.sum(c0))]))
+        res["oracle"] = E.report(ns)
+        res["oracle"]["seconds"] = time.perf_counter() - t0
+    return res
+
+
+def run_c2_lims(g):
+    """Row a4 at the headline shape: back_pass with control limits (boxQP branch, backward_pass.jl:43-62) + the clamped rollout
+    (forward_pass.jl:22-28) on C2's systems; limits +-0.15 around zero with u ~ 0.1 N(0,1)."""
+    import torch
+    from oracle import ddp_oracle as O
+    L, eng, dev, tn, empty, ev = g["L"], g["eng"], g["dev"], g["tn"], g["empty"], g["ev"]
+    n, m, T, B = g["n"], g["m"], g["T"], g["B"]
+    fx, fu, x, u, cx, cu, Q, R, cxu, lam = g["fx"], g["fu"], g["x"], g["u"], g["cx"], g["cu"], g["Q"], g["R"], g["cxu"], g["lam"]
+    args, rank = g["args"], g["rank"]
+    lims = torch.tensor([-0.15] * m + [0.15] * m, dtype=torch.float64, device=dev)      # (m,2) column-major: lower column, upper column
+    K2, k2, Vx2, dV2 = empty(B, T, n, m), empty(B, T, m), empty(B, T, n), empty(B, 2)
+    dv2 = torch.empty(B, dtype=torch.int32, device=dev)
+    xn2, un2, c2 = empty(B, T, n), empty(B, T, m), empty(B)
+    ba = L.BackPassArgs()
+    ba.cx, ba.cu = tn(cx, T * n, n), tn(cu, T * m, m)
+    ba.cxx, ba.cxu, ba.cuu = tn(Q, 0, 0), tn(cxu, 0, 0), tn(R, 0, 0)
+    ba.fx, ba.fu = tn(fx, n * n, 0), tn(fu, n * m, 0)
+    ba.lam, ba.reg_type = lam.data_ptr(), 1
+    ba.lims, ba.u = lims.data_ptr(), tn(u, T * m, m)
+    ba.diverge, ba.K, ba.k, ba.Vx, ba.dV = dv2.data_ptr(), K2.data_ptr(), k2.data_ptr(), Vx2.data_ptr(), dV2.data_ptr()
+    fa = L.ForwardPassArgs()
+    fa.K, fa.k = K2.data_ptr(), k2.data_ptr()
+    fa.x0, fa.x, fa.u = tn(x, T * n, 0), tn(x, T * n, n), tn(u, T * m, m)
+    fa.alpha_scalar, fa.u_scale = 1.0, 1.0
+    fa.lims = lims.data_ptr()
+    fa.xnew, fa.unew, fa.cost = xn2.data_ptr(), un2.data_ptr(), c2.data_ptr()
+    model = g["model"]
+
+    def one(parts):
+        if parts is not None:
+            parts.append(ev()); parts[-1].record()
+        eng._ck(eng.lib.ddp_back_pass_f64(eng.h, C.byref(ba)))
+        if parts is not None:
+            parts.append(ev()); parts[-1].record()
+        eng._ck(eng.lib.ddp_forward_pass_f64(eng.h, C.byref(model), C.byref(fa)))
+        if parts is not None:
+            parts.append(ev()); parts[-1].record()
+
+    steps, warm = max(2, min(args.steps, 3)), 3
+    ms, (bk, fw) = _timed(one, steps, warm, torch.cuda.synchronize)
+    rows_clamped = float((K2[:, :T - 1].abs().sum(dim=2) == 0).double().mean().item())     # K2 is (B,T,n,m): row i of K_t = K2[b,t,:,i]
+    res = dict(workload="C2 with control limits: back_pass (box-QP branch on bp_tile32x8_kernel<LIMS>, warp-cooperative projected Newton) + clamped "
+                        "forward_pass, linear n=32 m=8 T=256, 65536 trajectories, lims = +-0.15",
+               batch=B, steps=steps, warmup=warm, ms_per_iter=ms, iters_per_s=1e3 / ms, back_pass_ms=bk, forward_ms=fw,
+               clamped_control_frac=rows_clamped, diverged=int((dv2 > 0).sum().item()),
+               vs_no_limits=dict(back_pass_ms_no_limits=g.get("bk_plain"), note="the same sweep without limits is the headline's backward kernel"))
+    if rank == 0 and args.oracle_samples > 0:
+        ns = max(4, args.oracle_samples // 4)
+        idx = np.sort(np.random.default_rng(10).choice(B, size=ns, replace=False))
+        ii = torch.as_tensor(idx, device=dev)
+        gg = lambda t: _h(t[ii])
+        A_s, B_s = np.swapaxes(gg(fx), -1, -2), np.swapaxes(gg(fu), -1, -2)
+        x_s, u_s, cx_s, cu_s, lam_s = gg(x), gg(u), gg(cx), gg(cu), gg(lam)
+        K_s, k_s, Vx_s, dV_s, dv_s = np.swapaxes(gg(K2), -1, -2), gg(k2), gg(Vx2), gg(dV2), gg(dv2)
+        xn_s, un_s, c_s = gg(xn2), gg(un2), gg(c2)
+        Qh, Rh = _h(Q), _h(R)
+        lims_h = np.stack([np.full(m, -0.15), np.full(m, 0.15)], axis=1)
+        E = ErrTable()
+        t0 = time.perf_counter()
+        for j in range(ns):
+            d0, p0, Vx0, Vxx0, dV0 = O.back_pass(cx_s[j], cu_s[j], Qh, np.zeros((n, m)), Rh, A_s[j], B_s[j], float(lam_s[j]), 1, lims_h, x_s[j], u_s[j])
+            om = O.LinearModel(A_s[j], B_s[j], Qh, Rh)
+            xn0, un0, c0 = O.forward_pass(p0, x_s[j, 0], u_s[j], x_s[j], 1.0, om.f, om.costfun, lims_h)
+            E.same("diverge", int(dv_s[j]) == d0)
+            E.same("clamped rows of K (free sets of every step)", bool(np.array_equal(np.abs(K_s[j]).sum(axis=2) == 0, np.abs(p0.K).sum(axis=2) == 0)))
+            E.same("clamped controls of the rollout", bool(np.array_equal(np.abs(un_s[j]) == 0.15, np.abs(un0) == 0.15)))
+            E.rel("K", K_s[j], p0.K); E.rel("k", k_s[j], p0.k); E.rel("Vx", Vx_s[j], Vx0); E.rel("dV", dV_s[j], dV0)
+            E.rel("xnew", xn_s[j], xn0); E.rel("unew", un_s[j], un0); E.rel("cost", c_s[j], c0)
+        res["oracle"] = E.report(ns)
+        res["oracle"]["seconds"] = time.perf_counter() - t0
+    return res
+
+
 def run_solve_e2e(g):
     """What iLQG(f,costfun,df,x0,u0) actually moves (iLQG.jl:143-341): x0,u0 up once, then the whole outer loop on the device
     (ddp_ilqg_solve_f64), then x,u,K,k,cost down once.  Reported per accepted-or-rejected outer iteration."""
@@ -1081,7 +1238,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-sample", type=int, default=1024, help="trajectories in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--configs", default="c3,c4,c5,solve", help="other BASELINE configurations to measure in the same run (comma list; '' = none)")
+    ap.add_argument("--configs", default="c3,c4,c5,solve,c2lims,linesearch", help="other BASELINE configurations to measure in the same run (comma list; '' = none)")
     ap.add_argument("--oracle-samples", type=int, default=32, help="trajectories of each timed batch re-computed by the CPU oracle (0 = off)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
