@@ -53,7 +53,7 @@ class KlArgs(C.Structure):          # ddp_kl_args
     _fields_ = [("fx", Tensor), ("R1", Tensor), ("xnew", C.c_void_p), ("xold", C.c_void_p),
                 ("K_new", C.c_void_p), ("k_new", C.c_void_p), ("Sig_new", C.c_void_p),
                 ("K_prev", Tensor), ("k_prev", Tensor), ("Sig_prev", Tensor), ("Sigi_prev", Tensor),
-                ("kl_t", C.c_void_p), ("kl_mean", C.c_void_p)]
+                ("kl_t", C.c_void_p), ("kl_mean", C.c_void_p), ("Sx_tri", C.c_void_p), ("Sx_mode", C.c_int32), ("pad_", C.c_int32)]
 
 
 class IlqgOpts(C.Structure):        # ddp_ilqg_opts
@@ -79,7 +79,7 @@ class IlqgState(C.Structure):       # ddp_ilqg_state
 
 class IlqgklOpts(C.Structure):      # ddp_ilqgkl_opts
     _fields_ = [("kl_step", C.c_double), ("max_iter", C.c_int32), ("eta_bracket", C.c_double * 3),
-                ("del0", C.c_double), ("max_eta_retries", C.c_int32), ("lims", C.c_void_p)]
+                ("del0", C.c_double), ("max_eta_retries", C.c_int32), ("lims", C.c_void_p), ("no_covariance_cache", C.c_int32), ("pad_", C.c_int32)]
 
 
 class IlqgklState(C.Structure):     # ddp_ilqgkl_state

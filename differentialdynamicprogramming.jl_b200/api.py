@@ -622,13 +622,17 @@ def forward_costs(traj_new: GaussianPolicy, x0, u, x, alphas, f, costfun, lims, 
 # ---------------------------------------------------------------------------------------------
 
 
-def kl_div_wiki(xnew, xold, fx, R1, traj_new: GaussianPolicy, traj_prev: GaussianPolicy, *, engine: Engine = None):
+def kl_div_wiki(xnew, xold, fx, R1, traj_new: GaussianPolicy, traj_prev: GaussianPolicy, *, engine: Engine = None,
+                Sx_cache=None, Sx_mode: int = 0):
     """Per-step KL divergence between the new and previous policy (klutils.jl:70-100) with the state
     covariance of ``forward_covariance`` (forward_pass.jl:37-56) propagated on the device.
 
     The reference takes ``Σ_new`` from ``forward_covariance(model, x, u, traj_new)``, whose ``fx`` and
     ``R1`` come from the un-vendored LinearTimeVaryingModelsBase; here they are arguments.
     Returns ``(kl_t, kl_mean)``.
+
+    ``Sx_cache`` (a device buffer of ``engine.empty((B, N, 528))``) with ``Sx_mode`` 1 stores the state covariances of this call
+    (they depend on ``fx`` and ``R1`` only), ``Sx_mode`` 2 reads them back instead of propagating (``ddp_kl_args.Sx_tri``).
     """
     xnew = np.asarray(xnew, dtype=np.float64)
     batched = xnew.ndim == 3
@@ -652,6 +656,8 @@ def kl_div_wiki(xnew, xold, fx, R1, traj_new: GaussianPolicy, traj_prev: Gaussia
     dev, a.k_prev = _pack_vec(eng, np.asarray(traj_prev.k).reshape(B, N, m), B, N, m, "k_prev"); keep.append(dev)
     klt, klm = eng.empty((B, N)), eng.empty((B,))
     a.kl_t, a.kl_mean = klt.ptr, klm.ptr
+    if Sx_cache is not None:
+        a.Sx_tri, a.Sx_mode = Sx_cache.ptr, int(Sx_mode)
     eng._ck(eng.lib.ddp_kl_div_f64(eng.h, C.byref(a)))
     eng.synchronize()
     t, mn = klt.numpy(), klm.numpy()
@@ -879,7 +885,7 @@ KL_STATUS = {-1: "running", 0: "KL constraint satisfied", 1: "eta > 0.999 eta_ma
 
 def iLQGkl_device(dynamics, costfun, derivs, x0, traj_prev: GaussianPolicy, model, R1=None, *, kl_step=1.0, lims=None, max_iter=50,
                   etabracket=(1e-8, 1.0, 1e16), del0=1e-4, cost=None, max_eta_retries=200, force_generic=False,
-                  engine: Engine = None):
+                  engine: Engine = None, covariance_cache: bool = True):
     """Whole ``iLQGkl`` outer loop on the device for one trajectory or a batch (``ddp_ilqgkl_solve_f64``):
     iLQGkl.jl:93-183 with ``calc_eta`` (klutils.jl:110-130) as per-trajectory state machines.
 
@@ -887,7 +893,8 @@ def iLQGkl_device(dynamics, costfun, derivs, x0, traj_prev: GaussianPolicy, mode
     ``Sigma``/``Sigmai (…,N,m,m)``, ``cost`` the total (or per-step) cost of ``x0``.  Returns
     ``(xnew, unew, traj_new, Vx, Vxx1, costnew, trace)``; ``trace`` holds the per-trajectory final
     ``status, iter, eta bracket, divergence, dcost, expected, retries`` (no per-iteration history: nothing is
-    read back inside the loop except two counters).
+    read back inside the loop except two counters).  ``covariance_cache``: keep the state covariances of
+    ``forward_covariance`` from the first η iteration for the later ones (``ddp_ilqgkl_opts.no_covariance_cache = 0``).
     """
     fx_model, R1 = _split_model(model, R1)
     model = _model_of(dynamics, costfun)
@@ -906,6 +913,7 @@ def iLQGkl_device(dynamics, costfun, derivs, x0, traj_prev: GaussianPolicy, mode
     M, keep = _pack_model(eng, model, B, N, n, m)
     o = L.IlqgklOpts()
     o.kl_step, o.max_iter, o.del0, o.max_eta_retries = float(kl_step), int(max_iter), float(del0), int(max_eta_retries)
+    o.no_covariance_cache = 0 if covariance_cache else 1
     for i in range(3):
         o.eta_bracket[i] = float(etabracket[i])
     ld, _ = _lims_dev(eng, lims, m)

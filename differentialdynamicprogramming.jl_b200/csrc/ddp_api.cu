@@ -323,6 +323,9 @@ int ddp_kl_div_f64(ddp_handle_t h, const ddp_kl_args* a) {
     P.fx = mk(a->fx); P.R1 = mk(a->R1); P.Kp = mk(a->K_prev); P.kp = mk(a->k_prev); P.Sp = mk(a->Sig_prev); P.Sip = mk(a->Sigi_prev);
     P.xnew = a->xnew; P.xold = a->xold; P.Kn = a->K_new; P.kn = a->k_new; P.Sn = a->Sig_new;
     P.kl_t = a->kl_t; P.kl_mean = a->kl_mean; P.active = nullptr;
+    if (a->Sx_mode < 0 || a->Sx_mode > 2) return fail(h, DDP_ERR_INVALID, "ddp_kl_div_f64: Sx_mode must be 0, 1 or 2");
+    if (a->Sx_mode != 0 && !a->Sx_tri) return fail(h, DDP_ERR_INVALID, "ddp_kl_div_f64: Sx_mode 1 / 2 need Sx_tri");
+    P.Sx_tri = a->Sx_tri; P.sx_mode = a->Sx_mode;
     CU(h, cudaSetDevice(h->device));
     int rc = launch_kl_div(h, P);
     if (rc != 0) return cuda_fail(h, (cudaError_t)rc, "kl_div launch");

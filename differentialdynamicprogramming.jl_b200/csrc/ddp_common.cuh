@@ -77,6 +77,8 @@ struct KlParams {
     const double *xnew, *xold, *Kn, *kn, *Sn;
     double *kl_t, *kl_mean;
     const unsigned char* active;     // [B] or nullptr
+    double* Sx_tri = nullptr;        // (B,T,528) packed upper triangles of the state covariances, see ddp_kl_args
+    int sx_mode = 0;                 // 0 none, 1 store, 2 load
 };
 
 struct ddp_handle_s {

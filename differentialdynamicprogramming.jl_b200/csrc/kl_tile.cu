@@ -17,7 +17,11 @@
 //   kl_t = max(0, 1/2(tr(Sip Sn) + dk'Sip dk - m + logdet Sp - logdet Sn)
 //                 + 1/2(mu'dK'Sip dK mu + tr(dK'Sip dK S_t)) + dk'Sip dK mu)          (klutils.jl:75-91, 98)
 //
-// 248 DMMA per step; 16.6 KB of shared memory per warp, 8 warps per SM (255 registers).
+// 248 DMMA per step; 22.7 KB of shared memory per warp (Sigma_t, F, one step of staged operands), 8 warps per SM (255 registers).
+//
+// MODE (ddp_kl_args.Sx_mode): Sigma_t depends on fx and R1 only, so the eta iterations of one solve all propagate the same
+// matrices.  MODE 1 also stores the upper triangle of every Sigma_t (528 doubles, packed by columns); MODE 2 reads it back
+// instead of propagating: 40 DMMA per step, 14.7 KB of shared memory per warp, 12 warps per SM, bound by the 10.4 KB read per step.
 #include <type_traits>
 #include "ddp_common.cuh"
 
@@ -26,7 +30,10 @@ namespace {
 constexpr int KW = 4;                        // warps per CTA
 constexpr int KSV = 0;                       // Sigma_t  32 x 32 swizzled
 constexpr int KSF = 1024;                    // F = fx'  32 x 32 swizzled
-constexpr int KWARP_DOUBLES = 2048;
+constexpr int KOPS = 784;                    // one step's operands, raw: K_new 256 | K_prev 256 | xnew 32 | xold 32 | Sigma_i_prev 64 |
+                                             // Sigma_new 64 | Sigma_prev 64 | k_new 8 | k_prev 8   (landed by cp.async one step ahead)
+constexpr int KWARP_DOUBLES = 2048 + KOPS;   // Sigma_t | F | operands
+constexpr int KWARP_DOUBLES_CACHED = KOPS + 2 * 528;        // MODE 2: operands | two packed triangles (this step's, the next one's)
 constexpr int KTAB_DOUBLES = 10 * 32 * 2;    // R1 tiles in accumulator order (per CTA)
 
 __device__ __forceinline__ int swz(int i, int c) { return (i ^ (((c & 1) << 3) | (((c >> 1) & 3) << 1))) + 32 * c; }
@@ -47,18 +54,29 @@ __device__ __forceinline__ double rcp_nr(double d) {
     return y;
 }
 __device__ const double kl_zero8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+__device__ __forceinline__ void cpa16(double* dst_smem, const double* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src));
+}
+__device__ __forceinline__ void cpa8(double* dst_smem, const double* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src));
+}
+__device__ __forceinline__ void cpa_commit_wait() { asm volatile("cp.async.commit_group;\ncp.async.wait_all;" ::: "memory"); }
 constexpr int uidx(int at, int bt) { return at * 4 - (at * (at - 1)) / 2 + (bt - at); }   // upper-tile index of a 4 x 4 tiling, 10 tiles
 
-__global__ void __launch_bounds__(KW * 32, 2) kl_tile32x8_kernel(KlParams P) {
+template <int MODE>
+__global__ void __launch_bounds__(KW * 32, MODE == 2 ? 3 : 2) kl_tile32x8_kernel(KlParams P) {
     extern __shared__ double ksm[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int g = lane >> 2, q = lane & 3;
-    double* sV = ksm + (size_t)w * KWARP_DOUBLES + KSV;
-    double* sF = ksm + (size_t)w * KWARP_DOUBLES + KSF;
-    double* sTab = ksm + (size_t)KW * KWARP_DOUBLES;
+    constexpr int WD = (MODE == 2) ? KWARP_DOUBLES_CACHED : KWARP_DOUBLES;
+    double* sV = ksm + (size_t)w * WD + KSV;
+    double* sF = ksm + (size_t)w * WD + KSF;                         // (MODE 2 has no F: the operands start here)
+    double* sOp = ksm + (size_t)w * WD + (MODE == 2 ? 0 : 2048);
+    double* sSx = sOp + KOPS;                                        // MODE 2 only: buffer t & 1 holds Sigma_t, packed
+    double* sTab = ksm + (size_t)KW * WD;                            // (not MODE 2)
     const int N = P.T;
     // R1 (shared by the batch) in accumulator order, symmetrised (it is a covariance)
-    if (w == 0) {
+    if (MODE != 2 && w == 0) {
         const double* R1 = P.R1.p;
 #pragma unroll
         for (int at = 0; at < 4; at++) {
@@ -83,9 +101,39 @@ __global__ void __launch_bounds__(KW * 32, 2) kl_tile32x8_kernel(KlParams P) {
     const long long warps_total = (long long)gridDim.x * KW;
 
     for (long long b = (long long)blockIdx.x * KW + w; b < P.B; b += warps_total) {
-        if (P.active && !P.active[b]) continue;
+        const bool act = !(P.active && !P.active[b]);
+        if (!act && MODE != 1) continue;                   // MODE 1 fills the cache of EVERY trajectory (its KL outputs stay untouched)
         __syncwarp();
-        {   // Sigma_0 = R1 ; F = fx' (time-invariant)
+        // stage step t's operands (and, MODE 2, its packed Sigma_t): issued one step ahead, so the DRAM latency is under the
+        // previous step's arithmetic instead of in front of this step's first subtraction
+        auto fetch = [&](const int t) {
+            const long long bt = b * N + t;
+            const double* Kn = P.Kn + bt * 256;
+            const double* Kp = tp(P.Kp, b, t);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                cpa16(sOp + 2 * (lane + 32 * j), Kn + 2 * (lane + 32 * j));
+                cpa16(sOp + 256 + 2 * (lane + 32 * j), Kp + 2 * (lane + 32 * j));
+            }
+            if (lane < 16) cpa16(sOp + 512 + 2 * lane, P.xnew + bt * 32 + 2 * lane);
+            else cpa16(sOp + 544 + 2 * (lane - 16), P.xold + bt * 32 + 2 * (lane - 16));
+            const double* Sipm = tp(P.Sip, b, t);
+            cpa8(sOp + 576 + lane, Sipm + lane);
+            cpa8(sOp + 608 + lane, Sipm + 32 + lane);
+            cpa16(sOp + 640 + 2 * lane, P.Sn + bt * 64 + 2 * lane);
+            cpa16(sOp + 704 + 2 * lane, tp(P.Sp, b, t) + 2 * lane);
+            if (lane < 8) cpa8(sOp + 768 + lane, P.kn + bt * 8 + lane);
+            else if (lane < 16) cpa8(sOp + 768 + lane, (P.kp.p ? tp(P.kp, b, t) : kl_zero8) + (lane - 8));
+            if (MODE == 2) {
+                const double* src = P.Sx_tri + bt * 528;
+                double* dst = sSx + 528 * (t & 1);
+#pragma unroll
+                for (int j = 0; j < 9; j++)
+                    if (lane + 32 * j < 264) cpa16(dst + 2 * (lane + 32 * j), src + 2 * (lane + 32 * j));
+            }
+        };
+        fetch(0);
+        if (MODE != 2) {   // Sigma_0 = R1 ; F = fx' (time-invariant)
             const double* R1 = P.R1.p;
             for (int c = lane; c < 512; c += 32) {
                 const int col = c >> 4, i = (c & 15) << 1;
@@ -103,9 +151,27 @@ __global__ void __launch_bounds__(KW * 32, 2) kl_tile32x8_kernel(KlParams P) {
         // scheduler can interleave the pivot chains and the vector terms with the DMMA stream.
         auto step = [&](const int t, auto prop_tag) {
             constexpr bool prop = decltype(prop_tag)::value;
-            // ---- operands of the KL terms (global; consumed after / inside the tensor phase)
-            const double* Kn = P.Kn + (b * N + t) * 256;
-            const double* Kp = tp(P.Kp, b, t);
+            cpa_commit_wait();                             // this step's staged data has landed (this lane's copies) ...
+            __syncwarp();                                  // ... and every lane's; every lane is past its reads of the previous Sigma
+            // MODE 2: the fragments of Sigma_t are gathered straight from the packed triangle (no expansion into sV: its mirrored
+            // stores made the kernel shared-memory bound): rows 8p + 2q, 8p + 2q + 1 of column 8 jt + g
+            const double* sS = sSx + 528 * (t & 1);
+            auto sig2 = [&](const int p, const int jt) -> double2 {
+                const int r0 = 8 * p + 2 * q, c = 8 * jt + g;
+                if (jt > p) { const int i0 = c * (c + 1) / 2 + r0; return make_double2(sS[i0], sS[i0 + 1]); }
+                if (jt < p) return make_double2(sS[r0 * (r0 + 1) / 2 + c], sS[(r0 + 1) * (r0 + 2) / 2 + c]);
+                const int a0 = min(r0, c), b0 = max(r0, c), a1 = min(r0 + 1, c), b1 = max(r0 + 1, c);
+                return make_double2(sS[b0 * (b0 + 1) / 2 + a0], sS[b1 * (b1 + 1) / 2 + a1]);
+            };
+            if (MODE == 1) {                               // store Sigma_t (sV is stable here): column c, rows 0..c contiguous
+                double* o = P.Sx_tri + (b * N + t) * 528;
+#pragma unroll 4
+                for (int c = 0; c < 32; c++)
+                    if (lane <= c) o[c * (c + 1) / 2 + lane] = sV[swz(lane, c)];
+            }
+            // ---- operands of the KL terms (staged; consumed after / inside the tensor phase)
+            const double* Kn = sOp;
+            const double* Kp = sOp + 256;
             double2 dKa[4], dKb[4], mu2[4];
 #pragma unroll
             for (int p = 0; p < 4; p++) {
@@ -113,16 +179,18 @@ __global__ void __launch_bounds__(KW * 32, 2) kl_tile32x8_kernel(KlParams P) {
                 dKa[p] = make_double2(Kp[o] - Kn[o], Kp[o + 8] - Kn[o + 8]);                 // dK[g][8p+2q], dK[g][8p+2q+1]
                 const double2 kp2 = ld2(Kp + (8 * p + g) * 8 + 2 * q), kn2 = ld2(Kn + (8 * p + g) * 8 + 2 * q);
                 dKb[p] = make_double2(kp2.x - kn2.x, kp2.y - kn2.y);                         // dK[2q..2q+1][8p+g]
-                const double2 xn = ld2(P.xnew + (b * N + t) * 32 + 8 * p + 2 * q), xo = ld2(P.xold + (b * N + t) * 32 + 8 * p + 2 * q);
+                const double2 xn = ld2(sOp + 512 + 8 * p + 2 * q), xo = ld2(sOp + 544 + 8 * p + 2 * q);
                 mu2[p] = make_double2(xn.x - xo.x, xn.y - xo.y);
             }
-            const double* Sipm = tp(P.Sip, b, t);
+            const double* Sipm = sOp + 576;
             const double S0 = Sipm[g + 8 * (2 * q)], S1 = Sipm[g + 8 * (2 * q + 1)];         // Sip[g][2q..2q+1]
-            const double2 Sn2 = ld2(P.Sn + (b * N + t) * 64 + 8 * g + 2 * q);                // Sn[2q..2q+1][g]
-            const double2 Sp2 = ld2(tp(P.Sp, b, t) + 8 * g + 2 * q);                         // Sp[2q..2q+1][g]
-            const double* knm = P.kn + (b * N + t) * 8;
-            const double* kpm = P.kp.p ? tp(P.kp, b, t) : kl_zero8;
+            const double2 Sn2 = ld2(sOp + 640 + 8 * g + 2 * q);                              // Sn[2q..2q+1][g]
+            const double2 Sp2 = ld2(sOp + 704 + 8 * g + 2 * q);                              // Sp[2q..2q+1][g]
+            const double* knm = sOp + 768;
+            const double* kpm = sOp + 776;
             const double dk_own = kpm[g] - knm[g], dk0 = kpm[2 * q] - knm[2 * q], dk1 = kpm[2 * q + 1] - knm[2 * q + 1];
+            __syncwarp();                                  // every lane holds its operands: the staging buffer is free for the next
+            if (t + 1 < N) fetch(t + 1);                   // step (MODE 2: Sigma_{t+1} goes to the other triangle buffer)
             // ---- pivots of Sp' and Sn' (determinant of the transpose = determinant): accumulator layout, shuffles; one pivot
             //      of both matrices per call, interleaved with the DMMAs below
             double pdp = 1.0, pdn = 1.0;
@@ -150,7 +218,7 @@ __global__ void __launch_bounds__(KW * 32, 2) kl_tile32x8_kernel(KlParams P) {
             for (int p = 0; p < 4; p++) {
                 double2 fa[4], fb[4];
 #pragma unroll
-                for (int jt = 0; jt < 4; jt++) fb[jt] = ld2(&sV[FRAG(p, jt)]);
+                for (int jt = 0; jt < 4; jt++) fb[jt] = (MODE == 2) ? sig2(p, jt) : ld2(&sV[FRAG(p, jt)]);
 #pragma unroll
                 for (int jt = 0; jt < 4; jt++) dmma(Pt[jt][0], Pt[jt][1], dKa[p].x, fb[jt].x);
                 if (prop) {
@@ -207,7 +275,7 @@ __global__ void __launch_bounds__(KW * 32, 2) kl_tile32x8_kernel(KlParams P) {
                 v = (v != v) ? v : fmax(0.0, v);
                 // Julia's logdet throws for a negative (or zero) determinant -- not for any non-positive pivot: det = product of pivots
                 if (!(pdp > 0.0) || !(pdn > 0.0)) v = INFINITY;
-                if (P.kl_t && lane == 0) P.kl_t[b * N + t] = v;
+                if (P.kl_t && lane == 0 && act) P.kl_t[b * N + t] = v;
                 klsum += v;
             }
             // ---- Sigma_{t+1} = F' Sigma F + R1 (upper tiles), mirrored back into shared memory
@@ -254,9 +322,13 @@ __global__ void __launch_bounds__(KW * 32, 2) kl_tile32x8_kernel(KlParams P) {
                 __syncwarp();
             }
         };
-        for (int t = 0; t < N - 1; t++) step(t, std::true_type{});
-        step(N - 1, std::false_type{});
-        if (lane == 0) P.kl_mean[b] = klsum / (double)N;
+        if (MODE == 2) {
+            for (int t = 0; t < N; t++) step(t, std::false_type{});
+        } else {
+            for (int t = 0; t < N - 1; t++) step(t, std::true_type{});
+            step(N - 1, std::false_type{});
+        }
+        if (lane == 0 && act) P.kl_mean[b] = klsum / (double)N;
     }
 #undef FRAG
 #undef MIRR
@@ -271,13 +343,20 @@ int launch_kl_div_tile(ddp_handle_s* h, const KlParams& P, bool* handled) {
     if (P.n != 32 || P.m != 8 || P.T < 1) return 0;
     if (P.fx.st != 0 || P.R1.sb != 0 || P.R1.st != 0) return 0;          // time-invariant model Jacobian, shared noise covariance
     if (!al16t(P.Kp) || !al16t(P.Sp) || ((uintptr_t)P.Kn % 16) || ((uintptr_t)P.Sn % 16) || ((uintptr_t)P.xnew % 16) || ((uintptr_t)P.xold % 16)) return 0;
-    const size_t bytes = ((size_t)KW * KWARP_DOUBLES + KTAB_DOUBLES) * sizeof(double);
-    cudaError_t e = cudaFuncSetAttribute(kl_tile32x8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    const int mode = P.Sx_tri ? P.sx_mode : 0;
+    if (mode != 0 && ((uintptr_t)P.Sx_tri % 16)) return 0;
+    const size_t bytes = (mode == 2) ? (size_t)KW * KWARP_DOUBLES_CACHED * sizeof(double) : ((size_t)KW * KWARP_DOUBLES + KTAB_DOUBLES) * sizeof(double);
+    cudaError_t e = (mode == 2)   ? cudaFuncSetAttribute(kl_tile32x8_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)
+                    : (mode == 1) ? cudaFuncSetAttribute(kl_tile32x8_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)
+                                  : cudaFuncSetAttribute(kl_tile32x8_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return (int)e;
-    long long grid = (long long)h->sm_count * 2;     // 2 CTAs per SM (255 registers, no spills) measured faster than 3 (168 registers)
+    // propagating: 2 CTAs per SM (255 registers, no spills) measured faster than 3 (168 registers); cached: 3 CTAs per SM
+    long long grid = (long long)h->sm_count * (mode == 2 ? 3 : 2);
     const long long need = (P.B + KW - 1) / KW;
     if (grid > need) grid = need;
-    kl_tile32x8_kernel<<<(unsigned)grid, KW * 32, bytes, h->stream>>>(P);
+    if (mode == 2) kl_tile32x8_kernel<2><<<(unsigned)grid, KW * 32, bytes, h->stream>>>(P);
+    else if (mode == 1) kl_tile32x8_kernel<1><<<(unsigned)grid, KW * 32, bytes, h->stream>>>(P);
+    else kl_tile32x8_kernel<0><<<(unsigned)grid, KW * 32, bytes, h->stream>>>(P);
     h->launches++;
     *handled = true;
     return (int)cudaGetLastError();

@@ -1287,6 +1287,8 @@ int ddp_ilqgkl_solve_f64(ddp_handle_t h, const ddp_model* model, const ddp_ilqgk
     BackParams BP{};
     FwdParams FP{};
     KlParams KP{};
+    struct DevBuf { void* p = nullptr; ~DevBuf() { if (p) cudaFree(p); } } sx;      // cache of the state covariances (kl_tile.cu)
+    bool sx_filled = false;
 
     CUS(cudaSetDevice(h->device));
     CUS(mem.reserve((size_t)B * 8 * 40 + (size_t)B * T * (n + m) * 8 + (model->kind == DDP_MODEL_PENDCART ? (size_t)B * T * 160 : 0) + (1 << 16)));
@@ -1344,6 +1346,11 @@ int ddp_ilqgkl_solve_f64(ddp_handle_t h, const ddp_model* model, const ddp_ilqgk
     KP.Sp = mk(a->Sig_prev); KP.Sip = mk(a->Sigi_prev);
     KP.xnew = a->xnew; KP.xold = a->x; KP.Kn = a->K; KP.kn = a->k; KP.Sn = a->Sig;
     KP.kl_t = nullptr; KP.kl_mean = s.klmean; KP.active = s.active;
+    // forward_covariance's state block depends on fx_model and R1 only: keep it from the first eta iteration (kl_tile.cu MODE 1 / 2)
+    if (opts->kl_step > 0.0 && !opts->no_covariance_cache && n == 32 && m == 8 && !(h->flags & 1u) && max_iter > 1) {
+        if (cudaMalloc(&sx.p, (size_t)B * T * 528 * sizeof(double)) != cudaSuccess) { cudaGetLastError(); sx.p = nullptr; }
+        KP.Sx_tri = static_cast<double*>(sx.p);
+    }
 
     for (it = 1; it <= max_iter; it++) {
         // KL-augmented backward sweep with the eta-retry loop (iLQGkl.jl:97-124)
@@ -1363,7 +1370,11 @@ int ddp_ilqgkl_solve_f64(ddp_handle_t h, const ddp_model* model, const ddp_ilqgk
             if (hc[0] == 0) break;
         }
         CUS((cudaError_t)run_fwd(h, FP));
-        if (opts->kl_step > 0.0) CUS((cudaError_t)launch_kl_div(h, KP));
+        if (opts->kl_step > 0.0) {
+            KP.sx_mode = KP.Sx_tri ? (sx_filled ? 2 : 1) : 0;
+            CUS((cudaError_t)launch_kl_div(h, KP));
+            sx_filled = true;
+        }
         CUS(cudaMemsetAsync(s.counters, 0, 2 * sizeof(int), st));
         kl_eta_kernel<<<gB, 256, 0, st>>>(B, s, a->cost, a->costnew, opts->kl_step, it, max_iter);
         h->launches++;

@@ -50,7 +50,7 @@ extern "C" {
 #define DDP_API
 #endif
 
-#define DDP_VERSION 200          /* 0.2.0 */
+#define DDP_VERSION 201          /* 0.2.1 */
 #define DDP_MAX_N 64
 #define DDP_MAX_M 16
 
@@ -275,6 +275,15 @@ typedef struct ddp_kl_args {
     ddp_tensor Sigi_prev;        /* (m,m,T,B) */
     double* kl_t;                /* (T,B) per-step divergence (clipped at 0) or NULL               */
     double* kl_mean;             /* [B] mean over time                                             */
+    /* Cache of the state covariance.  forward_covariance's state block, Sigma_{t+1} = fx Sigma_t fx' + R1 (forward_pass.jl:46),
+     * depends on fx and R1 only -- not on the policy, the rollout or eta -- so every eta iteration of iLQGkl (iLQGkl.jl:93-183)
+     * recomputes the same matrices (208 of this call's 248 tensor tiles per step).  Sx_tri: DEVICE (528,T,B) doubles, the upper
+     * triangle of each Sigma_t packed by columns, or NULL.  Sx_mode 0: ignore; 1: compute as usual and also store; 2: read the
+     * stored matrices instead of propagating (results are bit-identical).  Honoured by the n=32, m=8 kernel; other shapes
+     * recompute in every mode. */
+    double* Sx_tri;
+    int32_t Sx_mode;
+    int32_t pad_;
 } ddp_kl_args;
 
 DDP_API int ddp_kl_div_f64(ddp_handle_t h, const ddp_kl_args* a);
@@ -340,6 +349,10 @@ typedef struct ddp_ilqgkl_opts {        /* defaults: iLQGkl.jl:25-42 */
     double del0;                        /* 1e-4                                                       */
     int32_t max_eta_retries;            /* bounds the reference's unbounded eta-retry loop (iLQGkl.jl:97); 0 => 200 */
     const double* lims;                 /* DEVICE (m,2) or NULL                                       */
+    int32_t no_covariance_cache;        /* 0: keep the state covariances of forward_covariance (they depend on fx_model and R1
+                                         * only) from the first eta iteration for the later ones when the (528,T,B) buffer can be
+                                         * allocated (n=32, m=8: 4.2 KB per step and trajectory); 1: recompute every iteration */
+    int32_t pad_;
 } ddp_ilqgkl_opts;
 
 typedef struct ddp_ilqgkl_state {

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol(ddp):
         assert hasattr(lib, name), name
     bound = {s[0] for s in ddp._lib.SYMBOLS}
     assert declared == bound                       # the ctypes mirror binds exactly the header's surface
-    assert ddp.load().ddp_version() == 200
+    assert ddp.load().ddp_version() == 201
 
 
 def struct_layout_from_header(ddp):

@@ -10,7 +10,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from helpers import make_batch_lq, relerr, relerr_elem
+from helpers import make_batch_lq, make_lq, relerr, relerr_elem
 from oracle import ddp_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -610,3 +610,72 @@ def test_boxqp_large(ddp, n):
             assert rb[b] == ro and np.array_equal(fb[b], fo) and relerr(xb[b], xo) < 1e-9
     with pytest.raises(ddp.PosDefException):
         ddp.boxQP(-H, g, lower, upper, np.zeros(n))
+
+
+def test_kl_state_covariance_cache(ddp):
+    """ddp_kl_args.Sx_tri: forward_covariance's state block (forward_pass.jl:46) depends on fx and R1 only.  Mode 1 stores the
+    packed upper triangles (equal to the oracle's sigma[:, :n, :n]), mode 2 evaluates a DIFFERENT new policy from the stored
+    matrices: both bit-identical to the propagating kernel (mode 0)."""
+    from test_gpu_misc import _prev_policy
+    n, m, N = 32, 8, 14
+    A, Bm, Q, R, x, u, cx, cu, prev = _prev_policy(n, m, N, 33)
+    rep = lambda a: np.tile(a, (N, 1, 1))
+    R1 = 1e-4 * np.eye(n) + 1e-5 * (lambda W: W @ W.T / n)(np.random.default_rng(4).standard_normal((n, n)))
+    om = O.LinearModel(A, Bm, Q, R)
+    gpp = ddp.GaussianPolicy(N, n, m, prev.K, prev.k, prev.Sigma, prev.Sigmai)
+    eng = ddp.Engine(n, m, N, 1)
+    cache = eng.empty((1, N, 528))
+    res = {}
+    for eta in (2.0, 7.0):
+        _, pnew, _, _, _ = O.back_pass_gps(cx, cu, rep(Q), rep(np.zeros((n, m))), rep(R), rep(A), rep(Bm), None, x, u,
+                                           (O.grad_kl(prev), np.array([1e-8, eta, 1e16])))
+        xnew, unew, _ = O.forward_pass(pnew, x[0], u, x, 1, om.f, om.costfun, None)
+        gpn = ddp.GaussianPolicy(N, n, m, pnew.K, pnew.k, pnew.Sigma, pnew.Sigmai)
+        res[eta] = (xnew, gpn, pnew)
+    xn, gpn, pnew = res[2.0]
+    kl_a, _ = ddp.kl_div_wiki(xn, x, A, R1, gpn, gpp, engine=eng)
+    kl_b, _ = ddp.kl_div_wiki(xn, x, A, R1, gpn, gpp, engine=eng, Sx_cache=cache, Sx_mode=1)
+    assert np.array_equal(kl_a, kl_b)
+    sig = O.forward_covariance(A, R1, pnew)[:, :n, :n]
+    tri = cache.numpy()[0]
+    iu = np.triu_indices(n)
+    order = np.lexsort((iu[0], iu[1]))                         # packed by columns: column c holds rows 0..c
+    for t in range(N):
+        assert relerr(tri[t], sig[t][iu[0][order], iu[1][order]]) < 1e-12
+    xn2, gpn2, pnew2 = res[7.0]
+    kl_c, m_c = ddp.kl_div_wiki(xn2, x, A, R1, gpn2, gpp, engine=eng)
+    kl_d, m_d = ddp.kl_div_wiki(xn2, x, A, R1, gpn2, gpp, engine=eng, Sx_cache=cache, Sx_mode=2)
+    assert np.array_equal(kl_c, kl_d) and m_c == m_d and not np.array_equal(kl_a, kl_c)
+    kl0 = O.kl_div_wiki(xn2, x, O.forward_covariance(A, R1, pnew2), pnew2, prev)
+    assert relerr(kl_d, kl0) < 1e-9
+    eng.close()
+
+
+def test_ilqgkl_device_with_and_without_covariance_cache(ddp):
+    """ddp_ilqgkl_opts.no_covariance_cache: the cached and the recomputing solve agree bit for bit."""
+    from helpers import rollout
+    n, m, N, B = 32, 8, 16, 4
+    rng = np.random.default_rng(91)
+    xs, us, Ks, Sigs, Sigis, costs, As, Bs = [], [], [], [], [], [], [], []
+    for b in range(B):
+        A, Bm, Q, R = make_lq(rng, n, m, h=0.1)
+        u = (0.05 + 0.1 * b) * rng.standard_normal((N, m))
+        x = rollout(A, Bm, np.ones(n), u)
+        d, p, _, _, _ = O.back_pass(x @ Q.T, u @ R.T, Q, np.zeros((n, m)), R, A, Bm, 1.0, 1, None, x, u)
+        assert d == 0
+        xs.append(x); us.append(u); Ks.append(p.K.copy()); Sigis.append(p.Sigmai.copy())
+        Sigs.append(np.array([np.linalg.inv(s_) for s_ in p.Sigmai])); As.append(A); Bs.append(Bm)
+        costs.append(np.sum(O.LinearModel(A, Bm, Q, R).costfun(x, u)))
+    R1 = 1e-3 * np.eye(n)
+    A4, B4 = np.stack(As)[:, None], np.stack(Bs)[:, None]
+    model = ddp.LinearModel(A4, B4, Q, R)
+    out = []
+    for cache in (True, False):
+        prev_d = ddp.GaussianPolicy(N, n, m, np.stack(Ks), np.stack(us), np.stack(Sigs), np.stack(Sigis))
+        out.append(ddp.iLQGkl_device(model.f, model.costfun, model.df, np.stack(xs), prev_d, A4, R1, kl_step=2.0, cost=np.array(costs),
+                                     covariance_cache=cache))
+    a, b = out
+    assert max(a[6]["iter"]) > 1
+    for key in ("iter", "eta", "eta_min", "eta_max", "divergence"):
+        assert np.array_equal(a[6][key], b[6][key]), key
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2].K, b[2].K)
