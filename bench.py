@@ -367,10 +367,14 @@ def main_gpu(args):
     try:
         dmma_peak, dmma_ms = eng0.selftest_peak("dmma", 3)
         dfma_peak, dfma_ms = eng0.selftest_peak("dfma", 3)
+        try:
+            mixed_peak, _ = eng0.selftest_peak("mixed", 3)
+        except Exception:
+            mixed_peak = None
         peak_how = (f"ddp_selftest_peak_f64 in this run, before the timed region: mma.sync.m8n8k4.f64 {dmma_peak:.2f} TFLOP/s ({dmma_ms:.2f} ms/launch), "
                     f"fma.rn.f64 {dfma_peak:.2f} TFLOP/s ({dfma_ms:.2f} ms/launch); burst figures of a kernel timed alone")
     except Exception as exc:
-        dmma_peak, dfma_peak = FP64_TENSOR_PEAK_FALLBACK, FP64_DFMA_PEAK_FALLBACK
+        dmma_peak, dfma_peak, mixed_peak = FP64_TENSOR_PEAK_FALLBACK, FP64_DFMA_PEAK_FALLBACK, None
         peak_how = f"fallback constants of profiles/microbench/ubench_r01_b200.txt (self test failed: {exc})"
     eng0.close()
 
@@ -661,6 +665,10 @@ def main_gpu(args):
                         "reported as reference_formulation_tflops and would read 1.0+ of the peak",
             reference_formulation_tflops=ref_tf, reference_formulation_frac=ref_tf / dmma_peak,
             fp64_dfma_peak=dfma_peak, fp64_dfma_frac=ach_tf / dfma_peak,
+            fp64_mixed_tflops=mixed_peak,
+            fp64_pipe_note="fp64_mixed_tflops: 8 DMMA + 32 DFMA per warp-iteration interleaved, all flops counted -- it stays below the DMMA peak, "
+                           "i.e. tensor tiles and scalar FP64 instructions share ONE datapath on this GPU: the sweep's ~205 scalar FP64 instructions "
+                           "per step (Gauss-Jordan, k, Vx, dV) take ~7 % of the pipe next to the 336 tiles (ncu: DMMA sub-pipe + FP64 pipe = 89 %)",
             kernel_ms=bk, share_of_step=bk / ms_per_step,
             hbm=dict(achieved=BYTES_BACK * B / (bk * 1e-3) * 1e-9, peak=hbm_peak, unit="GB/s",
                      frac=BYTES_BACK * B / (bk * 1e-3) * 1e-9 / hbm_peak, peak_source=f"MEASURED_PEAKS.json ({peak_kind})"),

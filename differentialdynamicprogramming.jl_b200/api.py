@@ -127,9 +127,10 @@ class Engine:
 
     def selftest_peak(self, kind: str = "dmma", reps: int = 3):
         """FP64 peak of this device in TFLOP/s measured by the library's own microkernels (ddp_selftest_peak_f64):
-        ``"dfma"`` (FMA pipe) or ``"dmma"`` (mma.sync.m8n8k4.f64, the instruction of the n=32, m=8 sweeps).  Returns (TFLOP/s, ms)."""
+        ``"dfma"`` (FMA pipe), ``"dmma"`` (mma.sync.m8n8k4.f64, the instruction of the n=32, m=8 sweeps) or ``"mixed"`` (both interleaved,
+        all flops counted).  Returns (TFLOP/s, ms)."""
         tf, ms = C.c_double(0.0), C.c_double(0.0)
-        self._ck(self.lib.ddp_selftest_peak_f64(self.h, {"dfma": 0, "dmma": 1}[kind], reps, C.byref(tf), C.byref(ms)))
+        self._ck(self.lib.ddp_selftest_peak_f64(self.h, {"dfma": 0, "dmma": 1, "mixed": 2}[kind], reps, C.byref(tf), C.byref(ms)))
         return tf.value, ms.value
 
     def empty(self, shape, dtype=np.float64) -> DevArray:

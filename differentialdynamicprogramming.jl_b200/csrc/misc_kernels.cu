@@ -322,11 +322,33 @@ __global__ void __launch_bounds__(256) peak_dmma_kernel(double* out, int iters) 
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// 8 DMMA + 32 DFMA per warp-iteration, all independent chains: do the FP64 tensor tiles and the scalar FP64 instructions share one
+// datapath?  Shared: the flop rate stays at the DMMA peak (the DFMAs take DMMA slots); separate pipes: 1.5x the DMMA peak.
+__global__ void __launch_bounds__(256) peak_mixed_kernel(double* out, int iters, double fa, double fb) {
+    double a = threadIdx.x * 1e-3, b = 1.0 + threadIdx.x * 1e-4;
+    double c[8][2], acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { c[i][0] = i; c[i][1] = -i; acc[i] = threadIdx.x * 1e-3 + i; }
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+#pragma unroll
+            for (int j = 0; j < 4; j++) acc[(i + 2 * j) & 7] = fma(acc[(i + 2 * j) & 7], fa, fb);
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += c[i][0] + c[i][1] + acc[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 }  // namespace
 
 extern "C" int ddp_selftest_peak_f64(ddp_handle_t h, int32_t kind, int32_t reps, double* tflops, double* ms_out) {
     if (!h) return DDP_ERR_INVALID;
-    if ((kind != 0 && kind != 1) || !tflops) { h->err = "ddp_selftest_peak_f64: kind must be 0 (DFMA) or 1 (DMMA), tflops is required"; return DDP_ERR_INVALID; }
+    if (kind < 0 || kind > 2 || !tflops) { h->err = "ddp_selftest_peak_f64: kind must be 0 (DFMA), 1 (DMMA) or 2 (both mixed), tflops is required"; return DDP_ERR_INVALID; }
     if (reps < 1) reps = 3;
     const int threads = 256, blocks = h->sm_count * 8;
     const int iters = kind == 0 ? 40000 : 8000;          // ~6 ms per launch either way
@@ -340,6 +362,7 @@ extern "C" int ddp_selftest_peak_f64(ddp_handle_t h, int32_t kind, int32_t reps,
     for (int r = 0; r <= reps && e == cudaSuccess; r++) {       // r == 0 is the warm-up
         cudaEventRecord(e0, h->stream);
         if (kind == 0) peak_dfma_kernel<<<blocks, threads, 0, h->stream>>>(out, iters, 1.0000001, 1e-9);
+        else if (kind == 2) peak_mixed_kernel<<<blocks, threads, 0, h->stream>>>(out, iters, 1.0000001, 1e-9);
         else peak_dmma_kernel<<<blocks, threads, 0, h->stream>>>(out, iters);
         h->launches++;
         cudaEventRecord(e1, h->stream);
@@ -353,7 +376,8 @@ extern "C" int ddp_selftest_peak_f64(ddp_handle_t h, int32_t kind, int32_t reps,
     if (out) cudaFree(out);
     if (e != cudaSuccess) { h->err = std::string("ddp_selftest_peak_f64: ") + cudaGetErrorString(e); return DDP_ERR_CUDA; }
     const double flops = kind == 0 ? 2.0 * 8 * (double)iters * (double)blocks * threads          // 8 FMAs per thread-iteration
-                                   : 2.0 * 256 * 8 * (double)iters * (double)blocks * (threads / 32);   // 8 m8n8k4 tiles (512 flop) per warp-iteration
+                       : kind == 1 ? 2.0 * 256 * 8 * (double)iters * (double)blocks * (threads / 32)    // 8 m8n8k4 tiles (512 flop) per warp-iteration
+                                   : (2.0 * 256 * 8 + 2.0 * 32 * 32) * (double)iters * (double)blocks * (threads / 32);   // + 32 warp-wide FMAs
     *tflops = flops / (best_ms * 1e-3) * 1e-12;
     if (ms_out) *ms_out = best_ms;
     return DDP_OK;

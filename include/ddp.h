@@ -450,7 +450,8 @@ DDP_API int ddp_ilqg_iter_f64(ddp_handle_t h, const ddp_model* model, ddp_iter_a
 
 /* ---- self test: the FP64 denominators of the roofline, measured on this device ------------------------------------------ */
 /* kind 0: DFMA (fma.rn.f64, 8 independent chains per thread); kind 1: DMMA (mma.sync.m8n8k4.f64, the instruction of the
- * n=32, m=8 sweep kernels).  Runs `reps` timed launches on the handle's stream (after one warm-up) and returns the best
+ * n=32, m=8 sweep kernels); kind 2: 8 DMMA + 32 DFMA per warp-iteration interleaved (all flops counted: a rate at the DMMA
+ * peak means the two instruction classes share one FP64 datapath).  Runs `reps` timed launches on the handle's stream (after one warm-up) and returns the best
  * TFLOP/s and its launch time.  Synchronous.  bench.py calls this before its timed region ("measure it"). */
 DDP_API int ddp_selftest_peak_f64(ddp_handle_t h, int32_t kind, int32_t reps, double* tflops, double* ms);
 
