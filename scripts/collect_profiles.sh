@@ -29,10 +29,12 @@ cap fwd_lin "fwd_lin32x8_kernel" 4 python bench.py --configs "" --steps 2 --no-c
 cap bp_small "bp_small" 1 python bench.py --configs c3 --steps 3 --no-cpu-baseline --e2e-steps 1 --oracle-samples 0
 cap fwd_pend "fwd_pend_staged" 2 python bench.py --configs c3 --steps 3 --no-cpu-baseline --e2e-steps 1 --oracle-samples 0
 cap kl_tile "kl_tile" 1 python bench.py --configs c4 --steps 2 --no-cpu-baseline --e2e-steps 1 --oracle-samples 0 --batch 16384
+cap kl_cached "kl_tile" 11 python bench.py --configs c4 --steps 2 --no-cpu-baseline --e2e-steps 1 --oracle-samples 0
+cap bp_tile_lims "bp_tile32x8" 7 python scripts/perf_lims.py 2368 3.0
 cap bp_tile_gps "bp_tile32x8_kernel<.*1, .0, .0, .0>|bp_tile32x8_kernelILb0ELb1" 0 python bench.py --configs c4 --steps 2 --no-cpu-baseline --e2e-steps 1 --oracle-samples 0 --batch 16384
 # sanitizer on the kernels added or rewritten this round (small shapes)
 timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 1 python -m pytest tests/test_gpu_round2.py tests/test_gpu_back_pass.py -q -x -k "not boxqp_large or 24" > $o/${tag}_memcheck.log 2>&1
 echo "memcheck exit $?" >> $o/${tag}_memcheck.log
-timeout 1500 compute-sanitizer --tool racecheck --error-exitcode 1 python -m pytest tests/test_gpu_round2.py tests/test_gpu_back_pass.py -q -x -k "small or tile32x8_boxqp or boxqp_large and 24 or chunked" > $o/${tag}_racecheck.log 2>&1
+timeout 1500 compute-sanitizer --tool racecheck --error-exitcode 1 python -m pytest tests/test_gpu_round2.py tests/test_gpu_back_pass.py -q -x -k "small or tile32x8_boxqp or with_limits or covariance_cache or boxqp_large and 24 or chunked" > $o/${tag}_racecheck.log 2>&1
 echo "racecheck exit $?" >> $o/${tag}_racecheck.log
 ls -la $o | grep ${tag}_ | tail -50
