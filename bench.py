@@ -685,6 +685,15 @@ def main_gpu(args):
                     break
                 except Exception:
                     pass
+        try:                                               # the one FP64 datapath's busy share under ncu (DMMA sub-pipe + scalar FP64 pipe)
+            import re as _re
+            txt = open(os.path.join(ROOT, "profiles", "ncu_bp_tile_r02.txt")).read()
+            pd = float(_re.search(r"pipe_tensor_subpipe_dmma\S*\s+([0-9.]+)", txt).group(1))
+            pf = float(_re.search(r"sm__inst_executed_pipe_fp64\S*\s+([0-9.]+)", txt).group(1))
+            roofline["fp64_datapath_busy_under_ncu"] = dict(dmma_pct=pd, scalar_fp64_pct=pf, total_pct=pd + pf,
+                                                            source="profiles/ncu_bp_tile_r02.txt (one ncu --set full capture of this kernel at B = 65536)")
+        except Exception:
+            pass
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
             try:
