@@ -44,8 +44,8 @@ constexpr int WARP_DOUBLES = SCX + 48;       // 2384 doubles = 19,072 B per warp
 constexpr int WARP_DOUBLES_LTV = WARP_DOUBLES;  // (a second [fx fu] buffer would cost 10 KB per warp and halve the residency: measured 113-134 ms)
 constexpr int COST_DOUBLES = 15 * 32 * 2;    // per-CTA table of the cost tiles in accumulator (fragment) order
 // per-warp scratch of the box-QP branch (LIMS variants): H = QuuF (8 x 8), its reduced factor R, Qux_reg / K (8 x 32), vectors
-constexpr int QH = 0, QR = 64, QQ = 128, QG = 384, QLO = 392, QUP = 400, QX0 = 408, QX = 416, QE = 424;     // QE: five exchange slots
-constexpr int QP_DOUBLES = QE + 40;
+constexpr int QH = 0, QR = 64, QQ = 128, QG = 384, QLO = 392, QUP = 400, QX0 = 408, QX = 416, QE = 424;     // QE: seven eight-double slots
+constexpr int QP_DOUBLES = QE + 56;
 
 // boxQP(QuuF, Qu, lims - u, k(i+1)) of backward_pass.jl:49 for m = 8 by the WHOLE WARP, in the oracle's arithmetic: every sum runs
 // in the oracle's index order with separate multiply and add (boxqp.cuh), so result code, free set and every bit of k are what
@@ -59,50 +59,52 @@ constexpr int QP_DOUBLES = QE + 40;
 //   Cholesky of H[free,free]       row by row: element (r,i) on lane i subtracts R[p,r] R[p,i], p ascending; R[:,r] from the scratch
 //   R'y = b, R z = y, search'grad  replicated: every lane runs the whole sequential solve on the factor in the scratch
 // All lanes hold the same scalars, so control flow is warp-uniform.  Not inlined: the tile kernel keeps its registers.
+// The factor lives in the scratch only (column j is written by lane j, row by row).
 // Outputs: k -> sq[QX..], the factor (uncompacted: R[p][j] at sq[QR + p + 8 j], valid where p <= j are both free) and 1 / R[j][j] at
 // sq[QG + j] (g is dead by then); returns the result code, *fm_out = free mask.
-__device__ __noinline__ int boxqp_warp8(double* sq, QPOpts o, int lane, unsigned* fm_out) {
-    const int i = lane & 7;
-    double Hrow[8], Hcol[8], Rc[8], xs[8];
-#pragma unroll
-    for (int j = 0; j < 8; j++) { Hrow[j] = sq[QH + i + 8 * j]; Rc[j] = 0.0; }
+// The code is kept SMALL on purpose (loops over the rows of the factor are rolled, the value function is a call): the sweep loop and
+// the QP must fit the instruction cache together -- the unrolled versions (41-81 KB) spent a third of their stalls on fetches.
+__device__ __forceinline__ void qp_share8(double* sq, const int slot, const int i, const double v, double (&out)[8]) {
+    sq[slot + i] = v;                                    // lanes with equal i write the same value
+    __syncwarp();
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        const double2 t = *reinterpret_cast<const double2*>(&sq[QH + 2 * j + 8 * i]);
-        Hcol[2 * j] = t.x;
-        Hcol[2 * j + 1] = t.y;
+        const double2 t = *reinterpret_cast<const double2*>(&sq[slot + 2 * j]);
+        out[2 * j] = t.x;
+        out[2 * j + 1] = t.y;
     }
+}
+
+// x'g + ((0.5 x') H) x with the sums in index order (qp_value); leaves x (all eight entries) in slot QE+0
+__device__ __noinline__ double qp_value_warp8(double* sq, const int i, const double xv, const double g) {
+    double xs[8], pq[8];
+    qp_share8(sq, QE + 0, i, xv, xs);
+    double t = 0.0;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const double2 h = *reinterpret_cast<const double2*>(&sq[QH + 2 * r + 8 * i]);      // H[2r..2r+1][i]
+        t = DADD(t, DMUL(DMUL(0.5, xs[2 * r]), h.x));                                      // (0.5 x' H)_i
+        t = DADD(t, DMUL(DMUL(0.5, xs[2 * r + 1]), h.y));
+    }
+    qp_share8(sq, QE + 8, i, DMUL(xv, g), pq);
+    double s1 = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) s1 = DADD(s1, pq[j]);
+    qp_share8(sq, QE + 16, i, DMUL(t, xv), pq);
+    double s2 = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) s2 = DADD(s2, pq[j]);
+    return DADD(s1, s2);
+}
+
+__device__ __noinline__ int boxqp_warp8(double* sq, QPOpts o, int lane, unsigned* fm_out) {
+    const int i = lane & 7;
+    double Hrow[8], xs[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) Hrow[j] = sq[QH + i + 8 * j];
     const double g = sq[QG + i], lower = sq[QLO + i], upper = sq[QUP + i];
     double x = clampd(sq[QX0 + i], lower, upper);                        // boxQP.jl:58
-    // all lanes: out[0..7] = the eight lanes' v.  Two uses of one slot are always separated by another __syncwarp.
-    auto share8 = [&](const int slot, const double v, double (&out)[8]) {
-        sq[slot + i] = v;
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const double2 t = *reinterpret_cast<const double2*>(&sq[slot + 2 * j]);
-            out[2 * j] = t.x;
-            out[2 * j + 1] = t.y;
-        }
-    };
-    // x'g + ((0.5 x') H) x with the sums in index order (qp_value); leaves xs = the argument on every lane
-    auto value_of = [&](const double xv) -> double {
-        share8(QE + 0, xv, xs);
-        double t = 0.0;
-#pragma unroll
-        for (int r = 0; r < 8; r++) t = DADD(t, DMUL(DMUL(0.5, xs[r]), Hcol[r]));      // (0.5 x' H)_i
-        double pq[8];
-        share8(QE + 8, DMUL(xv, g), pq);
-        double s1 = 0.0;
-#pragma unroll
-        for (int j = 0; j < 8; j++) s1 = DADD(s1, pq[j]);
-        share8(QE + 16, DMUL(t, xv), pq);
-        double s2 = 0.0;
-#pragma unroll
-        for (int j = 0; j < 8; j++) s2 = DADD(s2, pq[j]);
-        return DADD(s1, s2);
-    };
-    double value = value_of(x);                                          // :63
+    double value = qp_value_warp8(sq, i, x, g);                          // :63
     double oldvalue = 0.0;
     unsigned clamped = 0u, free_mask = 0xffu;
     int result = 0, iter = 1;
@@ -110,7 +112,13 @@ __device__ __noinline__ int boxqp_warp8(double* sq, QPOpts o, int lane, unsigned
         if (result != 0) break;
         if (iter > 1 && DSUB(oldvalue, value) < DMUL(o.min_rel_improve, fabs(oldvalue))) { result = 4; break; }     // :78
         oldvalue = value;
-        double s = 0.0;                                                  // xs = x on every lane (left by value_of)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {                                    // x, left in the slot by the value function
+            const double2 t = *reinterpret_cast<const double2*>(&sq[QE + 2 * j]);
+            xs[2 * j] = t.x;
+            xs[2 * j + 1] = t.y;
+        }
+        double s = 0.0;
 #pragma unroll
         for (int j = 0; j < 8; j++) s = DADD(s, DMUL(Hrow[j], xs[j]));
         const double grad = DADD(g, s);                                  // :85
@@ -118,27 +126,25 @@ __device__ __noinline__ int boxqp_warp8(double* sq, QPOpts o, int lane, unsigned
         clamped = __ballot_sync(0xffffffffu, (x == lower && grad > 0.0) || (x == upper && grad < 0.0)) & 0xffu;      // :92-94
         free_mask = 0xffu & ~clamped;
         if (clamped == 0xffu) { result = 6; break; }                     // :98
-        const bool me_free = (free_mask >> i) & 1u;
         if (iter == 1 || old_clamped != clamped) {                       // :104-117: upper factor of H[free,free], row by row
             bool fail = false;
-#pragma unroll
+#pragma unroll 1
             for (int r = 0; r < 8; r++) {
                 if (!((free_mask >> r) & 1u)) continue;                  // warp-uniform
-                double acc = Hcol[r];                                    // H[r][i] (upper triangle when r <= i)
+                double acc = sq[QH + r + 8 * i];                         // H[r][i] (upper triangle when r <= i)
 #pragma unroll
-                for (int p = 0; p < 8; p++)
-                    if (p < r && ((free_mask >> p) & 1u)) acc = DSUB(acc, DMUL(sq[QR + p + 8 * r], Rc[p]));     // - R[p][r] R[p][i]
+                for (int p = 0; p < 7; p++)                              // - R[p][r] R[p][i], p < r ascending (rows p of both columns are final)
+                    if (p < r && ((free_mask >> p) & 1u)) acc = DSUB(acc, DMUL(sq[QR + p + 8 * r], sq[QR + p + 8 * i]));
                 const double d = __shfl_sync(0xffffffffu, acc, r);       // the pivot: lane r's element
                 if (!(d > 0.0)) { fail = true; break; }
                 const double rrr = __dsqrt_rn(d);
-                Rc[r] = (i == r) ? rrr : DDIV(acc, rrr);                 // meaningful on the free lanes i >= r; never read elsewhere
-                sq[QR + r + 8 * i] = Rc[r];
+                sq[QR + r + 8 * i] = (i == r) ? rrr : DDIV(acc, rrr);    // meaningful on the free lanes i >= r; never read elsewhere
                 __syncwarp();
             }
             if (fail) { *fm_out = free_mask; return -1; }                // PosDefException
         }
         double gv[8];
-        share8(QE + 24, grad, gv);
+        qp_share8(sq, QE + 24, i, grad, gv);
         double gs = 0.0;                                                 // norm(grad[free]) :120
 #pragma unroll
         for (int p = 0; p < 8; p++)
@@ -147,54 +153,60 @@ __device__ __noinline__ int boxqp_warp8(double* sq, QPOpts o, int lane, unsigned
         double sc = 0.0;                                                 // grad_clamped = g + H (x .* clamped)  :127
 #pragma unroll
         for (int j = 0; j < 8; j++) sc = DADD(sc, DMUL(Hrow[j], ((clamped >> j) & 1u) ? xs[j] : DMUL(xs[j], 0.0)));
-        double v[8];
-        share8(QE + 32, DADD(g, sc), v);
-        // R' y = b, then R z = y: the oracle's loops (chol_solve) on the uncompacted factor, by every lane
-#pragma unroll
+        // R' y = b, then R z = y: the oracle's loops (chol_solve) on the uncompacted factor, by every lane (all lanes write the same
+        // values); b, y and z have a slot each, so no element is read after it was overwritten
+        double* vb = sq + QE + 32;
+        double* vy = sq + QE + 40;
+        double* vz = sq + QE + 48;
+        vb[i] = DADD(g, sc);
+        __syncwarp();
+#pragma unroll 1
         for (int a = 0; a < 8; a++) {
             if (!((free_mask >> a) & 1u)) continue;
-            double acc = v[a];
+            double acc = vb[a];
 #pragma unroll
-            for (int p = 0; p < 8; p++)
-                if (p < a && ((free_mask >> p) & 1u)) acc = DSUB(acc, DMUL(sq[QR + p + 8 * a], v[p]));
-            v[a] = DDIV(acc, sq[QR + a + 8 * a]);
+            for (int p = 0; p < 7; p++)
+                if (p < a && ((free_mask >> p) & 1u)) acc = DSUB(acc, DMUL(sq[QR + p + 8 * a], vy[p]));
+            vy[a] = DDIV(acc, sq[QR + a + 8 * a]);
+            __syncwarp();
         }
-#pragma unroll
+#pragma unroll 1
         for (int a = 7; a >= 0; a--) {
             if (!((free_mask >> a) & 1u)) continue;
-            double acc = v[a];
+            double acc = vy[a];
 #pragma unroll
-            for (int p = 0; p < 8; p++)
-                if (p > a && ((free_mask >> p) & 1u)) acc = DSUB(acc, DMUL(sq[QR + a + 8 * p], v[p]));
-            v[a] = DDIV(acc, sq[QR + a + 8 * a]);
+            for (int p = 1; p < 8; p++)
+                if (p > a && ((free_mask >> p) & 1u)) acc = DSUB(acc, DMUL(sq[QR + a + 8 * p], vz[p]));
+            vz[a] = DDIV(acc, sq[QR + a + 8 * a]);
+            __syncwarp();
         }
         double search = 0.0, sdotg = 0.0;                                // :129, :132
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            const double sj = ((free_mask >> j) & 1u) ? DSUB(-v[j], xs[j]) : 0.0;
+            const double sj = ((free_mask >> j) & 1u) ? DSUB(-vz[j], xs[j]) : 0.0;
             if (i == j) search = sj;
             sdotg = DADD(sdotg, DMUL(sj, gv[j]));
         }
+        __syncwarp();                                                    // every lane is done with the solve slot
         if (sdotg >= 0.0) break;                                         // :133 leaves result == 0
         double step = 1.0;                                               // :138
         double xc = clampd(DADD(x, DMUL(step, search)), lower, upper);
-        double vc = value_of(xc);
+        double vc = qp_value_warp8(sq, i, xc, g);
         while (DDIV(DSUB(vc, oldvalue), DMUL(step, sdotg)) < o.armijo) { // :142
             step = DMUL(step, o.step_dec);
             xc = clampd(DADD(x, DMUL(step, search)), lower, upper);
-            vc = value_of(xc);
+            vc = qp_value_warp8(sq, i, xc, g);
             if (step < o.min_step) { result = 2; break; }
         }
         x = xc;                                                          // :161
         value = vc;
         iter++;
-        (void)me_free;
     }
     if (iter == o.max_iter) result = 1;                                  // :167 (quirk Q4)
     __syncwarp();
     if (lane < 8) {
         sq[QX + i] = x;
-        sq[QG + i] = 1.0 / Rc[i];                                        // reciprocal pivots for the gain columns (garbage where clamped: unused)
+        sq[QG + i] = 1.0 / sq[QR + i + 8 * i];                           // reciprocal pivots for the gain columns (garbage where clamped: unused)
     }
     __syncwarp();
     *fm_out = free_mask;
