@@ -679,3 +679,25 @@ def test_ilqgkl_device_with_and_without_covariance_cache(ddp):
     for key in ("iter", "eta", "eta_min", "eta_max", "divergence"):
         assert np.array_equal(a[6][key], b[6][key]), key
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2].K, b[2].K)
+
+
+@pytest.mark.parametrize("scale,lam0,shift", [(0.03, 1e-2, 0.0), (0.3, 1e-4, 0.0), (3.0, 1.0, 0.0), (0.3, 1e-2, 0.25), (0.1, 1e-6, -0.1)])
+def test_tile32x8_boxqp_regimes(ddp, scale, lam0, shift):
+    """The warp-cooperative box QP of bp_tile32x8_kernel<LIMS> over several regimes -- almost everything clamped, almost nothing
+    clamped, boxes that do not contain u (every warm start is projected), weak regularisation: `diverge`, the clamped set of every
+    step and which entries of k sit exactly on a bound equal the oracle's; K, k, Vx, dV within 1e-8."""
+    B, n, m, N = 12, 32, 8, 14
+    A, Bm, Q, R, x, u = make_batch_lq(170 + int(1000 * scale), B, n, m, N)
+    rng = np.random.default_rng(int(1e6 * lam0) + 5)
+    cx, cu = x @ Q.T, u @ R.T
+    lims = np.stack([shift - scale * (0.2 + 0.3 * rng.random(m)), shift + scale * (0.2 + 0.3 * rng.random(m))], axis=-1)
+    lam = lam0 * (1 + np.arange(B))
+    d, pol, Vx, Vxx, dV = ddp.back_pass(cx, cu, Q, np.zeros((n, m)), R, A[:, None], Bm[:, None], lam, 1, lims, x, u)
+    for b in range(B):
+        d0, p0, Vx0, Vxx0, dV0 = O.back_pass(cx[b], cu[b], Q, np.zeros((n, m)), R, A[b], Bm[b], lam[b], 1, lims, x[b], u[b])
+        assert d[b] == d0, b
+        assert np.array_equal(np.all(pol.K[b] == 0, axis=-1), np.all(p0.K == 0, axis=-1)), b
+        for bound in (0, 1):
+            assert np.array_equal(pol.k[b] == (lims[:, bound] - u[b]), p0.k == (lims[:, bound] - u[b])), (b, bound)
+        for got, ref in ((pol.K[b], p0.K), (pol.k[b], p0.k), (Vx[b], Vx0), (dV[b], dV0)):
+            assert relerr_elem(got, ref) < TOL, b
