@@ -854,47 +854,40 @@ def run_c4(g):
         res["oracle"]["seconds"] = time.perf_counter() - t0
     klm_recompute = klm.clone()
     # the same iteration with forward_covariance's state block kept from an earlier eta iteration (it depends on fx and R1 only):
-    # ddp_kl_args.Sx_tri, mode 1 = store while computing, mode 2 = read back -- what ddp_ilqgkl_solve_f64 does from iteration 2 on
-    # when the (528,T,B) buffer fits.  Next to this benchmark's two 32 GiB gain histories the 66 GiB cache of 65536 trajectories
-    # does not fit in 178 GiB, so this variant runs on the FIRST HALF of the batch (a second handle over the same buffers).
+    # ddp_kl_args.Sx_tri, mode 1 = store while computing, mode 2 = read back -- what ddp_ilqgkl_solve_f64 does from iteration 2 on.
+    # Next to this benchmark's two 32 GiB gain histories the 66 GiB cache of all 65536 trajectories does not fit in 178 GiB:
+    # Sx_count = as many leading trajectories as the free memory holds, the rest is propagated as before (one launch each).
     cached = None
-    eng2 = None
     try:
-        Bh = B // 2
-        need_gb = Bh * T * 528 * 8 / 2**30
+        per_gb = T * 528 * 8 / 2**30
         free_gb = torch.cuda.mem_get_info()[0] / 2**30 + (torch.cuda.memory_reserved() - torch.cuda.memory_allocated()) / 2**30
-        if free_gb < need_gb + 2.0:
-            raise MemoryError(f"{need_gb:.1f} GiB for the (528,T,B/2) cache, {free_gb:.1f} GiB free")
-        eng2 = g["ddp"].Engine(n, m, T, Bh, device=g["local_rank"])
-        eng2.set_stream(torch.cuda.current_stream().cuda_stream)
-        Sx = empty(Bh, T, 528)
-        eng_full = eng
-        eng = eng2                                         # `one` launches through `eng`
-        ms_h, (bk_h, fw_h, kl_h) = _timed(one, steps, warm, torch.cuda.synchronize)          # recomputing, same half batch
-        ka.Sx_tri, ka.Sx_mode = Sx.data_ptr(), 1
+        nc = int(min(B, (free_gb - 3.0) / per_gb))
+        nc -= nc % 1184                                    # whole rounds of the resident warp set of a B200
+        if nc < B // 8:
+            raise MemoryError(f"{per_gb * B:.1f} GiB for the full (528,T,B) cache, {free_gb:.1f} GiB free")
+        torch.cuda.empty_cache()
+        Sx = empty(nc, T, 528)
+        ka.Sx_tri, ka.Sx_mode, ka.Sx_count = Sx.data_ptr(), 1, (nc if nc < B else 0)
         e0, e1 = ev(), ev()
         e0.record()
         eng._ck(eng.lib.ddp_kl_div_f64(eng.h, C.byref(ka)))
         e1.record(); torch.cuda.synchronize()
         store_ms = e0.elapsed_time(e1)
-        same_store = bool(torch.equal(klm[:Bh], klm_recompute[:Bh]))
+        same_store = bool(torch.equal(klm, klm_recompute))
         ka.Sx_mode = 2
         ms_c, (bk_c, fw_c, kl_c) = _timed(one, steps, warm, torch.cuda.synchronize)
-        eng = eng_full
-        cached = dict(batch=Bh, ms_per_iter=ms_c, back_pass_gps_ms=bk_c, forward_ms=fw_c, kl_ms=kl_c, kl_store_pass_ms=store_ms,
-                      recomputing_on_the_same_half_batch=dict(ms_per_iter=ms_h, kl_ms=kl_h),
-                      iteration_speedup=ms_h / ms_c, kl_speedup=kl_h / kl_c, cache_gib=need_gb,
-                      kl_mean_bitwise_equal_to_recompute=bool(torch.equal(klm[:Bh], klm_recompute[:Bh])) and same_store,
-                      kl_hbm_frac=(C4_BYTES_KL + 528 * 8 * T) * Bh / (kl_c * 1e-3) * 1e-9 / float(measured_peaks()[0].get("hbm_gbs", 6650.0)),
-                      note="iterations 2.. of one iLQGkl solve: Sigma_x(t) read from the cache written by iteration 1 (kl_store_pass_ms); "
-                           "32768 trajectories (half of C4's batch: the full cache does not fit beside K_prev and K_new), not scaled")
-        ka.Sx_tri, ka.Sx_mode = None, 0
+        cached = dict(batch=B, cached_trajectories=nc, cache_gib=nc * per_gb, ms_per_iter=ms_c, iters_per_s=1e3 / ms_c,
+                      back_pass_gps_ms=bk_c, forward_ms=fw_c, kl_ms=kl_c, kl_store_pass_ms=store_ms,
+                      iteration_speedup=ms / ms_c, kl_speedup=kl / kl_c,
+                      kl_mean_bitwise_equal_to_recompute=bool(torch.equal(klm, klm_recompute)) and same_store,
+                      note="iterations 2.. of one iLQGkl solve at the full C4 batch: Sigma_x(t) of the first cached_trajectories read from the "
+                           "cache written by iteration 1 (kl_store_pass_ms), the others propagated as in the uncached run; kl_mean compared "
+                           "bitwise with the recomputing run")
+        ka.Sx_tri, ka.Sx_mode, ka.Sx_count = None, 0, 0
         del Sx
     except Exception as exc:
         cached = dict(error=f"{type(exc).__name__}: {exc}")
-        ka.Sx_tri, ka.Sx_mode = None, 0
-    if eng2 is not None:
-        eng2.close()
+        ka.Sx_tri, ka.Sx_mode, ka.Sx_count = None, 0, 0
     res["covariance_cached"] = cached
     return res
 

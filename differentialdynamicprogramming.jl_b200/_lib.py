@@ -53,7 +53,7 @@ class KlArgs(C.Structure):          # ddp_kl_args
     _fields_ = [("fx", Tensor), ("R1", Tensor), ("xnew", C.c_void_p), ("xold", C.c_void_p),
                 ("K_new", C.c_void_p), ("k_new", C.c_void_p), ("Sig_new", C.c_void_p),
                 ("K_prev", Tensor), ("k_prev", Tensor), ("Sig_prev", Tensor), ("Sigi_prev", Tensor),
-                ("kl_t", C.c_void_p), ("kl_mean", C.c_void_p), ("Sx_tri", C.c_void_p), ("Sx_mode", C.c_int32), ("pad_", C.c_int32)]
+                ("kl_t", C.c_void_p), ("kl_mean", C.c_void_p), ("Sx_tri", C.c_void_p), ("Sx_mode", C.c_int32), ("pad_", C.c_int32), ("Sx_count", C.c_int64)]
 
 
 class IlqgOpts(C.Structure):        # ddp_ilqg_opts

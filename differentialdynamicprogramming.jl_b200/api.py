@@ -624,7 +624,7 @@ def forward_costs(traj_new: GaussianPolicy, x0, u, x, alphas, f, costfun, lims, 
 
 
 def kl_div_wiki(xnew, xold, fx, R1, traj_new: GaussianPolicy, traj_prev: GaussianPolicy, *, engine: Engine = None,
-                Sx_cache=None, Sx_mode: int = 0):
+                Sx_cache=None, Sx_mode: int = 0, Sx_count: int = 0):
     """Per-step KL divergence between the new and previous policy (klutils.jl:70-100) with the state
     covariance of ``forward_covariance`` (forward_pass.jl:37-56) propagated on the device.
 
@@ -633,7 +633,8 @@ def kl_div_wiki(xnew, xold, fx, R1, traj_new: GaussianPolicy, traj_prev: Gaussia
     Returns ``(kl_t, kl_mean)``.
 
     ``Sx_cache`` (a device buffer of ``engine.empty((B, N, 528))``) with ``Sx_mode`` 1 stores the state covariances of this call
-    (they depend on ``fx`` and ``R1`` only), ``Sx_mode`` 2 reads them back instead of propagating (``ddp_kl_args.Sx_tri``).
+    (they depend on ``fx`` and ``R1`` only), ``Sx_mode`` 2 reads them back instead of propagating (``ddp_kl_args.Sx_tri``);
+    ``Sx_count`` > 0: the buffer holds the first ``Sx_count`` trajectories only, the others are propagated in every call.
     """
     xnew = np.asarray(xnew, dtype=np.float64)
     batched = xnew.ndim == 3
@@ -658,7 +659,7 @@ def kl_div_wiki(xnew, xold, fx, R1, traj_new: GaussianPolicy, traj_prev: Gaussia
     klt, klm = eng.empty((B, N)), eng.empty((B,))
     a.kl_t, a.kl_mean = klt.ptr, klm.ptr
     if Sx_cache is not None:
-        a.Sx_tri, a.Sx_mode = Sx_cache.ptr, int(Sx_mode)
+        a.Sx_tri, a.Sx_mode, a.Sx_count = Sx_cache.ptr, int(Sx_mode), int(Sx_count)
     eng._ck(eng.lib.ddp_kl_div_f64(eng.h, C.byref(a)))
     eng.synchronize()
     t, mn = klt.numpy(), klm.numpy()

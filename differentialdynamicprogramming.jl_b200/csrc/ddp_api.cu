@@ -325,7 +325,8 @@ int ddp_kl_div_f64(ddp_handle_t h, const ddp_kl_args* a) {
     P.kl_t = a->kl_t; P.kl_mean = a->kl_mean; P.active = nullptr;
     if (a->Sx_mode < 0 || a->Sx_mode > 2) return fail(h, DDP_ERR_INVALID, "ddp_kl_div_f64: Sx_mode must be 0, 1 or 2");
     if (a->Sx_mode != 0 && !a->Sx_tri) return fail(h, DDP_ERR_INVALID, "ddp_kl_div_f64: Sx_mode 1 / 2 need Sx_tri");
-    P.Sx_tri = a->Sx_tri; P.sx_mode = a->Sx_mode;
+    if (a->Sx_count < 0 || a->Sx_count > h->B) return fail(h, DDP_ERR_INVALID, "ddp_kl_div_f64: Sx_count must be in 0..B");
+    P.Sx_tri = a->Sx_tri; P.sx_mode = a->Sx_mode; P.sx_count = a->Sx_count;
     CU(h, cudaSetDevice(h->device));
     int rc = launch_kl_div(h, P);
     if (rc != 0) return cuda_fail(h, (cudaError_t)rc, "kl_div launch");

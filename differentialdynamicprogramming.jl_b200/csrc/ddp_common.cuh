@@ -79,6 +79,8 @@ struct KlParams {
     const unsigned char* active;     // [B] or nullptr
     double* Sx_tri = nullptr;        // (B,T,528) packed upper triangles of the state covariances, see ddp_kl_args
     int sx_mode = 0;                 // 0 none, 1 store, 2 load
+    long long sx_count = 0;          // trajectories the cache holds (0 = all)
+    long long b_begin = 0, b_end = -1;   // trajectory range of one launch (kl_tile.cu; -1 = B)
 };
 
 struct ddp_handle_s {

@@ -100,7 +100,8 @@ __global__ void __launch_bounds__(KW * 32, MODE == 2 ? 3 : 2) kl_tile32x8_kernel
     const int c0src = 8 * q, c1src = 8 * q + 4;
     const long long warps_total = (long long)gridDim.x * KW;
 
-    for (long long b = (long long)blockIdx.x * KW + w; b < P.B; b += warps_total) {
+    const long long b_end = P.b_end < 0 ? P.B : P.b_end;
+    for (long long b = P.b_begin + (long long)blockIdx.x * KW + w; b < b_end; b += warps_total) {
         const bool act = !(P.active && !P.active[b]);
         if (!act && MODE != 1) continue;                   // MODE 1 fills the cache of EVERY trajectory (its KL outputs stay untouched)
         __syncwarp();
@@ -345,19 +346,29 @@ int launch_kl_div_tile(ddp_handle_s* h, const KlParams& P, bool* handled) {
     if (!al16t(P.Kp) || !al16t(P.Sp) || ((uintptr_t)P.Kn % 16) || ((uintptr_t)P.Sn % 16) || ((uintptr_t)P.xnew % 16) || ((uintptr_t)P.xold % 16)) return 0;
     const int mode = P.Sx_tri ? P.sx_mode : 0;
     if (mode != 0 && ((uintptr_t)P.Sx_tri % 16)) return 0;
-    const size_t bytes = (mode == 2) ? (size_t)KW * KWARP_DOUBLES_CACHED * sizeof(double) : ((size_t)KW * KWARP_DOUBLES + KTAB_DOUBLES) * sizeof(double);
-    cudaError_t e = (mode == 2)   ? cudaFuncSetAttribute(kl_tile32x8_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)
-                    : (mode == 1) ? cudaFuncSetAttribute(kl_tile32x8_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)
-                                  : cudaFuncSetAttribute(kl_tile32x8_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    if (e != cudaSuccess) return (int)e;
-    // propagating: 2 CTAs per SM (255 registers, no spills) measured faster than 3 (168 registers); cached: 3 CTAs per SM
-    long long grid = (long long)h->sm_count * (mode == 2 ? 3 : 2);
-    const long long need = (P.B + KW - 1) / KW;
-    if (grid > need) grid = need;
-    if (mode == 2) kl_tile32x8_kernel<2><<<(unsigned)grid, KW * 32, bytes, h->stream>>>(P);
-    else if (mode == 1) kl_tile32x8_kernel<1><<<(unsigned)grid, KW * 32, bytes, h->stream>>>(P);
-    else kl_tile32x8_kernel<0><<<(unsigned)grid, KW * 32, bytes, h->stream>>>(P);
-    h->launches++;
+    // one launch per trajectory range: [0, cached) in the cache mode, [cached, B) propagating
+    auto launch = [&](const int md, const long long b0, const long long b1) -> cudaError_t {
+        if (b1 <= b0) return cudaSuccess;
+        KlParams Q = P;
+        Q.b_begin = b0; Q.b_end = b1; Q.sx_mode = md;
+        const size_t bytes = (md == 2) ? (size_t)KW * KWARP_DOUBLES_CACHED * sizeof(double) : ((size_t)KW * KWARP_DOUBLES + KTAB_DOUBLES) * sizeof(double);
+        cudaError_t e = (md == 2)   ? cudaFuncSetAttribute(kl_tile32x8_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)
+                        : (md == 1) ? cudaFuncSetAttribute(kl_tile32x8_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)
+                                    : cudaFuncSetAttribute(kl_tile32x8_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return e;
+        // propagating: 2 CTAs per SM (255 registers, no spills) measured faster than 3 (168 registers); cached: 3 CTAs per SM
+        long long grid = (long long)h->sm_count * (md == 2 ? 3 : 2);
+        const long long need = (b1 - b0 + KW - 1) / KW;
+        if (grid > need) grid = need;
+        if (md == 2) kl_tile32x8_kernel<2><<<(unsigned)grid, KW * 32, bytes, h->stream>>>(Q);
+        else if (md == 1) kl_tile32x8_kernel<1><<<(unsigned)grid, KW * 32, bytes, h->stream>>>(Q);
+        else kl_tile32x8_kernel<0><<<(unsigned)grid, KW * 32, bytes, h->stream>>>(Q);
+        h->launches++;
+        return cudaGetLastError();
+    };
+    const long long cached = (mode == 0) ? 0 : ((P.sx_count > 0 && P.sx_count < P.B) ? P.sx_count : P.B);
+    cudaError_t e = launch(mode, 0, cached);
+    if (e == cudaSuccess) e = launch(0, cached, P.B);
     *handled = true;
-    return (int)cudaGetLastError();
+    return (int)e;
 }

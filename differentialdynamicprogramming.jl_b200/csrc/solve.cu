@@ -1348,8 +1348,14 @@ int ddp_ilqgkl_solve_f64(ddp_handle_t h, const ddp_model* model, const ddp_ilqgk
     KP.kl_t = nullptr; KP.kl_mean = s.klmean; KP.active = s.active;
     // forward_covariance's state block depends on fx_model and R1 only: keep it from the first eta iteration (kl_tile.cu MODE 1 / 2)
     if (opts->kl_step > 0.0 && !opts->no_covariance_cache && n == 32 && m == 8 && !(h->flags & 1u) && max_iter > 1) {
-        if (cudaMalloc(&sx.p, (size_t)B * T * 528 * sizeof(double)) != cudaSuccess) { cudaGetLastError(); sx.p = nullptr; }
+        // as many leading trajectories as fit (2 GiB are left alone); the rest is propagated in every iteration
+        size_t free_b = 0, total_b = 0;
+        const size_t per = (size_t)T * 528 * sizeof(double), margin = (size_t)2 << 30;
+        long long count = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && free_b > margin) count = (long long)std::min<size_t>((size_t)B, (free_b - margin) / per);
+        if (count >= std::max<long long>(1, B / 8) && cudaMalloc(&sx.p, (size_t)count * per) != cudaSuccess) { cudaGetLastError(); sx.p = nullptr; }
         KP.Sx_tri = static_cast<double*>(sx.p);
+        KP.sx_count = (sx.p && count < B) ? count : 0;
     }
 
     for (it = 1; it <= max_iter; it++) {

@@ -280,10 +280,12 @@ typedef struct ddp_kl_args {
      * recomputes the same matrices (208 of this call's 248 tensor tiles per step).  Sx_tri: DEVICE (528,T,B) doubles, the upper
      * triangle of each Sigma_t packed by columns, or NULL.  Sx_mode 0: ignore; 1: compute as usual and also store; 2: read the
      * stored matrices instead of propagating (results are bit-identical).  Honoured by the n=32, m=8 kernel; other shapes
-     * recompute in every mode. */
+     * recompute in every mode.  Sx_count: the buffer holds the first Sx_count trajectories only ((528,T,Sx_count); 0 = all B):
+     * the others are propagated in every call -- a partial cache for batches whose full cache does not fit in memory. */
     double* Sx_tri;
     int32_t Sx_mode;
     int32_t pad_;
+    int64_t Sx_count;
 } ddp_kl_args;
 
 DDP_API int ddp_kl_div_f64(ddp_handle_t h, const ddp_kl_args* a);
@@ -350,8 +352,9 @@ typedef struct ddp_ilqgkl_opts {        /* defaults: iLQGkl.jl:25-42 */
     int32_t max_eta_retries;            /* bounds the reference's unbounded eta-retry loop (iLQGkl.jl:97); 0 => 200 */
     const double* lims;                 /* DEVICE (m,2) or NULL                                       */
     int32_t no_covariance_cache;        /* 0: keep the state covariances of forward_covariance (they depend on fx_model and R1
-                                         * only) from the first eta iteration for the later ones when the (528,T,B) buffer can be
-                                         * allocated (n=32, m=8: 4.2 KB per step and trajectory); 1: recompute every iteration */
+                                         * only) from the first eta iteration for the later ones, for as many leading trajectories
+                                         * as the free device memory holds (n=32, m=8: 4.2 KB per step and trajectory);
+                                         * 1: recompute every iteration */
     int32_t pad_;
 } ddp_ilqgkl_opts;
 

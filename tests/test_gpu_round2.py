@@ -701,3 +701,32 @@ def test_tile32x8_boxqp_regimes(ddp, scale, lam0, shift):
             assert np.array_equal(pol.k[b] == (lims[:, bound] - u[b]), p0.k == (lims[:, bound] - u[b])), (b, bound)
         for got, ref in ((pol.K[b], p0.K), (pol.k[b], p0.k), (Vx[b], Vx0), (dV[b], dV0)):
             assert relerr_elem(got, ref) < TOL, b
+
+
+def test_kl_partial_state_covariance_cache(ddp):
+    """ddp_kl_args.Sx_count: a cache that holds the first trajectories only (the rest is propagated in every call) gives the
+    propagating kernel's per-step divergences bit for bit, for every trajectory."""
+    from test_gpu_misc import _prev_policy
+    n, m, N, B = 32, 8, 10, 5
+    xs, xo, Ks, ks, Ss, Sis, Kp, kp, Sp, Sip, As = ([] for _ in range(11))
+    R1 = 2e-4 * np.eye(n)
+    for b in range(B):
+        A, Bm, Q, R, x, u, cx, cu, prev = _prev_policy(n, m, N, 40 + b)
+        rep = lambda a: np.tile(a, (N, 1, 1))
+        _, pnew, _, _, _ = O.back_pass_gps(cx, cu, rep(Q), rep(np.zeros((n, m))), rep(R), rep(A), rep(Bm), None, x, u,
+                                           (O.grad_kl(prev), np.array([1e-8, 1.0 + b, 1e16])))
+        om = O.LinearModel(A, Bm, Q, R)
+        xnew, _, _ = O.forward_pass(pnew, x[0], u, x, 1, om.f, om.costfun, None)
+        xs.append(xnew); xo.append(x); Ks.append(pnew.K); ks.append(pnew.k); Ss.append(pnew.Sigma); Sis.append(pnew.Sigmai)
+        Kp.append(prev.K); kp.append(prev.k); Sp.append(prev.Sigma); Sip.append(prev.Sigmai); As.append(A)
+    st = lambda l: np.stack(l)
+    gpn = ddp.GaussianPolicy(N, n, m, st(Ks), st(ks), st(Ss), st(Sis))
+    gpp = ddp.GaussianPolicy(N, n, m, st(Kp), st(kp), st(Sp), st(Sip))
+    A4 = st(As)[:, None]
+    eng = ddp.Engine(n, m, N, B)
+    cache = eng.empty((3, N, 528))
+    ref, _ = ddp.kl_div_wiki(st(xs), st(xo), A4, R1, gpn, gpp, engine=eng)
+    a1, _ = ddp.kl_div_wiki(st(xs), st(xo), A4, R1, gpn, gpp, engine=eng, Sx_cache=cache, Sx_mode=1, Sx_count=3)
+    a2, _ = ddp.kl_div_wiki(st(xs), st(xo), A4, R1, gpn, gpp, engine=eng, Sx_cache=cache, Sx_mode=2, Sx_count=3)
+    assert np.array_equal(ref, a1) and np.array_equal(ref, a2) and np.all(ref > 0)
+    eng.close()
