@@ -4,7 +4,15 @@
 // (n=32,m=8 class, DMMA tiles) and back_pass_small.cu (n<=8, thread-per-trajectory) take the
 // benchmarked shapes; everything else lands here.
 //
+// WPT (warp per trajectory): the same code with one WARP per trajectory -- four trajectories per CTA, each warp on its own
+// slice of shared memory, __syncwarp instead of __syncthreads.  For small shapes (n <= 16: the reference's demo_linear /
+// test_readme shape n=10, m=2) a phase has ~100 independent elements, so 128 threads only wait for each other
+// (ncu at n=10, m=2: 55 % of the stalls on the barrier, 4 CTAs per SM); the arithmetic is the same, element by element.
+// The serial factorisation / QP is instantiated for the smallest bound MM in {2,4,8,16} that holds m (the fully unrolled
+// MM = 16 code was 25 % instruction-fetch stalls at m = 2).
+//
 // Replaces back_pass / back_pass_gps of src/backward_pass.jl:162-252, :259-350 (+ macros :3-79).
+#include <cstdlib>
 #include "boxqp.cuh"
 
 namespace {
@@ -89,22 +97,66 @@ __device__ void inv_gj(int m, double* A, double* Ainv) {
     }
 }
 
-template <bool GPS>
-__global__ void __launch_bounds__(NT) bp_generic_kernel(BackParams P) {
+// factorisation / QP of one step by one thread (fixed sequential order shared with the oracle): returns 1 when the sweep diverges
+template <int MM>
+__device__ __noinline__ int factor_step(const int m, const bool use_qp, const QPOpts& qp, const double* QuuF, const double* Qu,
+                                        const double* lo, const double* up, const double* kw, double* k, double* R, int* flags) {
+    if (!use_qp) {
+        int idx[MM];
+        for (int a = 0; a < m; a++) idx[a] = a;
+        if (!chol_upper_sub<MM>(QuuF, m, idx, m, R, m)) return 1;
+        for (int a = 0; a < m; a++) k[a] = Qu[a];
+        chol_solve<MM>(R, m, m, k);
+        for (int a = 0; a < m; a++) k[a] = -k[a];
+        flags[1] = (m >= 32) ? -1 : (int)((1u << m) - 1u);
+        flags[2] = m;
+        return 0;
+    }
+    unsigned fm = 0;
+    int nfac = 0;
+    const int res = boxqp_seq<MM>(m, QuuF, m, Qu, lo, up, kw, qp, k, R, m, &fm, &nfac);
+    flags[1] = (int)fm;
+    flags[2] = __popc(fm);
+    return res < 1 ? 1 : 0;                                // :50-56
+}
+
+// K[free, j] = -R \ (R' \ Qux_reg[free, j]), clamped rows zero (:42 / :57-61)
+template <int MM>
+__device__ __noinline__ void gain_column(const int m, const unsigned fm, const int nf, const double* R, const double* qcol, double* kcol) {
+    double v[MM];
+    int p = 0;
+    for (int a = 0; a < m; a++)
+        if ((fm >> a) & 1u) v[p++] = qcol[a];
+    if (nf > 0) chol_solve<MM>(R, m, nf, v);
+    p = 0;
+    for (int a = 0; a < m; a++) kcol[a] = ((fm >> a) & 1u) ? -v[p++] : 0.0;
+}
+
+template <bool GPS, bool WPT>
+__global__ void __launch_bounds__(NT, WPT ? 8 : 4) bp_generic_kernel(BackParams P) {
     extern __shared__ double smem_raw[];
     const int n = P.n, m = P.m, N = P.T;
     const int ldn = n | 1, ldm = m | 1;
-    const int tid = threadIdx.x;
+    constexpr int NTL = WPT ? 32 : NT;                     // threads that share one trajectory
+    const int tid = WPT ? (threadIdx.x & 31) : threadIdx.x;
     Smem s;
-    carve(smem_raw, n, m, GPS, s);
+    carve(smem_raw + (WPT ? (size_t)(threadIdx.x >> 5) * smem_doubles(n, m, GPS) : 0), n, m, GPS, s);
+    auto sync = [&]() { if (WPT) __syncwarp(); else __syncthreads(); };
+    // element e = tid + k NTL of a column-major block with d rows: (row, column) advanced without a division per element
+    const int rc0_n = tid % n, rc1_n = tid / n, rcd0_n = NTL % n, rcd1_n = NTL / n;
+    const int rc0_m = tid % m, rc1_m = tid / m, rcd0_m = NTL % m, rcd1_m = NTL / m;
+#define FOR_RC(e, r, c, count, d) \
+    for (int e = tid, r = rc0_##d, c = rc1_##d; e < (count); e += NTL, r += rcd0_##d, c += rcd1_##d, (r >= d ? (r -= d, ++c) : 0))
     const bool use_qp = (P.lims != nullptr) && !(P.lims[0] > P.lims[m]);   // backward_pass.jl:31
     const long long nn = (long long)n * n, mn = (long long)m * n, mm = (long long)m * m;
     if (P.redo_count && *P.redo_count == 0) return;          // follow-up launch of the tile kernel with nothing handed over
 
-    for (long long b = blockIdx.x; b < P.B; b += gridDim.x) {
+    const long long b_first = WPT ? (long long)blockIdx.x * (NT / 32) + (threadIdx.x >> 5) : (long long)blockIdx.x;
+    const long long b_step = WPT ? (long long)gridDim.x * (NT / 32) : (long long)gridDim.x;
+    for (long long b = b_first; b < P.B; b += b_step) {
         if (P.active && !P.active[b]) continue;
         if (P.redo && !P.redo[b]) continue;
-        __syncthreads();
+        sync();
         const double lam = GPS ? 0.0 : P.lambda[b];
         const double eta = GPS ? P.eta[b] : 1.0;
         double* Kb = P.K + b * (long long)N * mn;
@@ -122,34 +174,33 @@ __global__ void __launch_bounds__(NT) bp_generic_kernel(BackParams P) {
             const double* cxN = tp(P.cx, b, N - 1);
             const double* cxxN = tp(P.cxx, b, N - 1);
             const double* cuuN = tp(P.cuu, b, N - 1);
-            for (int i = tid; i < n; i += NT) { s.Vx[i] = cxN[i]; Vxb[(long long)(N - 1) * n + i] = cxN[i]; }
-            for (int e = tid; e < n * n; e += NT) {
-                int i = e % n, j = e / n;
+            for (int i = tid; i < n; i += NTL) { s.Vx[i] = cxN[i]; Vxb[(long long)(N - 1) * n + i] = cxN[i]; }
+            FOR_RC(e, i, j, n * n, n) {
                 double v = cxxN[e];
                 s.V[i + ldn * j] = v;
                 if (Vxxb) Vxxb[(long long)(N - 1) * nn + e] = v;
                 if (Vtb && i <= j) Vtb[(long long)(N - 1) * trn + (long long)j * (j + 1) / 2 + i] = v;
             }
-            for (int e = tid; e < m * n; e += NT) Kb[(long long)(N - 1) * mn + e] = 0.0;
-            for (int a = tid; a < m; a += NT) { kb[(long long)(N - 1) * m + a] = 0.0; s.kw[a] = 0.0; }
+            for (int e = tid; e < m * n; e += NTL) Kb[(long long)(N - 1) * mn + e] = 0.0;
+            for (int a = tid; a < m; a += NTL) { kb[(long long)(N - 1) * m + a] = 0.0; s.kw[a] = 0.0; }
             if (GPS) {
                 const double* SiN = tp(P.Sip, b, N - 1);
-                for (int e = tid; e < m * m; e += NT) {
+                for (int e = tid; e < m * m; e += NTL) {
                     double v = cuuN[e] / eta + SiN[e];
                     s.Quu[e] = v;
                     s.QuuF[e] = v;
                     if (Quub) Quub[(long long)(N - 1) * mm + e] = v;
                     if (Qtb && (e % m) <= (e / m)) Qtb[(long long)(N - 1) * trm + (long long)(e / m) * (e / m + 1) / 2 + (e % m)] = v;
                 }
-                __syncthreads();
+                sync();
                 if (tid == 0) inv_gj(m, s.QuuF, s.Inv);
-                __syncthreads();
-                for (int e = tid; e < m * m; e += NT) {
+                sync();
+                for (int e = tid; e < m * m; e += NTL) {
                     if (Quuib) Quuib[(long long)(N - 1) * mm + e] = s.Inv[e];
                     if (Qitb && (e % m) <= (e / m)) Qitb[(long long)(N - 1) * trm + (long long)(e / m) * (e / m + 1) / 2 + (e % m)] = s.Inv[e];
                 }
             } else if (Quub || Qtb) {
-                for (int e = tid; e < m * m; e += NT) {
+                for (int e = tid; e < m * m; e += NTL) {
                     if (Quub) Quub[(long long)(N - 1) * mm + e] = cuuN[e];
                     if (Qtb && (e % m) <= (e / m)) Qtb[(long long)(N - 1) * trm + (long long)(e / m) * (e / m + 1) / 2 + (e % m)] = cuuN[e];
                 }
@@ -164,39 +215,37 @@ __global__ void __launch_bounds__(NT) bp_generic_kernel(BackParams P) {
             if (!lti || i == N - 2) {
                 const double* fxi = tp(P.fx, b, i);
                 const double* fui = tp(P.fu, b, i);
-                for (int e = tid; e < n * n; e += NT) s.Fx[(e % n) + ldn * (e / n)] = fxi[e];
-                for (int e = tid; e < n * m; e += NT) s.Fu[(e % n) + ldn * (e / n)] = fui[e];
+                FOR_RC(e, r_, c_, n * n, n) s.Fx[r_ + ldn * c_] = fxi[e];
+                FOR_RC(e, r_, c_, n * m, n) s.Fu[r_ + ldn * c_] = fui[e];
             }
             if (GPS) {
                 const double* Kpi = tp(P.Kp, b, i);
                 const double* Sii = tp(P.Sip, b, i);
-                for (int e = tid; e < m * n; e += NT) s.Kp[(e % m) + ldm * (e / m)] = Kpi[e];
-                for (int e = tid; e < m * m; e += NT) s.Si[e] = Sii[e];
-                for (int a = tid; a < m; a += NT) s.kp[a] = P.kp.p ? tp(P.kp, b, i)[a] : 0.0;
+                FOR_RC(e, r_, c_, m * n, m) s.Kp[r_ + ldm * c_] = Kpi[e];
+                for (int e = tid; e < m * m; e += NTL) s.Si[e] = Sii[e];
+                for (int a = tid; a < m; a += NTL) s.kp[a] = P.kp.p ? tp(P.kp, b, i)[a] : 0.0;
             }
-            __syncthreads();
+            sync();
             // ---- W = Vxx fx, Z = Vxx fu
-            for (int e = tid; e < n * (n + m); e += NT) {
-                int r = e % n, c = e / n;
+            FOR_RC(e, r, c, n * (n + m), n) {
                 const double* col = (c < n) ? (s.Fx + ldn * c) : (s.Fu + ldn * (c - n));
                 double acc = 0.0;
                 for (int q = 0; q < n; q++) acc = fma(s.V[r + ldn * q], col[q], acc);
                 if (c < n) s.W[r + ldn * c] = acc; else s.Z[r + ldn * (c - n)] = acc;
             }
             if (GPS) {   // S = Σi K_prev ; Sik = Σi k_prev
-                for (int e = tid; e < m * n; e += NT) {
-                    int a = e % m, j = e / m;
+                FOR_RC(e, a, j, m * n, m) {
                     double acc = 0.0;
                     for (int q = 0; q < m; q++) acc = fma(s.Si[a + m * q], s.Kp[q + ldm * j], acc);
                     s.S[a + ldm * j] = acc;
                 }
-                for (int a = tid; a < m; a += NT) {
+                for (int a = tid; a < m; a += NTL) {
                     double acc = 0.0;
                     for (int q = 0; q < m; q++) acc = fma(s.Si[a + m * q], s.kp[q], acc);
                     s.Sik[a] = acc;
                 }
             }
-            __syncthreads();
+            sync();
             // ---- Q expansion (backward_pass.jl:240-247)
             {
                 const double* cxi = tp(P.cx, b, i);
@@ -204,8 +253,7 @@ __global__ void __launch_bounds__(NT) bp_generic_kernel(BackParams P) {
                 const double* cxxi = tp(P.cxx, b, i);
                 const double* cxui = tp(P.cxu, b, i);
                 const double* cuui = tp(P.cuu, b, i);
-                for (int e = tid; e < n * n; e += NT) {          // Qxx = cxx + fx' W
-                    int r = e % n, c = e / n;
+                FOR_RC(e, r, c, n * n, n) {          // Qxx = cxx + fx' W
                     double acc = 0.0;
                     for (int q = 0; q < n; q++) acc = fma(s.Fx[q + ldn * r], s.W[q + ldn * c], acc);
                     double v = cxxi[e] + acc;
@@ -222,8 +270,7 @@ __global__ void __launch_bounds__(NT) bp_generic_kernel(BackParams P) {
                     }
                     s.Qxx[r + ldn * c] = v;
                 }
-                for (int e = tid; e < m * n; e += NT) {          // Qux = cxu' + fu' W
-                    int a = e % m, j = e / m;
+                FOR_RC(e, a, j, m * n, m) {          // Qux = cxu' + fu' W
                     double acc = 0.0;
                     for (int q = 0; q < n; q++) acc = fma(s.Fu[q + ldn * a], s.W[q + ldn * j], acc);
                     double v = cxui[j + n * a] + acc;
@@ -246,8 +293,7 @@ __global__ void __launch_bounds__(NT) bp_generic_kernel(BackParams P) {
                     s.Qux[a + ldm * j] = v;
                     s.Quxr[a + ldm * j] = vr;
                 }
-                for (int e = tid; e < m * m; e += NT) {          // Quu = cuu + fu' Z
-                    int a = e % m, c = e / m;
+                FOR_RC(e, a, c, m * m, m) {          // Quu = cuu + fu' Z
                     double acc = 0.0;
                     for (int q = 0; q < n; q++) acc = fma(s.Fu[q + ldn * a], s.Z[q + ldn * c], acc);
                     double v = cuui[e] + acc;
@@ -272,7 +318,7 @@ __global__ void __launch_bounds__(NT) bp_generic_kernel(BackParams P) {
                     s.Quu[e] = v;
                     s.QuuF[e] = vf;
                 }
-                for (int r = tid; r < n; r += NT) {              // Qx = cx + fx' Vx
+                for (int r = tid; r < n; r += NTL) {              // Qx = cx + fx' Vx
                     double acc = 0.0;
                     for (int q = 0; q < n; q++) acc = fma(s.Fx[q + ldn * r], s.Vx[q], acc);
                     double v = cxi[r] + acc;
@@ -283,7 +329,7 @@ __global__ void __launch_bounds__(NT) bp_generic_kernel(BackParams P) {
                     }
                     s.Qx[r] = v;
                 }
-                for (int a = tid; a < m; a += NT) {              // Qu = cu + fu' Vx
+                for (int a = tid; a < m; a += NTL) {              // Qu = cu + fu' Vx
                     double acc = 0.0;
                     for (int q = 0; q < n; q++) acc = fma(s.Fu[q + ldn * a], s.Vx[q], acc);
                     double v = cui[a] + acc;
@@ -297,73 +343,52 @@ __global__ void __launch_bounds__(NT) bp_generic_kernel(BackParams P) {
                     }
                 }
             }
-            __syncthreads();
+            sync();
             if (GPS) {                                            // Quu = ½(Quu + Quu')  :301
-                for (int e = tid; e < m * m; e += NT) {
-                    int a = e % m, c = e / m;
+                FOR_RC(e, a, c, m * m, m) {
                     if (a < c) {                                  // each unordered pair owned by one thread
                         double w = 0.5 * (s.Quu[a + m * c] + s.Quu[c + m * a]);
                         s.Quu[a + m * c] = w; s.Quu[c + m * a] = w;
                         s.QuuF[a + m * c] = w; s.QuuF[c + m * a] = w;
                     }
                 }
-                __syncthreads();
+                sync();
             }
             // ---- factorisation / QP (one thread, fixed sequential order shared with the oracle)
             if (tid == 0) {
-                int st = 0;
-                if (!use_qp) {
-                    int idx[DDP_MAX_M];
-                    for (int a = 0; a < m; a++) idx[a] = a;
-                    if (!chol_upper_sub<DDP_MAX_M>(s.QuuF, m, idx, m, s.R, m)) {
-                        st = 1;
-                    } else {
-                        for (int a = 0; a < m; a++) s.k[a] = s.Qu[a];
-                        chol_solve<DDP_MAX_M>(s.R, m, m, s.k);
-                        for (int a = 0; a < m; a++) s.k[a] = -s.k[a];
-                        s.flags[1] = (m >= 32) ? -1 : (int)((1u << m) - 1u);
-                        s.flags[2] = m;
-                    }
-                } else {
-                    unsigned fm = 0;
-                    int nfac = 0;
-                    int res = boxqp_seq<DDP_MAX_M>(m, s.QuuF, m, s.Qu, s.lo, s.up, s.kw, P.qp, s.k, s.R, m, &fm, &nfac);
-                    if (res < 1) st = 1;                           // :50-56
-                    s.flags[1] = (int)fm;
-                    s.flags[2] = __popc(fm);
-                }
+                int st;
+                if (m <= 2) st = factor_step<2>(m, use_qp, P.qp, s.QuuF, s.Qu, s.lo, s.up, s.kw, s.k, s.R, s.flags);
+                else if (m <= 4) st = factor_step<4>(m, use_qp, P.qp, s.QuuF, s.Qu, s.lo, s.up, s.kw, s.k, s.R, s.flags);
+                else if (m <= 8) st = factor_step<8>(m, use_qp, P.qp, s.QuuF, s.Qu, s.lo, s.up, s.kw, s.k, s.R, s.flags);
+                else st = factor_step<DDP_MAX_M>(m, use_qp, P.qp, s.QuuF, s.Qu, s.lo, s.up, s.kw, s.k, s.R, s.flags);
                 s.flags[0] = st;
             }
-            __syncthreads();
+            sync();
             if (s.flags[0] != 0) { diverge = i + 1; break; }
             // ---- gains K (:42 / :57-61): one column per thread
             {
                 const unsigned fm = (unsigned)s.flags[1];
                 const int nf = s.flags[2];
-                for (int j = tid; j < n; j += NT) {
-                    double v[DDP_MAX_M];
-                    int p = 0;
-                    for (int a = 0; a < m; a++)
-                        if ((fm >> a) & 1u) v[p++] = s.Quxr[a + ldm * j];
-                    if (nf > 0) chol_solve<DDP_MAX_M>(s.R, m, nf, v);
-                    p = 0;
-                    for (int a = 0; a < m; a++) s.K[a + ldm * j] = ((fm >> a) & 1u) ? -v[p++] : 0.0;
+                for (int j = tid; j < n; j += NTL) {
+                    if (m <= 2) gain_column<2>(m, fm, nf, s.R, s.Quxr + ldm * j, s.K + ldm * j);
+                    else if (m <= 4) gain_column<4>(m, fm, nf, s.R, s.Quxr + ldm * j, s.K + ldm * j);
+                    else if (m <= 8) gain_column<8>(m, fm, nf, s.R, s.Quxr + ldm * j, s.K + ldm * j);
+                    else gain_column<DDP_MAX_M>(m, fm, nf, s.R, s.Quxr + ldm * j, s.K + ldm * j);
                 }
             }
-            __syncthreads();
+            sync();
             // ---- QK = Quu K, Quuk = Quu k
-            for (int e = tid; e < m * n; e += NT) {
-                int a = e % m, j = e / m;
+            FOR_RC(e, a, j, m * n, m) {
                 double acc = 0.0;
                 for (int q = 0; q < m; q++) acc = fma(s.Quu[a + m * q], s.K[q + ldm * j], acc);
                 s.QK[a + ldm * j] = acc;
             }
-            for (int a = tid; a < m; a += NT) {
+            for (int a = tid; a < m; a += NTL) {
                 double acc = 0.0;
                 for (int q = 0; q < m; q++) acc = fma(s.Quu[a + m * q], s.k[q], acc);
                 s.Quuk[a] = acc;
             }
-            __syncthreads();
+            sync();
             // ---- value backup (:64-72)
             if (tid == 0) {
                 double a0 = 0.0, a1 = 0.0;
@@ -371,7 +396,7 @@ __global__ void __launch_bounds__(NT) bp_generic_kernel(BackParams P) {
                 dV0 += a0;
                 dV1 += 0.5 * a1;
             }
-            for (int r = tid; r < n; r += NT) {
+            for (int r = tid; r < n; r += NTL) {
                 double t1 = 0.0, t2 = 0.0, t3 = 0.0;
                 for (int q = 0; q < m; q++) {
                     t1 = fma(s.K[q + ldm * r], s.Quuk[q], t1);
@@ -380,8 +405,7 @@ __global__ void __launch_bounds__(NT) bp_generic_kernel(BackParams P) {
                 }
                 s.VxN[r] = ((s.Qx[r] + t1) + t2) + t3;
             }
-            for (int e = tid; e < n * n; e += NT) {
-                int r = e % n, c = e / n;
+            FOR_RC(e, r, c, n * n, n) {
                 double t1 = 0.0, t2 = 0.0, t3 = 0.0;
                 for (int q = 0; q < m; q++) {
                     t1 = fma(s.K[q + ldm * r], s.QK[q + ldm * c], t1);
@@ -390,46 +414,45 @@ __global__ void __launch_bounds__(NT) bp_generic_kernel(BackParams P) {
                 }
                 s.W[r + ldn * c] = ((s.Qxx[r + ldn * c] + t1) + t2) + t3;
             }
-            if (GPS && tid == 32) {                               // Σ = inv(Quu)  :346
+            if (GPS && tid == (WPT ? 1 : 32)) {                               // Σ = inv(Quu)  :346
                 for (int e = 0; e < m * m; e++) s.QuuF[e] = s.Quu[e];
                 inv_gj(m, s.QuuF, s.Inv);
             }
-            __syncthreads();
+            sync();
             // ---- symmetrise, commit, store
-            for (int e = tid; e < n * n; e += NT) {
-                int r = e % n, c = e / n;
+            FOR_RC(e, r, c, n * n, n) {
                 double v = 0.5 * (s.W[r + ldn * c] + s.W[c + ldn * r]);
                 s.V[r + ldn * c] = v;
                 if (Vxxb) Vxxb[(long long)i * nn + e] = v;
                 if (Vtb && r <= c) Vtb[(long long)i * trn + (long long)c * (c + 1) / 2 + r] = v;
             }
-            for (int r = tid; r < n; r += NT) { s.Vx[r] = s.VxN[r]; Vxb[(long long)i * n + r] = s.VxN[r]; }
-            for (int e = tid; e < m * n; e += NT) Kb[(long long)i * mn + e] = s.K[(e % m) + ldm * (e / m)];
-            for (int a = tid; a < m; a += NT) { kb[(long long)i * m + a] = s.k[a]; s.kw[a] = s.k[a]; }
-            for (int e = tid; e < m * m; e += NT) {
-                const long long te = (long long)(e / m) * (e / m + 1) / 2 + (e % m);
-                const bool up = (e % m) <= (e / m);
+            for (int r = tid; r < n; r += NTL) { s.Vx[r] = s.VxN[r]; Vxb[(long long)i * n + r] = s.VxN[r]; }
+            FOR_RC(e, r_, c_, m * n, m) Kb[(long long)i * mn + e] = s.K[r_ + ldm * c_];
+            for (int a = tid; a < m; a += NTL) { kb[(long long)i * m + a] = s.k[a]; s.kw[a] = s.k[a]; }
+            if (Quub || Qtb || Quuib || Qitb) FOR_RC(e, r_, c_, m * m, m) {
+                const long long te = (long long)c_ * (c_ + 1) / 2 + r_;
+                const bool up = r_ <= c_;
                 if (Quub) Quub[(long long)i * mm + e] = s.Quu[e];
                 if (Qtb && up) Qtb[(long long)i * trm + te] = s.Quu[e];
                 if (Quuib) Quuib[(long long)i * mm + e] = s.Inv[e];
                 if (Qitb && up) Qitb[(long long)i * trm + te] = s.Inv[e];
             }
-            __syncthreads();
+            sync();
         }
         // ---- epilogue
         if (diverge > 0) {
             // the reference returns with everything below the failed step still zero (quirk Q10)
             const int upto = diverge - 1;   // 0-based failed step; steps 0..upto stay zero
-            for (long long e = tid; e < (long long)(upto + 1) * mn; e += NT) Kb[e] = 0.0;
-            for (long long e = tid; e < (long long)(upto + 1) * m; e += NT) kb[e] = 0.0;
-            for (long long e = tid; e < (long long)(upto + 1) * n; e += NT) Vxb[e] = 0.0;
+            for (long long e = tid; e < (long long)(upto + 1) * mn; e += NTL) Kb[e] = 0.0;
+            for (long long e = tid; e < (long long)(upto + 1) * m; e += NTL) kb[e] = 0.0;
+            for (long long e = tid; e < (long long)(upto + 1) * n; e += NTL) Vxb[e] = 0.0;
             if (Vxxb)
-                for (long long e = tid; e < (long long)(upto + 1) * nn; e += NT) Vxxb[e] = 0.0;
+                for (long long e = tid; e < (long long)(upto + 1) * nn; e += NTL) Vxxb[e] = 0.0;
             if (Vtb)
-                for (long long e = tid; e < (long long)(upto + 1) * trn; e += NT) Vtb[e] = 0.0;
+                for (long long e = tid; e < (long long)(upto + 1) * trn; e += NTL) Vtb[e] = 0.0;
         }
         if (P.Vxx1)
-            for (int e = tid; e < n * n; e += NT)
+            for (int e = tid; e < n * n; e += NTL)
                 P.Vxx1[b * nn + e] = (diverge > 0) ? 0.0 : s.V[(e % n) + ldn * (e / n)];
         if (tid == 0) {
             P.diverge[b] = diverge;
@@ -460,20 +483,32 @@ int prepare_redo(ddp_handle_s* h, BackParams& P) {
 }
 
 int launch_back_pass_generic(ddp_handle_s* h, const BackParams& P, bool gps) {
-    size_t bytes = smem_doubles(P.n, P.m, gps) * sizeof(double);
-    if ((long long)bytes > h->max_smem_optin) return (int)cudaErrorInvalidValue;
+    const size_t per_traj = smem_doubles(P.n, P.m, gps) * sizeof(double);
+    if ((long long)per_traj > h->max_smem_optin) return (int)cudaErrorInvalidValue;
+    // small shapes: one warp per trajectory, four trajectories per CTA (see the header); DDP_GENERIC_NO_WPT=1 forces the CTA form
+    static const bool no_wpt = getenv("DDP_GENERIC_NO_WPT") != nullptr;
+    const bool wpt = !no_wpt && P.n <= 16 && (long long)(per_traj * (NT / 32)) <= h->max_smem_optin;
+    const size_t bytes = wpt ? per_traj * (NT / 32) : per_traj;
     cudaError_t e;
-    if (gps) e = cudaFuncSetAttribute(bp_generic_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    else e = cudaFuncSetAttribute(bp_generic_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (gps) e = wpt ? cudaFuncSetAttribute(bp_generic_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)
+                     : cudaFuncSetAttribute(bp_generic_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    else e = wpt ? cudaFuncSetAttribute(bp_generic_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)
+                 : cudaFuncSetAttribute(bp_generic_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return (int)e;
     int per_sm = (int)((size_t)h->max_smem_optin / (bytes + 1024));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 16) per_sm = 16;
     long long grid = (long long)h->sm_count * per_sm;
-    if (grid > P.B) grid = P.B;
+    const long long need = wpt ? (P.B + NT / 32 - 1) / (NT / 32) : P.B;
+    if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    if (gps) bp_generic_kernel<true><<<(unsigned)grid, NT, bytes, h->stream>>>(P);
-    else bp_generic_kernel<false><<<(unsigned)grid, NT, bytes, h->stream>>>(P);
+    if (gps) {
+        if (wpt) bp_generic_kernel<true, true><<<(unsigned)grid, NT, bytes, h->stream>>>(P);
+        else bp_generic_kernel<true, false><<<(unsigned)grid, NT, bytes, h->stream>>>(P);
+    } else {
+        if (wpt) bp_generic_kernel<false, true><<<(unsigned)grid, NT, bytes, h->stream>>>(P);
+        else bp_generic_kernel<false, false><<<(unsigned)grid, NT, bytes, h->stream>>>(P);
+    }
     h->launches++;
     return (int)cudaGetLastError();
 }
