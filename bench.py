@@ -623,6 +623,13 @@ def main_gpu(args):
     # =============================================================================================================
     # whole solve end to end: iLQG(f,costfun,df,x0,u0) moves x0,u0 up once and x,u,K,k down once (iLQG.jl:143-341)
     # =============================================================================================================
+    if "c1" in want and world == 1:
+        try:
+            results["c1"] = run_c1(common)
+        except Exception as exc:
+            results["c1"] = dict(error=f"{type(exc).__name__}: {exc}")
+        torch.cuda.empty_cache()
+
     if "solve" in want and world == 1:
         try:
             results["solve_e2e"] = run_solve_e2e(common)
@@ -1028,6 +1035,70 @@ def run_c2_lims(g):
     return res
 
 
+def run_c1(g):
+    """BASELINE configs[0]'s problem as a batch: demo_linear (demo_linear.jl:5-60) n=10 m=2 T=1000, 16384 trajectories -- one
+    back_pass + forward_pass on the coverage kernels (bp_generic_kernel in its warp-per-trajectory form, fwd_generic_kernel)."""
+    import torch
+    from oracle import ddp_oracle as O
+    ddp, L, dev, tn, ev = g["ddp"], g["L"], g["dev"], g["tn"], g["ev"]
+    args, rank = g["args"], g["rank"]
+    n, m, T, B, h = 10, 2, 1000, 16384, 0.01
+    f64 = torch.float64
+    empty = lambda *s_: torch.empty(*s_, dtype=f64, device=dev)
+    gen = torch.Generator(device=dev); gen.manual_seed(31)
+    G = torch.randn(B, n, n, dtype=f64, device=dev, generator=gen)
+    fx = torch.linalg.matrix_exp(h * (G - G.transpose(1, 2))).transpose(1, 2).contiguous()
+    fu = (h * torch.randn(B, n, m, dtype=f64, device=dev, generator=gen)).transpose(1, 2).contiguous()
+    x0 = torch.ones(B, n, dtype=f64, device=dev)
+    u = 0.1 * torch.randn(B, T, m, dtype=f64, device=dev, generator=gen)
+    Q = (h * torch.eye(n, dtype=f64, device=dev)).contiguous(); R = (0.1 * h * torch.eye(m, dtype=f64, device=dev)).contiguous()
+    cxu = torch.zeros(m, n, dtype=f64, device=dev); lam = torch.ones(B, dtype=f64, device=dev)
+    eng = ddp.Engine(n, m, T, B, device=g["local_rank"])
+    eng.set_stream(torch.cuda.current_stream().cuda_stream)
+    model = L.Model(); model.kind = 1
+    model.A, model.Bm, model.Q, model.R, model.flags = tn(fx, n * n, 0), tn(fu, n * m, 0), tn(Q, 0, 0), tn(R, 0, 0), 1
+    x, c0, un, cx, cu = empty(B, T, n), empty(B), empty(B, T, m), empty(B, T, n), empty(B, T, m)
+    fa = L.ForwardPassArgs(); fa.x0, fa.u = tn(x0, n, 0), tn(u, T * m, m); fa.alpha_scalar = fa.u_scale = 1.0
+    fa.xnew, fa.unew, fa.cost, fa.cx, fa.cu = x.data_ptr(), un.data_ptr(), c0.data_ptr(), cx.data_ptr(), cu.data_ptr()
+    eng._ck(eng.lib.ddp_forward_pass_f64(eng.h, C.byref(model), C.byref(fa)))
+    K, k, Vx, dV = empty(B, T, n, m), empty(B, T, m), empty(B, T, n), empty(B, 2)
+    dv = torch.empty(B, dtype=torch.int32, device=dev)
+    ba = L.BackPassArgs()
+    ba.cx, ba.cu, ba.cxx, ba.cxu, ba.cuu = tn(cx, T * n, n), tn(cu, T * m, m), tn(Q, 0, 0), tn(cxu, 0, 0), tn(R, 0, 0)
+    ba.fx, ba.fu, ba.lam, ba.reg_type = tn(fx, n * n, 0), tn(fu, n * m, 0), lam.data_ptr(), 1
+    ba.diverge, ba.K, ba.k, ba.Vx, ba.dV = dv.data_ptr(), K.data_ptr(), k.data_ptr(), Vx.data_ptr(), dV.data_ptr()
+    xn, unw, cst = empty(B, T, n), empty(B, T, m), empty(B)
+    fp = L.ForwardPassArgs()
+    fp.K, fp.k = K.data_ptr(), k.data_ptr()
+    fp.x0, fp.x, fp.u = tn(x, T * n, 0), tn(x, T * n, n), tn(u, T * m, m)
+    fp.alpha_scalar, fp.u_scale = 1.0, 1.0
+    fp.xnew, fp.unew, fp.cost = xn.data_ptr(), unw.data_ptr(), cst.data_ptr()
+
+    def one(parts):
+        if parts is not None:
+            parts.append(ev()); parts[-1].record()
+        eng._ck(eng.lib.ddp_back_pass_f64(eng.h, C.byref(ba)))
+        if parts is not None:
+            parts.append(ev()); parts[-1].record()
+        eng._ck(eng.lib.ddp_forward_pass_f64(eng.h, C.byref(model), C.byref(fp)))
+        if parts is not None:
+            parts.append(ev()); parts[-1].record()
+
+    steps, warm = max(2, min(args.steps, 3)), 3
+    ms, (bk, fw) = _timed(one, steps, warm, torch.cuda.synchronize)
+    res = dict(workload="C1 batched: demo_linear n=10 m=2 T=1000 (BASELINE.json configs[0]'s problem; the reference runs one trajectory), 16384 "
+                        "trajectories, one back_pass + forward_pass(alpha=1) on the coverage kernels (bp_generic_kernel<warp per trajectory>, fwd_generic_kernel)",
+               batch=B, steps=steps, warmup=warm, ms_per_iter=ms, iters_per_s=1e3 / ms, back_pass_ms=bk, forward_ms=fw,
+               trajectory_steps_per_s=B * T / (ms * 1e-3), diverged=int((dv > 0).sum().item()))
+    if rank == 0 and args.oracle_samples > 0:
+        ns = max(2, args.oracle_samples // 8)
+        idx = np.sort(np.random.default_rng(12).choice(B, size=ns, replace=False))
+        rep = check_linear(idx, fx, fu, x, u, cx, cu, Q, R, lam, K, k, Vx, None, dV, dv, xn, unw, cst)
+        res["oracle"] = rep
+    eng.close()
+    return res
+
+
 def run_solve_e2e(g):
     """What iLQG(f,costfun,df,x0,u0) actually moves (iLQG.jl:143-341): x0,u0 up once, then the whole outer loop on the device
     (ddp_ilqg_solve_f64), then x,u,K,k,cost down once.  Reported per accepted-or-rejected outer iteration."""
@@ -1292,7 +1363,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-sample", type=int, default=1024, help="trajectories in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--configs", default="c3,c4,c5,solve,c2lims,linesearch", help="other BASELINE configurations to measure in the same run (comma list; '' = none)")
+    ap.add_argument("--configs", default="c1,c3,c4,c5,solve,c2lims,linesearch", help="other BASELINE configurations to measure in the same run (comma list; '' = none)")
     ap.add_argument("--oracle-samples", type=int, default=32, help="trajectories of each timed batch re-computed by the CPU oracle (0 = off)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
