@@ -485,9 +485,13 @@ int prepare_redo(ddp_handle_s* h, BackParams& P) {
 int launch_back_pass_generic(ddp_handle_s* h, const BackParams& P, bool gps) {
     const size_t per_traj = smem_doubles(P.n, P.m, gps) * sizeof(double);
     if ((long long)per_traj > h->max_smem_optin) return (int)cudaErrorInvalidValue;
-    // small shapes: one warp per trajectory, four trajectories per CTA (see the header); DDP_GENERIC_NO_WPT=1 forces the CTA form
-    static const bool no_wpt = getenv("DDP_GENERIC_NO_WPT") != nullptr;
-    const bool wpt = !no_wpt && P.n <= 16 && (long long)(per_traj * (NT / 32)) <= h->max_smem_optin;
+    // small shapes: one warp per trajectory, four trajectories per CTA (see the header); DDP_GENERIC_WPT=0 / 1 forces the CTA /
+    // the warp form (read at every launch: the tests compare the two)
+    const char* env_wpt = getenv("DDP_GENERIC_WPT");
+    const bool no_wpt = env_wpt && env_wpt[0] == '0', force_wpt = env_wpt && env_wpt[0] == '1';
+    // (a small batch does not fill the SMs either way: there the CTA form's four warps per trajectory give the lower latency --
+    // one demo_linear trajectory, whole solve: 89 ms against 133 ms)
+    const bool wpt = !no_wpt && P.n <= 16 && (force_wpt || P.B > (long long)h->sm_count * 8) && (long long)(per_traj * (NT / 32)) <= h->max_smem_optin;
     const size_t bytes = wpt ? per_traj * (NT / 32) : per_traj;
     cudaError_t e;
     if (gps) e = wpt ? cudaFuncSetAttribute(bp_generic_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)

@@ -730,3 +730,46 @@ def test_kl_partial_state_covariance_cache(ddp):
     a2, _ = ddp.kl_div_wiki(st(xs), st(xo), A4, R1, gpn, gpp, engine=eng, Sx_cache=cache, Sx_mode=2, Sx_count=3)
     assert np.array_equal(ref, a1) and np.array_equal(ref, a2) and np.all(ref > 0)
     eng.close()
+
+
+@pytest.mark.parametrize("n,m,N,lims,regType", [(10, 2, 40, None, 1), (6, 2, 25, 0.2, 2), (16, 4, 18, 0.3, 1), (13, 3, 20, None, 2)])
+def test_generic_kernel_warp_per_trajectory_form(ddp, monkeypatch, n, m, N, lims, regType):
+    """bp_generic_kernel<WPT>: one warp per trajectory (what large batches of small problems run, e.g. the reference's demo shape
+    n=10, m=2) against the CTA-per-trajectory form: the same arithmetic element by element, so every output is bit-identical;
+    and against the oracle."""
+    B = 7
+    A, Bm, Q, R, x, u = make_batch_lq(300 + n, B, n, m, N)
+    cx, cu = x @ Q.T, u @ R.T
+    lim = None if lims is None else np.tile(np.array([[-lims, lims]]), (m, 1))
+    lam = 1e-2 * (1 + np.arange(B))
+    outs = {}
+    for form in ("0", "1"):
+        monkeypatch.setenv("DDP_GENERIC_WPT", form)
+        outs[form] = ddp.back_pass(cx, cu, Q, np.zeros((n, m)), R, A[:, None], Bm[:, None], lam, regType, lim, x, u, force_generic=True)
+    monkeypatch.delenv("DDP_GENERIC_WPT")
+    a, b = outs["0"], outs["1"]
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1].K, b[1].K) and np.array_equal(a[1].k, b[1].k)
+    assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3]) and np.array_equal(a[4], b[4])
+    for t in range(B):
+        d0, p0, Vx0, Vxx0, dV0 = O.back_pass(cx[t], cu[t], Q, np.zeros((n, m)), R, A[t], Bm[t], lam[t], regType, lim, x[t], u[t])
+        assert b[0][t] == d0
+        for got, ref in ((b[1].K[t], p0.K), (b[1].k[t], p0.k), (b[2][t], Vx0), (b[3][t], Vxx0), (b[4][t], dV0)):
+            assert relerr_elem(got, ref) < TOL
+
+
+def test_generic_gps_kernel_warp_per_trajectory_form(ddp, monkeypatch):
+    """the KL-augmented sweep on the same two forms of the generic kernel: bit-identical."""
+    from test_gpu_misc import _prev_policy
+    n, m, N = 8, 2, 30
+    A, Bm, Q, R, x, u, cx, cu, prev = _prev_policy(n, m, N, 21)
+    rep = lambda a_: np.tile(a_, (N, 1, 1))
+    gp = ddp.GaussianPolicy(N, n, m, prev.K, prev.k, prev.Sigma, prev.Sigmai)
+    outs = {}
+    for form in ("0", "1"):
+        monkeypatch.setenv("DDP_GENERIC_WPT", form)
+        outs[form] = ddp.back_pass_gps(cx, cu, rep(Q), rep(np.zeros((n, m))), rep(R), rep(A), rep(Bm), None, x, u, (gp, 2.0), force_generic=True)
+    monkeypatch.delenv("DDP_GENERIC_WPT")
+    a, b = outs["0"], outs["1"]
+    assert a[0] == b[0] == 0
+    for u_, v_ in ((a[1].K, b[1].K), (a[1].k, b[1].k), (a[1].Sigma, b[1].Sigma), (a[1].Sigmai, b[1].Sigmai), (a[2], b[2]), (a[3], b[3]), (a[4], b[4])):
+        assert np.array_equal(u_, v_)
