@@ -12,6 +12,8 @@ timeout 900 python bench.py > $o/${tag}_bench.json 2> $o/${tag}_bench.err
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $o/${tag}_bench_ref.json 2> $o/${tag}_bench_ref.err
 timeout 600 python scripts/perf_lims.py 9472 0.3 > $o/${tag}_lims_tight.json 2> $o/${tag}_lims.err
 timeout 600 python scripts/perf_lims.py 9472 3.0 > $o/${tag}_lims_loose.json 2>> $o/${tag}_lims.err
+timeout 200 python scripts/perf_c1.py 16384 > $o/${tag}_c1.json 2>&1
+timeout 200 python scripts/perf_single.py > $o/${tag}_single.json 2>&1
 timeout 200 python scripts/perf_probe.py 9472 ltv > $o/${tag}_ltv.log 2>&1
 timeout 300 python scripts/bench_configs.py solve c3 65536 > $o/${tag}_solve_c3.json 2>&1
 python scripts/pcie_scaling.py > $o/${tag}_pcie_1gpu.json 2>&1
@@ -35,6 +37,8 @@ cap bp_tile_gps "bp_tile32x8_kernel<.*1, .0, .0, .0>|bp_tile32x8_kernelILb0ELb1"
 # sanitizer on the kernels added or rewritten this round (small shapes)
 timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 1 python -m pytest tests/test_gpu_round2.py tests/test_gpu_back_pass.py -q -x -k "not boxqp_large or 24" > $o/${tag}_memcheck.log 2>&1
 echo "memcheck exit $?" >> $o/${tag}_memcheck.log
-timeout 1500 compute-sanitizer --tool racecheck --error-exitcode 1 python -m pytest tests/test_gpu_round2.py tests/test_gpu_back_pass.py -q -x -k "small or tile32x8_boxqp or with_limits or covariance_cache or boxqp_large and 24 or chunked" > $o/${tag}_racecheck.log 2>&1
+timeout 900 compute-sanitizer --tool synccheck --error-exitcode 1 python -m pytest tests/test_gpu_round2.py -q -x -k "tile32x8_boxqp or with_limits or regimes or covariance_cache or partial_state or warp_per_trajectory" > $o/${tag}_synccheck.log 2>&1
+echo "synccheck exit $?" >> $o/${tag}_synccheck.log
+timeout 1500 compute-sanitizer --tool racecheck --error-exitcode 1 python -m pytest tests/test_gpu_round2.py tests/test_gpu_back_pass.py -q -x -k "small or tile32x8_boxqp or with_limits or regimes or covariance_cache or partial_state or warp_per_trajectory or boxqp_large and 24 or chunked" > $o/${tag}_racecheck.log 2>&1
 echo "racecheck exit $?" >> $o/${tag}_racecheck.log
 ls -la $o | grep ${tag}_ | tail -50

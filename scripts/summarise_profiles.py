@@ -14,7 +14,8 @@ src, dst = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 copies = {f"{tag}_bench.json": f"bench_{tag}.json", f"{tag}_bench_ref.json": f"bench_ref_{tag}.json", f"{tag}_launches.csv": f"launches_{tag}.csv",
           f"{tag}_lims_loose.json": f"lims_loose_{tag}.json", f"{tag}_lims_tight.json": f"lims_tight_{tag}.json", f"{tag}_ltv.log": f"ltv_{tag}.log",
           f"{tag}_memcheck.log": f"sanitizer_memcheck_{tag}.log", f"{tag}_racecheck.log": f"sanitizer_racecheck_{tag}.log",
-          f"{tag}_smoke.log": f"smoke_{tag}.log", f"{tag}_solve_c3.json": f"solve_c3_{tag}.json"}
+          f"{tag}_smoke.log": f"smoke_{tag}.log", f"{tag}_solve_c3.json": f"solve_c3_{tag}.json",
+          f"{tag}_synccheck.log": f"sanitizer_synccheck_{tag}.log", f"{tag}_c1.json": f"c1_{tag}.json", f"{tag}_single.json": f"single_trajectory_{tag}.json"}
 for k in ("bp_tile", "fwd_lin", "bp_small", "fwd_pend", "kl_tile", "kl_cached", "bp_tile_lims", "bp_tile_gps"):
     copies[f"{tag}_{k}.txt"] = f"ncu_{k}_{tag}.txt"
 for a, b in copies.items():
