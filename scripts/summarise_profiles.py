@@ -32,7 +32,7 @@ ALG = {  # algorithmic bytes per trajectory and the batch 
     "bp_small": ("bp_small_kernel<4,1> at B = 262144", None, 262144),
     "fwd_pend": ("fwd_pend_staged_kernel at B = 262144", None, 262144),
     "kl_tile": ("kl_tile32x8_kernel<0> at B = 16384", None, 16384),
-    "kl_cached": ("kl_tile32x8_kernel<2> at B = 32768", 8.0 * (T * (2 * 256 + 2 * 32 + 8 + 3 * 64 + 528) + 1), 32768),
+    "kl_cached": ("kl_tile32x8_kernel<2> on the 50912 cached trajectories of the C4 batch", 8.0 * (T * (2 * 256 + 2 * 32 + 8 + 3 * 64 + 528) + 1), 50912),
 }
 old = {}
 for t in (tag, "r02"):
