@@ -822,11 +822,10 @@ __global__ void __launch_bounds__(wpb(LTV) * 32, (EXP & 4) ? 3 : 2) bp_tile32x8_
                 vxn[t] = qxv + sacc;
             }
             {
-                double d0 = k_own * Qu_own, d1 = k_own * Quuk_own;        // one term per group; sum over g
-#pragma unroll
-                for (int o = 4; o < 32; o <<= 1) { d0 += shx(d0, o); d1 += shx(d1, o); }
-                dV0 += d0;
-                dV1 += 0.5 * d1;
+                // one term per group g (the four lanes of a group hold the same one); the sum over the groups is taken once,
+                // after the sweep: the per-step butterfly was a dependent shuffle chain in every tail
+                dV0 = fma(k_own, Qu_own, dV0);
+                dV1 = fma(0.5 * k_own, Quuk_own, dV1);
             }
             // ---- outputs of this step
             {
@@ -922,6 +921,8 @@ __global__ void __launch_bounds__(wpb(LTV) * 32, (EXP & 4) ? 3 : 2) bp_tile32x8_
                 st2(P.Vxx1 + b * 1024 + col * 32 + r, t.x, t.y);
             }
         }
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) { dV0 += shx(dV0, o); dV1 += shx(dV1, o); }      // sum over the eight groups
         if (lane == 0) {
             P.diverge[b] = diverge;
             P.dV[2 * b] = dV0;
