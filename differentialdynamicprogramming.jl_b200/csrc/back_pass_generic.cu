@@ -461,6 +461,7 @@ __global__ void __launch_bounds__(NT, WPT ? 8 : 4) bp_generic_kernel(BackParams 
         }
     }
 }
+#undef FOR_RC
 
 }  // namespace
 
