@@ -487,6 +487,15 @@ __global__ void __launch_bounds__(wpb(LTV) * 32, (EXP & 4) ? 3 : 2) bp_tile32x8_
             if (LTV) {
                 cp_async_wait_all();
                 __syncwarp();
+                // the next step's [fx fu] (10 KB = 80 lines) is pulled into L2 now, a whole tensor phase before the cp.async refill
+                // below asks for it: the refill has only the step's non-tensor tail to land in, too short for a DRAM round trip
+                if (i > 0) {
+                    const char* pfx = reinterpret_cast<const char*>(tp(P.fx, b, i - 1));
+                    const char* pfu = reinterpret_cast<const char*>(tp(P.fu, b, i - 1));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pfx + 128 * lane));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pfx + 128 * (lane + 32)));
+                    if (lane < 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(pfu + 128 * lane));
+                }
             }
             // this step's cost gradients -> shared memory (group A; no registers are held across the tensor phase)
             if (lane < 16) cp_async16(&sCx[2 * lane], cxb + (long long)i * P.cx.st + 2 * lane);
